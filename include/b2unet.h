@@ -1,0 +1,221 @@
+/*
+ * b2unet.h -- C ABI of libb2unet.so: the B200 (sm_100a) implementation of Lifelong-nnUNet's per-step training hot path.
+ *
+ * The reference (MECLabTUDA/Lifelong-nnUNet @ fb55c48) is pure Python/PyTorch and has NO FFI of its own; each entry
+ * point below therefore cites the reference call it replaces (paths relative to the reference's nnunet_ext/).
+ * Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller (PyTorch) owns all memory: parameters, workspaces, outputs; the library never allocates device
+ *     memory behind the caller's back and never synchronises the host (all work is enqueued on `stream`);
+ *   - return value: 0 = ok, negative = error (see b2_last_error()); no C++ exceptions cross the ABI;
+ *   - activations live in HBM as NDHWC ("channels-last-3d"), fp32 (B2_F32 parity mode) or bf16 (B2_BF16);
+ *     parameters, gradients, logits, losses, Fisher / importance maps are always fp32.
+ */
+#ifndef B2UNET_H_
+#define B2UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2_stream_t; /* cudaStream_t */
+
+enum { B2_F32 = 0, B2_BF16 = 1 };
+enum { B2_OK = 0, B2_EINVAL = -1, B2_ECUDA = -2, B2_ENOMEM = -3, B2_EUNSUPPORTED = -4 };
+
+/* version / diagnostics */
+int b2_version(void);
+const char* b2_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+long long b2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Network plan.  Replaces the module graph built by nnunet's nnUNetTrainerV2.initialize_network() ->
+ * Generic_UNet(...) (ctor args restated at training/network_training/nnViTUNetTrainer.py:101-125) and the forward of
+ * network_architecture/generic_ViT_UNet.py:222-230,261-286 (the "copied from original implementation" part).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_unet_geometry {
+    int32_t batch;                /* patches per step on this GPU */
+    int32_t in_channels;
+    int32_t num_classes;
+    int32_t base_features;        /* 32 for plans v2.1 */
+    int32_t max_features;         /* 320 (3D) */
+    int32_t num_pool;             /* number of poolings == number of decoder levels (<= 7) */
+    int32_t patch[3];             /* D, H, W */
+    int32_t pool[7][3];           /* pool_op_kernel_sizes, stride per axis (1 or 2) */
+    int32_t act_dtype;            /* B2_F32 | B2_BF16 : storage type of activations */
+    float   lrelu_slope;          /* 1e-2 */
+    float   norm_eps;             /* 1e-5 */
+} b2_unet_geometry;
+
+typedef struct b2_unet_plan b2_unet_plan;
+
+int b2_unet_plan_create(const b2_unet_geometry* geom, b2_unet_plan** out);
+void b2_unet_plan_destroy(b2_unet_plan* plan);
+
+/* Parameter table.  Entry i describes the i-th parameter tensor in the plan's canonical order; `name` is the
+ * dotted PyTorch state_dict key of the reference module tree (test/network_architecture/test_MultiHead_Module.py:
+ * 281-432), e.g. "conv_blocks_context.0.blocks.0.conv.weight"; shape is the PyTorch shape (fp32, contiguous). */
+typedef struct b2_param_info {
+    char    name[96];
+    int32_t ndim;
+    int64_t shape[5];
+    int64_t numel;
+} b2_param_info;
+int b2_unet_num_params(const b2_unet_plan* plan);
+int b2_unet_param_info(const b2_unet_plan* plan, int idx, b2_param_info* out);
+
+/* bytes of the activation workspace (holds every tensor kept for backward) and of the scratch workspace */
+size_t b2_unet_workspace_bytes(const b2_unet_plan* plan);
+/* shape of deep-supervision output `level` (0 = full resolution): writes {D,H,W}; logits are NCDHW fp32 */
+int b2_unet_output_shape(const b2_unet_plan* plan, int level, int32_t dhw[3]);
+
+/* forward:  replaces `output = self.network(data)` (training/network_training/multihead/nnUNetTrainerMultiHead.py:
+ * 621/633).  params[i] = device pointer of parameter i (fp32).  input = NCDHW fp32 (as the trainer hands it over).
+ * logits[l] = caller-allocated NCDHW fp32 output for level l (num_pool entries, highest resolution first, exactly the
+ * tuple generic_ViT_UNet.py:282-284 returns).  With keep_for_backward == 0 the pass is inference-only (teacher /
+ * validation forwards: plop:258, mib:141, lwf:315-346). */
+int b2_unet_forward(b2_unet_plan* plan, const float* const* params, const float* input, void* workspace,
+                    float* const* logits, int keep_for_backward, b2_stream_t stream);
+
+/* backward: replaces `l.backward()` through the network (MultiHead:627/639).  dlogits[l] may be NULL (level without
+ * loss contribution, e.g. weight 0).  grads[i] = fp32 gradient buffer of parameter i, OVERWRITTEN (not accumulated);
+ * parameters that receive no gradient are zero-filled and flagged in has_grad_host[i] = 0 (caller may map that to
+ * `param.grad is None`, ewc:300-301).  Bit-reproducible: no floating-point atomics anywhere. */
+int b2_unet_backward(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
+                     float* const* grads, int32_t* has_grad_host, b2_stream_t stream);
+
+/* Raw (pre-norm) output of conv module `conv_idx` kept by the last forward, as an NDHWC view into the workspace --
+ * what the reference's forward hooks capture (plop:330-353: output.detach() of every conv.Conv* module).
+ * conv_idx enumerates modules in named_modules() order of the reference tree; see b2_unet_num_convs/_conv_name. */
+typedef struct b2_act_view {
+    void*   ptr;
+    int32_t n, d, h, w, c;
+    int32_t pitch;     /* elements between consecutive voxels (>= c) */
+    int32_t dtype;
+} b2_act_view;
+int b2_unet_num_convs(const b2_unet_plan* plan);
+int b2_unet_conv_name(const b2_unet_plan* plan, int conv_idx, char name[96]);
+int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx, b2_act_view* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Deep-supervision Dice+CE loss, value and gradient in one sweep.  Replaces nnunet MultipleOutputLoss2(DC_and_CE_loss
+ * ({'batch_dice':..,'smooth':1e-5,'do_bg':False},{})) built at MultiHead:1385-1386.
+ * logits: (B,C,V) fp32; target: (B,1,V) fp32 class ids; weight = ds weight of this level; dlogits (nullable) gets
+ * weight * d(CE + dice)/dlogits.  loss_out[0] += weight * loss (device scalar, caller zeroes it).  scratch >=
+ * b2_dsloss_scratch_bytes(B,C,V).
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t b2_dsloss_scratch_bytes(int B, int C, int64_t V);
+int b2_dsloss_fwd_bwd(const float* logits, const float* target, int B, int C, int64_t V, float weight, int batch_dice,
+                      float smooth, int do_bg, int ignore_index /* <0: none */, int with_dice, float* dlogits,
+                      float* loss_out, void* scratch, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * EWC / RW quadratic penalty over a list of parameter tensors (multi-tensor, one launch).
+ * Replaces the per-tensor Python loops of training/loss_functions/deep_supervision.py:65-80 (EWC:
+ * coef = lambda/2, importance = NULL) and :115-132 (RW: coef = lambda, importance = S).
+ * value: loss_out[0] += coef * sum_i (F_i [+ S_i]) (theta_i - theta*_i)^2 ; gradient: grads[t][i] += 2 coef (...)(...)
+ * (grads may be NULL -> value only).  table_dev: device copy of `n_tensors` b2_pen_entry records.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_pen_entry {
+    const float* theta;
+    const float* theta_star;
+    const float* fisher;
+    const float* importance;   /* NULL for EWC */
+    float*       grad;         /* NULL -> no gradient written */
+    int64_t      numel;
+} b2_pen_entry;
+size_t b2_quadpen_scratch_bytes(int n_tensors, int64_t total_numel);
+int b2_quadpen_fwd_bwd(const b2_pen_entry* table_host, int n_tensors, float coef, float* loss_out, void* scratch,
+                       b2_stream_t stream);
+
+/* Fisher / Riemannian-walk updates (multi-tensor, elementwise => bit-stable given bit-stable grads).
+ * b2_fisher_square: F = g^2                                   (ewc:303)
+ * b2_rw_update:     S += relu(g (prev-theta) / (0.5 F (theta-prev)^2 + eps)) [if prev != NULL]; prev = theta;
+ *                   F = alpha g^2 + (1-alpha) F               (rw:240-262) */
+typedef struct b2_rw_entry {
+    const float* theta;
+    const float* grad;
+    float*       prev;         /* theta_prev, updated in place */
+    float*       fisher;
+    float*       score;
+    int64_t      numel;
+} b2_rw_entry;
+int b2_fisher_square(const float* const* grads_host, float* const* fisher_host, const int64_t* numel_host,
+                     int n_tensors, void* scratch, b2_stream_t stream);
+int b2_rw_update(const b2_rw_entry* table_host, int n_tensors, float alpha, float eps, int have_prev, void* scratch,
+                 b2_stream_t stream);
+size_t b2_multitensor_scratch_bytes(int n_tensors);
+
+/* clip_grad_norm_(params, max_norm) + SGD(momentum, nesterov, weight_decay) in two launches.
+ * Replaces MultiHead:629-630/640-641 with the optimizer of MultiHead:294-301.  norm_out (device float, nullable)
+ * receives the total gradient L2 norm before clipping. */
+typedef struct b2_sgd_entry {
+    float*       theta;
+    const float* grad;
+    float*       momentum;
+    int64_t      numel;
+} b2_sgd_entry;
+size_t b2_sgd_scratch_bytes(int n_tensors, int64_t total_numel);
+int b2_sgd_clip_step(const b2_sgd_entry* table_host, int n_tensors, float lr, float momentum, float weight_decay,
+                     int nesterov, float max_norm, int first_step, float* norm_out, void* scratch, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Distillation terms (value only or value+gradient), one sweep over student+teacher logits each.
+ * b2_kd_lwf : deep_supervision.py:185-199 -- KL(softmax(t/T) || softmax(p/T)), 'batchmean' (sum / B), value only
+ *             (both operands are detached in the reference, lwf:343-349).
+ * b2_kd_mib : knowledge_distillation.py:11-32 (equal class counts) -- -mean_v (1/C) sum_c softmax(alpha t)_c lsm(x)_c,
+ *             value + gradient wrt x scaled by `scale` (= w_i * lkd, deep_supervision.py:411-413).
+ * b2_plop_pseudo: deep_supervision.py:287-332 -- pseudo-label CE with entropy thresholds, value + gradient.
+ * b2_pod_local:   embeddings.py:9-42 on an NDHWC activation pair, value only (both detached, plop:348-352).
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t b2_kd_scratch_bytes(int B, int C, int64_t V);
+int b2_kd_lwf(const float* pred, const float* teacher, int B, int C, int64_t V, float temperature, float* loss_out,
+              void* scratch, b2_stream_t stream);
+int b2_kd_mib(const float* x, const float* teacher, int B, int C, int64_t V, float alpha, float scale, float* dlogits,
+              float* loss_out, void* scratch, b2_stream_t stream);
+int b2_plop_pseudo(const float* x, const float* x_old, const float* target, int B, int C, int D, int H, int W,
+                   const float* thresholds, float max_entropy, float weight, float* dlogits, float* loss_out,
+                   void* scratch, b2_stream_t stream);
+size_t b2_pod_scratch_bytes(const b2_act_view* a, int scales);
+int b2_pod_local(const b2_act_view* a, const b2_act_view* a_old, int scales, float* value_out, void* scratch,
+                 b2_stream_t stream);
+
+/* hard tp/fp/fn per sample and foreground class (MultiHead:938-951): counts_out[(b*(C-1)+c-1)*3 + {0,1,2}] */
+int b2_online_eval(const float* logits, const float* target, int B, int C, int64_t V, float* counts_out,
+                   void* scratch /* >= b2_kd_scratch_bytes */, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Building blocks, exported so tests can check every kernel against the oracle in isolation.
+ * Weight layouts: `w_pt` = PyTorch Conv3d weight [Cout][Cin][3][3][3]; the plan keeps per-step shadows
+ * w_f = [27][Cin][Cout] and w_b = [27][Cout][Cin] (activation dtype for tensor-core paths, fp32 otherwise).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_conv_desc {
+    int32_t n, d, h, w;       /* input spatial */
+    int32_t cin, cout;
+    int32_t stride[3];        /* 1 or 2 per axis; kernel 3, pad 1 */
+    int32_t in_pitch, out_pitch;
+    int32_t dtype;
+} b2_conv_desc;
+size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d);
+/* z = conv3d(x, w, bias); stats[n][c] = {mean, rstd} of z over the spatial axes (for the InstanceNorm that follows) */
+int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* w_pt, const float* bias, void* z, float* stats,
+                  float eps, void* scratch, b2_stream_t stream);
+/* dx (nullable) = conv_transpose3d(dz, w); dw, dbias = parameter gradients (PyTorch layouts, overwritten) */
+int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx, int accumulate_dx,
+                  float* dw, float* dbias, void* scratch, b2_stream_t stream);
+/* y = lrelu(gamma * (z - mean) * rstd + beta) */
+int b2_norm_lrelu_fwd(const void* z, const float* stats, const float* gamma, const float* beta, void* y, int n,
+                      int64_t vox, int c, int z_pitch, int y_pitch, int dtype, float slope, b2_stream_t stream);
+int b2_norm_lrelu_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma, void* dz,
+                      float* dgamma, float* dbeta, int n, int64_t vox, int c, int z_pitch, int y_pitch, int dy_pitch,
+                      int dz_pitch, int dtype, float slope, void* scratch, b2_stream_t stream);
+size_t b2_norm_scratch_bytes(int n, int64_t vox, int c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2UNET_H_ */

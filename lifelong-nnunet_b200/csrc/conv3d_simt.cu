@@ -1,0 +1,483 @@
+// conv3d_simt.cu -- fp32-accumulate SIMT implicit-GEMM 3x3x3 convolution (forward, dgrad, wgrad) on NDHWC tensors.
+//
+// This is the PARITY path (B2_F32 activations: exact fp32 FMA arithmetic, logits within 1e-3 of the oracle) and the
+// fallback for shapes the tcgen05 path (conv3d_tc.cu) does not cover (Cin < 16, odd channel counts).
+// Replaces cuDNN's conv fwd/dgrad/wgrad behind nn.Conv3d of nnunet's ConvDropoutNormNonlin.
+//
+//   fwd   : z[n,o,co]  = bias[co] + sum_{t,ci} x[n, o*s + t - 1, ci] * Wf[t][ci][co]
+//           + per-CTA partial (sum z, sum z^2) per (n,co) for the InstanceNorm that follows
+//   dgrad : dx[n,i,ci] = sum_{t,co} [ (i - t + 1) % s == 0 ] dz[n, (i - t + 1)/s, co] * Wb[t][co][ci]
+//   wgrad : dW[t][ci][co] = sum_{n,o} x[n, o*s + t - 1, ci] * dz[n,o,co]   (deterministic split + ordered reduce)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2 {
+
+struct GatherGeom {
+    int N;
+    int Ds, Hs, Ws;  // spatial dims of the tensor being gathered (x for fwd, dz for dgrad)
+    int Dd, Hd, Wd;  // spatial dims of the tensor being produced
+    int Cs, Cd;      // GEMM K-per-tap / GEMM N
+    int sd, sh, sw;  // stride of the convolution
+    int src_pitch, dst_pitch;
+    int tiles_per_sample;
+};
+
+constexpr int BM = 128, BK = 16, NTHREADS = 256;
+
+// source coordinate of tap `t` for destination coordinate `o` along one axis; returns -1 when out of range
+template <int MODE>
+__device__ __forceinline__ int src_coord(int o, int t, int s, int S) {
+    if (MODE == 0) {
+        int i = o * s + t - 1;
+        return (i >= 0 && i < S) ? i : -1;
+    } else {
+        int num = o - t + 1;
+        if (num < 0) return -1;
+        int q = num / s;
+        if (q * s != num || q >= S) return -1;
+        return q;
+    }
+}
+
+template <typename T, int BN, int MODE, bool VEC>
+__global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(GatherGeom g, const T* __restrict__ src,
+                                                             const float* __restrict__ Wm,
+                                                             const float* __restrict__ bias, T* __restrict__ dst,
+                                                             int accumulate, float* __restrict__ stat_part) {
+    constexpr int TN = BN / 16;
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+    __shared__ float red[16][BN];
+
+    const int tid = threadIdx.x;
+    const int n = blockIdx.x / g.tiles_per_sample;
+    const int tile = blockIdx.x % g.tiles_per_sample;
+    const int n0 = blockIdx.y * BN;
+    const long long Vd = (long long)g.Dd * g.Hd * g.Wd;
+    const int Ktot = 27 * g.Cs;
+    const int nchunks = (Ktot + BK - 1) / BK;
+
+    // A-load role: one voxel row, 8 consecutive k
+    const int am = tid % BM, akh = tid / BM;
+    const long long av = (long long)tile * BM + am;
+    const bool avalid = av < Vd;
+    int od = 0, oh = 0, ow = 0;
+    if (avalid) {
+        ow = (int)(av % g.Wd);
+        long long r = av / g.Wd;
+        oh = (int)(r % g.Hd);
+        od = (int)(r / g.Hd);
+    }
+    const T* src_n = src + (long long)n * g.Ds * g.Hs * g.Ws * g.src_pitch;
+
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        // ---- gather A ----
+        float a8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+        if (VEC) {
+            const int cpt = g.Cs / BK;
+            const int tap = ch / cpt, c0 = (ch % cpt) * BK + akh * 8;
+            if (avalid) {
+                int id = src_coord<MODE>(od, tap / 9, g.sd, g.Ds);
+                int ih = src_coord<MODE>(oh, (tap / 3) % 3, g.sh, g.Hs);
+                int iw = src_coord<MODE>(ow, tap % 3, g.sw, g.Ws);
+                if ((id | ih | iw) >= 0) {
+                    const T* p = src_n + (((long long)id * g.Hs + ih) * g.Ws + iw) * g.src_pitch + c0;
+                    load8(p, a8);
+                }
+            }
+        } else {
+            if (avalid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    int k = ch * BK + akh * 8 + j;
+                    if (k < Ktot) {
+                        int tap = k / g.Cs, c = k % g.Cs;
+                        int id = src_coord<MODE>(od, tap / 9, g.sd, g.Ds);
+                        int ih = src_coord<MODE>(oh, (tap / 3) % 3, g.sh, g.Hs);
+                        int iw = src_coord<MODE>(ow, tap % 3, g.sw, g.Ws);
+                        if ((id | ih | iw) >= 0)
+                            a8[j] = to_f(src_n[(((long long)id * g.Hs + ih) * g.Ws + iw) * g.src_pitch + c]);
+                    }
+                }
+            }
+        }
+        // ---- load B ----
+        float b[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int idx = tid * TN + j;
+            int kr = idx / BN, col = idx % BN;
+            int kg = ch * BK + kr;
+            b[j] = (kg < Ktot && n0 + col < g.Cd) ? Wm[(long long)kg * g.Cd + n0 + col] : 0.f;
+        }
+        __syncthreads();  // previous iteration's reads done
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[akh * 8 + j][am] = a8[j];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int idx = tid * TN + j;
+            Bs[idx / BN][idx % BN] = b[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[8], bb[TN];
+            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bb[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+    }
+
+    // ---- epilogue ----
+    float s1[TN], s2[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    T* dst_n = dst + (long long)n * Vd * g.dst_pitch;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long long v = (long long)tile * BM + ty * 8 + i;
+        if (v < Vd) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                int col = n0 + tx * TN + j;
+                if (col < g.Cd) {
+                    float r = acc[i][j];
+                    if (bias) r += bias[col];
+                    T* p = dst_n + v * g.dst_pitch + col;
+                    if (accumulate) r += to_f(*p);
+                    *p = from_f<T>(r);
+                    s1[j] += r;
+                    s2[j] += r * r;
+                }
+            }
+        }
+    }
+    if (stat_part) {
+        // fixed-order reduction over the 16 row-groups of the tile => bit-reproducible statistics
+        float* out = stat_part + ((long long)(n * g.tiles_per_sample + tile) * g.Cd) * 2;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < TN; ++j) red[ty][tx * TN + j] = pass == 0 ? s1[j] : s2[j];
+            __syncthreads();
+            if (tid < BN && n0 + tid < g.Cd) {
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) s += red[r][tid];
+                out[(n0 + tid) * 2 + pass] = s;
+            }
+        }
+    }
+}
+
+// mean / rstd from per-tile partial sums; one block per (n, 32 channels); fixed summation order, double accumulation.
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ part, int tiles, int C,
+                                                             double inv_count, float eps, float* __restrict__ stats) {
+    __shared__ double sh[8][32][2];
+    const int n = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        const float* p = part + ((long long)n * tiles) * C * 2;
+        for (int t = lane; t < tiles; t += 8) {
+            s1 += (double)p[((long long)t * C + c) * 2];
+            s2 += (double)p[((long long)t * C + c) * 2 + 1];
+        }
+    }
+    sh[lane][threadIdx.x & 31][0] = s1;
+    sh[lane][threadIdx.x & 31][1] = s2;
+    __syncthreads();
+    if (lane == 0 && c < C) {
+        double a = 0.0, b = 0.0;
+        for (int l = 0; l < 8; ++l) { a += sh[l][threadIdx.x][0]; b += sh[l][threadIdx.x][1]; }
+        double mean = a * inv_count;
+        double var = b * inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[((long long)n * C + c) * 2] = (float)mean;
+        stats[((long long)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+// PyTorch [Cout][Cin][27] -> Wf [27][Cin][Cout] and Wb [27][Cout][Cin]
+__global__ void weight_shadow_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ wf,
+                                     float* __restrict__ wb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)Cout * Cin * 27;
+    if (i >= tot) return;
+    int t = (int)(i % 27);
+    long long r = i / 27;
+    int ci = (int)(r % Cin), co = (int)(r / Cin);
+    float v = w[i];
+    if (wf) wf[((long long)t * Cin + ci) * Cout + co] = v;
+    if (wb) wb[((long long)t * Cout + co) * Cin + ci] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad: each CTA owns a (ci-block, co-block) pair and a strided list of output-voxel chunks; the x halo of the chunk
+// and the dz chunk are staged in shared memory as fp32; 27 x 4 accumulators per thread; partials written once.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradGeom {
+    int N, Di, Hi, Wi, Do, Ho, Wo, Cin, Cout, sd, sh, sw, x_pitch, dz_pitch;
+    int cd, chh, cw;        // chunk extent in output voxels
+    int hd, hh, hw;         // halo extent in input voxels
+    int nd, nh, nw;         // chunks per axis
+    int nchunks, nsplit;    // chunks over all samples; CTAs along grid.x
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradGeom g, const T* __restrict__ x, const T* __restrict__ dz,
+                                                    float* __restrict__ part_w, float* __restrict__ part_b) {
+    extern __shared__ __align__(16) float smem[];
+    const int halo_vox = g.hd * g.hh * g.hw;
+    const int chunk_vox = g.cd * g.chh * g.cw;
+    float* xs = smem;                      // [halo_vox][32]
+    float* zs = smem + (size_t)halo_vox * 32;  // [chunk_vox][32]
+
+    const int tid = threadIdx.x;
+    const int ci0 = blockIdx.y * 32, co0 = blockIdx.z * 32;
+    const int ci = tid >> 3, cog = tid & 7;
+    float acc[27][4];
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool do_bias = (blockIdx.y == 0) && (ci == 0) && part_b;
+
+    for (int chunk = blockIdx.x; chunk < g.nchunks; chunk += g.nsplit) {
+        int c = chunk;
+        const int kw = c % g.nw; c /= g.nw;
+        const int kh = c % g.nh; c /= g.nh;
+        const int kd = c % g.nd; c /= g.nd;
+        const int n = c;
+        const int od0 = kd * g.cd, oh0 = kh * g.chh, ow0 = kw * g.cw;
+        const int id0 = od0 * g.sd - 1, ih0 = oh0 * g.sh - 1, iw0 = ow0 * g.sw - 1;
+        __syncthreads();
+        // stage x halo: 32 channels per voxel
+        for (int e = tid; e < halo_vox * 32; e += 256) {
+            int cc = e & 31, hv = e >> 5;
+            int w_ = hv % g.hw, r = hv / g.hw;
+            int h_ = r % g.hh, d_ = r / g.hh;
+            int id = id0 + d_, ih = ih0 + h_, iw = iw0 + w_;
+            float v = 0.f;
+            if (id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi && iw >= 0 && iw < g.Wi && ci0 + cc < g.Cin)
+                v = to_f(x[((((long long)n * g.Di + id) * g.Hi + ih) * g.Wi + iw) * g.x_pitch + ci0 + cc]);
+            xs[e] = v;
+        }
+        for (int e = tid; e < chunk_vox * 32; e += 256) {
+            int cc = e & 31, cv = e >> 5;
+            int w_ = cv % g.cw, r = cv / g.cw;
+            int h_ = r % g.chh, d_ = r / g.chh;
+            int od = od0 + d_, oh = oh0 + h_, ow = ow0 + w_;
+            float v = 0.f;
+            if (od < g.Do && oh < g.Ho && ow < g.Wo && co0 + cc < g.Cout)
+                v = to_f(dz[((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * g.dz_pitch + co0 + cc]);
+            zs[e] = v;
+        }
+        __syncthreads();
+        for (int d_ = 0; d_ < g.cd; ++d_)
+            for (int h_ = 0; h_ < g.chh; ++h_)
+                for (int w_ = 0; w_ < g.cw; ++w_) {
+                    const int cv = (d_ * g.chh + h_) * g.cw + w_;
+                    const float4 z4 = *reinterpret_cast<const float4*>(&zs[cv * 32 + cog * 4]);
+                    if (do_bias) { bsum[0] += z4.x; bsum[1] += z4.y; bsum[2] += z4.z; bsum[3] += z4.w; }
+                    const int hb = ((d_ * g.sd) * g.hh + h_ * g.sh) * g.hw + w_ * g.sw;
+#pragma unroll
+                    for (int t = 0; t < 27; ++t) {
+                        const int off = ((t / 9) * g.hh + (t / 3) % 3) * g.hw + (t % 3);
+                        const float xv = xs[(hb + off) * 32 + ci];
+                        acc[t][0] = fmaf(xv, z4.x, acc[t][0]);
+                        acc[t][1] = fmaf(xv, z4.y, acc[t][1]);
+                        acc[t][2] = fmaf(xv, z4.z, acc[t][2]);
+                        acc[t][3] = fmaf(xv, z4.w, acc[t][3]);
+                    }
+                }
+    }
+    // partial layout: [split][27][Cin][Cout]
+    if (ci0 + ci < g.Cin) {
+        float* out = part_w + (long long)blockIdx.x * 27 * g.Cin * g.Cout;
+#pragma unroll
+        for (int t = 0; t < 27; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int co = co0 + cog * 4 + j;
+                if (co < g.Cout) out[((long long)t * g.Cin + ci0 + ci) * g.Cout + co] = acc[t][j];
+            }
+    }
+    if (do_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int co = co0 + cog * 4 + j;
+            if (co < g.Cout) part_b[(long long)blockIdx.x * g.Cout + co] = bsum[j];
+        }
+    }
+}
+
+// dW_pt[co][ci][t] = sum_split part[split][t][ci][co]  (ordered);  dbias likewise
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nsplit,
+                                    int Cin, int Cout, float* __restrict__ dw, float* __restrict__ db) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = 27LL * Cin * Cout;
+    if (i < tot) {
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += part_w[(long long)k * tot + i];
+        int co = (int)(i % Cout);
+        long long r = i / Cout;
+        int ci = (int)(r % Cin), t = (int)(r / Cin);
+        dw[((long long)co * Cin + ci) * 27 + t] = s;
+    } else if (db && i < tot + Cout) {
+        int co = (int)(i - tot);
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += part_b[(long long)k * Cout + co];
+        db[co] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------------
+static inline int out_dim(int i, int s) { return (i + 2 - 3) / s + 1; }
+
+template <typename T, int MODE>
+static int launch_gemm(const GatherGeom& g, const T* src, const float* Wm, const float* bias, T* dst, int accumulate,
+                       float* stat_part, cudaStream_t st) {
+    const bool vec = (g.Cs % 16 == 0) && (g.src_pitch % 8 == 0);
+    const bool wide = g.Cd > 32;
+    dim3 grid(g.N * g.tiles_per_sample, wide ? cdiv(g.Cd, 64) : 1);
+    if (wide) {
+        if (vec) B2_LAUNCH((conv_gemm_kernel<T, 64, MODE, true>), grid, NTHREADS, 0, st, g, src, Wm, bias, dst, accumulate, stat_part);
+        else     B2_LAUNCH((conv_gemm_kernel<T, 64, MODE, false>), grid, NTHREADS, 0, st, g, src, Wm, bias, dst, accumulate, stat_part);
+    } else {
+        if (vec) B2_LAUNCH((conv_gemm_kernel<T, 32, MODE, true>), grid, NTHREADS, 0, st, g, src, Wm, bias, dst, accumulate, stat_part);
+        else     B2_LAUNCH((conv_gemm_kernel<T, 32, MODE, false>), grid, NTHREADS, 0, st, g, src, Wm, bias, dst, accumulate, stat_part);
+    }
+    return B2_OK;
+}
+
+size_t conv_stat_part_floats(const ConvShape& s) {
+    long long Vo = (long long)out_dim(s.d, s.stride[0]) * out_dim(s.h, s.stride[1]) * out_dim(s.w, s.stride[2]);
+    return (size_t)s.n * cdiv(Vo, BM) * s.cout * 2;
+}
+
+template <typename T>
+int conv3d_fwd_simt(const ConvShape& s, const T* x, const float* wf, const float* bias, T* z, float* stat_part,
+                    float* stats, float eps, cudaStream_t st) {
+    GatherGeom g;
+    g.N = s.n; g.Ds = s.d; g.Hs = s.h; g.Ws = s.w;
+    g.Dd = out_dim(s.d, s.stride[0]); g.Hd = out_dim(s.h, s.stride[1]); g.Wd = out_dim(s.w, s.stride[2]);
+    g.Cs = s.cin; g.Cd = s.cout; g.sd = s.stride[0]; g.sh = s.stride[1]; g.sw = s.stride[2];
+    g.src_pitch = s.in_pitch; g.dst_pitch = s.out_pitch;
+    long long Vd = (long long)g.Dd * g.Hd * g.Wd;
+    g.tiles_per_sample = cdiv(Vd, BM);
+    int rc = launch_gemm<T, 0>(g, x, wf, bias, z, 0, stats ? stat_part : nullptr, st);
+    if (rc) return rc;
+    if (stats) {
+        dim3 grid(s.n, cdiv(s.cout, 32));
+        B2_LAUNCH(stats_finalize_kernel, grid, 256, 0, st, stat_part, g.tiles_per_sample, s.cout, 1.0 / (double)Vd, eps, stats);
+    }
+    return B2_OK;
+}
+
+template <typename T>
+int conv3d_dgrad_simt(const ConvShape& s, const T* dz, const float* wb, T* dx, int accumulate, cudaStream_t st) {
+    GatherGeom g;
+    g.N = s.n;
+    g.Ds = out_dim(s.d, s.stride[0]); g.Hs = out_dim(s.h, s.stride[1]); g.Ws = out_dim(s.w, s.stride[2]);
+    g.Dd = s.d; g.Hd = s.h; g.Wd = s.w;
+    g.Cs = s.cout; g.Cd = s.cin; g.sd = s.stride[0]; g.sh = s.stride[1]; g.sw = s.stride[2];
+    g.src_pitch = s.out_pitch; g.dst_pitch = s.in_pitch;
+    long long Vd = (long long)g.Dd * g.Hd * g.Wd;
+    g.tiles_per_sample = cdiv(Vd, BM);
+    return launch_gemm<T, 1>(g, dz, wb, nullptr, dx, accumulate, nullptr, st);
+}
+
+static void wgrad_plan(const ConvShape& s, WgradGeom& g) {
+    g.N = s.n; g.Di = s.d; g.Hi = s.h; g.Wi = s.w;
+    g.Do = out_dim(s.d, s.stride[0]); g.Ho = out_dim(s.h, s.stride[1]); g.Wo = out_dim(s.w, s.stride[2]);
+    g.Cin = s.cin; g.Cout = s.cout; g.sd = s.stride[0]; g.sh = s.stride[1]; g.sw = s.stride[2];
+    g.x_pitch = s.in_pitch; g.dz_pitch = s.out_pitch;
+    // chunk: start from 4x8x8 outputs and shrink until the fp32 halo fits in ~100 KB of shared memory
+    int cd = 4, ch = 8, cw = 8;
+    auto smem = [&](int a, int b, int c) {
+        long long halo = (long long)((a - 1) * g.sd + 3) * ((b - 1) * g.sh + 3) * ((c - 1) * g.sw + 3);
+        return (halo + (long long)a * b * c) * 32 * 4;
+    };
+    while (smem(cd, ch, cw) > 100 * 1024) {
+        if (cd > 1 && cd * g.sd >= ch * g.sh) cd /= 2;
+        else if (ch > 1 && ch * g.sh >= cw * g.sw) ch /= 2;
+        else if (cw > 1) cw /= 2;
+        else if (cd > 1) cd /= 2;
+        else ch /= 2;
+    }
+    if (cd > g.Do) cd = g.Do;
+    if (ch > g.Ho) ch = g.Ho;
+    if (cw > g.Wo) cw = g.Wo;
+    g.cd = cd; g.chh = ch; g.cw = cw;
+    g.hd = (cd - 1) * g.sd + 3; g.hh = (ch - 1) * g.sh + 3; g.hw = (cw - 1) * g.sw + 3;
+    g.nd = cdiv(g.Do, cd); g.nh = cdiv(g.Ho, ch); g.nw = cdiv(g.Wo, cw);
+    g.nchunks = g.N * g.nd * g.nh * g.nw;
+    int blocks = cdiv(g.Cin, 32) * cdiv(g.Cout, 32);
+    int target = 2 * num_sms();
+    int ns = target / blocks;
+    if (ns < 1) ns = 1;
+    if (ns > g.nchunks) ns = g.nchunks;
+    g.nsplit = ns;
+}
+
+size_t conv_wgrad_part_floats(const ConvShape& s) {
+    WgradGeom g;
+    wgrad_plan(s, g);
+    return (size_t)g.nsplit * (27ULL * s.cin * s.cout + s.cout);
+}
+
+template <typename T>
+int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, float* dw, float* dbias,
+                      cudaStream_t st) {
+    WgradGeom g;
+    wgrad_plan(s, g);
+    float* part_w = part;
+    float* part_b = part + (size_t)g.nsplit * 27 * s.cin * s.cout;
+    size_t smem = ((size_t)g.hd * g.hh * g.hw + (size_t)g.cd * g.chh * g.cw) * 32 * sizeof(float);
+    static bool attr_done[2] = {false, false};
+    constexpr int ti = sizeof(T) == 4 ? 0 : 1;
+    if (!attr_done[ti]) {
+        B2_CUDA(cudaFuncSetAttribute(wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_done[ti] = true;
+    }
+    dim3 grid(g.nsplit, cdiv(s.cin, 32), cdiv(s.cout, 32));
+    B2_LAUNCH(wgrad_kernel<T>, grid, 256, smem, st, g, x, dz, part_w, dbias ? part_b : nullptr);
+    long long tot = 27LL * s.cin * s.cout + (dbias ? s.cout : 0);
+    B2_LAUNCH(wgrad_reduce_kernel, cdiv(tot, 256), 256, 0, st, part_w, part_b, g.nsplit, s.cin, s.cout, dw, dbias);
+    return B2_OK;
+}
+
+int weight_shadow(const float* w, int cout, int cin, float* wf, float* wb, cudaStream_t st) {
+    long long tot = (long long)cout * cin * 27;
+    B2_LAUNCH(weight_shadow_kernel, cdiv(tot, 256), 256, 0, st, w, cout, cin, wf, wb);
+    return B2_OK;
+}
+
+template int conv3d_fwd_simt<float>(const ConvShape&, const float*, const float*, const float*, float*, float*, float*, float, cudaStream_t);
+template int conv3d_fwd_simt<__nv_bfloat16>(const ConvShape&, const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, float*, float*, float, cudaStream_t);
+template int conv3d_dgrad_simt<float>(const ConvShape&, const float*, const float*, float*, int, cudaStream_t);
+template int conv3d_dgrad_simt<__nv_bfloat16>(const ConvShape&, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, cudaStream_t);
+template int conv3d_wgrad_simt<float>(const ConvShape&, const float*, const float*, float*, float*, float*, cudaStream_t);
+template int conv3d_wgrad_simt<__nv_bfloat16>(const ConvShape&, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, float*, cudaStream_t);
+
+}  // namespace b2

@@ -1,0 +1,72 @@
+// kernels.h -- internal (C++) launcher declarations shared by the translation units of libb2unet.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b2 {
+
+struct ConvShape {
+    int n, d, h, w;      // input spatial extent
+    int cin, cout;
+    int stride[3];
+    int in_pitch, out_pitch;
+};
+
+// ---- conv3d_simt.cu -------------------------------------------------------------------------------------------
+size_t conv_stat_part_floats(const ConvShape& s);
+size_t conv_wgrad_part_floats(const ConvShape& s);
+int weight_shadow(const float* w_pt, int cout, int cin, float* wf, float* wb, cudaStream_t st);
+template <typename T>
+int conv3d_fwd_simt(const ConvShape& s, const T* x, const float* wf, const float* bias, T* z, float* stat_part,
+                    float* stats, float eps, cudaStream_t st);
+template <typename T>
+int conv3d_dgrad_simt(const ConvShape& s, const T* dz, const float* wb, T* dx, int accumulate, cudaStream_t st);
+template <typename T>
+int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, float* dw, float* dbias,
+                      cudaStream_t st);
+
+// ---- norm.cu ----------------------------------------------------------------------------------------------------
+// y = lrelu(gamma*(z-mean)*rstd + beta)
+template <typename T>
+int norm_lrelu_fwd(const T* z, const float* stats, const float* gamma, const float* beta, T* y, int n, long long vox,
+                   int c, int z_pitch, int y_pitch, float slope, cudaStream_t st);
+size_t norm_bwd_scratch_floats(int n, long long vox, int c);
+// dz = d(loss)/dz given dy; dgamma/dbeta overwritten. scratch: norm_bwd_scratch_floats floats.
+template <typename T>
+int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, T* dz, float* dgamma,
+                   float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
+                   float slope, float* scratch, cudaStream_t st);
+
+// ---- updown.cu --------------------------------------------------------------------------------------------------
+struct TconvShape {
+    int n, d, h, w;      // input spatial extent
+    int cin, cout;
+    int k[3];            // kernel == stride (1 or 2 per axis)
+    int in_pitch, out_pitch;
+};
+// w_pt: PyTorch ConvTranspose3d weight [Cin][Cout][kd][kh][kw]; wq: shadow [K8][Cin][Cout]
+int tconv_shadow(const float* w_pt, int cin, int cout, int k8, float* wq, cudaStream_t st);
+template <typename T>
+int tconv_fwd_q(const TconvShape& s, const T* x, const float* wq, T* y, cudaStream_t st);
+size_t tconv_bwd_scratch_floats(const TconvShape& s);
+template <typename T>
+int tconv_bwd(const TconvShape& s, const T* x, const T* dy, const float* w_pt, T* dx, float* dw, float* scratch,
+              cudaStream_t st);
+// 1x1x1 head: logits NCDHW fp32 [n][ncls][vox] = y[n][vox][:] . w[ncls][c]
+template <typename T>
+int seghead_fwd(const T* y, const float* w, float* logits, int n, long long vox, int c, int ncls, int y_pitch,
+                cudaStream_t st);
+size_t seghead_bwd_scratch_floats(int n, long long vox, int c, int ncls);
+// dy (+)= w^T dlogits ; dw overwritten
+template <typename T>
+int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int accumulate, float* dw, int n,
+                long long vox, int c, int ncls, int y_pitch, int dy_pitch, float* scratch, cudaStream_t st);
+// NCDHW fp32 -> NDHWC T
+template <typename T>
+int nchw_to_ndhwc(const float* src, T* dst, int n, int c, long long vox, int dst_pitch, cudaStream_t st);
+
+int num_sms();
+
+}  // namespace b2

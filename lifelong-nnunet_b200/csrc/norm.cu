@@ -1,0 +1,233 @@
+// norm.cu -- InstanceNorm3d(affine, eps) + LeakyReLU, forward apply and backward, on NDHWC tensors.
+// Replaces nn.InstanceNorm3d + nn.LeakyReLU of nnunet's ConvDropoutNormNonlin (Appendix A).
+// The statistics themselves come out of the convolution epilogue (conv3d_*.cu); here:
+//   fwd : y  = lrelu(gamma * (z - mean) * rstd + beta)
+//   bwd : du = dy * (y > 0 ? 1 : slope);  S1 = sum du, S2 = sum du*zhat  (per n,c; ordered two-stage reduction)
+//         dz = gamma * rstd * (du - S1/V - zhat * S2/V);  dgamma = sum_n S2;  dbeta = sum_n S1
+// All kernels are HBM-bound streaming kernels: 128-bit accesses, grid sized to a multiple of the SM count.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2 {
+
+template <typename T, int VW> struct Vec;
+template <typename T> struct Vec<T, 8> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[8]) { load8(p, v); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[8]) { store8(p, v); }
+};
+template <typename T> struct Vec<T, 4> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[4]) { load4(p, v); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[4]) { store4(p, v); }
+};
+template <typename T> struct Vec<T, 1> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[1]) { v[0] = to_f(*p); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[1]) { *p = from_f<T>(v[0]); }
+};
+
+template <typename T, int VW>
+__global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       T* __restrict__ y, int n, long long vox, int c, int z_pitch,
+                                                       int y_pitch, float slope) {
+    const int ncg = c / VW;
+    const long long total = (long long)n * vox * ncg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        const long long v = i / ncg;  // n*vox + voxel
+        const int nn = (int)(v / vox);
+        const int c0 = cg * VW;
+        float a[VW], o[VW];
+        Vec<T, VW>::ld(z + v * z_pitch + c0, a);
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            const float mean = stats[((long long)nn * c + c0 + j) * 2], rstd = stats[((long long)nn * c + c0 + j) * 2 + 1];
+            const float u = gamma[c0 + j] * ((a[j] - mean) * rstd) + beta[c0 + j];
+            o[j] = u > 0.f ? u : u * slope;
+        }
+        Vec<T, VW>::st(y + v * y_pitch + c0, o);
+    }
+}
+
+template <typename T, int VW>
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restrict__ z, const T* __restrict__ y,
+                                                              const T* __restrict__ dy, const float* __restrict__ stats,
+                                                              int slabs, long long vox, int c, int z_pitch, int y_pitch,
+                                                              int dy_pitch, float slope, float* __restrict__ part) {
+    extern __shared__ float sh[];  // [R][c][2]
+    const int ncg = c / VW;
+    const int R = 256 / ncg;
+    const int n = blockIdx.y, slab = blockIdx.x;
+    const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
+    const long long per = (vox + slabs - 1) / slabs;
+    const long long v0 = (long long)slab * per, v1 = (v0 + per < vox) ? v0 + per : vox;
+    float s1[VW], s2[VW], mean[VW], rstd[VW];
+    const int c0 = cg * VW;
+    if (r < R) {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            s1[j] = 0.f; s2[j] = 0.f;
+            mean[j] = stats[((long long)n * c + c0 + j) * 2];
+            rstd[j] = stats[((long long)n * c + c0 + j) * 2 + 1];
+        }
+        for (long long v = v0 + r; v < v1; v += R) {
+            const long long row = (long long)n * vox + v;
+            float a[VW], b[VW], g[VW];
+            Vec<T, VW>::ld(z + row * z_pitch + c0, a);
+            Vec<T, VW>::ld(y + row * y_pitch + c0, b);
+            Vec<T, VW>::ld(dy + row * dy_pitch + c0, g);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const float du = b[j] > 0.f ? g[j] : g[j] * slope;
+                s1[j] += du;
+                s2[j] += du * ((a[j] - mean[j]) * rstd[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            sh[((size_t)r * c + c0 + j) * 2] = s1[j];
+            sh[((size_t)r * c + c0 + j) * 2 + 1] = s2[j];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < c * 2; e += 256) {
+        float s = 0.f;
+        for (int q = 0; q < R; ++q) s += sh[(size_t)q * c * 2 + e];
+        part[(((long long)n * slabs + slab) * c) * 2 + e] = s;
+    }
+}
+
+// sums[n][c] = {S1, S2}; dgamma[c] = sum_n S2; dbeta[c] = sum_n S1   (block = 32 channels x 8 slab lanes)
+__global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, int n, int slabs, int c,
+                                                                float* __restrict__ sums, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+    __shared__ double sh[8][32][2];
+    const int cc = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+    double g = 0.0, b = 0.0;
+    for (int nn = 0; nn < n; ++nn) {
+        double s1 = 0.0, s2 = 0.0;
+        if (cc < c)
+            for (int t = lane; t < slabs; t += 8) {
+                s1 += (double)part[(((long long)nn * slabs + t) * c + cc) * 2];
+                s2 += (double)part[(((long long)nn * slabs + t) * c + cc) * 2 + 1];
+            }
+        __syncthreads();
+        sh[lane][threadIdx.x & 31][0] = s1;
+        sh[lane][threadIdx.x & 31][1] = s2;
+        __syncthreads();
+        if (lane == 0 && cc < c) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int l = 0; l < 8; ++l) { a1 += sh[l][threadIdx.x][0]; a2 += sh[l][threadIdx.x][1]; }
+            sums[((long long)nn * c + cc) * 2] = (float)a1;
+            sums[((long long)nn * c + cc) * 2 + 1] = (float)a2;
+            b += a1;
+            g += a2;
+        }
+    }
+    if (lane == 0 && cc < c) {
+        if (dgamma) dgamma[cc] = (float)g;
+        if (dbeta) dbeta[cc] = (float)b;
+    }
+}
+
+template <typename T, int VW>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ y,
+                                                             const T* __restrict__ dy, const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ sums, T* __restrict__ dz, int n,
+                                                             long long vox, int c, int z_pitch, int y_pitch, int dy_pitch,
+                                                             int dz_pitch, float slope, float inv_v) {
+    const int ncg = c / VW;
+    const long long total = (long long)n * vox * ncg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        const long long row = i / ncg;
+        const int nn = (int)(row / vox);
+        const int c0 = cg * VW;
+        float a[VW], b[VW], g[VW], o[VW];
+        Vec<T, VW>::ld(z + row * z_pitch + c0, a);
+        Vec<T, VW>::ld(y + row * y_pitch + c0, b);
+        Vec<T, VW>::ld(dy + row * dy_pitch + c0, g);
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            const long long sc = (long long)nn * c + c0 + j;
+            const float mean = stats[sc * 2], rstd = stats[sc * 2 + 1];
+            const float zh = (a[j] - mean) * rstd;
+            const float du = b[j] > 0.f ? g[j] : g[j] * slope;
+            o[j] = gamma[c0 + j] * rstd * (du - sums[sc * 2] * inv_v - zh * sums[sc * 2 + 1] * inv_v);
+        }
+        Vec<T, VW>::st(dz + row * dz_pitch + c0, o);
+    }
+}
+
+static int pick_vw(int c, int p0, int p1, int p2, int p3, size_t esz) {
+    auto ok = [&](int vw) {
+        return c % vw == 0 && p0 % vw == 0 && p1 % vw == 0 && p2 % vw == 0 && p3 % vw == 0;
+    };
+    (void)esz;
+    if (ok(8)) return 8;
+    if (ok(4)) return 4;
+    return 1;
+}
+
+static int stream_grid(long long total_threads) {
+    long long blocks = (total_threads + 255) / 256;
+    long long cap = (long long)num_sms() * 16;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <typename T>
+int norm_lrelu_fwd(const T* z, const float* stats, const float* gamma, const float* beta, T* y, int n, long long vox,
+                   int c, int z_pitch, int y_pitch, float slope, cudaStream_t st) {
+    const int vw = pick_vw(c, z_pitch, y_pitch, 8, 8, sizeof(T));
+    const long long total = (long long)n * vox * (c / vw);
+    const int grid = stream_grid(total);
+    if (vw == 8) B2_LAUNCH((norm_fwd_kernel<T, 8>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
+    else if (vw == 4) B2_LAUNCH((norm_fwd_kernel<T, 4>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
+    else B2_LAUNCH((norm_fwd_kernel<T, 1>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
+    return B2_OK;
+}
+
+static int norm_slabs(int n, long long vox) {
+    long long want = (4LL * num_sms() + n - 1) / n;
+    long long maxs = (vox + 63) / 64;
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+size_t norm_bwd_scratch_floats(int n, long long vox, int c) {
+    return (size_t)n * norm_slabs(n, vox) * c * 2 + (size_t)n * c * 2;
+}
+
+template <typename T>
+int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, T* dz, float* dgamma,
+                   float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
+                   float slope, float* scratch, cudaStream_t st) {
+    B2_CHECK_ARG(c <= 1024);
+    int vw = pick_vw(c, z_pitch, y_pitch, dy_pitch, dz_pitch, sizeof(T));
+    B2_CHECK_ARG(c / vw <= 256);
+    const int slabs = norm_slabs(n, vox);
+    float* part = scratch;
+    float* sums = scratch + (size_t)n * slabs * c * 2;
+    const int ncg = c / vw, R = 256 / ncg;
+    const size_t sh = (size_t)R * c * 2 * sizeof(float);
+    dim3 grid(slabs, n);
+    if (vw == 8) B2_LAUNCH((norm_bwd_reduce_kernel<T, 8>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
+    else if (vw == 4) B2_LAUNCH((norm_bwd_reduce_kernel<T, 4>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
+    else B2_LAUNCH((norm_bwd_reduce_kernel<T, 1>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
+    B2_LAUNCH(norm_bwd_finalize_kernel, cdiv(c, 32), 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
+    const long long total = (long long)n * vox * (c / vw);
+    const int g2 = stream_grid(total);
+    const float inv_v = (float)(1.0 / (double)vox);
+    if (vw == 8) B2_LAUNCH((norm_bwd_apply_kernel<T, 8>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
+    else if (vw == 4) B2_LAUNCH((norm_bwd_apply_kernel<T, 4>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
+    else B2_LAUNCH((norm_bwd_apply_kernel<T, 1>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
+    return B2_OK;
+}
+
+template int norm_lrelu_fwd<float>(const float*, const float*, const float*, const float*, float*, int, long long, int, int, int, float, cudaStream_t);
+template int norm_lrelu_fwd<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, const float*, __nv_bfloat16*, int, long long, int, int, int, float, cudaStream_t);
+template int norm_lrelu_bwd<float>(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
+template int norm_lrelu_bwd<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
+
+}  // namespace b2

@@ -1,0 +1,506 @@
+// plan.cu -- the network plan (layer graph, HBM layout of the workspace) and the forward / backward orchestration of
+// the 3D Generic_UNet, plus the C ABI of include/b2unet.h.
+//
+// Graph semantics: nnunet@77bc485 Generic_UNet as constructed by nnUNetTrainerV2.initialize_network (SURVEY.md
+// Appendix A; ctor args restated at reference nnunet_ext/training/network_training/nnViTUNetTrainer.py:101-125;
+// forward restated at reference nnunet_ext/network_architecture/generic_ViT_UNet.py:222-230,261-286).
+//
+// HBM layout of the caller-provided workspace (one blob, offsets fixed at plan creation):
+//   [activations: NDHWC, act dtype]   x_in, per conv block raw output z and activated output y; the encoder skips and
+//                                      the transposed-conv outputs live side by side in per-level "concat" buffers
+//                                      (pitch 2C) so torch.cat never happens
+//   [activation gradients, act dtype]  one buffer per y tensor (+ concat buffers) and one reusable dz buffer
+//   [fp32 statistics]                  per conv block (n,c) {mean, rstd}
+//   [fp32 weight shadows]              per conv: Wf [27][Cin][Cout], Wb [27][Cout][Cin]; per tconv: Wq [K8][Cin][Cout]
+//   [fp32 scratch]                     partial sums of the ordered reductions (max over layers, reused in stream order)
+#include <string.h>
+
+#include <array>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2 {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+struct Act {
+    size_t off = 0;  // element offset inside the region (act or grad)
+    int c = 0, pitch = 0;
+    int n = 0, d = 0, h = 0, w = 0;
+    long long vox() const { return (long long)d * h * w; }
+    size_t elems() const { return (size_t)n * vox() * pitch; }
+};
+
+struct ConvBlock {
+    std::string prefix;  // e.g. "conv_blocks_context.0.blocks.0"
+    ConvShape shape;
+    Act in, z, y;        // activations
+    Act din, dy;         // gradients (din.c == 0 -> no dgrad)
+    int din_accumulate = 0;
+    int p_w = -1, p_b = -1, p_g = -1, p_be = -1;
+    size_t stats_off = 0, wf_off = 0, wb_off = 0;  // fp32 offsets
+};
+
+struct Tconv {
+    std::string prefix;  // "tu.0"
+    TconvShape shape;
+    Act in, out, din, dout;
+    int p_w = -1;
+    size_t wq_off = 0;
+};
+
+struct Head {
+    std::string prefix;  // "seg_outputs.0"
+    Act in, din;
+    int c = 0, level = 0;
+    int p_w = -1;
+};
+
+struct ParamInfo { std::string name; std::vector<int64_t> shape; int64_t numel; };
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_unet_plan {
+    b2_unet_geometry g;
+    std::vector<int> feats;
+    std::vector<std::array<int, 3>> sizes;
+    std::vector<ConvBlock> convs;      // execution order of the 3x3x3 blocks
+    std::vector<Tconv> tconvs;
+    std::vector<Head> heads;
+    std::vector<ParamInfo> params;
+    // execution order of conv modules for hooks: entries (kind, index): 0 conv block, 1 tconv
+    std::vector<std::pair<int, int>> conv_modules;
+    Act x_in, dz_tmp;
+    size_t act_elems = 0, grad_elems = 0, f32_floats = 0, scratch_floats = 0;
+    size_t off_act = 0, off_grad = 0, off_f32 = 0, off_scratch = 0, total_bytes = 0;
+    int esz = 4;
+};
+
+namespace b2 {
+
+static int add_param(b2_unet_plan* p, const std::string& name, std::vector<int64_t> shape) {
+    ParamInfo pi;
+    pi.name = name;
+    pi.shape = shape;
+    pi.numel = 1;
+    for (auto s : shape) pi.numel *= s;
+    p->params.push_back(pi);
+    return (int)p->params.size() - 1;
+}
+
+static Act alloc_act(size_t& cursor, int n, int d, int h, int w, int c, int pitch = 0) {
+    Act a;
+    a.n = n; a.d = d; a.h = h; a.w = w; a.c = c; a.pitch = pitch ? pitch : c;
+    a.off = cursor;
+    cursor += (a.elems() + 63) / 64 * 64;
+    return a;
+}
+
+static Act slice(const Act& base, int c0, int c) {
+    Act a = base;
+    a.off = base.off + c0;
+    a.c = c;
+    return a;
+}
+
+template <typename T> static inline T* P(void* ws, const b2_unet_plan* p, const Act& a, bool grad) {
+    return reinterpret_cast<T*>((char*)ws + (grad ? p->off_grad : p->off_act)) + a.off;
+}
+static inline float* F32(void* ws, const b2_unet_plan* p, size_t off) { return reinterpret_cast<float*>((char*)ws + p->off_f32) + off; }
+static inline float* SCR(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_scratch); }
+
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
+static int build_plan(b2_unet_plan* p) {
+    const b2_unet_geometry& g = p->g;
+    const int P_ = g.num_pool, N = g.batch;
+    p->esz = g.act_dtype == B2_BF16 ? 2 : 4;
+    p->feats.clear();
+    p->sizes.clear();
+    int f = g.base_features;
+    for (int d = 0; d <= P_; ++d) {
+        p->feats.push_back(f < g.max_features ? f : g.max_features);
+        f = (int)(f * 2);
+    }
+    {
+        int d = g.patch[0], h = g.patch[1], w = g.patch[2];
+        p->sizes.push_back({d, h, w});
+        for (int i = 0; i < P_; ++i) {
+            if (d % g.pool[i][0] || h % g.pool[i][1] || w % g.pool[i][2]) return fail(B2_EINVAL, "patch not divisible by pool strides%s", "");
+            d /= g.pool[i][0]; h /= g.pool[i][1]; w /= g.pool[i][2];
+            p->sizes.push_back({d, h, w});
+        }
+    }
+    size_t ac = 0, gc = 0, fc = 0;
+    p->x_in = alloc_act(ac, N, g.patch[0], g.patch[1], g.patch[2], g.in_channels);
+    // concat buffers per encoder level 0..P-1 (activation + gradient)
+    std::vector<Act> cat(P_), dcat(P_);
+    for (int l = 0; l < P_; ++l) {
+        cat[l] = alloc_act(ac, N, p->sizes[l][0], p->sizes[l][1], p->sizes[l][2], 2 * p->feats[l]);
+        dcat[l] = alloc_act(gc, N, p->sizes[l][0], p->sizes[l][1], p->sizes[l][2], 2 * p->feats[l]);
+    }
+    size_t max_z = 0;
+    auto add_conv = [&](const std::string& prefix, const Act& in, const Act& din, int din_acc, int cout, const int stride[3],
+                        const Act* y_fixed, const Act* dy_fixed) {
+        ConvBlock cb;
+        cb.prefix = prefix;
+        cb.shape.n = N; cb.shape.d = in.d; cb.shape.h = in.h; cb.shape.w = in.w;
+        cb.shape.cin = in.c; cb.shape.cout = cout;
+        for (int i = 0; i < 3; ++i) cb.shape.stride[i] = stride[i];
+        const int od = (in.d - 1) / stride[0] + 1, oh = (in.h - 1) / stride[1] + 1, ow = (in.w - 1) / stride[2] + 1;
+        cb.in = in;
+        cb.din = din;
+        cb.din_accumulate = din_acc;
+        cb.z = alloc_act(ac, N, od, oh, ow, cout);
+        if (y_fixed) { cb.y = *y_fixed; cb.dy = *dy_fixed; }
+        else { cb.y = alloc_act(ac, N, od, oh, ow, cout); cb.dy = alloc_act(gc, N, od, oh, ow, cout); }
+        cb.shape.in_pitch = in.pitch;
+        cb.shape.out_pitch = cb.z.pitch;
+        cb.p_w = add_param(p, prefix + ".conv.weight", {cout, in.c, 3, 3, 3});
+        cb.p_b = add_param(p, prefix + ".conv.bias", {cout});
+        cb.p_g = add_param(p, prefix + ".instnorm.weight", {cout});
+        cb.p_be = add_param(p, prefix + ".instnorm.bias", {cout});
+        cb.stats_off = fc; fc += (size_t)N * cout * 2;
+        cb.wf_off = fc; fc += (size_t)27 * in.c * cout;
+        cb.wb_off = fc; fc += (size_t)27 * in.c * cout;
+        max_z = max_sz(max_z, cb.z.elems());
+        p->scratch_floats = max_sz(p->scratch_floats, conv_stat_part_floats(cb.shape));
+        p->scratch_floats = max_sz(p->scratch_floats, conv_wgrad_part_floats(cb.shape));
+        p->scratch_floats = max_sz(p->scratch_floats, norm_bwd_scratch_floats(N, cb.z.vox(), cout));
+        p->convs.push_back(cb);
+        p->conv_modules.push_back({0, (int)p->convs.size() - 1});
+        return p->convs.back();
+    };
+    const int one[3] = {1, 1, 1};
+    Act cur = p->x_in, dcur;  // dcur.c == 0: no gradient wrt the network input
+    char buf[128];
+    for (int d = 0; d <= P_; ++d) {
+        const int* st0 = d == 0 ? one : g.pool[d - 1];
+        const int fo = p->feats[d];
+        const bool skip_level = d < P_;
+        Act ysk, dysk;
+        if (skip_level) { ysk = slice(cat[d], fo, fo); dysk = slice(dcat[d], fo, fo); }
+        if (d < P_) snprintf(buf, sizeof(buf), "conv_blocks_context.%d.blocks.0", d);
+        else snprintf(buf, sizeof(buf), "conv_blocks_context.%d.0.blocks.0", d);
+        // gradient wrt the stage input accumulates into the skip gradient of the previous level (already holding the
+        // decoder's contribution)
+        ConvBlock b0 = add_conv(buf, cur, dcur, d > 0 ? 1 : 0, fo, st0, nullptr, nullptr);
+        if (d < P_) snprintf(buf, sizeof(buf), "conv_blocks_context.%d.blocks.1", d);
+        else snprintf(buf, sizeof(buf), "conv_blocks_context.%d.1.blocks.0", d);
+        ConvBlock b1 = add_conv(buf, b0.y, b0.dy, 0, fo, one, skip_level ? &ysk : nullptr, skip_level ? &dysk : nullptr);
+        cur = b1.y;
+        dcur = b1.dy;
+    }
+    // decoder
+    for (int u = 0; u < P_; ++u) {
+        const int lvl = P_ - 1 - u;
+        const int fs = p->feats[lvl];
+        Tconv t;
+        snprintf(buf, sizeof(buf), "tu.%d", u);
+        t.prefix = buf;
+        t.shape.n = N; t.shape.d = cur.d; t.shape.h = cur.h; t.shape.w = cur.w;
+        t.shape.cin = cur.c; t.shape.cout = fs;
+        for (int i = 0; i < 3; ++i) t.shape.k[i] = g.pool[lvl][i];
+        t.in = cur; t.din = dcur;
+        t.out = slice(cat[lvl], 0, fs);
+        t.dout = slice(dcat[lvl], 0, fs);
+        t.shape.in_pitch = cur.pitch; t.shape.out_pitch = t.out.pitch;
+        const int k8 = t.shape.k[0] * t.shape.k[1] * t.shape.k[2];
+        t.p_w = add_param(p, t.prefix + ".weight", {cur.c, fs, t.shape.k[0], t.shape.k[1], t.shape.k[2]});
+        t.wq_off = fc; fc += (size_t)k8 * cur.c * fs;
+        p->scratch_floats = max_sz(p->scratch_floats, tconv_bwd_scratch_floats(t.shape));
+        p->tconvs.push_back(t);
+        p->conv_modules.push_back({1, (int)p->tconvs.size() - 1});
+        snprintf(buf, sizeof(buf), "conv_blocks_localization.%d.0.blocks.0", u);
+        ConvBlock l0 = add_conv(buf, cat[lvl], dcat[lvl], 0, fs, one, nullptr, nullptr);
+        snprintf(buf, sizeof(buf), "conv_blocks_localization.%d.1.blocks.0", u);
+        ConvBlock l1 = add_conv(buf, l0.y, l0.dy, 0, fs, one, nullptr, nullptr);
+        cur = l1.y;
+        dcur = l1.dy;
+        Head hd;
+        snprintf(buf, sizeof(buf), "seg_outputs.%d", u);
+        hd.prefix = buf;
+        hd.in = cur; hd.din = dcur; hd.c = fs; hd.level = lvl;
+        hd.p_w = add_param(p, hd.prefix + ".weight", {g.num_classes, fs, 1, 1, 1});
+        p->scratch_floats = max_sz(p->scratch_floats, seghead_bwd_scratch_floats(N, cur.vox(), fs, g.num_classes));
+        p->heads.push_back(hd);
+    }
+    p->dz_tmp.off = gc;
+    gc += (max_z + 63) / 64 * 64;
+    p->act_elems = ac; p->grad_elems = gc; p->f32_floats = fc;
+    p->off_act = 0;
+    p->off_grad = align_up(ac * p->esz, 1024);
+    p->off_f32 = p->off_grad + align_up(gc * p->esz, 1024);
+    p->off_scratch = p->off_f32 + align_up(fc * 4, 1024);
+    p->total_bytes = p->off_scratch + align_up(p->scratch_floats * 4, 1024);
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int forward_t(b2_unet_plan* p, const float* const* prm, const float* input, void* ws, float* const* logits,
+                     cudaStream_t st) {
+    const b2_unet_geometry& g = p->g;
+    int rc;
+    if ((rc = nchw_to_ndhwc<T>(input, P<T>(ws, p, p->x_in, false), g.batch, g.in_channels, p->x_in.vox(), p->x_in.pitch, st))) return rc;
+    size_t ci = 0, ti = 0;
+    auto run_conv = [&](ConvBlock& cb) -> int {
+        float* wf = F32(ws, p, cb.wf_off);
+        float* wb = F32(ws, p, cb.wb_off);
+        float* stats = F32(ws, p, cb.stats_off);
+        int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, wf, wb, st);
+        if (r) return r;
+        r = conv3d_fwd_simt<T>(cb.shape, P<T>(ws, p, cb.in, false), wf, prm[cb.p_b], P<T>(ws, p, cb.z, false), SCR(ws, p), stats, g.norm_eps, st);
+        if (r) return r;
+        return norm_lrelu_fwd<T>(P<T>(ws, p, cb.z, false), stats, prm[cb.p_g], prm[cb.p_be], P<T>(ws, p, cb.y, false), g.batch,
+                                 cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, g.lrelu_slope, st);
+    };
+    for (int d = 0; d <= g.num_pool; ++d) {
+        if ((rc = run_conv(p->convs[ci++]))) return rc;
+        if ((rc = run_conv(p->convs[ci++]))) return rc;
+    }
+    for (int u = 0; u < g.num_pool; ++u) {
+        Tconv& t = p->tconvs[ti++];
+        float* wq = F32(ws, p, t.wq_off);
+        const int k8 = t.shape.k[0] * t.shape.k[1] * t.shape.k[2];
+        if ((rc = tconv_shadow(prm[t.p_w], t.shape.cin, t.shape.cout, k8, wq, st))) return rc;
+        if ((rc = tconv_fwd_q<T>(t.shape, P<T>(ws, p, t.in, false), wq, P<T>(ws, p, t.out, false), st))) return rc;
+        if ((rc = run_conv(p->convs[ci++]))) return rc;
+        if ((rc = run_conv(p->convs[ci++]))) return rc;
+        Head& h = p->heads[u];
+        if (logits[h.level])
+            if ((rc = seghead_fwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], logits[h.level], g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, st))) return rc;
+    }
+    return B2_OK;
+}
+
+template <typename T>
+static int backward_t(b2_unet_plan* p, const float* const* prm, const float* const* dlogits, void* ws,
+                      float* const* grads, int32_t* has_grad, cudaStream_t st) {
+    const b2_unet_geometry& g = p->g;
+    const int P_ = g.num_pool;
+    int rc;
+    for (size_t i = 0; i < p->params.size(); ++i) if (has_grad) has_grad[i] = 1;
+    T* dz = reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off;
+    auto conv_bwd = [&](ConvBlock& cb) -> int {
+        float* stats = F32(ws, p, cb.stats_off);
+        int r = norm_lrelu_bwd<T>(P<T>(ws, p, cb.z, false), P<T>(ws, p, cb.y, false), P<T>(ws, p, cb.dy, true), stats, prm[cb.p_g], dz,
+                                  grads[cb.p_g], grads[cb.p_be], g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch,
+                                  cb.dy.pitch, cb.shape.cout, g.lrelu_slope, SCR(ws, p), st);
+        if (r) return r;
+        ConvShape s = cb.shape;
+        s.out_pitch = cb.shape.cout;  // dz is dense
+        r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+        if (r) return r;
+        if (cb.din.c > 0) {
+            ConvShape sd = s;
+            sd.in_pitch = cb.din.pitch;
+            r = conv3d_dgrad_simt<T>(sd, dz, F32(ws, p, cb.wb_off), P<T>(ws, p, cb.din, true), cb.din_accumulate, st);
+            if (r) return r;
+        }
+        return B2_OK;
+    };
+    // decoder, from full resolution (u = P-1) down to u = 0
+    for (int u = P_ - 1; u >= 0; --u) {
+        Head& h = p->heads[u];
+        const float* dl = dlogits[h.level];
+        const bool first_writer = (u == P_ - 1);
+        if (dl) {
+            if ((rc = seghead_bwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], dl, P<T>(ws, p, h.din, true), first_writer ? 0 : 1, grads[h.p_w],
+                                     g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, h.din.pitch, SCR(ws, p), st))) return rc;
+        } else {
+            B2_CUDA(cudaMemsetAsync(grads[h.p_w], 0, p->params[h.p_w].numel * sizeof(float), st));
+            if (has_grad) has_grad[h.p_w] = 0;
+            if (first_writer) B2_CUDA(cudaMemsetAsync(P<T>(ws, p, h.din, true), 0, h.din.elems() * sizeof(T), st));
+        }
+        ConvBlock& l1 = p->convs[2 * (P_ + 1) + 2 * u + 1];
+        ConvBlock& l0 = p->convs[2 * (P_ + 1) + 2 * u];
+        if ((rc = conv_bwd(l1))) return rc;
+        if ((rc = conv_bwd(l0))) return rc;
+        Tconv& t = p->tconvs[u];
+        if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w], P<T>(ws, p, t.din, true), grads[t.p_w], SCR(ws, p), st))) return rc;
+    }
+    for (int d = P_; d >= 0; --d) {
+        if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;
+        if ((rc = conv_bwd(p->convs[2 * d]))) return rc;
+    }
+    return B2_OK;
+}
+
+}  // namespace b2
+
+// ===============================================================================================================
+// C ABI
+// ===============================================================================================================
+extern "C" int b2_version(void) { return 100; }
+extern "C" const char* b2_last_error(void) { return g_last_error.c_str(); }
+extern "C" long long b2_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b2_unet_plan_create(const b2_unet_geometry* geom, b2_unet_plan** out) {
+    B2_CHECK_ARG(geom && out);
+    B2_CHECK_ARG(geom->batch >= 1 && geom->in_channels >= 1 && geom->num_classes >= 2 && geom->num_classes <= 8);
+    B2_CHECK_ARG(geom->num_pool >= 1 && geom->num_pool <= 7 && geom->base_features >= 1 && geom->max_features >= geom->base_features);
+    B2_CHECK_ARG(geom->act_dtype == B2_F32 || geom->act_dtype == B2_BF16);
+    for (int i = 0; i < geom->num_pool; ++i)
+        for (int j = 0; j < 3; ++j) B2_CHECK_ARG(geom->pool[i][j] == 1 || geom->pool[i][j] == 2);
+    b2_unet_plan* p = new (std::nothrow) b2_unet_plan();
+    if (!p) return fail(B2_ENOMEM, "out of host memory%s", "");
+    p->g = *geom;
+    int rc = build_plan(p);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return B2_OK;
+}
+
+extern "C" void b2_unet_plan_destroy(b2_unet_plan* plan) { delete plan; }
+
+extern "C" int b2_unet_num_params(const b2_unet_plan* plan) { return plan ? (int)plan->params.size() : B2_EINVAL; }
+
+extern "C" int b2_unet_param_info(const b2_unet_plan* plan, int idx, b2_param_info* out) {
+    B2_CHECK_ARG(plan && out && idx >= 0 && idx < (int)plan->params.size());
+    const ParamInfo& pi = plan->params[idx];
+    memset(out, 0, sizeof(*out));
+    strncpy(out->name, pi.name.c_str(), sizeof(out->name) - 1);
+    out->ndim = (int)pi.shape.size();
+    for (size_t i = 0; i < pi.shape.size(); ++i) out->shape[i] = pi.shape[i];
+    out->numel = pi.numel;
+    return B2_OK;
+}
+
+extern "C" size_t b2_unet_workspace_bytes(const b2_unet_plan* plan) { return plan ? plan->total_bytes : 0; }
+
+extern "C" int b2_unet_output_shape(const b2_unet_plan* plan, int level, int32_t dhw[3]) {
+    B2_CHECK_ARG(plan && dhw && level >= 0 && level < plan->g.num_pool);
+    for (int i = 0; i < 3; ++i) dhw[i] = plan->sizes[level][i];
+    return B2_OK;
+}
+
+extern "C" int b2_unet_forward(b2_unet_plan* plan, const float* const* params, const float* input, void* workspace,
+                               float* const* logits, int keep_for_backward, b2_stream_t stream) {
+    B2_CHECK_ARG(plan && params && input && workspace && logits);
+    (void)keep_for_backward;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->g.act_dtype == B2_F32) return forward_t<float>(plan, params, input, workspace, logits, st);
+    return forward_t<__nv_bfloat16>(plan, params, input, workspace, logits, st);
+}
+
+extern "C" int b2_unet_backward(b2_unet_plan* plan, const float* const* params, const float* const* dlogits,
+                                void* workspace, float* const* grads, int32_t* has_grad_host, b2_stream_t stream) {
+    B2_CHECK_ARG(plan && params && dlogits && workspace && grads);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->g.act_dtype == B2_F32) return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, st);
+    return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, st);
+}
+
+extern "C" int b2_unet_num_convs(const b2_unet_plan* plan) { return plan ? (int)plan->conv_modules.size() : B2_EINVAL; }
+
+extern "C" int b2_unet_conv_name(const b2_unet_plan* plan, int conv_idx, char name[96]) {
+    B2_CHECK_ARG(plan && name && conv_idx >= 0 && conv_idx < (int)plan->conv_modules.size());
+    auto km = plan->conv_modules[conv_idx];
+    std::string s = km.first == 0 ? plan->convs[km.second].prefix + ".conv" : plan->tconvs[km.second].prefix;
+    memset(name, 0, 96);
+    strncpy(name, s.c_str(), 95);
+    return B2_OK;
+}
+
+extern "C" int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx, b2_act_view* out) {
+    B2_CHECK_ARG(plan && workspace && out && conv_idx >= 0 && conv_idx < (int)plan->conv_modules.size());
+    auto km = plan->conv_modules[conv_idx];
+    const Act& a = km.first == 0 ? plan->convs[km.second].z : plan->tconvs[km.second].out;
+    out->ptr = (char*)workspace + plan->off_act + a.off * plan->esz;
+    out->n = a.n; out->d = a.d; out->h = a.h; out->w = a.w; out->c = a.c; out->pitch = a.pitch;
+    out->dtype = plan->g.act_dtype;
+    return B2_OK;
+}
+
+// ---- building blocks (tests) ------------------------------------------------------------------------------------
+static ConvShape to_shape(const b2_conv_desc* d) {
+    ConvShape s;
+    s.n = d->n; s.d = d->d; s.h = d->h; s.w = d->w; s.cin = d->cin; s.cout = d->cout;
+    for (int i = 0; i < 3; ++i) s.stride[i] = d->stride[i];
+    s.in_pitch = d->in_pitch; s.out_pitch = d->out_pitch;
+    return s;
+}
+
+extern "C" size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d) {
+    if (!d) return 0;
+    ConvShape s = to_shape(d);
+    size_t w = (size_t)27 * s.cin * s.cout;
+    size_t part = conv_stat_part_floats(s);
+    size_t wg = conv_wgrad_part_floats(s);
+    return align_up((2 * w + (part > wg ? part : wg) + 64) * sizeof(float));
+}
+
+extern "C" int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* w_pt, const float* bias, void* z,
+                             float* stats, float eps, void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(d && x && w_pt && z && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvShape s = to_shape(d);
+    float* wf = (float*)scratch;
+    float* wb = wf + (size_t)27 * s.cin * s.cout;
+    float* part = wb + (size_t)27 * s.cin * s.cout;
+    int rc = weight_shadow(w_pt, s.cout, s.cin, wf, wb, st);
+    if (rc) return rc;
+    if (d->dtype == B2_F32) return conv3d_fwd_simt<float>(s, (const float*)x, wf, bias, (float*)z, part, stats, eps, st);
+    return conv3d_fwd_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, wf, bias, (__nv_bfloat16*)z, part, stats, eps, st);
+}
+
+extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx,
+                             int accumulate_dx, float* dw, float* dbias, void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(d && x && dz && w_pt && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvShape s = to_shape(d);
+    float* wf = (float*)scratch;
+    float* wb = wf + (size_t)27 * s.cin * s.cout;
+    float* part = wb + (size_t)27 * s.cin * s.cout;
+    int rc = weight_shadow(w_pt, s.cout, s.cin, wf, wb, st);
+    if (rc) return rc;
+    if (d->dtype == B2_F32) {
+        if (dw && (rc = conv3d_wgrad_simt<float>(s, (const float*)x, (const float*)dz, part, dw, dbias, st))) return rc;
+        if (dx && (rc = conv3d_dgrad_simt<float>(s, (const float*)dz, wb, (float*)dx, accumulate_dx, st))) return rc;
+    } else {
+        if (dw && (rc = conv3d_wgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
+        if (dx && (rc = conv3d_dgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)dz, wb, (__nv_bfloat16*)dx, accumulate_dx, st))) return rc;
+    }
+    return B2_OK;
+}
+
+extern "C" size_t b2_norm_scratch_bytes(int n, int64_t vox, int c) { return align_up(norm_bwd_scratch_floats(n, vox, c) * sizeof(float)); }
+
+extern "C" int b2_norm_lrelu_fwd(const void* z, const float* stats, const float* gamma, const float* beta, void* y, int n,
+                                 int64_t vox, int c, int z_pitch, int y_pitch, int dtype, float slope, b2_stream_t stream) {
+    B2_CHECK_ARG(z && stats && gamma && beta && y);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2_F32) return norm_lrelu_fwd<float>((const float*)z, stats, gamma, beta, (float*)y, n, vox, c, z_pitch, y_pitch, slope, st);
+    return norm_lrelu_fwd<__nv_bfloat16>((const __nv_bfloat16*)z, stats, gamma, beta, (__nv_bfloat16*)y, n, vox, c, z_pitch, y_pitch, slope, st);
+}
+
+extern "C" int b2_norm_lrelu_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma,
+                                 void* dz, float* dgamma, float* dbeta, int n, int64_t vox, int c, int z_pitch, int y_pitch,
+                                 int dy_pitch, int dz_pitch, int dtype, float slope, void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(z && y && dy && stats && gamma && dz && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == B2_F32)
+        return norm_lrelu_bwd<float>((const float*)z, (const float*)y, (const float*)dy, stats, gamma, (float*)dz, dgamma, dbeta, n, vox, c,
+                                     z_pitch, y_pitch, dy_pitch, dz_pitch, slope, (float*)scratch, st);
+    return norm_lrelu_bwd<__nv_bfloat16>((const __nv_bfloat16*)z, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, stats, gamma,
+                                         (__nv_bfloat16*)dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope,
+                                         (float*)scratch, st);
+}

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads and exports every symbol include/b2unet.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import util  # noqa: F401  (sys.path)
+
+
+def _declared():
+    hdr = open(os.path.join(util.ROOT, "include", "b2unet.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from b200unet import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build with `python -c 'import __graft_entry__ as g; g.build()'`"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert set(names) == set(_lib.SIGNATURES.keys()), set(names) ^ set(_lib.SIGNATURES.keys())
+
+
+def test_plan_metadata_matches_reference_module_tree():
+    """plan parameter table == state_dict keys/shapes of the oracle's Generic_UNet (host-only calls)"""
+    from b200unet.configs import CONFIGS
+    from b200unet.generic_UNet import Generic_UNet, _Plan
+    from b200unet import _lib
+    import torch
+    for name in ("tiny", "tiny3", "cfg1"):
+        geom = CONFIGS[name]
+        onet = util.oracle_net(geom)
+        net = Generic_UNet(geom.in_channels, geom.base_features, geom.num_classes, geom.num_pool,
+                           pool_op_kernel_sizes=[list(k) for k in geom.pool], max_num_features=geom.max_features)
+        osd, sd = onet.state_dict(), net.state_dict()
+        assert list(osd.keys()) == list(sd.keys())
+        assert all(osd[k].shape == sd[k].shape for k in sd)
+        lib = _lib.load()
+        g = _lib.Geometry()
+        g.batch, g.in_channels, g.num_classes = geom.batch, geom.in_channels, geom.num_classes
+        g.base_features, g.max_features, g.num_pool = geom.base_features, geom.max_features, geom.num_pool
+        for i in range(3):
+            g.patch[i] = geom.patch[i]
+        for l, k in enumerate(geom.pool):
+            for i in range(3):
+                g.pool[l][i] = k[i]
+        g.act_dtype, g.lrelu_slope, g.norm_eps = 0, 1e-2, 1e-5
+        h = ctypes.c_void_p()
+        _lib.check(lib.b2_unet_plan_create(ctypes.byref(g), ctypes.byref(h)))
+        info = _lib.ParamInfo()
+        names = {}
+        for i in range(lib.b2_unet_num_params(h)):
+            _lib.check(lib.b2_unet_param_info(h, i, ctypes.byref(info)))
+            names[info.name.decode()] = tuple(info.shape[j] for j in range(info.ndim))
+        assert set(names) == set(dict(onet.named_parameters()).keys())
+        for k, s in names.items():
+            assert tuple(osd[k].shape) == s, k
+        assert lib.b2_unet_workspace_bytes(h) > 0
+        assert lib.b2_unet_num_convs(h) == 2 * (geom.num_pool + 1) + 3 * geom.num_pool
+        lib.b2_unet_plan_destroy(h)
+
+
+def test_invalid_geometry_is_rejected():
+    from b200unet import _lib
+    lib = _lib.load()
+    g = _lib.Geometry()
+    h = ctypes.c_void_p()
+    assert lib.b2_unet_plan_create(ctypes.byref(g), ctypes.byref(h)) != 0
+    assert b"invalid argument" in lib.b2_last_error()

@@ -1,0 +1,88 @@
+"""GPU parity: the CUDA Generic_UNet (through the C ABI) against the oracle on identical weights and inputs.
+Tolerance (north_star / SURVEY.md 8(d)): fp32 mode, logits / loss / per-tensor gradients within 1e-3 relative
+(||a-b||_inf / max(||b||_inf, 1e-6))."""
+import pytest
+import torch
+
+from util import cuda_net, oracle_net, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _run_pair(geom_name, seed=1234):
+    from b200unet.configs import CONFIGS
+    from b200unet import synth
+    from oracle import cl_losses
+    geom = CONFIGS[geom_name]
+    data, targets = synth.make_batch(geom, seed=seed)
+    onet = oracle_net(geom)
+    # make the affine parameters non-trivial so their gradients are exercised
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, p in onet.named_parameters():
+            if "instnorm.weight" in n:
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            if "instnorm.bias" in n or "conv.bias" in n:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    weights = cl_losses.ds_loss_weights(geom.num_pool)
+    oo = onet(data)
+    ol = cl_losses.multiple_output_loss2(oo, targets, weights)
+    ol.backward()
+    cnet = cuda_net(geom, onet.state_dict())
+    co = cnet(data.cuda())
+    return geom, onet, oo, ol, cnet, co, targets, weights
+
+
+@pytest.mark.parametrize("geom_name", ["tiny", "tiny3"])
+def test_forward_logits(geom_name):
+    geom, onet, oo, ol, cnet, co, targets, weights = _run_pair(geom_name)
+    assert len(co) == len(oo) == geom.num_pool
+    for a, b in zip(co, oo):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < TOL
+
+
+@pytest.mark.parametrize("geom_name", ["tiny", "tiny3"])
+def test_backward_grads_with_torch_loss(geom_name):
+    """network backward through the C ABI, loss evaluated by the oracle's own loss code on the CUDA logits"""
+    from oracle import cl_losses
+    geom, onet, oo, ol, cnet, co, targets, weights = _run_pair(geom_name)
+    cl = cl_losses.multiple_output_loss2(co, [t.cuda() for t in targets], weights)
+    assert abs(float(cl) - float(ol)) <= TOL * max(abs(float(ol)), 1e-6)
+    cl.backward()
+    od = dict(onet.named_parameters())
+    for n, p in cnet.named_parameters():
+        ref = od[n].grad
+        if ref is None:
+            assert p.grad is None, n
+            continue
+        assert p.grad is not None, n
+        scale = max(float(ref.abs().max()), 1e-6)
+        if "conv.bias" in n and "seg" not in n:
+            # gradient of a bias that feeds InstanceNorm is exactly 0 in exact arithmetic: compare absolutely
+            # against the scale of the weight gradient of the same conv
+            wscale = float(od[n.replace("bias", "weight")].grad.abs().max())
+            assert float((p.grad.cpu() - ref).abs().max()) < TOL * max(wscale, 1e-6), n
+        else:
+            assert float((p.grad.cpu() - ref).abs().max()) / scale < TOL, (n, float((p.grad.cpu() - ref).abs().max()) / scale)
+
+
+def test_backward_bit_stable():
+    """Fisher accumulation must be bit-pattern-stable across runs: identical gradients on repeated runs"""
+    from oracle import cl_losses
+    geom, onet, oo, ol, cnet, co, targets, weights = _run_pair("tiny")
+    from b200unet import synth
+    data, _ = synth.make_batch(geom)
+    ref = None
+    for _ in range(3):
+        cnet.zero_grad(set_to_none=True)
+        out = cnet(data.cuda())
+        l = cl_losses.multiple_output_loss2(out, [t.cuda() for t in targets], weights)
+        l.backward()
+        cur = torch.cat([p.grad.flatten() for p in cnet.parameters() if p.grad is not None]).clone()
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(ref.view(torch.int32), cur.view(torch.int32))
