@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-step training hot path (BASELINE.json: "3D patches/sec (EWC on)").
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch path on the host CPU cores
+
+Workload (config.workload): BASELINE.json configs[1] -- nnUNetTrainerEWC, 5-stage 3D U-Net, 64x128x128 synthetic
+hippocampus-shaped patches, batch 2 per GPU, one stored EWC task, bf16 activations (fp32 accumulation, fp32 params).
+A "step" = zero_grad -> forward -> Dice+CE (+EWC) -> backward -> [grad all-reduce] -> clip(12) -> SGD-Nesterov.
+
+  value        patches/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e          patches/s through trainer.run_iteration(generator) with pinned HOST buffers: H2D of data+targets and
+               D2H of the loss inside the timed region
+  roofline     the dominant kernel (3x3x3 conv forward of the full-resolution 32->32 layer), timed live with CUDA
+               events: achieved = algorithmic FLOPs / duration, peak = MEASURED_PEAKS.json bf16 burst
+  cpu_baseline the oracle port of the reference step (PyTorch CPU fp32) on a bounded sample, rank 0, N=1 only
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "lifelong-nnunet_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOAD = "cfg2"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["source"] = "measured"
+        return d
+    return dict(FALLBACK_PEAKS)
+
+
+def workload_desc(geom, precision, n_gpus):
+    return {"workload": "%s: nnUNetTrainerEWC, %d-stage 3D U-Net, %dx%dx%d synthetic 1-ch patches, batch %d/GPU, "
+                        "EWC on (1 stored task, lambda 0.4), %s activations" %
+                        (geom.name, geom.num_pool, geom.patch[0], geom.patch[1], geom.patch[2], geom.batch, precision),
+            "global_batch": geom.batch * n_gpus, "patch": list(geom.patch), "parallelism": "dp%d" % n_gpus,
+            "pool_op_kernel_sizes": [list(k) for k in geom.pool], "num_classes": geom.num_classes,
+            "l2_policy": "inputs+activations (>3 GB per step) exceed the 126 MB L2; no explicit flush",
+            "fwd_bwd_gflop_per_patch": round(3 * geom.fwd_flops_per_patch() / 1e9, 1)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's PyTorch step on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(geom, batch):
+    from b200unet import synth
+    from oracle import cl_losses, step
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = step.build_network(geom.in_channels, geom.base_features, geom.num_classes, [list(k) for k in geom.pool],
+                             max_num_features=geom.max_features)
+    fisher, params = synth.make_ewc_state(list(net.named_parameters()))
+    weights = cl_losses.ds_loss_weights(geom.num_pool)
+    opt = step.make_optimizer(net)
+    loss_fn = step.ewc_loss_fn(net, weights, {"A": fisher}, {"A": params}, 0.4)
+    data, targets = synth.make_batch(geom, batch=batch)
+
+    def one():
+        return step.run_iteration(net, opt, data, targets, loss_fn)[0]
+    return one
+
+
+def time_cpu(geom, batch, steps, warmup):
+    one = cpu_reference_step_fn(geom, batch)
+    for _ in range(warmup):
+        one()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, geom):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, min(args.warmup, 1)   # bounded: every CPU step is seconds long
+    ts = time_cpu(geom, geom.batch, steps, warmup)
+    total = sum(ts)
+    val = geom.batch * len(ts) / total
+    sample = "%d timed + %d warm-up steps of the full workload batch (B=%d), oracle port (PyTorch CPU fp32, eager)" % (len(ts), warmup, geom.batch)
+    line = {"impl": "reference", "metric": "3D patches/sec (EWC on)", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": len(ts), "warmup": warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_desc(geom, "fp32 (CPU)", 1),
+            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        hi = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(hi) if hi else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_batch_generator(data, targets):
+    hd = data.pin_memory()
+    ht = [t.pin_memory() for t in targets]
+    while True:
+        yield {'data': hd, 'target': ht}
+
+
+def device_batch_generator(data, targets):
+    while True:
+        yield {'data': data, 'target': targets}
+
+
+def time_dominant_kernel(geom, precision, steps, warmup):
+    """CUDA-event timing of the dominant kernel in isolation: forward 3x3x3 conv of the full-resolution
+    base->base layer (conv_blocks_context.0.blocks.1) at the workload's batch."""
+    import ctypes as C
+    from b200unet import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, (D, H, W), Cc = geom.batch, geom.patch, geom.base_features
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    x = torch.randn((B, D, H, W, Cc), device=dev).to(dt)
+    z = torch.empty_like(x)
+    w = torch.randn((Cc, Cc, 3, 3, 3), device=dev) * 0.05
+    bias = torch.zeros(Cc, device=dev)
+    stats = torch.empty((B, Cc, 2), device=dev)
+    desc = _lib.ConvDesc()
+    desc.n, desc.d, desc.h, desc.w, desc.cin, desc.cout = B, D, H, W, Cc, Cc
+    for i in range(3):
+        desc.stride[i] = 1
+    desc.in_pitch = desc.out_pitch = Cc
+    desc.dtype = _lib.B2_F32 if precision == "fp32" else _lib.B2_BF16
+    scr = torch.empty(int(lib.b2_conv3d_scratch_bytes(C.byref(desc))), dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def call():
+        _lib.check(lib.b2_conv3d_fwd(C.byref(desc), x.data_ptr(), w.data_ptr(), bias.data_ptr(), z.data_ptr(),
+                                     stats.data_ptr(), 1e-5, scr.data_ptr(), st))
+    for _ in range(max(warmup, 3)):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(steps, 5)
+    e0.record()
+    for _ in range(n):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * B * D * H * W * Cc * Cc * 27
+    return ms, flops
+
+
+def run_ours(args, geom):
+    import torch.distributed as dist
+    from b200unet import _lib, synth
+    from b200unet.trainers import DataParallelGroup, nnUNetTrainerEWC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ddp = DataParallelGroup()
+    precision = args.precision
+
+    trainer = nnUNetTrainerEWC(geom, precision=precision, device=dev, ddp=ddp, seed=0)
+    trainer.initialize()
+    fisher, params = synth.make_ewc_state(list(trainer.network.named_parameters()), seed=7)
+    trainer.fisher["task_prev"] = {k: v.to(dev) for k, v in fisher.items()}
+    trainer.params["task_prev"] = {k: v.to(dev) for k, v in params.items()}
+    trainer.loss.update_ewc_params(trainer.fisher, trainer.params)
+    trainer.loss.update_network_params(trainer.network.named_parameters())
+
+    data, targets = synth.make_batch(geom, seed=1234 + rank)     # rank-seeded patches
+    h2d = data.numel() * 4 + sum(t.numel() * 4 for t in targets)
+    gen_host = pinned_batch_generator(data, targets)
+    gen_dev = device_batch_generator(data.to(dev), [t.to(dev) for t in targets])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(gen, steps, detach):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            trainer.run_iteration(gen, do_backprop=True, run_online_evaluation=False, detach=detach)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        trainer.run_iteration(gen_dev, detach=False)
+    sampler = ClockSampler(local)
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.start()
+    ms_dev, _ = timed(gen_dev, args.steps, detach=False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    for _ in range(2):
+        trainer.run_iteration(gen_host, detach=True)
+    _, ms_e2e = timed(gen_host, args.steps, detach=True)
+
+    patches = geom.batch * world * args.steps
+    value = patches / (ms_dev / 1e3)
+    e2e = patches / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    gflop_patch = 3 * geom.fwd_flops_per_patch() / 1e9
+    kms, kflops = time_dominant_kernel(geom, precision, args.steps, warm)
+    peak_tf = peaks["bf16_tflops"]
+    achieved_tf = kflops / (kms * 1e-3) / 1e12
+    line = {"metric": "3D patches/sec (EWC on)", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_desc(geom, precision, world),
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "api": "nnUNetTrainerEWC.run_iteration(generator of pinned host batches)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv3d 3x3x3 forward, %d->%d @ %dx%dx%d x B%d (conv_blocks_context.0.blocks.1)" %
+                                  (geom.base_features, geom.base_features, geom.patch[0], geom.patch[1], geom.patch[2], geom.batch),
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "kernel_ms": kms, "traffic": None,
+                         "step_frac_of_sustained_peak": value / world * gflop_patch / 1e3 / peaks.get("bf16_tflops_sustained", peak_tf)}}
+    if world == 1 and not args.no_cpu_baseline:
+        ts = time_cpu(geom, geom.batch, 1, 1)
+        line["cpu_baseline"] = {"value": geom.batch / ts[0], "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "1 timed step (after 1 warm-up) of the full workload batch (B=%d), oracle port of the "
+                                          "reference step (PyTorch CPU fp32 eager, %d threads)" % (geom.batch, os.cpu_count())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from b200unet.configs import CONFIGS
+    geom = CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, geom)
+    else:
+        run_ours(args, geom)
+
+
+if __name__ == "__main__":
+    main()

@@ -280,7 +280,14 @@ class Generic_UNet(nn.Module):
             self._plans[key] = plan
         return plan
 
+    def _apply(self, fn, *a, **kw):
+        self._plans = {}          # device / dtype moves invalidate plans (workspaces live on the old device)
+        return super()._apply(fn, *a, **kw)
+
     def _ordered_params(self, plan):
+        cached = getattr(plan, "_params", None)
+        if cached is not None:
+            return cached
         table = dict(self.named_parameters())
         out = []
         for name, shape in zip(plan.param_names, plan.param_shapes):
@@ -288,11 +295,15 @@ class Generic_UNet(nn.Module):
             if tuple(p.shape) != shape or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("parameter %s: expected contiguous fp32 %s, got %s %s" % (name, shape, p.dtype, tuple(p.shape)))
             out.append(p)
+        plan._params = out
         return out
 
     def _conv_modules(self, plan):
-        mods = dict(self.named_modules())
-        return [mods[n] for n in plan.conv_names]
+        cached = getattr(plan, "_conv_mods", None)
+        if cached is None:
+            mods = dict(self.named_modules())
+            cached = plan._conv_mods = [mods[n] for n in plan.conv_names]
+        return cached
 
     def forward(self, x):
         if not x.is_cuda:
@@ -307,19 +318,20 @@ class Generic_UNet(nn.Module):
                 outs = _UNetFunction.forward(_NullCtx(), self, plan, x, *params)
         self._last_plan = plan
         # fire forward hooks of the conv modules with the raw conv outputs (reference plop:330-353)
-        mods = None
-        for i, name in enumerate(plan.conv_names):
-            if mods is None:
-                mods = self._conv_modules(plan)
-            m = mods[i]
+        # in execution order: encoder convs, then per decoder level tu.u, loc.u.0, loc.u.1, seg_outputs.u
+        mods = self._conv_modules(plan)
+        n_enc = 2 * (self.num_pool + 1)
+        for i, m in enumerate(mods):
             if m._forward_hooks:
                 out_view, _ = plan.conv_output(i)
                 for hook in list(m._forward_hooks.values()):
                     hook(m, (None,), out_view)
-        for u, m in enumerate(self.seg_outputs):
-            if m._forward_hooks:
-                for hook in list(m._forward_hooks.values()):
-                    hook(m, (None,), outs[self.num_pool - 1 - u])
+            if i >= n_enc and (i - n_enc) % 3 == 2:
+                u = (i - n_enc) // 3
+                sm = self.seg_outputs[u]
+                if sm._forward_hooks:
+                    for hook in list(sm._forward_hooks.values()):
+                        hook(sm, (None,), outs[self.num_pool - 1 - u])
         outs = tuple(self.final_nonlin(o) for o in outs)
         if self._deep_supervision and self.do_ds:
             return outs

@@ -129,7 +129,7 @@ def test_pod_and_plop():
         ref = cl_losses.local_pod(layers[k], layers_old[k], 3)
         got = local_POD(layers[k].cuda(), layers_old[k].cuda(), 3)
         assert abs(float(got) - float(ref)) < TOL * abs(float(ref)), k
-    shapes = [(4, 8, 8), (2, 4, 4)]
+    shapes = [(4, 8, 8), (4, 6, 6)]
     weights = [2.0 / 3, 1.0 / 3]
     xs = [_logits(2, 3, s, 60 + i).requires_grad_() for i, s in enumerate(shapes)]
     xo = [_logits(2, 3, s, 70 + i, scale=6.0) for i, s in enumerate(shapes)]
@@ -142,10 +142,28 @@ def test_pod_and_plop():
     cu = lambda d: {k: v.cuda() for k, v in d.items()}
     loss.update_plop_params(cu(layers_old), cu(layers), {i: t.cuda() for i, t in thr.items()}, 1.0)
     got = loss(cx, [t.cuda() for t in xo], [y.cuda() for y in ys])
+    assert not torch.isnan(ref)
     assert abs(float(got) - float(ref)) < TOL * abs(float(ref))
     got.backward()
     for a, b in zip(cx, xs):
         assert rel_err(a.grad, b.grad) < TOL
+
+
+def test_plop_column_without_background_is_nan_like_the_reference():
+    """edge case (Q10): a (b, w) column with no background voxel gives 0/0 = NaN in the reference; same here"""
+    from b200unet.deep_supervision import MultipleOutputLossPLOP
+    from oracle import cl_losses
+    x, xo = _logits(2, 3, (2, 4, 4), 1), _logits(2, 3, (2, 4, 4), 2)
+    y = _target(2, 3, (2, 4, 4), 3)
+    y[0, 0, :, :, 1] = 2.0
+    thr = torch.tensor([0.4, 0.5, 0.6])
+    ref = cl_losses.plop_pseudo_label_loss(x, xo, y.squeeze(1), thr, 1.0)
+    assert torch.isnan(ref)
+    loss = MultipleOutputLossPLOP(nr_classes=2, pod_lambda=1e-2, scales=3, weight_factors=[1.0])
+    lay = {"a": torch.randn(2, 4, 2, 8, 8).cuda()}
+    loss.update_plop_params(lay, lay, {0: thr.cuda()}, 1.0)
+    got = loss([x.cuda()], [xo.cuda()], [y.cuda()])
+    assert torch.isnan(got)
 
 
 def test_sgd_clip_and_fisher_rw():

@@ -1,0 +1,184 @@
+"""GPU parity of the trainer-level hot path (run_iteration of the nnUNetTrainer* mirrors, through the C ABI) against
+the oracle's restated iteration (oracle/step.py: reference MultiHead:606-656) on identical weights and batches.
+Tolerances: loss values / parameters after N steps within 1e-3 relative; hard Dice within 1e-3; Fisher bit-stable."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _setup(trainer_cls, geom_name="tiny", **kw):
+    from b200unet import synth
+    from b200unet.configs import CONFIGS
+    from oracle import step
+    geom = CONFIGS[geom_name]
+    onet = step.build_network(geom.in_channels, geom.base_features, geom.num_classes, [list(k) for k in geom.pool],
+                              max_num_features=geom.max_features)
+    tr = trainer_cls(geom, precision="fp32", **kw)
+    tr.initialize()
+    tr.network.load_state_dict(onet.state_dict())
+    data, targets = synth.make_batch(geom)
+    gen = iter(lambda: {'data': data.numpy(), 'target': [t.numpy() for t in targets]}, None)
+    return geom, onet, tr, data, targets, gen
+
+
+def test_sequential_20_steps_loss_params_dice():
+    """'Dice vs ref': after 20 identical SGD steps on the fixed batch, hard Dice within 1e-3 of the oracle"""
+    from b200unet.trainers import nnUNetTrainerSequential
+    from oracle import cl_losses, step
+    geom, onet, tr, data, targets, gen = _setup(nnUNetTrainerSequential)
+    oopt = step.make_optimizer(onet)
+    lf = step.base_loss_fn(cl_losses.ds_loss_weights(geom.num_pool))
+    for it in range(20):
+        ol, oout = step.run_iteration(onet, oopt, data, targets, lf)
+        cl = float(tr.run_iteration(gen, run_online_evaluation=(it == 19)))
+        assert abs(cl - ol) < TOL * max(abs(ol), 1e-6), (it, cl, ol)
+    osd = onet.state_dict()
+    for n, p in tr.network.named_parameters():
+        assert rel_err(p, osd[n]) < TOL, n
+    with torch.no_grad():
+        d_o = cl_losses.hard_dice(onet(data)[0], targets[0])
+        d_c = cl_losses.hard_dice(tr.network(data.cuda())[0].cpu(), targets[0])
+    assert abs(d_o - d_c) < 1e-3
+    dice_online = tr.finish_online_evaluation()
+    assert len(dice_online) == geom.num_classes - 1 and all(0 <= d <= 1 for d in dice_online)
+
+
+def test_ewc_iterations_and_fisher():
+    from b200unet import synth
+    from b200unet.trainers import nnUNetTrainerEWC
+    from oracle import cl_losses, step
+    geom, onet, tr, data, targets, gen = _setup(nnUNetTrainerEWC, task="B")
+    fisher, params = synth.make_ewc_state(list(onet.named_parameters()))
+    tr.fisher["A"] = {k: v.cuda() for k, v in fisher.items()}
+    tr.params["A"] = {k: v.cuda() for k, v in params.items()}
+    tr.loss.update_ewc_params(tr.fisher, tr.params)
+    tr.loss.update_network_params(tr.network.named_parameters())
+    weights = cl_losses.ds_loss_weights(geom.num_pool)
+    oopt = step.make_optimizer(onet)
+    lf = step.ewc_loss_fn(onet, weights, {"A": fisher}, {"A": params}, 0.4)
+    for it in range(3):
+        ol, _ = step.run_iteration(onet, oopt, data, targets, lf)
+        cl = float(tr.run_iteration(gen))
+        assert abs(cl - ol) < TOL * abs(ol), (it, cl, ol)
+    osd = onet.state_dict()
+    for n, p in tr.network.named_parameters():
+        assert rel_err(p, osd[n]) < TOL, n
+    # after_train: Fisher = (last batch gradient)^2, grad None -> tensor([1]) (ewc:298-304)
+    oopt.zero_grad()
+    out = onet(data)
+    lf(out, targets).backward()
+    of, op = cl_losses.ewc_fisher_from_grads(list(onet.named_parameters()))
+    runs = []
+    for _ in range(3):
+        tr.after_train(gen, num_batches=1)
+        runs.append({k: v.clone() for k, v in tr.fisher["B"].items()})
+        del tr.fisher["B"], tr.params["B"]
+        tr.loss.update_ewc_params(tr.fisher, tr.params)
+    for k in of:
+        if of[k].numel() == 1 and runs[0][k].numel() == 1:
+            assert float(runs[0][k]) == 1.0, k
+            continue
+        scale = float(of[k].abs().max())
+        if "conv.bias" in k and "seg" not in k:
+            continue   # (numerically zero gradient)^2
+        assert float((runs[0][k].cpu() - of[k]).abs().max()) <= 3e-3 * max(scale, 1e-12), k
+    for r in runs[1:]:     # bit-pattern stable across runs
+        for k in r:
+            assert torch.equal(r[k].view(torch.int32) if r[k].dtype == torch.float32 else r[k], runs[0][k].view(torch.int32) if runs[0][k].dtype == torch.float32 else runs[0][k]), k
+
+
+def test_rw_updates_match_oracle():
+    from b200unet.trainers import nnUNetTrainerRW
+    from oracle import cl_losses, step
+    geom, onet, tr, data, targets, gen = _setup(nnUNetTrainerRW, fisher_update_after=1)
+    tr.start_task("A")
+    oopt = step.make_optimizer(onet)
+    lf = step.base_loss_fn(cl_losses.ds_loss_weights(geom.num_pool))
+    named = dict(onet.named_parameters())
+    of = {n: torch.zeros_like(p) for n, p in named.items()}
+    osc = {n: torch.zeros_like(p) for n, p in named.items()}
+    prev = None
+    for it in range(3):
+        step.run_iteration(onet, oopt, data, targets, lf)
+        tr.run_iteration(gen)
+        newprev = {}
+        for n, p in named.items():
+            if p.grad is None:
+                continue
+            of[n], osc[n] = cl_losses.rw_update(p.detach(), p.grad.detach(), None if prev is None else prev[n], of[n], osc[n], 0.9)
+            newprev[n] = p.detach().clone()
+        prev = newprev
+    for n in named:
+        if named[n].grad is None:
+            continue
+        if "conv.bias" in n and "seg" not in n:
+            continue
+        assert rel_err(tr.fisher["A"][n], of[n]) < 5e-3, n
+    tr.finish_task()
+    assert all(float(v.min()) >= 0 for v in tr.scores["A"].values())
+
+
+@pytest.mark.parametrize("which", ["mib", "pod", "plop", "lwf"])
+def test_teacher_trainers_match_oracle_losses(which):
+    """teacher-in-the-loop trainers: loss value of one iteration vs the oracle composition on the same tensors"""
+    from b200unet import trainers as T
+    from oracle import cl_losses
+    cls = {"mib": T.nnUNetTrainerMiB, "pod": T.nnUNetTrainerPOD, "plop": T.nnUNetTrainerPLOP, "lwf": T.nnUNetTrainerLWF}[which]
+    geom, onet, tr, data, targets, gen = _setup(cls)
+    weights = cl_losses.ds_loss_weights(geom.num_pool)
+    # "previous task": perturb the student after cloning the teacher
+    oteacher = copy.deepcopy(onet)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for p in onet.parameters():
+            p.add_(0.01 * torch.randn(p.shape, generator=g))
+    if which == "lwf":
+        tr.finish_task()                      # head of task A = current seg_outputs
+        tr.task = "B"
+        tr.network.load_state_dict(onet.state_dict())
+        tr.store_target_logits([data])
+        # oracle: old head on the current body vs stored logits (computed with the body at storage time = teacher body)
+        def ofwd(net_body, head_from):
+            net = copy.deepcopy(net_body)
+            net.seg_outputs.load_state_dict(head_from.seg_outputs.state_dict())
+            with torch.no_grad():
+                return net(data)[0]
+        pred, stored = ofwd(onet, oteacher), ofwd(oteacher, oteacher)
+        out = onet(data)
+        ref = cl_losses.multiple_output_loss2(out, targets, weights) + cl_losses.lwf_distillation(pred, stored, 2.0)
+    else:
+        tr.start_new_task() if which != "mib" else tr.make_teacher()
+        tr.network.load_state_dict(onet.state_dict())
+        out, out_o = onet(data), oteacher(data)
+        if which == "mib":
+            ref = cl_losses.mib_loss(out, [o.detach() for o in out_o], targets, weights, 1.0, 10)
+        else:
+            acts, acts_o = {}, {}
+            def grab(net, store):
+                hs = []
+                for name, m in net.named_modules():
+                    if 'conv.Conv' in str(type(m)):
+                        hs.append(m.register_forward_hook(lambda mod, i, o, name=name: store.__setitem__(name, o.detach())))
+                return hs
+            h1, h2 = grab(onet, acts), grab(oteacher, acts_o)
+            out, out_o = onet(data), oteacher(data)
+            for h in h1 + h2:
+                h.remove()
+            if which == "pod":
+                ref = cl_losses.multiple_output_loss2(out, targets, weights) + cl_losses.pod_running(acts, acts_o, 1e-2, 3)
+            else:
+                thr = {i: torch.full((geom.num_classes,), 1e-3) for i in range(geom.num_pool)}
+                ref = cl_losses.plop_loss(out, [o.detach() for o in out_o], targets, weights, thr,
+                                          float(np.log(geom.num_classes)), acts, acts_o, 1e-2, 3)
+    got = float(tr.run_iteration(gen, do_backprop=True))
+    if np.isnan(float(ref)):
+        assert np.isnan(got)
+    else:
+        assert abs(got - float(ref)) < TOL * abs(float(ref)), (got, float(ref))
