@@ -280,6 +280,14 @@ class Generic_UNet(nn.Module):
             self._plans[key] = plan
         return plan
 
+    def __getstate__(self):
+        # plans own C handles and HBM workspaces: never copied / pickled (copy.deepcopy of the network is how the
+        # reference creates teachers, mib:90-97 / plop:184-195)
+        d = self.__dict__.copy()
+        d['_plans'] = {}
+        d.pop('_last_plan', None)
+        return d
+
     def _apply(self, fn, *a, **kw):
         self._plans = {}          # device / dtype moves invalidate plans (workspaces live on the old device)
         return super()._apply(fn, *a, **kw)
