@@ -31,6 +31,9 @@ int b2_version(void);
 const char* b2_last_error(void);
 /* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
 long long b2_launch_count(void);
+/* runtime switches: "tensor_cores" (1 = tcgen05 path for bf16 where supported [default], 0 = SIMT only),
+ * "tc_strided" (1 = strided convs also on the tensor-core path).  Must be set before plans are created. */
+int b2_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Network plan.  Replaces the module graph built by nnunet's nnUNetTrainerV2.initialize_network() ->

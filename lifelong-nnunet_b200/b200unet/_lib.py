@@ -58,6 +58,7 @@ SIGNATURES = {
     "b2_version": (_I, []),
     "b2_last_error": (C.c_char_p, []),
     "b2_launch_count": (C.c_longlong, []),
+    "b2_set_option": (_I, [C.c_char_p, _I]),
     "b2_unet_plan_create": (_I, [C.POINTER(Geometry), C.POINTER(_VP)]),
     "b2_unet_plan_destroy": (None, [_VP]),
     "b2_unet_num_params": (_I, [_VP]),

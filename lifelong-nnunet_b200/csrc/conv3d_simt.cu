@@ -350,6 +350,74 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// per-(n,c) statistics of a bf16/fp32 NDHWC tensor (InstanceNorm), two-stage ordered reduction
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int VW>
+__global__ void __launch_bounds__(256) stats_reduce_kernel(const T* __restrict__ z, int slabs, long long vox, int c, int pitch,
+                                                           float* __restrict__ part) {
+    extern __shared__ float sh[];  // [R][c][2]
+    const int ncg = c / VW;
+    const int R = 256 / ncg;
+    const int n = blockIdx.y, slab = blockIdx.x;
+    const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
+    const long long per = (vox + slabs - 1) / slabs;
+    const long long v0 = (long long)slab * per, v1 = (v0 + per < vox) ? v0 + per : vox;
+    const int c0 = cg * VW;
+    if (r < R) {
+        float s1[VW], s2[VW];
+#pragma unroll
+        for (int j = 0; j < VW; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        for (long long v = v0 + r; v < v1; v += R) {
+            float a[VW];
+            if (VW == 8) load8(z + ((long long)n * vox + v) * pitch + c0, *reinterpret_cast<float(*)[8]>(a));
+            else a[0] = to_f(z[((long long)n * vox + v) * pitch + c0]);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) {
+            sh[((size_t)r * c + c0 + j) * 2] = s1[j];
+            sh[((size_t)r * c + c0 + j) * 2 + 1] = s2[j];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < c * 2; e += 256) {
+        float s = 0.f;
+        for (int q = 0; q < R; ++q) s += sh[(size_t)q * c * 2 + e];
+        part[(((long long)n * slabs + slab) * c) * 2 + e] = s;
+    }
+}
+
+static int stats_slabs(int n, long long vox) {
+    long long want = (4LL * num_sms() + n - 1) / n;
+    long long maxs = (vox + 255) / 256;
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+
+size_t instnorm_stats_scratch_floats(int n, long long vox, int c) { return (size_t)n * stats_slabs(n, vox) * c * 2; }
+
+template <typename T>
+int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* part, float* stats, float eps, cudaStream_t st) {
+    const bool v8 = (c % 8 == 0) && (pitch % 8 == 0);
+    const int vw = v8 ? 8 : 1;
+    B2_CHECK_ARG(c / vw <= 256);
+    const int slabs = stats_slabs(n, vox);
+    const int R = 256 / (c / vw);
+    const size_t sh = (size_t)R * c * 2 * sizeof(float);
+    dim3 grid(slabs, n);
+    if (v8) B2_LAUNCH((stats_reduce_kernel<T, 8>), grid, 256, sh, st, z, slabs, vox, c, pitch, part);
+    else B2_LAUNCH((stats_reduce_kernel<T, 1>), grid, 256, sh, st, z, slabs, vox, c, pitch, part);
+    dim3 g2(n, cdiv(c, 32));
+    B2_LAUNCH(stats_finalize_kernel, g2, 256, 0, st, part, slabs, c, 1.0 / (double)vox, eps, stats);
+    return B2_OK;
+}
+template int instnorm_stats<float>(const float*, int, long long, int, int, float*, float*, float, cudaStream_t);
+template int instnorm_stats<__nv_bfloat16>(const __nv_bfloat16*, int, long long, int, int, float*, float*, float, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
 static inline int out_dim(int i, int s) { return (i + 2 - 3) / s + 1; }

@@ -27,6 +27,19 @@ template <typename T>
 int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, float* dw, float* dbias,
                       cudaStream_t st);
 
+// per-(n,c) {mean, rstd} of an NDHWC tensor (used when the conv epilogue does not produce the partial sums)
+size_t instnorm_stats_scratch_floats(int n, long long vox, int c);
+template <typename T>
+int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* part, float* stats, float eps, cudaStream_t st);
+
+// ---- conv3d_tc.cu (tcgen05 / TMA path, bf16) ----------------------------------------------------------------------
+bool conv_tc_supported(int K, int Nout);
+int weight_shadow_bf16(const float* w_pt, int cout, int cin, __nv_bfloat16* wk, __nv_bfloat16* wd, cudaStream_t st);
+int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
+                   int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
+                   int accumulate, cudaStream_t st);
+extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
+
 // ---- norm.cu ----------------------------------------------------------------------------------------------------
 // y = lrelu(gamma*(z-mean)*rstd + beta)
 template <typename T>

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <array>
+#include <type_traits>
 
 #include <string>
 #include <vector>
@@ -27,6 +28,8 @@ namespace b2 {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+int g_use_tc = 1;
+int g_tc_strided = 1;
 
 int num_sms() {
     static int n = 0;
@@ -54,6 +57,8 @@ struct ConvBlock {
     int din_accumulate = 0;
     int p_w = -1, p_b = -1, p_g = -1, p_be = -1;
     size_t stats_off = 0, wf_off = 0, wb_off = 0;  // fp32 offsets
+    size_t wk_off = 0, wd_off = 0;                 // bf16 shadows for the tensor-core path (offsets in floats)
+    bool tc_fwd = false, tc_dgrad = false;
 };
 
 struct Tconv {
@@ -180,6 +185,16 @@ static int build_plan(b2_unet_plan* p) {
         cb.stats_off = fc; fc += (size_t)N * cout * 2;
         cb.wf_off = fc; fc += (size_t)27 * in.c * cout;
         cb.wb_off = fc; fc += (size_t)27 * in.c * cout;
+        fc = (fc + 63) / 64 * 64;
+        const bool strided = stride[0] != 1 || stride[1] != 1 || stride[2] != 1;
+        const bool tc_ok = g.act_dtype == B2_BF16 && g_use_tc && conv_tc_supported(in.c, cout) && in.pitch % 8 == 0;
+        cb.tc_fwd = tc_ok && (!strided || g_tc_strided);
+        cb.tc_dgrad = tc_ok && !strided && din.c > 0 && din.pitch % 8 == 0;
+        if (tc_ok) {
+            cb.wk_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
+            cb.wd_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
+            p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, (long long)od * oh * ow, cout));
+        }
         max_z = max_sz(max_z, cb.z.elems());
         p->scratch_floats = max_sz(p->scratch_floats, conv_stat_part_floats(cb.shape));
         p->scratch_floats = max_sz(p->scratch_floats, conv_wgrad_part_floats(cb.shape));
@@ -267,8 +282,27 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         float* stats = F32(ws, p, cb.stats_off);
         int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, wf, wb, st);
         if (r) return r;
-        r = conv3d_fwd_simt<T>(cb.shape, P<T>(ws, p, cb.in, false), wf, prm[cb.p_b], P<T>(ws, p, cb.z, false), SCR(ws, p), stats, g.norm_eps, st);
-        if (r) return r;
+        bool done = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (cb.tc_fwd || cb.tc_dgrad) {
+                r = weight_shadow_bf16(prm[cb.p_w], cb.shape.cout, cb.shape.cin, (__nv_bfloat16*)F32(ws, p, cb.wk_off),
+                                       (__nv_bfloat16*)F32(ws, p, cb.wd_off), st);
+                if (r) return r;
+            }
+            if (cb.tc_fwd) {
+                r = conv_tc_launch(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch,
+                                   (const __nv_bfloat16*)F32(ws, p, cb.wk_off), cb.shape.cout, prm[cb.p_b], P<T>(ws, p, cb.z, false),
+                                   cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st);
+                if (r) return r;
+                r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
+                if (r) return r;
+                done = true;
+            }
+        }
+        if (!done) {
+            r = conv3d_fwd_simt<T>(cb.shape, P<T>(ws, p, cb.in, false), wf, prm[cb.p_b], P<T>(ws, p, cb.z, false), SCR(ws, p), stats, g.norm_eps, st);
+            if (r) return r;
+        }
         return norm_lrelu_fwd<T>(P<T>(ws, p, cb.z, false), stats, prm[cb.p_g], prm[cb.p_be], P<T>(ws, p, cb.y, false), g.batch,
                                  cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, g.lrelu_slope, st);
     };
@@ -310,10 +344,23 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
         if (r) return r;
         if (cb.din.c > 0) {
-            ConvShape sd = s;
-            sd.in_pitch = cb.din.pitch;
-            r = conv3d_dgrad_simt<T>(sd, dz, F32(ws, p, cb.wb_off), P<T>(ws, p, cb.din, true), cb.din_accumulate, st);
-            if (r) return r;
+            bool done = false;
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                if (cb.tc_dgrad) {
+                    const int one[3] = {1, 1, 1};
+                    r = conv_tc_launch(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout,
+                                       (const __nv_bfloat16*)F32(ws, p, cb.wd_off), cb.shape.cin, nullptr, P<T>(ws, p, cb.din, true),
+                                       cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, cb.din_accumulate, st);
+                    if (r) return r;
+                    done = true;
+                }
+            }
+            if (!done) {
+                ConvShape sd = s;
+                sd.in_pitch = cb.din.pitch;
+                r = conv3d_dgrad_simt<T>(sd, dz, F32(ws, p, cb.wb_off), P<T>(ws, p, cb.din, true), cb.din_accumulate, st);
+                if (r) return r;
+            }
         }
         return B2_OK;
     };
@@ -350,6 +397,12 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
 // C ABI
 // ===============================================================================================================
 extern "C" int b2_version(void) { return 100; }
+extern "C" int b2_set_option(const char* name, int value) {
+    B2_CHECK_ARG(name);
+    if (!strcmp(name, "tensor_cores")) { g_use_tc = value; return B2_OK; }
+    if (!strcmp(name, "tc_strided")) { g_tc_strided = value; return B2_OK; }
+    return fail(B2_EINVAL, "unknown option %s", name);
+}
 extern "C" const char* b2_last_error(void) { return g_last_error.c_str(); }
 extern "C" long long b2_launch_count(void) { return g_launches.load(); }
 
@@ -459,6 +512,19 @@ extern "C" int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* 
     int rc = weight_shadow(w_pt, s.cout, s.cin, wf, wb, st);
     if (rc) return rc;
     if (d->dtype == B2_F32) return conv3d_fwd_simt<float>(s, (const float*)x, wf, bias, (float*)z, part, stats, eps, st);
+    const bool strided = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
+    if (g_use_tc && conv_tc_supported(s.cin, s.cout) && (!strided || g_tc_strided) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
+        // bf16 shadow aliases the (unused) fp32 forward shadow
+        __nv_bfloat16* wk = (__nv_bfloat16*)wf;
+        rc = weight_shadow_bf16(w_pt, s.cout, s.cin, wk, nullptr, st);
+        if (rc) return rc;
+        const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
+        rc = conv_tc_launch((const __nv_bfloat16*)x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, wk, s.cout, bias, (__nv_bfloat16*)z, od, oh, ow,
+                            s.out_pitch, s.stride, 0, st);
+        if (rc) return rc;
+        if (stats) return instnorm_stats<__nv_bfloat16>((const __nv_bfloat16*)z, s.n, (long long)od * oh * ow, s.cout, s.out_pitch, part, stats, eps, st);
+        return B2_OK;
+    }
     return conv3d_fwd_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, wf, bias, (__nv_bfloat16*)z, part, stats, eps, st);
 }
 
@@ -477,7 +543,14 @@ extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* d
         if (dx && (rc = conv3d_dgrad_simt<float>(s, (const float*)dz, wb, (float*)dx, accumulate_dx, st))) return rc;
     } else {
         if (dw && (rc = conv3d_wgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
-        if (dx && (rc = conv3d_dgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)dz, wb, (__nv_bfloat16*)dx, accumulate_dx, st))) return rc;
+        const bool strided = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
+        if (dx && g_use_tc && !strided && conv_tc_supported(s.cout, s.cin) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
+            __nv_bfloat16* wd = (__nv_bfloat16*)wf;   // forward fp32 shadow is unused from here on
+            if ((rc = weight_shadow_bf16(w_pt, s.cout, s.cin, nullptr, wd, st))) return rc;
+            const int one[3] = {1, 1, 1};
+            if ((rc = conv_tc_launch((const __nv_bfloat16*)dz, s.n, s.d, s.h, s.w, s.cout, s.out_pitch, wd, s.cin, nullptr,
+                                     (__nv_bfloat16*)dx, s.d, s.h, s.w, s.in_pitch, one, accumulate_dx, st))) return rc;
+        } else if (dx && (rc = conv3d_dgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)dz, wb, (__nv_bfloat16*)dx, accumulate_dx, st))) return rc;
     }
     return B2_OK;
 }
