@@ -126,7 +126,7 @@ class nnUNetTrainerMultiHead:
     def _sync_gradients(self):
         if self.ddp is None:
             return
-        plan = self.network._last_plan
+        plan = getattr(self.network, "_last_plan", None)
         flat = getattr(plan, "last_flat_grad", None)
         params = [p for p in self.network.parameters() if p.grad is not None]
         if flat is not None and all(p.grad.data_ptr() >= flat.data_ptr() and
