@@ -32,6 +32,9 @@ SHAPES = [
     (2, 4, 4, 4, 320, 320, (1, 1, 1)),        # 64 voxels/sample: the box spans the batch axis; N split in 2 x 160
     (2, 6, 10, 12, 128, 64, (1, 1, 1)),       # ragged everywhere
     (1, 8, 16, 16, 1, 32, (1, 1, 1)),         # first layer: SIMT path even in bf16
+    (2, 8, 16, 16, 32, 16, (1, 1, 1)),        # small-channel decoder block of the test geometries
+    (2, 4, 8, 8, 16, 32, (2, 2, 2)),
+    (2, 8, 16, 16, 8, 8, (1, 1, 1)),
 ]
 
 
@@ -61,7 +64,7 @@ def test_conv_forward_and_stats(shape, mode):
         ops.set_option("tensor_cores", 1)
 
 
-@pytest.mark.parametrize("shape", SHAPES[:6])
+@pytest.mark.parametrize("shape", SHAPES[:6] + SHAPES[7:])
 @pytest.mark.parametrize("mode", ["fp32", "bf16_tc"])
 def test_conv_backward(shape, mode):
     from b200unet import ops

@@ -40,8 +40,15 @@ def test_sequential_20_steps_loss_params_dice():
         cl = float(tr.run_iteration(gen, run_online_evaluation=(it == 19)))
         assert abs(cl - ol) < TOL * max(abs(ol), 1e-6), (it, cl, ol)
     osd = onet.state_dict()
+    report, bad = [], []
     for n, p in tr.network.named_parameters():
-        assert rel_err(p, osd[n]) < TOL, n
+        if "conv.bias" in n and "seg" not in n:
+            continue          # zero-gradient parameters (bias before InstanceNorm) stay at numerical noise
+        e = rel_err(p, osd[n])
+        report.append("%-60s %.3e" % (n, e))
+        if not e < TOL:
+            bad.append(n)
+    assert not bad, "\n".join(report)
     with torch.no_grad():
         d_o = cl_losses.hard_dice(onet(data)[0], targets[0])
         d_c = cl_losses.hard_dice(tr.network(data.cuda())[0].cpu(), targets[0])
@@ -69,6 +76,8 @@ def test_ewc_iterations_and_fisher():
         assert abs(cl - ol) < TOL * abs(ol), (it, cl, ol)
     osd = onet.state_dict()
     for n, p in tr.network.named_parameters():
+        if "conv.bias" in n and "seg" not in n:
+            continue
         assert rel_err(p, osd[n]) < TOL, n
     # after_train: Fisher = (last batch gradient)^2, grad None -> tensor([1]) (ewc:298-304)
     oopt.zero_grad()
@@ -115,12 +124,17 @@ def test_rw_updates_match_oracle():
             of[n], osc[n] = cl_losses.rw_update(p.detach(), p.grad.detach(), None if prev is None else prev[n], of[n], osc[n], 0.9)
             newprev[n] = p.detach().clone()
         prev = newprev
+    report, bad = [], []
     for n in named:
         if named[n].grad is None:
             continue
         if "conv.bias" in n and "seg" not in n:
             continue
-        assert rel_err(tr.fisher["A"][n], of[n]) < 5e-3, n
+        e = rel_err(tr.fisher["A"][n], of[n])
+        report.append("%-60s %.3e" % (n, e))
+        if not e < 5e-3:
+            bad.append(n)
+    assert not bad, "\n".join(report)
     tr.finish_task()
     assert all(float(v.min()) >= 0 for v in tr.scores["A"].values())
 
@@ -142,8 +156,8 @@ def test_teacher_trainers_match_oracle_losses(which):
     if which == "lwf":
         tr.finish_task()                      # head of task A = current seg_outputs
         tr.task = "B"
+        tr.store_target_logits([data])        # stored once at the start of the new task (old body)
         tr.network.load_state_dict(onet.state_dict())
-        tr.store_target_logits([data])
         # oracle: old head on the current body vs stored logits (computed with the body at storage time = teacher body)
         def ofwd(net_body, head_from):
             net = copy.deepcopy(net_body)
