@@ -535,6 +535,12 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
     return B2_OK;
 }
 
+int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, int cout, float* dw, float* db, cudaStream_t st) {
+    long long tot = 27LL * cin * cout + (db ? cout : 0);
+    B2_LAUNCH(wgrad_reduce_kernel, cdiv(tot, 256), 256, 0, st, part_w, part_b, nsplit, cin, cout, dw, db);
+    return B2_OK;
+}
+
 int weight_shadow(const float* w, int cout, int cin, float* wf, float* wb, cudaStream_t st) {
     long long tot = (long long)cout * cin * 27;
     B2_LAUNCH(weight_shadow_kernel, cdiv(tot, 256), 256, 0, st, w, cout, cin, wf, wb);

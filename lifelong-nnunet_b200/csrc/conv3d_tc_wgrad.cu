@@ -1,0 +1,358 @@
+// conv3d_tc_wgrad.cu -- weight gradient of the 3x3x3 convolution on the tensor cores (bf16 operands, fp32 accumulate).
+//
+//   dW[t][ci][co] = sum_v x[v*s + t - 1][ci] * dz[v][co]
+//
+// GEMM view: D[m, n] with m = (tap, ci) stacked to 128 rows, n = co (block of <= 256), K = voxels.  Both operands are
+// channel-contiguous NDHWC boxes (the same TMA boxes the forward uses), i.e. MN-major UMMA operands: a box of 128 voxels
+// x 64 channels lands in shared memory as 128 rows of 128 B and is consumed as a [64 (MN) x 128 (K)] tile, 16 voxels per
+// tcgen05.mma.  One accumulator group (128 x co_blk fp32 in TMEM) per 128 stacked rows; a CTA keeps up to 512 TMEM
+// columns of groups resident over its whole range of voxel tiles (split-K over voxels across CTAs), then writes one fp32
+// partial; the ordered reduction over CTAs (wgrad_reduce_kernel) makes the result bit-reproducible -- no atomics.
+//
+// Warp roles as in conv3d_tc.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace b2 {
+
+struct TcWgradParams {
+    int N, Do, Ho, Wo;           // dz extent
+    int TN, TD, TH, TW;          // voxel box (128 voxels)
+    int nt_n, nt_d, nt_h, nt_w;
+    int sd, sh, sw;
+    int Cin, Cout;
+    int ci_sub;                  // channels per A chunk (32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B)
+    int a_chunks;                // chunks per group (128 / ci_sub)
+    int stack_taps;              // 1: chunks of a group are consecutive taps (Cin <= 64); 0: consecutive ci sub-blocks
+    int ci_items;                // work items along ci
+    int co_blk, co_blks;         // output-channel block and count
+    int co_sub, b_chunks;        // channels per B chunk (32/64), chunks per dz tile
+    int groups;                  // accumulator groups per CTA (groups * co_blk <= 512)
+    int tapsets;                 // work items along taps
+    int taps_per_group;          // stack_taps ? a_chunks : 1
+    int nsplit;                  // CTAs per work item (split over voxel tiles)
+    int num_vtiles;
+    int a_stages;
+    uint32_t idesc;
+    uint32_t tmem_cols;
+    // MN-major descriptor strides (bytes)
+    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+};
+
+// MN-major UMMA descriptor: `row_bytes` = bytes of one K row (one voxel's channel chunk: 64 or 128)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t row_bytes, uint32_t lbo, uint32_t sbo) {
+    const uint64_t layout = row_bytes == 128 ? 2 : 4;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_ASTAGES = 6;
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, TcWgradParams p,
+                float* __restrict__ part) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t fullA[WG_MAX_ASTAGES], emptyA[WG_MAX_ASTAGES], fullB[2], emptyB[2], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_chunk_bytes = 128u * p.ci_sub * 2;
+    const uint32_t A_BYTES = a_chunk_bytes * p.a_chunks;          // 32 KB
+    const uint32_t b_chunk_bytes = 128u * p.co_sub * 2;
+    const uint32_t B_BYTES = b_chunk_bytes * p.b_chunks;
+    uint8_t* smemB = smem + (size_t)p.a_stages * A_BYTES;
+
+    // work item decode: blockIdx.x = ((item * nsplit) + split); item = (ci_item, co_blk, tapset)
+    const int split = blockIdx.x % p.nsplit;
+    int item = blockIdx.x / p.nsplit;
+    const int tapset = item % p.tapsets; item /= p.tapsets;
+    const int cob = item % p.co_blks; item /= p.co_blks;
+    const int ci_item = item;
+    const int tap0 = tapset * p.groups * p.taps_per_group;      // first tap of this CTA
+    int my_groups = p.groups;                                    // groups that contain at least one valid tap
+    {
+        const int remaining = 27 - tap0;
+        const int need = (remaining + p.taps_per_group - 1) / p.taps_per_group;
+        if (need < my_groups) my_groups = need;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmZ);
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+                int t = vt;
+                const int tw = t % p.nt_w; t /= p.nt_w;
+                const int th = t % p.nt_h; t /= p.nt_h;
+                const int td = t % p.nt_d; t /= p.nt_d;
+                const int tn = t;
+                const int w0 = tw * p.TW, h0 = th * p.TH, d0 = td * p.TD, n0 = tn * p.TN;
+                // dz tile
+                mbar_wait(&emptyB[bs], bph ^ 1);
+                mbar_expect_tx(&fullB[bs], B_BYTES);
+                for (int c = 0; c < p.b_chunks; ++c)
+                    tma_load_5d(&tmZ, &fullB[bs], smemB + (size_t)bs * B_BYTES + (size_t)c * b_chunk_bytes,
+                                cob * p.co_blk + c * p.co_sub, w0, h0, d0, n0);
+                if (++bs == 2) { bs = 0; bph ^= 1; }
+                // x tiles, one stage per group
+                for (int g = 0; g < my_groups; ++g) {
+                    mbar_wait(&emptyA[as], aph ^ 1);
+                    mbar_expect_tx(&fullA[as], A_BYTES);
+                    for (int c = 0; c < p.a_chunks; ++c) {
+                        int tap, cch;
+                        if (p.stack_taps) { tap = tap0 + g * p.a_chunks + c; cch = 0; }
+                        else { tap = tap0 + g; cch = ci_item * 128 + c * p.ci_sub; }
+                        if (tap > 26) tap = 26;  // rows of non-existent taps are ignored by the epilogue
+                        tma_load_5d(&tmX, &fullA[as], smem + (size_t)as * A_BYTES + (size_t)c * a_chunk_bytes, cch,
+                                    w0 * p.sw + tap % 3 - 1, h0 * p.sh + (tap / 3) % 3 - 1, d0 * p.sd + tap / 9 - 1, n0);
+                    }
+                    if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        bool first = true;
+        for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+            mbar_wait(&fullB[bs], bph);
+            for (int g = 0; g < my_groups; ++g) {
+                mbar_wait(&fullA[as], aph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + (size_t)as * A_BYTES);
+                    const uint32_t sb = smem_u32(smemB + (size_t)bs * B_BYTES);
+                    const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {   // 128 voxels = 8 x K16
+                        const uint64_t adesc = umma_desc_mnmajor(sa + k * 16 * a_row, a_row, p.a_lbo, p.a_sbo);
+                        const uint64_t bdesc = umma_desc_mnmajor(sb + k * 16 * b_row, b_row, p.b_lbo, p.b_sbo);
+                        umma_bf16(tmem_base + (uint32_t)(g * p.co_blk), adesc, bdesc, p.idesc, (!first || k != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&emptyA[as]);
+                    if (g == my_groups - 1) umma_commit(&emptyB[bs]);
+                }
+                __syncwarp();
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            }
+            first = false;
+            if (++bs == 2) { bs = 0; bph ^= 1; }
+        }
+        if (elect_one()) umma_commit(&done_bar);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int chunk = r / p.ci_sub, cil = r % p.ci_sub;
+        const bool has_work = split < p.num_vtiles;   // a CTA without voxel tiles writes zeros
+        if (has_work) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+        }
+        float* out = part + (size_t)split * 27 * p.Cin * p.Cout;
+        for (int g = 0; g < my_groups; ++g) {
+            int tap, ci;
+            if (p.stack_taps) { tap = tap0 + g * p.a_chunks + chunk; ci = cil; }
+            else { tap = tap0 + g; ci = ci_item * 128 + chunk * p.ci_sub + cil; }
+            const bool valid = tap < 27 && ci < p.Cin;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.co_blk);
+            for (int c0 = 0; c0 < p.co_blk; c0 += 32) {
+                uint32_t v[32];
+                if (has_work) {
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = 0u;
+                }
+                if (valid) {
+                    float* dstp = out + ((size_t)tap * p.Cin + ci) * p.Cout + cob * p.co_blk + c0;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dstp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                           __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// dbias[co] = sum over all voxels of dz: ordered two-stage column sum
+__global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* __restrict__ dz, long long rows, int c, int pitch,
+                                                          int slabs, float* __restrict__ part) {
+    // thread = (column, lane); lanes stride rows
+    const int lanes = 256 / c > 0 ? 256 / c : 1;
+    const int col = threadIdx.x % c, ln = threadIdx.x / c;
+    extern __shared__ float sh[];
+    const long long per = (rows + slabs - 1) / slabs;
+    const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+    float s = 0.f;
+    if (ln < lanes)
+        for (long long r = r0 + ln; r < r1; r += lanes) s += __bfloat162float(dz[r * pitch + col]);
+    if (ln < lanes) sh[ln * c + col] = s;
+    __syncthreads();
+    if (threadIdx.x < c) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += sh[l * c + threadIdx.x];
+        part[(long long)blockIdx.x * c + threadIdx.x] = t;
+    }
+}
+// wide layers (c > 256): thread per column, rows sequential (their volumes are tiny)
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* __restrict__ dz, long long rows, int c, int pitch,
+                                                          int slabs, float* __restrict__ part) {
+    const long long per = (rows + slabs - 1) / slabs;
+    const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+    for (int col = threadIdx.x; col < c; col += 256) {
+        float s = 0.f;
+        for (long long r = r0; r < r1; ++r) s += __bfloat162float(dz[r * pitch + col]);
+        part[(long long)blockIdx.x * c + col] = s;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int slabs, int c, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float s = 0.f;
+    for (int k = 0; k < slabs; ++k) s += part[(long long)k * c + i];
+    out[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int g_wgrad_desc_mode = 0;   // probe switch for the MN-major descriptor stride convention (tests/tools only)
+
+static int pow2_le2(int v, int cap) {
+    int p = 1;
+    while (p * 2 <= v && p * 2 <= cap) p *= 2;
+    return p;
+}
+
+bool wgrad_tc_supported(int cin, int cout) {
+    if (cin % 32 != 0 || cout % 32 != 0) return false;
+    if (cin > 64 && cin % 64 != 0) return false;
+    if (cout > 32 && cout % 64 != 0) return false;
+    return true;
+}
+
+static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p) {
+    p.N = s.n;
+    p.Do = (s.d - 1) / s.stride[0] + 1; p.Ho = (s.h - 1) / s.stride[1] + 1; p.Wo = (s.w - 1) / s.stride[2] + 1;
+    p.sd = s.stride[0]; p.sh = s.stride[1]; p.sw = s.stride[2];
+    p.TW = pow2_le2(p.Wo, 8);
+    p.TH = pow2_le2(p.Ho, 128 / p.TW > 8 ? 8 : 128 / p.TW);
+    p.TD = pow2_le2(p.Do, 128 / (p.TW * p.TH));
+    p.TN = 128 / (p.TW * p.TH * p.TD);
+    p.nt_w = cdiv(p.Wo, p.TW); p.nt_h = cdiv(p.Ho, p.TH); p.nt_d = cdiv(p.Do, p.TD); p.nt_n = cdiv(s.n, p.TN);
+    p.num_vtiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n;
+    p.Cin = s.cin; p.Cout = s.cout;
+    if (s.cin <= 64) { p.ci_sub = s.cin; p.stack_taps = 1; p.ci_items = 1; }
+    else { p.ci_sub = 64; p.stack_taps = 0; p.ci_items = cdiv(s.cin, 128); }
+    p.a_chunks = 128 / p.ci_sub;
+    p.taps_per_group = p.stack_taps ? p.a_chunks : 1;
+    p.co_blks = cdiv(s.cout, 256);
+    while (s.cout % p.co_blks != 0 || (s.cout / p.co_blks) % 32 != 0) ++p.co_blks;
+    p.co_blk = s.cout / p.co_blks;
+    p.co_sub = p.co_blk % 64 == 0 ? 64 : 32;
+    p.b_chunks = p.co_blk / p.co_sub;
+    const int total_groups = cdiv(27, p.taps_per_group);
+    int gmax = 512 / p.co_blk;
+    if (gmax > total_groups) gmax = total_groups;
+    p.groups = gmax;
+    p.tapsets = cdiv(total_groups, gmax);
+    const int items = p.ci_items * p.co_blks * p.tapsets;
+    int ns = (2 * num_sms()) / items;
+    if (ns < 1) ns = 1;
+    if (ns > p.num_vtiles) ns = p.num_vtiles;
+    p.nsplit = ns;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.groups * p.co_blk)) cols *= 2;
+    p.tmem_cols = cols;
+    // kind::f16, bf16 x bf16 -> f32, A and B MN-major (bits 15, 16), M = 128, N = co_blk
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.co_blk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
+    // canonical MN-major layout (cute::UMMA, see tc_common.cuh): LBO = distance between MN chunks (one TMA box each),
+    // SBO = distance between 8-row K groups
+    p.a_lbo = 128u * a_row; p.a_sbo = 8u * a_row;
+    p.b_lbo = 128u * b_row; p.b_sbo = 8u * b_row;
+    if (g_wgrad_desc_mode == 1) { uint32_t t = p.a_lbo; p.a_lbo = p.a_sbo; p.a_sbo = t; t = p.b_lbo; p.b_lbo = p.b_sbo; p.b_sbo = t; }
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    int st = (int)((200u * 1024 - 2 * B_BYTES) / A_BYTES);
+    if (st > WG_MAX_ASTAGES) st = WG_MAX_ASTAGES;
+    if (st < 2) st = 2;
+    p.a_stages = st;
+}
+
+size_t wgrad_tc_part_floats(const ConvShape& s) {
+    TcWgradParams p;
+    wgrad_tc_plan(s, p);
+    size_t colsum = (size_t)(2 * num_sms()) * s.cout;
+    return (size_t)p.nsplit * 27 * s.cin * s.cout + colsum + 64;
+}
+
+// wgrad_reduce_kernel lives in conv3d_simt.cu
+int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, int cout, float* dw, float* db, cudaStream_t st);
+
+int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
+                    cudaStream_t st) {
+    B2_CHECK_ARG(wgrad_tc_supported(s.cin, s.cout) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0);
+    TcWgradParams p;
+    wgrad_tc_plan(s, p);
+    CUtensorMap tmX, tmZ;
+    int rc = make_act_map(&tmX, x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, p.ci_sub, p.TN, p.TD, p.TH, p.TW, p.sd, p.sh, p.sw);
+    if (rc) return rc;
+    rc = make_act_map(&tmZ, dz, s.n, p.Do, p.Ho, p.Wo, s.cout, s.out_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
+    if (rc) return rc;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
+    if (smem > 227 * 1024) return fail(B2_EUNSUPPORTED, "wgrad_tc: tile does not fit shared memory%s", "");
+    static bool attr = false;
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part);
+    float* part_b = nullptr;
+    int slabs = 1;
+    if (dbias) {
+        part_b = part + (size_t)p.nsplit * 27 * s.cin * s.cout;
+        const long long rows = (long long)s.n * p.Do * p.Ho * p.Wo;
+        slabs = 2 * num_sms();
+        if (slabs > rows) slabs = (int)rows;
+        if (s.cout <= 256) {
+            const int lanes = 256 / s.cout;
+            B2_LAUNCH(colsum_part_kernel, slabs, 256, (size_t)lanes * s.cout * sizeof(float), st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+        } else {
+            B2_LAUNCH(colsum_wide_kernel, slabs, 256, 0, st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+        }
+    }
+    // ordered reduction over the split CTAs, written in PyTorch layout [co][ci][27]
+    rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
+    if (rc) return rc;
+    if (dbias) B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
+    return B2_OK;
+}
+
+}  // namespace b2

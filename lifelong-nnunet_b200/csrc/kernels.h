@@ -38,6 +38,11 @@ int weight_shadow_bf16(const float* w_pt, int cout, int cin, __nv_bfloat16* wk, 
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
                    int accumulate, cudaStream_t st);
+bool wgrad_tc_supported(int cin, int cout);
+size_t wgrad_tc_part_floats(const ConvShape& s);
+int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
+                    cudaStream_t st);
+extern int g_wgrad_desc_mode, g_tc_wgrad;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 
 // ---- norm.cu ----------------------------------------------------------------------------------------------------

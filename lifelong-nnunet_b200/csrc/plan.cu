@@ -30,6 +30,7 @@ thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
 int g_use_tc = 1;
 int g_tc_strided = 1;
+int g_tc_wgrad = 0;   // experimental until validated on hardware
 
 int num_sms() {
     static int n = 0;
@@ -58,7 +59,7 @@ struct ConvBlock {
     int p_w = -1, p_b = -1, p_g = -1, p_be = -1;
     size_t stats_off = 0, wf_off = 0, wb_off = 0;  // fp32 offsets
     size_t wk_off = 0, wd_off = 0;                 // bf16 shadows for the tensor-core path (offsets in floats)
-    bool tc_fwd = false, tc_dgrad = false;
+    bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false;
 };
 
 struct Tconv {
@@ -190,6 +191,8 @@ static int build_plan(b2_unet_plan* p) {
         const bool tc_ok = g.act_dtype == B2_BF16 && g_use_tc && conv_tc_supported(in.c, cout) && in.pitch % 8 == 0;
         cb.tc_fwd = tc_ok && (!strided || g_tc_strided);
         cb.tc_dgrad = tc_ok && !strided && din.c > 0 && din.pitch % 8 == 0;
+        cb.tc_wgrad = tc_ok && g_tc_wgrad && wgrad_tc_supported(in.c, cout) && (!strided || g_tc_strided);
+        if (cb.tc_wgrad) p->scratch_floats = max_sz(p->scratch_floats, wgrad_tc_part_floats(cb.shape));
         if (tc_ok) {
             cb.wk_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             cb.wd_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
@@ -341,8 +344,18 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         if (r) return r;
         ConvShape s = cb.shape;
         s.out_pitch = cb.shape.cout;  // dz is dense
-        r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
-        if (r) return r;
+        bool wdone = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (cb.tc_wgrad) {
+                r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+                if (r) return r;
+                wdone = true;
+            }
+        }
+        if (!wdone) {
+            r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+            if (r) return r;
+        }
         if (cb.din.c > 0) {
             bool done = false;
             if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -401,6 +414,8 @@ extern "C" int b2_set_option(const char* name, int value) {
     B2_CHECK_ARG(name);
     if (!strcmp(name, "tensor_cores")) { g_use_tc = value; return B2_OK; }
     if (!strcmp(name, "tc_strided")) { g_tc_strided = value; return B2_OK; }
+    if (!strcmp(name, "tc_wgrad")) { g_tc_wgrad = value; return B2_OK; }
+    if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
     return fail(B2_EINVAL, "unknown option %s", name);
 }
 extern "C" const char* b2_last_error(void) { return g_last_error.c_str(); }
@@ -498,6 +513,9 @@ extern "C" size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d) {
     size_t w = (size_t)27 * s.cin * s.cout;
     size_t part = conv_stat_part_floats(s);
     size_t wg = conv_wgrad_part_floats(s);
+    if (wgrad_tc_supported(s.cin, s.cout)) { size_t t = wgrad_tc_part_floats(s); if (t > wg) wg = t; }
+    size_t st2 = instnorm_stats_scratch_floats(s.n, (long long)s.d * s.h * s.w, s.cout);
+    if (st2 > part) part = st2;
     return align_up((2 * w + (part > wg ? part : wg) + 64) * sizeof(float));
 }
 
@@ -542,7 +560,10 @@ extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* d
         if (dw && (rc = conv3d_wgrad_simt<float>(s, (const float*)x, (const float*)dz, part, dw, dbias, st))) return rc;
         if (dx && (rc = conv3d_dgrad_simt<float>(s, (const float*)dz, wb, (float*)dx, accumulate_dx, st))) return rc;
     } else {
-        if (dw && (rc = conv3d_wgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
+        const bool strided_w = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
+        if (dw && g_use_tc && g_tc_wgrad && wgrad_tc_supported(s.cin, s.cout) && (!strided_w || g_tc_strided) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
+            if ((rc = conv3d_wgrad_tc(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
+        } else if (dw && (rc = conv3d_wgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
         const bool strided = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
         if (dx && g_use_tc && !strided && conv_tc_supported(s.cout, s.cin) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
             __nv_bfloat16* wd = (__nv_bfloat16*)wf;   // forward fp32 shadow is unused from here on
