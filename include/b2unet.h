@@ -103,6 +103,9 @@ typedef struct b2_act_view {
 int b2_unet_num_convs(const b2_unet_plan* plan);
 int b2_unet_conv_name(const b2_unet_plan* plan, int conv_idx, char name[96]);
 int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx, b2_act_view* out);
+/* development aid: view of conv block `block_idx` (execution order of the 3x3x3 blocks): which = 0 raw output z,
+ * 1 activated output y, 2 gradient wrt y, 3 block input, 4 gradient wrt the block input */
+int b2_unet_debug_view(const b2_unet_plan* plan, void* workspace, int block_idx, int which, b2_act_view* out);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Deep-supervision Dice+CE loss, value and gradient in one sweep.  Replaces nnunet MultipleOutputLoss2(DC_and_CE_loss

@@ -70,6 +70,7 @@ SIGNATURES = {
     "b2_unet_num_convs": (_I, [_VP]),
     "b2_unet_conv_name": (_I, [_VP, _I, C.c_char_p]),
     "b2_unet_conv_output": (_I, [_VP, _VP, _I, C.POINTER(ActView)]),
+    "b2_unet_debug_view": (_I, [_VP, _VP, _I, _I, C.POINTER(ActView)]),
     "b2_dsloss_scratch_bytes": (_SZ, [_I, _I, _I64]),
     "b2_dsloss_fwd_bwd": (_I, [_VP, _VP, _I, _I, _I64, _F, _I, _F, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "b2_quadpen_scratch_bytes": (_SZ, [_I, _I64]),

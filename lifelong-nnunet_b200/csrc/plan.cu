@@ -488,6 +488,17 @@ extern "C" int b2_unet_conv_name(const b2_unet_plan* plan, int conv_idx, char na
     return B2_OK;
 }
 
+extern "C" int b2_unet_debug_view(const b2_unet_plan* plan, void* workspace, int block_idx, int which, b2_act_view* out) {
+    B2_CHECK_ARG(plan && workspace && out && block_idx >= 0 && block_idx < (int)plan->convs.size() && which >= 0 && which <= 4);
+    const ConvBlock& cb = plan->convs[block_idx];
+    const Act& a = which == 0 ? cb.z : which == 1 ? cb.y : which == 2 ? cb.dy : which == 3 ? cb.in : cb.din;
+    const bool grad = which == 2 || which == 4;
+    out->ptr = (char*)workspace + (grad ? plan->off_grad : plan->off_act) + a.off * plan->esz;
+    out->n = a.n; out->d = a.d; out->h = a.h; out->w = a.w; out->c = a.c; out->pitch = a.pitch;
+    out->dtype = plan->g.act_dtype;
+    return B2_OK;
+}
+
 extern "C" int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx, b2_act_view* out) {
     B2_CHECK_ARG(plan && workspace && out && conv_idx >= 0 && conv_idx < (int)plan->conv_modules.size());
     auto km = plan->conv_modules[conv_idx];
