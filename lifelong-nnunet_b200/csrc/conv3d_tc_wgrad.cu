@@ -329,9 +329,9 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     if (rc) return rc;
     const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
     const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
-    if (smem > 227 * 1024) return fail(B2_EUNSUPPORTED, "wgrad_tc: tile does not fit shared memory%s", "");
+    if (smem > 220 * 1024) return fail(B2_EUNSUPPORTED, "wgrad_tc: tile does not fit shared memory%s", "");
     static bool attr = false;
-    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
     B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part);
     float* part_b = nullptr;
