@@ -72,5 +72,7 @@ CONFIGS = {
     "cfg4": UNetGeometry("cfg4", (48, 192, 192), (P2, P2, P2, P1, P1), 1, 2, 32, 320, 2),
     # tiny geometry for parity tests / smoke
     "tiny": UNetGeometry("tiny", (16, 32, 32), (P2, P2), 1, 3, 8, 320, 2),
+    # tensor-core capable small geometry (channels multiples of 32; a (1,2,2) pool)
+    "tiny32": UNetGeometry("tiny32", (8, 32, 32), (P2, P1), 1, 3, 32, 320, 2),
     "tiny3": UNetGeometry("tiny3", (8, 32, 32), (P2, P2, P1), 2, 3, 8, 24, 2),
 }

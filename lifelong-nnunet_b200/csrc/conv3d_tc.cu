@@ -14,6 +14,8 @@
 //
 // Replaces cuDNN's conv3d behind nn.Conv3d of nnunet's ConvDropoutNormNonlin (reference call sites: the
 // `self.network(data)` of nnUNetTrainerMultiHead.py:621/633 and its backward :627/639).
+#include <string.h>
+
 #include "tc_common.cuh"
 #include "kernels.h"
 
@@ -42,18 +44,25 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 
 // ---------------------------------------------------------------------------------------------------------------
 struct TcConvParams {
-    int N, D, H, W;              // extent of the PRODUCED tensor
+    int N, D, H, W;              // extent of the PRODUCED tensor (bounds of the stores)
+    int LD, LH, LW;              // logical grid the voxel boxes tile (== D,H,W unless the output is a strided sub-lattice)
     int dst_pitch;
     int TN, TD, TH, TW;          // voxel box of a tile (product == 128)
     int nt_n, nt_d, nt_h, nt_w;  // tiles per axis
-    int nblk, BN;                // output-channel blocks and their width
+    int nblk, BN;                // output-column blocks and their width
     int kchunks;                 // K / KC
-    int rows_per_tap;            // rows of the weight matrix per tap (== total N)
-    int sd, sh, sw;              // conv stride (source coordinate = out * s + tap - 1)
+    int rows_per_tap;            // rows of the weight matrix per tap block
+    int sd, sh, sw;              // source coordinate = logical * s + tap_off
+    int os_d, os_h, os_w;        // produced coordinate = logical * os + oo (+ q offset when q_scatter)
+    int oo_d, oo_h, oo_w;
+    int q_scatter, nblk_per_q, qk_h, qk_w;   // transposed-conv forward: column block -> (q, channel block)
+    int ntaps;
     int stages;
     int num_tiles;
     uint32_t idesc;
     uint32_t tmem_cols;
+    signed char tap_off[27][3];  // source offset (d, h, w) per tap, padding included
+    unsigned char tap_w[27];     // weight row-block of the tap
 };
 
 constexpr int TC_THREADS = 192;
@@ -86,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int kiters = 27 * p.kchunks;
+    const int kiters = p.ntaps * p.kchunks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -100,15 +109,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int th = t % p.nt_h; t /= p.nt_h;
                 const int td = t % p.nt_d; t /= p.nt_d;
                 const int tn = t;
-                const int w0 = tw * p.TW * p.sw - 1, h0 = th * p.TH * p.sh - 1, d0 = td * p.TD * p.sd - 1, n0 = tn * p.TN;
+                const int w0 = tw * p.TW * p.sw, h0 = th * p.TH * p.sh, d0 = td * p.TD * p.sd, n0 = tn * p.TN;
                 for (int it = 0; it < kiters; ++it) {
                     const int tap = it / p.kchunks, kc = it % p.kchunks;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                    tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + tap % 3, h0 + (tap / 3) % 3, d0 + tap / 9, n0);
-                    tma_load_2d(&tmB, &full_bar[stage], sb, kc * KC, tap * p.rows_per_tap + nb * p.BN);
+                    tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
+                                d0 + p.tap_off[tap][0], n0);
+                    tma_load_2d(&tmB, &full_bar[stage], sb, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -158,9 +168,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int th = t % p.nt_h; t /= p.nt_h;
             const int td = t % p.nt_d; t /= p.nt_d;
             const int tn = t;
-            const int ow = tw * p.TW + w_, oh = th * p.TH + h_, od = td * p.TD + d_, on = tn * p.TN + n_;
-            const bool valid = ow < p.W && oh < p.H && od < p.D && on < p.N;
-            __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + nb * p.BN;
+            const int lw = tw * p.TW + w_, lh = th * p.TH + h_, ld = td * p.TD + d_, on = tn * p.TN + n_;
+            int ow = lw * p.os_w + p.oo_w, oh = lh * p.os_h + p.oo_h, od = ld * p.os_d + p.oo_d;
+            int chan0 = nb * p.BN;
+            if (p.q_scatter) {
+                const int q = nb / p.nblk_per_q;
+                ow += q % p.qk_w; oh += (q / p.qk_w) % p.qk_h; od += q / (p.qk_w * p.qk_h);
+                chan0 = (nb % p.nblk_per_q) * p.BN;
+            }
+            const bool valid = lw < p.LW && lh < p.LH && ld < p.LD && on < p.N && ow < p.W && oh < p.H && od < p.D;
+            __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -175,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             f[e] = __uint_as_float(v[j + e]);
-                            if (bias) f[e] += bias[nb * p.BN + c0 + j + e];
+                            if (bias) f[e] += bias[chan0 + c0 + j + e];
                         }
                         if (accumulate) {
                             float o[8];
@@ -277,26 +294,43 @@ int weight_shadow_bf16(const float* w, int cout, int cin, __nv_bfloat16* wk, __n
     return B2_OK;
 }
 
-// Generic launcher.  src: NDHWC bf16 [N, Ds, Hs, Ws, K] (pitch src_pitch); wmat: [27][Nout][K] bf16; dst: NDHWC bf16
-// [N, Dd, Hd, Wd, Nout] with source coordinate = dst * stride + tap - 1.
-int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
-                   int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st) {
-    B2_CHECK_ARG(conv_tc_supported(K, Nout));
-    B2_CHECK_ARG(src_pitch % 8 == 0 && dst_pitch % 8 == 0);
-    const int KC = (K % 64 == 0) ? 64 : 32;
-    int nblk = cdiv(Nout, 256);
-    while (Nout % nblk != 0 || (Nout / nblk) % 32 != 0) ++nblk;
-    const int BN = Nout / nblk;
+// Generic launcher of the gather-GEMM.  src: NDHWC bf16 [N, Ds, Hs, Ws, K] (pitch src_pitch); wmat: [row blocks][Nout][K]
+// bf16; dst: NDHWC bf16 [N, Dd, Hd, Wd, *] (pitch dst_pitch).  See TcGather for the tap / lattice description.
+int conv_tc_gather(const TcGather& g, cudaStream_t st) {
+    B2_CHECK_ARG(conv_tc_supported(g.K, g.Nout));
+    B2_CHECK_ARG(g.src_pitch % 8 == 0 && g.dst_pitch % 8 == 0 && g.ntaps >= 1 && g.ntaps <= 27);
+    const int KC = (g.K % 64 == 0) ? 64 : 32;
+    int nblk, BN;
+    if (g.q_scatter) {
+        // column blocks must not straddle q: block the per-q channel count
+        int per = cdiv(g.q_channels, 256);
+        while (g.q_channels % per != 0 || (g.q_channels / per) % 32 != 0) ++per;
+        BN = g.q_channels / per;
+        nblk = g.Nout / BN;
+    } else {
+        nblk = cdiv(g.Nout, 256);
+        while (g.Nout % nblk != 0 || (g.Nout / nblk) % 32 != 0) ++nblk;
+        BN = g.Nout / nblk;
+    }
     TcConvParams p;
-    p.N = N; p.D = Dd; p.H = Hd; p.W = Wd; p.dst_pitch = dst_pitch;
-    p.TW = pow2_le(Wd, 8);
-    p.TH = pow2_le(Hd, 128 / p.TW > 8 ? 8 : 128 / p.TW);
-    p.TD = pow2_le(Dd, 128 / (p.TW * p.TH));
+    memset(&p, 0, sizeof(p));
+    p.N = g.N; p.D = g.Dd; p.H = g.Hd; p.W = g.Wd; p.dst_pitch = g.dst_pitch;
+    p.LD = g.LD; p.LH = g.LH; p.LW = g.LW;
+    p.TW = pow2_le(g.LW, 8);
+    p.TH = pow2_le(g.LH, 128 / p.TW > 8 ? 8 : 128 / p.TW);
+    p.TD = pow2_le(g.LD, 128 / (p.TW * p.TH));
     p.TN = 128 / (p.TW * p.TH * p.TD);
-    p.nt_w = cdiv(Wd, p.TW); p.nt_h = cdiv(Hd, p.TH); p.nt_d = cdiv(Dd, p.TD); p.nt_n = cdiv(N, p.TN);
-    p.nblk = nblk; p.BN = BN; p.kchunks = K / KC; p.rows_per_tap = Nout;
-    p.sd = stride[0]; p.sh = stride[1]; p.sw = stride[2];
+    p.nt_w = cdiv(g.LW, p.TW); p.nt_h = cdiv(g.LH, p.TH); p.nt_d = cdiv(g.LD, p.TD); p.nt_n = cdiv(g.N, p.TN);
+    p.nblk = nblk; p.BN = BN; p.kchunks = g.K / KC; p.rows_per_tap = g.rows_per_tap;
+    p.sd = g.stride[0]; p.sh = g.stride[1]; p.sw = g.stride[2];
+    p.os_d = g.os[0]; p.os_h = g.os[1]; p.os_w = g.os[2];
+    p.oo_d = g.oo[0]; p.oo_h = g.oo[1]; p.oo_w = g.oo[2];
+    p.q_scatter = g.q_scatter; p.nblk_per_q = g.q_scatter ? g.q_channels / BN : 1; p.qk_h = g.qk[1]; p.qk_w = g.qk[2];
+    p.ntaps = g.ntaps;
+    for (int t = 0; t < g.ntaps; ++t) {
+        for (int a = 0; a < 3; ++a) p.tap_off[t][a] = (signed char)g.tap_off[t][a];
+        p.tap_w[t] = (unsigned char)g.tap_w[t];
+    }
     p.num_tiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n * nblk;
     p.idesc = umma_idesc_bf16(128, BN);
     uint32_t cols = 32;
@@ -311,20 +345,139 @@ int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int 
     const size_t smem = (size_t)stages * stage_bytes + 1024;
 
     CUtensorMap tmA, tmB;
-    int rc = make_act_map(&tmA, src, N, Ds, Hs, Ws, K, src_pitch, KC, p.TN, p.TD, p.TH, p.TW, p.sd, p.sh, p.sw);
+    int rc = make_act_map(&tmA, g.src, g.N, g.Ds, g.Hs, g.Ws, g.K, g.src_pitch, KC, p.TN, p.TD, p.TH, p.TW, p.sd, p.sh, p.sw);
     if (rc) return rc;
-    rc = make_w_map(&tmB, wmat, 27 * Nout, K, KC, BN);
+    rc = make_w_map(&tmB, g.wmat, g.w_rows, g.K, KC, BN);
     if (rc) return rc;
 
     static bool attr64 = false, attr32 = false;
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     if (KC == 64) {
         if (!attr64) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr64 = true; }
-        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate);
+        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate);
     } else {
         if (!attr32) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr32 = true; }
-        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate);
+        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate);
     }
+    return B2_OK;
+}
+
+static void fill_common(TcGather& g, const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch,
+                        const __nv_bfloat16* wmat, int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd,
+                        int dst_pitch, int accumulate) {
+    memset(&g, 0, sizeof(g));
+    g.src = src; g.N = N; g.Ds = Ds; g.Hs = Hs; g.Ws = Ws; g.K = K; g.src_pitch = src_pitch;
+    g.wmat = wmat; g.Nout = Nout; g.rows_per_tap = Nout; g.bias = bias;
+    g.dst = dst; g.Dd = Dd; g.Hd = Hd; g.Wd = Wd; g.dst_pitch = dst_pitch; g.accumulate = accumulate;
+    g.LD = Dd; g.LH = Hd; g.LW = Wd;
+    for (int a = 0; a < 3; ++a) { g.stride[a] = 1; g.os[a] = 1; g.oo[a] = 0; g.qk[a] = 1; }
+}
+
+// 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)
+int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
+                   int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
+                   int accumulate, cudaStream_t st) {
+    TcGather g;
+    fill_common(g, src, N, Ds, Hs, Ws, K, src_pitch, wmat, Nout, bias, dst, Dd, Hd, Wd, dst_pitch, accumulate);
+    for (int a = 0; a < 3; ++a) g.stride[a] = stride[a];
+    g.ntaps = 27; g.w_rows = 27 * Nout;
+    for (int t = 0; t < 27; ++t) {
+        g.tap_off[t][0] = t / 9 - 1; g.tap_off[t][1] = (t / 3) % 3 - 1; g.tap_off[t][2] = t % 3 - 1;
+        g.tap_w[t] = t;
+    }
+    return conv_tc_gather(g, st);
+}
+
+// dgrad of a STRIDED 3x3x3 conv: one launch per output-parity class; class p receives the taps t with (p - t + 1) even
+// and reads dz at j + (p - t + 1) / 2.  wd = flipped/transposed shadow [26 - t][ci][co] (weight_shadow_bf16).
+int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
+                          int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
+                          cudaStream_t st) {
+    const int dims_in[3] = {Di, Hi, Wi};
+    for (int pd = 0; pd < stride[0]; ++pd)
+        for (int ph = 0; ph < stride[1]; ++ph)
+            for (int pw = 0; pw < stride[2]; ++pw) {
+                const int par[3] = {pd, ph, pw};
+                TcGather g;
+                fill_common(g, dz, N, Do, Ho, Wo, Cout, dz_pitch, wd, Cin, nullptr, dx, Di, Hi, Wi, dx_pitch, accumulate);
+                g.w_rows = 27 * Cin;
+                int L[3];
+                for (int a = 0; a < 3; ++a) {
+                    g.os[a] = stride[a]; g.oo[a] = par[a];
+                    L[a] = stride[a] == 1 ? dims_in[a] : (dims_in[a] - par[a] + 1) / 2;
+                }
+                g.LD = L[0]; g.LH = L[1]; g.LW = L[2];
+                if (L[0] <= 0 || L[1] <= 0 || L[2] <= 0) continue;
+                // taps per axis: (tap index, source offset)
+                int cnt[3], tt[3][3], off[3][3];
+                for (int a = 0; a < 3; ++a) {
+                    cnt[a] = 0;
+                    for (int t = 0; t < 3; ++t) {
+                        const int num = par[a] - t + 1;
+                        if (stride[a] == 1) { tt[a][cnt[a]] = t; off[a][cnt[a]] = 1 - t; ++cnt[a]; }
+                        else if ((num & 1) == 0) { tt[a][cnt[a]] = t; off[a][cnt[a]] = num / 2; ++cnt[a]; }
+                    }
+                }
+                g.ntaps = 0;
+                for (int i = 0; i < cnt[0]; ++i)
+                    for (int j = 0; j < cnt[1]; ++j)
+                        for (int k = 0; k < cnt[2]; ++k) {
+                            const int t = tt[0][i] * 9 + tt[1][j] * 3 + tt[2][k];
+                            g.tap_off[g.ntaps][0] = off[0][i]; g.tap_off[g.ntaps][1] = off[1][j]; g.tap_off[g.ntaps][2] = off[2][k];
+                            g.tap_w[g.ntaps] = 26 - t;
+                            ++g.ntaps;
+                        }
+                int rc = conv_tc_gather(g, st);
+                if (rc) return rc;
+            }
+    return B2_OK;
+}
+
+// transposed conv (kernel == stride) forward: out[(2v + q), co] = sum_ci x[v, ci] * W[ci][co][q]; wq: [(q, co)][ci] bf16
+int tconv_tc_fwd(const __nv_bfloat16* x, int N, int D, int H, int W, int Cin, int x_pitch, const __nv_bfloat16* wq, int Cout,
+                 const int k[3], __nv_bfloat16* y, int y_pitch, cudaStream_t st) {
+    const int k8 = k[0] * k[1] * k[2];
+    TcGather g;
+    fill_common(g, x, N, D, H, W, Cin, x_pitch, wq, k8 * Cout, nullptr, y, D * k[0], H * k[1], W * k[2], y_pitch, 0);
+    g.LD = D; g.LH = H; g.LW = W;
+    g.ntaps = 1; g.w_rows = k8 * Cout; g.rows_per_tap = k8 * Cout;
+    g.tap_off[0][0] = g.tap_off[0][1] = g.tap_off[0][2] = 0; g.tap_w[0] = 0;
+    for (int a = 0; a < 3; ++a) { g.os[a] = k[a]; g.qk[a] = k[a]; }
+    g.q_scatter = 1; g.q_channels = Cout;
+    return conv_tc_gather(g, st);
+}
+
+// transposed conv dgrad: dx[v, ci] = sum_q sum_co dy[(2v + q), co] * W[ci][co][q]; wqd: [q][ci][co] bf16
+int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout, int dy_pitch, const __nv_bfloat16* wqd, int Cin,
+                   const int k[3], __nv_bfloat16* dx, int dx_pitch, cudaStream_t st) {
+    const int k8 = k[0] * k[1] * k[2];
+    TcGather g;
+    fill_common(g, dy, N, D * k[0], H * k[1], W * k[2], Cout, dy_pitch, wqd, Cin, nullptr, dx, D, H, W, dx_pitch, 0);
+    for (int a = 0; a < 3; ++a) g.stride[a] = k[a];
+    g.ntaps = k8; g.w_rows = k8 * Cin;
+    for (int q = 0; q < k8; ++q) {
+        g.tap_off[q][2] = q % k[2]; g.tap_off[q][1] = (q / k[2]) % k[1]; g.tap_off[q][0] = q / (k[2] * k[1]);
+        g.tap_w[q] = q;
+    }
+    return conv_tc_gather(g, st);
+}
+
+// PyTorch ConvTranspose3d weight [Cin][Cout][K8] fp32 -> wq [(q, co)][ci] and wqd [q][ci][co] (bf16)
+__global__ void tconv_shadow_bf16_kernel(const float* __restrict__ w, int Cin, int Cout, int K8, __nv_bfloat16* __restrict__ wq,
+                                         __nv_bfloat16* __restrict__ wqd) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)Cin * Cout * K8;
+    if (i >= tot) return;
+    int q = (int)(i % K8);
+    long long r = i / K8;
+    int co = (int)(r % Cout), ci = (int)(r / Cout);
+    __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wq) wq[((long long)q * Cout + co) * Cin + ci] = v;
+    if (wqd) wqd[((long long)q * Cin + ci) * Cout + co] = v;
+}
+int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st) {
+    long long tot = (long long)cin * cout * k8;
+    B2_LAUNCH(tconv_shadow_bf16_kernel, cdiv(tot, 256), 256, 0, st, w_pt, cin, cout, k8, wq, wqd);
     return B2_OK;
 }
 

@@ -35,6 +35,26 @@ int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* pa
 // ---- conv3d_tc.cu (tcgen05 / TMA path, bf16) ----------------------------------------------------------------------
 bool conv_tc_supported(int K, int Nout);
 int weight_shadow_bf16(const float* w_pt, int cout, int cin, __nv_bfloat16* wk, __nv_bfloat16* wd, cudaStream_t st);
+struct TcGather {
+    const __nv_bfloat16* src; int N, Ds, Hs, Ws, K, src_pitch;     // gathered tensor (NDHWC) and its channel count (GEMM K)
+    const __nv_bfloat16* wmat; int w_rows, rows_per_tap, Nout;      // weight matrix [w_rows][K]; GEMM N
+    const float* bias;
+    __nv_bfloat16* dst; int Dd, Hd, Wd, dst_pitch, accumulate;      // produced tensor
+    int LD, LH, LW;                                                 // logical grid tiled by the 128-voxel boxes
+    int stride[3];                                                  // source = logical * stride + tap_off
+    int os[3], oo[3];                                               // produced = logical * os + oo
+    int ntaps; int tap_off[27][3]; int tap_w[27];
+    int q_scatter, q_channels, qk[3];                               // transposed-conv forward column->voxel scatter
+};
+int conv_tc_gather(const TcGather& g, cudaStream_t st);
+int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
+                          int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
+                          cudaStream_t st);
+int tconv_tc_fwd(const __nv_bfloat16* x, int N, int D, int H, int W, int Cin, int x_pitch, const __nv_bfloat16* wq, int Cout,
+                 const int k[3], __nv_bfloat16* y, int y_pitch, cudaStream_t st);
+int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout, int dy_pitch, const __nv_bfloat16* wqd, int Cin,
+                   const int k[3], __nv_bfloat16* dx, int dx_pitch, cudaStream_t st);
+int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st);
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
                    int accumulate, cudaStream_t st);

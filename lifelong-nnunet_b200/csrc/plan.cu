@@ -30,7 +30,7 @@ thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
 int g_use_tc = 1;
 int g_tc_strided = 1;
-int g_tc_wgrad = 0;   // experimental until validated on hardware
+int g_tc_wgrad = 1;
 
 int num_sms() {
     static int n = 0;
@@ -59,7 +59,7 @@ struct ConvBlock {
     int p_w = -1, p_b = -1, p_g = -1, p_be = -1;
     size_t stats_off = 0, wf_off = 0, wb_off = 0;  // fp32 offsets
     size_t wk_off = 0, wd_off = 0;                 // bf16 shadows for the tensor-core path (offsets in floats)
-    bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false;
+    bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_strided = false;
 };
 
 struct Tconv {
@@ -67,7 +67,8 @@ struct Tconv {
     TconvShape shape;
     Act in, out, din, dout;
     int p_w = -1;
-    size_t wq_off = 0;
+    size_t wq_off = 0, wqb_off = 0, wqd_off = 0;   // fp32 shadow; bf16 shadows for the tensor-core path
+    bool tc = false;
 };
 
 struct Head {
@@ -191,6 +192,7 @@ static int build_plan(b2_unet_plan* p) {
         const bool tc_ok = g.act_dtype == B2_BF16 && g_use_tc && conv_tc_supported(in.c, cout) && in.pitch % 8 == 0;
         cb.tc_fwd = tc_ok && (!strided || g_tc_strided);
         cb.tc_dgrad = tc_ok && !strided && din.c > 0 && din.pitch % 8 == 0;
+        cb.tc_dgrad_strided = tc_ok && strided && g_tc_strided && din.c > 0 && din.pitch % 8 == 0;
         cb.tc_wgrad = tc_ok && g_tc_wgrad && wgrad_tc_supported(in.c, cout) && (!strided || g_tc_strided);
         if (cb.tc_wgrad) p->scratch_floats = max_sz(p->scratch_floats, wgrad_tc_part_floats(cb.shape));
         if (tc_ok) {
@@ -243,6 +245,12 @@ static int build_plan(b2_unet_plan* p) {
         const int k8 = t.shape.k[0] * t.shape.k[1] * t.shape.k[2];
         t.p_w = add_param(p, t.prefix + ".weight", {cur.c, fs, t.shape.k[0], t.shape.k[1], t.shape.k[2]});
         t.wq_off = fc; fc += (size_t)k8 * cur.c * fs;
+        fc = (fc + 63) / 64 * 64;
+        t.tc = g.act_dtype == B2_BF16 && g_use_tc && cur.c % 32 == 0 && fs % 32 == 0 && cur.pitch % 8 == 0 && dcur.pitch % 8 == 0;
+        if (t.tc) {
+            t.wqb_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
+            t.wqd_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
+        }
         p->scratch_floats = max_sz(p->scratch_floats, tconv_bwd_scratch_floats(t.shape));
         p->tconvs.push_back(t);
         p->conv_modules.push_back({1, (int)p->tconvs.size() - 1});
@@ -287,7 +295,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         if (r) return r;
         bool done = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            if (cb.tc_fwd || cb.tc_dgrad) {
+            if (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided) {
                 r = weight_shadow_bf16(prm[cb.p_w], cb.shape.cout, cb.shape.cin, (__nv_bfloat16*)F32(ws, p, cb.wk_off),
                                        (__nv_bfloat16*)F32(ws, p, cb.wd_off), st);
                 if (r) return r;
@@ -317,8 +325,21 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         Tconv& t = p->tconvs[ti++];
         float* wq = F32(ws, p, t.wq_off);
         const int k8 = t.shape.k[0] * t.shape.k[1] * t.shape.k[2];
-        if ((rc = tconv_shadow(prm[t.p_w], t.shape.cin, t.shape.cout, k8, wq, st))) return rc;
-        if ((rc = tconv_fwd_q<T>(t.shape, P<T>(ws, p, t.in, false), wq, P<T>(ws, p, t.out, false), st))) return rc;
+        bool tdone = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (t.tc) {
+                if ((rc = tconv_shadow_bf16(prm[t.p_w], t.shape.cin, t.shape.cout, k8, (__nv_bfloat16*)F32(ws, p, t.wqb_off),
+                                            (__nv_bfloat16*)F32(ws, p, t.wqd_off), st))) return rc;
+                if ((rc = tconv_tc_fwd(P<T>(ws, p, t.in, false), g.batch, t.in.d, t.in.h, t.in.w, t.shape.cin, t.in.pitch,
+                                       (const __nv_bfloat16*)F32(ws, p, t.wqb_off), t.shape.cout, t.shape.k, P<T>(ws, p, t.out, false),
+                                       t.out.pitch, st))) return rc;
+                tdone = true;
+            }
+        }
+        if (!tdone) {
+            if ((rc = tconv_shadow(prm[t.p_w], t.shape.cin, t.shape.cout, k8, wq, st))) return rc;
+            if ((rc = tconv_fwd_q<T>(t.shape, P<T>(ws, p, t.in, false), wq, P<T>(ws, p, t.out, false), st))) return rc;
+        }
         if ((rc = run_conv(p->convs[ci++]))) return rc;
         if ((rc = run_conv(p->convs[ci++]))) return rc;
         Head& h = p->heads[u];
@@ -366,6 +387,12 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                                        cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, cb.din_accumulate, st);
                     if (r) return r;
                     done = true;
+                } else if (cb.tc_dgrad_strided) {
+                    r = conv_tc_dgrad_strided(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout,
+                                              (const __nv_bfloat16*)F32(ws, p, cb.wd_off), cb.shape.cin, P<T>(ws, p, cb.din, true),
+                                              cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, cb.shape.stride, cb.din_accumulate, st);
+                    if (r) return r;
+                    done = true;
                 }
             }
             if (!done) {
@@ -395,7 +422,17 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         if ((rc = conv_bwd(l1))) return rc;
         if ((rc = conv_bwd(l0))) return rc;
         Tconv& t = p->tconvs[u];
-        if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w], P<T>(ws, p, t.din, true), grads[t.p_w], SCR(ws, p), st))) return rc;
+        bool tdg = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (t.tc) {
+                if ((rc = tconv_tc_dgrad(P<T>(ws, p, t.dout, true), g.batch, t.in.d, t.in.h, t.in.w, t.shape.cout, t.dout.pitch,
+                                         (const __nv_bfloat16*)F32(ws, p, t.wqd_off), t.shape.cin, t.shape.k, P<T>(ws, p, t.din, true),
+                                         t.din.pitch, st))) return rc;
+                tdg = true;
+            }
+        }
+        if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w],
+                               tdg ? (T*)nullptr : P<T>(ws, p, t.din, true), grads[t.p_w], SCR(ws, p), st))) return rc;
     }
     for (int d = P_; d >= 0; --d) {
         if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;
@@ -582,6 +619,12 @@ extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* d
             const int one[3] = {1, 1, 1};
             if ((rc = conv_tc_launch((const __nv_bfloat16*)dz, s.n, s.d, s.h, s.w, s.cout, s.out_pitch, wd, s.cin, nullptr,
                                      (__nv_bfloat16*)dx, s.d, s.h, s.w, s.in_pitch, one, accumulate_dx, st))) return rc;
+        } else if (dx && g_use_tc && strided && g_tc_strided && conv_tc_supported(s.cout, s.cin) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
+            __nv_bfloat16* wd = (__nv_bfloat16*)wf;
+            if ((rc = weight_shadow_bf16(w_pt, s.cout, s.cin, nullptr, wd, st))) return rc;
+            const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
+            if ((rc = conv_tc_dgrad_strided((const __nv_bfloat16*)dz, s.n, od, oh, ow, s.cout, s.out_pitch, wd, s.cin, (__nv_bfloat16*)dx,
+                                            s.d, s.h, s.w, s.in_pitch, s.stride, accumulate_dx, st))) return rc;
         } else if (dx && (rc = conv3d_dgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)dz, wb, (__nv_bfloat16*)dx, accumulate_dx, st))) return rc;
     }
     return B2_OK;
