@@ -209,6 +209,40 @@ class MultipleOutputLossEWC(MultipleOutputLoss2):
             loss = self._penalty(loss, self.ewc_lambda / 2)
         return loss
 
+    @torch.no_grad()
+    def penalty_into_grads(self, coef=None, importance=None):
+        """Trainer fast path: evaluate the penalty of every stored task and ADD its analytic gradient straight into the
+        existing ``param.grad`` buffers (one launch per task, no autograd nodes, no per-tensor torch ops).  Same task /
+        generator semantics as ``forward`` (Q1/Q2).  Returns the penalty value as a 0-dim tensor."""
+        lib = _lib.load()
+        coef = self.ewc_lambda / 2 if coef is None else coef
+        total = None
+        for task in self.tasks:
+            sel = [(n, p) for n, p in self.network_params if _match(n, self.match_case, self.match, self.match_true)]
+            if not sel:
+                continue
+            dev = sel[0][1].device
+            for _, p in sel:          # the penalty reaches parameters the data term does not (e.g. a zero-weight head)
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            table = (_lib.PenEntry * len(sel))()
+            keep, numel = [], 0
+            for i, (n, p) in enumerate(sel):
+                f, st = self.fisher[task][n], self.params[task][n]
+                if f.numel() != p.numel():
+                    f = f.float().expand_as(p).contiguous()
+                im = None if importance is None else importance[task][n]
+                keep.append((f, st, im))
+                table[i].theta, table[i].theta_star, table[i].fisher = p.data_ptr(), st.data_ptr(), f.data_ptr()
+                table[i].importance = None if im is None else im.data_ptr()
+                table[i].grad, table[i].numel = p.grad.data_ptr(), p.numel()
+                numel += p.numel()
+            out = torch.zeros(1, dtype=torch.float32, device=dev)
+            scr = _scratch(lib.b2_quadpen_scratch_bytes(len(sel), numel), dev)
+            _lib.check(lib.b2_quadpen_fwd_bwd(table, len(sel), float(coef), out.data_ptr(), scr.data_ptr(), _stream(dev)))
+            total = out[0] if total is None else total + out[0]
+        return total
+
 
 class MultipleOutputLossRW(MultipleOutputLossEWC):
     def __init__(self, loss, weight_factors=None, ewc_lambda=0.4, fisher=dict(), params=dict(),

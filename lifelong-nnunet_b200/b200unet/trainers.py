@@ -225,28 +225,30 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
                                              self.params, self.network.named_parameters())
 
     def _forward_loss(self, data, target):
-        if self.ddp is None:
-            return super()._forward_loss(data, target)
-        # data parallel: keep the penalty out of the all-reduced gradient (it is identical on every rank)
+        # the data term goes through autograd; the penalty (value + analytic gradient) is added after backward, straight
+        # into param.grad -- after the gradient all-reduce under data parallelism, because it is identical on every rank
         output = self.network(data)
-        self._pending_penalty = True
         return output, self.loss(output, target, reg=False)
+
+    def _penalty_after_backward(self):
+        return self.loss.penalty_into_grads(self.ewc_lambda / 2)
 
     def _backward(self, l):
         l.backward()
         self._sync_gradients()
-        if self.ddp is not None and getattr(self, "_pending_penalty", False):
-            self._pending_penalty = False
-            zero = torch.zeros((), device=self.device)
-            pen = self.loss._penalty(zero, self.ewc_lambda / 2)
-            if pen.requires_grad:
-                pen.backward()
-            self._last_penalty = pen.detach()
+        self._last_penalty = self._penalty_after_backward()
 
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
-        loss = super().run_iteration(data_generator, do_backprop, run_online_evaluation, detach, no_loss)
-        if self.ddp is not None and loss is not None and hasattr(self, "_last_penalty"):
-            loss = loss + (self._last_penalty.cpu().numpy() if detach else self._last_penalty)
+        self._last_penalty = None
+        loss = super().run_iteration(data_generator, do_backprop, run_online_evaluation, False, no_loss)
+        if loss is not None:
+            if not do_backprop:      # validation iterations: value of the regulariser without touching gradients
+                self.loss.update_network_params(self.network.named_parameters())
+                loss = self.loss._penalty(loss.detach(), self.ewc_lambda / 2)
+            elif self._last_penalty is not None:
+                loss = loss.detach() + self._last_penalty
+            if detach:
+                loss = loss.detach().cpu().numpy()
         # reference ewc:247 -- a fresh generator for the next iteration
         self.loss.update_network_params(self.network.named_parameters())
         return loss
@@ -298,8 +300,20 @@ class nnUNetTrainerRW(nnUNetTrainerMultiHead):
         self.loss.update_rw_params(self.fisher, self.params, self.scores)
         self.loss.update_network_params(self.network.named_parameters())
 
+    def _forward_loss(self, data, target):
+        output = self.network(data)
+        return output, ds.MultipleOutputLossEWC.forward(self.loss, output, target, reg=False)
+
+    def _backward(self, l):
+        l.backward()
+        self._sync_gradients()
+        self._last_penalty = self.loss.penalty_into_grads(self.rw_lambda, self.loss.parameter_importance)
+
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
+        self._last_penalty = None
         loss = super().run_iteration(data_generator, do_backprop, run_online_evaluation, False, no_loss)
+        if loss is not None and self._last_penalty is not None:
+            loss = loss.detach() + self._last_penalty
         self._update_f_s_values()
         if detach and loss is not None:
             loss = loss.detach().cpu().numpy()

@@ -417,6 +417,75 @@ int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* pa
 template int instnorm_stats<float>(const float*, int, long long, int, int, float*, float*, float, cudaStream_t);
 template int instnorm_stats<__nv_bfloat16>(const __nv_bfloat16*, int, long long, int, int, float*, float*, float, cudaStream_t);
 
+static inline int out_dim_(int i, int s) { return (i + 2 - 3) / s + 1; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad for Cin <= 4 (the first layer): thread = (output channel, row lane); each CTA walks (n, d, h) rows of the output,
+// streaming dz once (HBM-bound) and reading the 27 x-neighbours through L1; per-CTA partials, ordered reduce.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) wgrad_smallcin_kernel(WgradGeom g, const T* __restrict__ x, const T* __restrict__ dz,
+                                                             float* __restrict__ part_w, float* __restrict__ part_b) {
+    extern __shared__ float sh[];  // [lanes][27*CIN + 1][Cout]
+    const int cout = g.Cout;
+    const int lanes = 256 / cout;
+    const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
+    float acc[27 * CIN];
+#pragma unroll
+    for (int i = 0; i < 27 * CIN; ++i) acc[i] = 0.f;
+    float bsum = 0.f;
+    const long long rows = (long long)g.N * g.Do * g.Ho;
+    if (lane < lanes) {
+        for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+            const int oh = (int)(r % g.Ho);
+            long long t = r / g.Ho;
+            const int od = (int)(t % g.Do), n = (int)(t / g.Do);
+            const T* zrow = dz + (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo * g.dz_pitch;
+            const T* xrow[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int id = od * g.sd + k / 3 - 1, ih = oh * g.sh + k % 3 - 1;
+                xrow[k] = (id >= 0 && id < g.Di && ih >= 0 && ih < g.Hi)
+                              ? x + (((long long)n * g.Di + id) * g.Hi + ih) * g.Wi * g.x_pitch : nullptr;
+            }
+            for (int ow = lane; ow < g.Wo; ow += lanes) {
+                const float z = to_f(zrow[(long long)ow * g.dz_pitch + co]);
+                bsum += z;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (xrow[k] == nullptr) continue;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int iw = ow * g.sw + kw - 1;
+                        if (iw < 0 || iw >= g.Wi) continue;
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci)
+                            acc[(k * 3 + kw) * CIN + ci] = fmaf(to_f(xrow[k][(long long)iw * g.x_pitch + ci]), z, acc[(k * 3 + kw) * CIN + ci]);
+                    }
+                }
+            }
+        }
+        float* s = sh + (size_t)lane * (27 * CIN + 1) * cout;
+#pragma unroll
+        for (int i = 0; i < 27 * CIN; ++i) s[i * cout + co] = acc[i];
+        s[27 * CIN * cout + co] = bsum;
+    }
+    __syncthreads();
+    // ordered sum over lanes; partial layout [split][27][Cin][Cout] (+ bias partial)
+    for (int e = threadIdx.x; e < (27 * CIN + 1) * cout; e += 256) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sh[(size_t)l * (27 * CIN + 1) * cout + e];
+        if (e < 27 * CIN * cout) part_w[(long long)blockIdx.x * 27 * CIN * cout + e] = s;
+        else if (part_b) part_b[(long long)blockIdx.x * cout + (e - 27 * CIN * cout)] = s;
+    }
+}
+
+static int smallcin_splits(const ConvShape& s) {
+    long long rows = (long long)s.n * out_dim_(s.d, s.stride[0]) * out_dim_(s.h, s.stride[1]);
+    long long want = 8LL * num_sms();
+    return (int)(rows < want ? rows : want);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
@@ -509,6 +578,7 @@ static void wgrad_plan(const ConvShape& s, WgradGeom& g) {
 }
 
 size_t conv_wgrad_part_floats(const ConvShape& s) {
+    if (s.cin <= 4 && s.cout <= 256) return (size_t)smallcin_splits(s) * (27ULL * s.cin * s.cout + s.cout);
     WgradGeom g;
     wgrad_plan(s, g);
     return (size_t)g.nsplit * (27ULL * s.cin * s.cout + s.cout);
@@ -519,6 +589,23 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
                       cudaStream_t st) {
     WgradGeom g;
     wgrad_plan(s, g);
+    if (s.cin <= 4 && s.cout <= 256) {
+        const int ns = smallcin_splits(s);
+        float* pw = part;
+        float* pb = part + (size_t)ns * 27 * s.cin * s.cout;
+        const int lanes = 256 / s.cout;
+        const size_t sh = (size_t)lanes * (27 * s.cin + 1) * s.cout * sizeof(float);
+        B2_CHECK_ARG(sh <= 48 * 1024);
+        switch (s.cin) {
+            case 1: B2_LAUNCH((wgrad_smallcin_kernel<T, 1>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
+            case 2: B2_LAUNCH((wgrad_smallcin_kernel<T, 2>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
+            case 3: B2_LAUNCH((wgrad_smallcin_kernel<T, 3>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
+            default: B2_LAUNCH((wgrad_smallcin_kernel<T, 4>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
+        }
+        long long tot2 = 27LL * s.cin * s.cout + (dbias ? s.cout : 0);
+        B2_LAUNCH(wgrad_reduce_kernel, cdiv(tot2, 256), 256, 0, st, pw, pb, ns, s.cin, s.cout, dw, dbias);
+        return B2_OK;
+    }
     float* part_w = part;
     float* part_b = part + (size_t)g.nsplit * 27 * s.cin * s.cout;
     size_t smem = ((size_t)g.hd * g.hh * g.hw + (size_t)g.cd * g.chh * g.cw) * 32 * sizeof(float);
@@ -542,6 +629,7 @@ int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, 
 }
 
 int weight_shadow(const float* w, int cout, int cin, float* wf, float* wb, cudaStream_t st) {
+    if (!wf && !wb) return B2_OK;
     long long tot = (long long)cout * cin * 27;
     B2_LAUNCH(weight_shadow_kernel, cdiv(tot, 256), 256, 0, st, w, cout, cin, wf, wb);
     return B2_OK;

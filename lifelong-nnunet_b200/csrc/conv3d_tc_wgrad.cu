@@ -10,6 +10,8 @@
 // partial; the ordered reduction over CTAs (wgrad_reduce_kernel) makes the result bit-reproducible -- no atomics.
 //
 // Warp roles as in conv3d_tc.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include <string.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -37,6 +39,8 @@ struct TcWgradParams {
     uint32_t tmem_cols;
     // MN-major descriptor strides (bytes)
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+    int ntaps;
+    signed char tap_off[27][3];   // offset of the shifted operand per tap (padding included)
 };
 
 // MN-major UMMA descriptor: `row_bytes` = bytes of one K row (one voxel's channel chunk: 64 or 128)
@@ -78,7 +82,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int tap0 = tapset * p.groups * p.taps_per_group;      // first tap of this CTA
     int my_groups = p.groups;                                    // groups that contain at least one valid tap
     {
-        const int remaining = 27 - tap0;
+        const int remaining = p.ntaps - tap0;
         const int need = (remaining + p.taps_per_group - 1) / p.taps_per_group;
         if (need < my_groups) my_groups = need;
     }
@@ -123,9 +127,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         int tap, cch;
                         if (p.stack_taps) { tap = tap0 + g * p.a_chunks + c; cch = 0; }
                         else { tap = tap0 + g; cch = ci_item * 128 + c * p.ci_sub; }
-                        if (tap > 26) tap = 26;  // rows of non-existent taps are ignored by the epilogue
+                        if (tap > p.ntaps - 1) tap = p.ntaps - 1;  // rows of non-existent taps are ignored by the epilogue
                         tma_load_5d(&tmX, &fullA[as], smem + (size_t)as * A_BYTES + (size_t)c * a_chunk_bytes, cch,
-                                    w0 * p.sw + tap % 3 - 1, h0 * p.sh + (tap / 3) % 3 - 1, d0 * p.sd + tap / 9 - 1, n0);
+                                    w0 * p.sw + p.tap_off[tap][2], h0 * p.sh + p.tap_off[tap][1], d0 * p.sd + p.tap_off[tap][0], n0);
                     }
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 }
@@ -170,12 +174,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&done_bar, 0);
             tc_fence_after();
         }
-        float* out = part + (size_t)split * 27 * p.Cin * p.Cout;
+        float* out = part + (size_t)split * p.ntaps * p.Cin * p.Cout;
         for (int g = 0; g < my_groups; ++g) {
             int tap, ci;
             if (p.stack_taps) { tap = tap0 + g * p.a_chunks + chunk; ci = cil; }
             else { tap = tap0 + g; ci = ci_item * 128 + chunk * p.ci_sub + cil; }
-            const bool valid = tap < 27 && ci < p.Cin;
+            const bool valid = tap < p.ntaps && ci < p.Cin;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.co_blk);
             for (int c0 = 0; c0 < p.co_blk; c0 += 32) {
                 uint32_t v[32];
@@ -259,7 +263,10 @@ bool wgrad_tc_supported(int cin, int cout) {
     return true;
 }
 
-static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p) {
+static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) {
+    memset(&p, 0, sizeof(p));
+    p.ntaps = ntaps;
+    for (int t = 0; t < 27; ++t) { p.tap_off[t][0] = t / 9 - 1; p.tap_off[t][1] = (t / 3) % 3 - 1; p.tap_off[t][2] = t % 3 - 1; }
     p.N = s.n;
     p.Do = (s.d - 1) / s.stride[0] + 1; p.Ho = (s.h - 1) / s.stride[1] + 1; p.Wo = (s.w - 1) / s.stride[2] + 1;
     p.sd = s.stride[0]; p.sh = s.stride[1]; p.sw = s.stride[2];
@@ -279,7 +286,7 @@ static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p) {
     p.co_blk = s.cout / p.co_blks;
     p.co_sub = p.co_blk % 64 == 0 ? 64 : 32;
     p.b_chunks = p.co_blk / p.co_sub;
-    const int total_groups = cdiv(27, p.taps_per_group);
+    const int total_groups = cdiv(ntaps, p.taps_per_group);
     int gmax = 512 / p.co_blk;
     if (gmax > total_groups) gmax = total_groups;
     p.groups = gmax;
@@ -334,24 +341,74 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
     B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part);
-    float* part_b = nullptr;
-    int slabs = 1;
-    if (dbias) {
-        part_b = part + (size_t)p.nsplit * 27 * s.cin * s.cout;
-        const long long rows = (long long)s.n * p.Do * p.Ho * p.Wo;
-        slabs = 2 * num_sms();
-        if (slabs > rows) slabs = (int)rows;
-        if (s.cout <= 256) {
-            const int lanes = 256 / s.cout;
-            B2_LAUNCH(colsum_part_kernel, slabs, 256, (size_t)lanes * s.cout * sizeof(float), st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
-        } else {
-            B2_LAUNCH(colsum_wide_kernel, slabs, 256, 0, st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
-        }
-    }
+    // The bias of a conv that feeds InstanceNorm has an exactly-zero gradient in exact arithmetic (the norm removes the
+    // per-channel mean); PyTorch's value is pure rounding noise.  The bf16 path writes the exact value.
+    if (dbias) B2_CUDA(cudaMemsetAsync(dbias, 0, s.cout * sizeof(float), st));
     // ordered reduction over the split CTAs, written in PyTorch layout [co][ci][27]
     rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
     if (rc) return rc;
-    if (dbias) B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
+    return B2_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// transposed-conv (kernel == stride) weight gradient on the same kernel: dW[ci][co][q] = sum_v x[v][ci] * dy[k*v + q][co].
+// The shifted operand is dy ("taps" = q, traversal stride k), the fixed operand is x: D[(q, co)][ci].
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void tconv_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int k8, int Cin, int Cout, float* __restrict__ dw) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [q][co][ci]
+    const long long tot = (long long)k8 * Cout * Cin;
+    if (i >= tot) return;
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[(long long)k * tot + i];
+    const int ci = (int)(i % Cin);
+    long long r = i / Cin;
+    const int co = (int)(r % Cout), q = (int)(r / Cout);
+    dw[((long long)ci * Cout + co) * k8 + q] = s;
+}
+
+static void tconv_wgrad_tc_plan(const TconvShape& s, TcWgradParams& p) {
+    const int k8 = s.k[0] * s.k[1] * s.k[2];
+    // roles: "Cin" of the kernel = channels of the shifted operand (dy: Cout), "Cout" = channels of the fixed one (x: Cin)
+    ConvShape c;
+    c.n = s.n; c.d = s.d * s.k[0]; c.h = s.h * s.k[1]; c.w = s.w * s.k[2];
+    c.cin = s.cout; c.cout = s.cin;
+    c.stride[0] = s.k[0]; c.stride[1] = s.k[1]; c.stride[2] = s.k[2];
+    c.in_pitch = s.out_pitch; c.out_pitch = s.in_pitch;
+    wgrad_tc_plan(c, p, k8);
+    // the voxel boxes tile the INPUT grid of the transposed conv (wgrad_tc_plan derives it as (dim-1)/k+1 == s.d ...)
+    for (int q = 0; q < k8; ++q) {
+        p.tap_off[q][2] = q % s.k[2]; p.tap_off[q][1] = (q / s.k[2]) % s.k[1]; p.tap_off[q][0] = q / (s.k[2] * s.k[1]);
+    }
+}
+
+bool tconv_wgrad_tc_supported(int cin, int cout) { return wgrad_tc_supported(cout, cin); }
+
+size_t tconv_wgrad_tc_part_floats(const TconvShape& s) {
+    TcWgradParams p;
+    tconv_wgrad_tc_plan(s, p);
+    return (size_t)p.nsplit * p.ntaps * s.cin * s.cout + 64;
+}
+
+int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* part, float* dw, cudaStream_t st) {
+    B2_CHECK_ARG(tconv_wgrad_tc_supported(s.cin, s.cout) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0);
+    TcWgradParams p;
+    tconv_wgrad_tc_plan(s, p);
+    CUtensorMap tmA, tmB;   // A: dy (shifted, strided traversal), B: x (fixed)
+    int rc = make_act_map(&tmA, dy, s.n, s.d * s.k[0], s.h * s.k[1], s.w * s.k[2], s.cout, s.out_pitch, p.ci_sub, p.TN, p.TD, p.TH, p.TW,
+                          s.k[0], s.k[1], s.k[2]);
+    if (rc) return rc;
+    rc = make_act_map(&tmB, x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
+    if (rc) return rc;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
+    if (smem > 220 * 1024) return fail(B2_EUNSUPPORTED, "tconv_wgrad_tc: tile does not fit shared memory%s", "");
+    static bool attr = false;
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part);
+    const long long tot = (long long)p.ntaps * s.cin * s.cout;
+    B2_LAUNCH(tconv_wgrad_reduce_kernel, cdiv(tot, 256), 256, 0, st, part, p.nsplit, p.ntaps, s.cin, s.cout, dw);
     return B2_OK;
 }
 

@@ -7,6 +7,13 @@
 
 namespace b2 {
 
+struct TconvShape {
+    int n, d, h, w;      // input spatial extent
+    int cin, cout;
+    int k[3];            // kernel == stride (1 or 2 per axis)
+    int in_pitch, out_pitch;
+};
+
 struct ConvShape {
     int n, d, h, w;      // input spatial extent
     int cin, cout;
@@ -62,6 +69,9 @@ bool wgrad_tc_supported(int cin, int cout);
 size_t wgrad_tc_part_floats(const ConvShape& s);
 int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
                     cudaStream_t st);
+bool tconv_wgrad_tc_supported(int cin, int cout);
+size_t tconv_wgrad_tc_part_floats(const TconvShape& s);
+int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* part, float* dw, cudaStream_t st);
 extern int g_wgrad_desc_mode, g_tc_wgrad;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 
@@ -78,12 +88,6 @@ int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, cons
                    float slope, float* scratch, cudaStream_t st);
 
 // ---- updown.cu --------------------------------------------------------------------------------------------------
-struct TconvShape {
-    int n, d, h, w;      // input spatial extent
-    int cin, cout;
-    int k[3];            // kernel == stride (1 or 2 per axis)
-    int in_pitch, out_pitch;
-};
 // w_pt: PyTorch ConvTranspose3d weight [Cin][Cout][kd][kh][kw]; wq: shadow [K8][Cin][Cout]
 int tconv_shadow(const float* w_pt, int cin, int cout, int k8, float* wq, cudaStream_t st);
 template <typename T>

@@ -247,6 +247,8 @@ static int build_plan(b2_unet_plan* p) {
         t.wq_off = fc; fc += (size_t)k8 * cur.c * fs;
         fc = (fc + 63) / 64 * 64;
         t.tc = g.act_dtype == B2_BF16 && g_use_tc && cur.c % 32 == 0 && fs % 32 == 0 && cur.pitch % 8 == 0 && dcur.pitch % 8 == 0;
+        if (t.tc && g_tc_wgrad && tconv_wgrad_tc_supported(cur.c, fs))
+            p->scratch_floats = max_sz(p->scratch_floats, tconv_wgrad_tc_part_floats(t.shape));
         if (t.tc) {
             t.wqb_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
             t.wqd_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
@@ -291,7 +293,12 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         float* wf = F32(ws, p, cb.wf_off);
         float* wb = F32(ws, p, cb.wb_off);
         float* stats = F32(ws, p, cb.stats_off);
-        int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, wf, wb, st);
+        bool need_wf = true, need_wb = cb.din.c > 0;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            need_wf = !cb.tc_fwd;
+            need_wb = cb.din.c > 0 && !(cb.tc_dgrad || cb.tc_dgrad_strided);
+        }
+        int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, need_wf ? wf : nullptr, need_wb ? wb : nullptr, st);
         if (r) return r;
         bool done = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -431,8 +438,16 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                 tdg = true;
             }
         }
-        if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w],
-                               tdg ? (T*)nullptr : P<T>(ws, p, t.din, true), grads[t.p_w], SCR(ws, p), st))) return rc;
+        bool twg = false;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (t.tc && g_tc_wgrad && tconv_wgrad_tc_supported(t.shape.cin, t.shape.cout)) {
+                if ((rc = tconv_wgrad_tc(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), SCR(ws, p), grads[t.p_w], st))) return rc;
+                twg = true;
+            }
+        }
+        if (!(tdg && twg))
+            if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w],
+                                   tdg ? (T*)nullptr : P<T>(ws, p, t.din, true), twg ? (float*)nullptr : grads[t.p_w], SCR(ws, p), st))) return rc;
     }
     for (int d = P_; d >= 0; --d) {
         if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;

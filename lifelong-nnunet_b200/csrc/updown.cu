@@ -289,30 +289,41 @@ __global__ void __launch_bounds__(256) seghead_dgrad_kernel(const float* __restr
     }
 }
 
-// dw[k][c] partial per slab: thread = (channel, row-lane)
-template <typename T>
+// dw[k][c] partial per slab: thread = (channel group of VW, row lane); VW-wide vector loads of y
+template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_wgrad_kernel(const T* __restrict__ y, const float* __restrict__ dl,
                                                             int slabs, int n, long long vox, int c, int ncls,
                                                             int y_pitch, float* __restrict__ part) {
     extern __shared__ float sh[];  // [R][ncls][c]
-    const int R = 256 / c > 0 ? 256 / c : 1;
-    const int cc = threadIdx.x % c, r = threadIdx.x / c;
+    const int ncg = c / VW;
+    const int R = 256 / ncg;
+    const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
     const long long total = (long long)n * vox;
     const long long per = (total + slabs - 1) / slabs;
     const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < total ? v0 + per : total;
-    float acc[MAXCLS];
+    float acc[MAXCLS][VW];
 #pragma unroll
-    for (int k = 0; k < MAXCLS; ++k) acc[k] = 0.f;
-    if (r < R && threadIdx.x < R * c) {
+    for (int k = 0; k < MAXCLS; ++k)
+#pragma unroll
+        for (int j = 0; j < VW; ++j) acc[k][j] = 0.f;
+    if (r < R) {
         for (long long v = v0 + r; v < v1; v += R) {
-            const float a = to_f(y[v * y_pitch + cc]);
+            float a[VW];
+            if (VW == 8) load8(y + v * y_pitch + cg * VW, *reinterpret_cast<float(*)[8]>(a));
+            else a[0] = to_f(y[v * y_pitch + cg]);
             const int nn = (int)(v / vox);
             const long long vv = v % vox;
 #pragma unroll
             for (int k = 0; k < MAXCLS; ++k)
-                if (k < ncls) acc[k] = fmaf(a, dl[((long long)nn * ncls + k) * vox + vv], acc[k]);
+                if (k < ncls) {
+                    const float d = dl[((long long)nn * ncls + k) * vox + vv];
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) acc[k][j] = fmaf(a[j], d, acc[k][j]);
+                }
         }
-        for (int k = 0; k < ncls; ++k) sh[((size_t)r * ncls + k) * c + cc] = acc[k];
+        for (int k = 0; k < ncls; ++k)
+#pragma unroll
+            for (int j = 0; j < VW; ++j) sh[((size_t)r * ncls + k) * c + cg * VW + j] = acc[k][j];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < ncls * c; e += 256) {
@@ -336,8 +347,8 @@ int seghead_fwd(const T* y, const float* w, float* logits, int n, long long vox,
 
 static int seghead_slabs(int n, long long vox) {
     long long total = (long long)n * vox;
-    long long s = 2LL * num_sms();
-    long long maxs = (total + 255) / 256;
+    long long s = 8LL * num_sms();
+    long long maxs = (total + 1023) / 1024;
     if (s > maxs) s = maxs;
     if (s < 1) s = 1;
     return (int)s;
@@ -360,9 +371,13 @@ int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int acc
     }
     if (dw) {
         int slabs = seghead_slabs(n, vox);
-        int R = 256 / c > 0 ? 256 / c : 1;
+        const bool v8 = (c % 8 == 0) && (y_pitch % 8 == 0);
+        const int ncg = v8 ? c / 8 : c;
+        const int R = 256 / ncg;
         size_t sh = (size_t)R * ncls * c * sizeof(float);
-        B2_LAUNCH(seghead_wgrad_kernel<T>, slabs, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
+        B2_CHECK_ARG(sh <= 48 * 1024);
+        if (v8) B2_LAUNCH((seghead_wgrad_kernel<T, 8>), slabs, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
+        else B2_LAUNCH((seghead_wgrad_kernel<T, 1>), slabs, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
         long long tot = (long long)ncls * c;
         B2_LAUNCH(ordered_reduce_kernel, cdiv(tot, 256), 256, 0, st, scratch, slabs, tot, dw);
     }
