@@ -425,10 +425,9 @@ static inline int out_dim_(int i, int s) { return (i + 2 - 3) / s + 1; }
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) wgrad_smallcin_kernel(WgradGeom g, const T* __restrict__ x, const T* __restrict__ dz,
-                                                             float* __restrict__ part_w, float* __restrict__ part_b) {
+                                                             float* __restrict__ part_w, float* __restrict__ part_b, int lanes) {
     extern __shared__ float sh[];  // [lanes][27*CIN + 1][Cout]
     const int cout = g.Cout;
-    const int lanes = 256 / cout;
     const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
     float acc[27 * CIN];
 #pragma unroll
@@ -593,14 +592,16 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
         const int ns = smallcin_splits(s);
         float* pw = part;
         float* pb = part + (size_t)ns * 27 * s.cin * s.cout;
-        const int lanes = 256 / s.cout;
-        const size_t sh = (size_t)lanes * (27 * s.cin + 1) * s.cout * sizeof(float);
-        B2_CHECK_ARG(sh <= 48 * 1024);
+        int lanes = 256 / s.cout;
+        const size_t per_lane = (size_t)(27 * s.cin + 1) * s.cout * sizeof(float);
+        if ((size_t)lanes * per_lane > 48 * 1024) lanes = (int)(48 * 1024 / per_lane);
+        B2_CHECK_ARG(lanes >= 1);
+        const size_t sh = (size_t)lanes * per_lane;
         switch (s.cin) {
-            case 1: B2_LAUNCH((wgrad_smallcin_kernel<T, 1>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
-            case 2: B2_LAUNCH((wgrad_smallcin_kernel<T, 2>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
-            case 3: B2_LAUNCH((wgrad_smallcin_kernel<T, 3>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
-            default: B2_LAUNCH((wgrad_smallcin_kernel<T, 4>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr); break;
+            case 1: B2_LAUNCH((wgrad_smallcin_kernel<T, 1>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr, lanes); break;
+            case 2: B2_LAUNCH((wgrad_smallcin_kernel<T, 2>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr, lanes); break;
+            case 3: B2_LAUNCH((wgrad_smallcin_kernel<T, 3>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr, lanes); break;
+            default: B2_LAUNCH((wgrad_smallcin_kernel<T, 4>), ns, 256, sh, st, g, x, dz, pw, dbias ? pb : nullptr, lanes); break;
         }
         long long tot2 = 27LL * s.cin * s.cout + (dbias ? s.cout : 0);
         B2_LAUNCH(wgrad_reduce_kernel, cdiv(tot2, 256), 256, 0, st, pw, pb, ns, s.cin, s.cout, dw, dbias);

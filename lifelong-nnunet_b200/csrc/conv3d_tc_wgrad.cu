@@ -325,7 +325,7 @@ size_t wgrad_tc_part_floats(const ConvShape& s) {
 int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, int cout, float* dw, float* db, cudaStream_t st);
 
 int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
-                    cudaStream_t st) {
+                    bool bias_feeds_norm, cudaStream_t st) {
     B2_CHECK_ARG(wgrad_tc_supported(s.cin, s.cout) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0);
     TcWgradParams p;
     wgrad_tc_plan(s, p);
@@ -342,8 +342,22 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
     B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part);
     // The bias of a conv that feeds InstanceNorm has an exactly-zero gradient in exact arithmetic (the norm removes the
-    // per-channel mean); PyTorch's value is pure rounding noise.  The bf16 path writes the exact value.
-    if (dbias) B2_CUDA(cudaMemsetAsync(dbias, 0, s.cout * sizeof(float), st));
+    // per-channel mean); PyTorch's value there is pure rounding noise, so the network plan asks for the exact value.
+    if (dbias && bias_feeds_norm) {
+        B2_CUDA(cudaMemsetAsync(dbias, 0, s.cout * sizeof(float), st));
+    } else if (dbias) {
+        float* part_b = part + (size_t)p.nsplit * 27 * s.cin * s.cout;
+        const long long rows = (long long)s.n * p.Do * p.Ho * p.Wo;
+        int slabs = 2 * num_sms();
+        if (slabs > rows) slabs = (int)rows;
+        if (s.cout <= 256) {
+            const int lanes = 256 / s.cout;
+            B2_LAUNCH(colsum_part_kernel, slabs, 256, (size_t)lanes * s.cout * sizeof(float), st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+        } else {
+            B2_LAUNCH(colsum_wide_kernel, slabs, 256, 0, st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+        }
+        B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
+    }
     // ordered reduction over the split CTAs, written in PyTorch layout [co][ci][27]
     rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
     if (rc) return rc;

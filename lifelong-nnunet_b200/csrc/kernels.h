@@ -68,7 +68,7 @@ int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int 
 bool wgrad_tc_supported(int cin, int cout);
 size_t wgrad_tc_part_floats(const ConvShape& s);
 int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
-                    cudaStream_t st);
+                    bool bias_feeds_norm, cudaStream_t st);
 bool tconv_wgrad_tc_supported(int cin, int cout);
 size_t tconv_wgrad_tc_part_floats(const TconvShape& s);
 int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* part, float* dw, cudaStream_t st);

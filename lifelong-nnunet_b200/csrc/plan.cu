@@ -375,7 +375,7 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         bool wdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (cb.tc_wgrad) {
-                r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+                r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], true, st);
                 if (r) return r;
                 wdone = true;
             }
@@ -625,7 +625,7 @@ extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* d
     } else {
         const bool strided_w = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
         if (dw && g_use_tc && g_tc_wgrad && wgrad_tc_supported(s.cin, s.cout) && (!strided_w || g_tc_strided) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
-            if ((rc = conv3d_wgrad_tc(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
+            if ((rc = conv3d_wgrad_tc(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, false, st))) return rc;
         } else if (dw && (rc = conv3d_wgrad_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, dw, dbias, st))) return rc;
         const bool strided = s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1;
         if (dx && g_use_tc && !strided && conv_tc_supported(s.cout, s.cin) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
