@@ -249,7 +249,7 @@ int make_act_map(CUtensorMap* m, const void* ptr, int N, int D, int H, int W, in
 }
 
 // 2D weight map: rows = taps * Ntotal, cols = K (K contiguous)
-static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int KC, int BN) {
+int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int KC, int BN) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return fail(B2_ECUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -377,6 +377,8 @@ static void fill_common(TcGather& g, const __nv_bfloat16* src, int N, int Ds, in
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
                    int accumulate, cudaStream_t st) {
+    if (stride[0] == 1 && stride[1] == 1 && stride[2] == 1 && conv_tc_halo_supported(K, Nout, N, Dd, Hd, Wd))
+        return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st);
     TcGather g;
     fill_common(g, src, N, Ds, Hs, Ws, K, src_pitch, wmat, Nout, bias, dst, Dd, Hd, Wd, dst_pitch, accumulate);
     for (int a = 0; a < 3; ++a) g.stride[a] = stride[a];

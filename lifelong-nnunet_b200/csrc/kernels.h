@@ -72,6 +72,10 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
 bool tconv_wgrad_tc_supported(int cin, int cout);
 size_t tconv_wgrad_tc_part_floats(const TconvShape& s);
 int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* part, float* dw, cudaStream_t st);
+bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W);
+int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
+                        const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st);
+extern int g_use_halo;
 extern int g_wgrad_desc_mode, g_tc_wgrad;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 

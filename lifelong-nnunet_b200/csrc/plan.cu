@@ -467,6 +467,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "tensor_cores")) { g_use_tc = value; return B2_OK; }
     if (!strcmp(name, "tc_strided")) { g_tc_strided = value; return B2_OK; }
     if (!strcmp(name, "tc_wgrad")) { g_tc_wgrad = value; return B2_OK; }
+    if (!strcmp(name, "tc_halo")) { g_use_halo = value; return B2_OK; }
     if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
     return fail(B2_EINVAL, "unknown option %s", name);
 }

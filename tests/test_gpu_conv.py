@@ -35,20 +35,26 @@ SHAPES = [
     (2, 8, 16, 16, 32, 16, (1, 1, 1)),        # small-channel decoder block of the test geometries
     (2, 4, 8, 8, 16, 32, (2, 2, 2)),
     (2, 8, 16, 16, 8, 8, (1, 1, 1)),
+    # halo-reuse kernel (thin layers, H >= 16, W >= 8): ragged d / h, resident and streamed weights
+    (2, 20, 32, 40, 32, 64, (1, 1, 1)),
+    (1, 9, 24, 16, 64, 64, (1, 1, 1)),
+    (2, 16, 16, 8, 32, 128, (1, 1, 1)),
+    (1, 12, 48, 24, 64, 32, (1, 1, 1)),
 ]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("mode", ["fp32", "bf16_tc", "bf16_simt"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16_tc", "bf16_tc_nohalo", "bf16_simt"])
 def test_conv_forward_and_stats(shape, mode):
     from b200unet import ops
     N, D, H, W, cin, cout, stride = shape
     x, w, b = _case(N, D, H, W, cin, cout, 1)
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     ops.set_option("tensor_cores", 0 if mode == "bf16_simt" else 1)
+    ops.set_option("tc_halo", 0 if mode == "bf16_tc_nohalo" else 1)
     try:
         xr = x.to(dt).float()
-        wr = w.to(dt).float() if mode == "bf16_tc" and cin % 32 == 0 else w
+        wr = w.to(dt).float() if mode.startswith("bf16_tc") and cin % 32 == 0 else w
         ref = F.conv3d(xr, wr, b, stride=stride, padding=1)
         z, stats = ops.conv3d_fwd(_ndhwc(x, dt), w.cuda(), b.cuda(), stride)
         torch.cuda.synchronize()
@@ -62,9 +68,10 @@ def test_conv_forward_and_stats(shape, mode):
         assert rel_err(stats[..., 1], rstd) < max(tol, 2e-3)
     finally:
         ops.set_option("tensor_cores", 1)
+        ops.set_option("tc_halo", 1)
 
 
-@pytest.mark.parametrize("shape", SHAPES[:6] + SHAPES[7:])
+@pytest.mark.parametrize("shape", SHAPES[:6] + SHAPES[7:])  # all but the 1-channel first layer (no dgrad there)
 @pytest.mark.parametrize("mode", ["fp32", "bf16_tc"])
 def test_conv_backward(shape, mode):
     from b200unet import ops
