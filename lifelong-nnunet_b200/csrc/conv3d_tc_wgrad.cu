@@ -426,4 +426,106 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     return B2_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// First layer (Cin <= 1..4, 27*Cin <= 32): im2col ONLY for this layer -- a [voxels][32] bf16 patch matrix P (27*Cin taps +
+// zero padding, 64 B per voxel) turns the layer into a 1-tap GEMM that the tensor-core kernels above handle:
+// forward z = P * Wp^T (conv_tc_gather, ntaps = 1), weight gradient dWp = P^T dz (wgrad_tc_kernel, ntaps = 1).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patch_matrix_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int cin,
+                                                           int x_pitch, __nv_bfloat16* __restrict__ P) {
+    // thread = (voxel, 8-wide group of the 32 patch columns): 16-byte stores
+    const long long total = (long long)N * D * H * W * 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i & 3);
+        long long v = i >> 2;
+        const int w = (int)(v % W); long long r = v / W;
+        const int h = (int)(r % H); r /= H;
+        const int d = (int)(r % D);
+        const int n = (int)(r / D);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < 27 * cin) {
+                const int t = k / cin, ci = k % cin;
+                const int id = d + t / 9 - 1, ih = h + (t / 3) % 3 - 1, iw = w + t % 3 - 1;
+                if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    val = __bfloat162float(x[((((long long)n * D + id) * H + ih) * W + iw) * x_pitch + ci]);
+            }
+            o[j] = val;
+        }
+        store8(P + v * 32 + g * 8, o);
+    }
+}
+
+// PyTorch [Cout][Cin][27] -> Wp [Cout][32] bf16 (k = t*Cin + ci, zero padded)
+__global__ void patch_weight_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cout * 32) return;
+    const int k = i & 31, co = i >> 5;
+    float v = 0.f;
+    if (k < 27 * cin) { const int t = k / cin, ci = k % cin; v = w[((long long)co * cin + ci) * 27 + t]; }
+    wp[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void patch_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int cin, int cout, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [k < 32][co]
+    if (i >= 32 * cout) return;
+    const int co = i % cout, k = i / cout;
+    if (k >= 27 * cin) return;
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[(long long)sp * 32 * cout + i];
+    const int t = k / cin, ci = k % cin;
+    dw[((long long)co * cin + ci) * 27 + t] = s;
+}
+
+bool first_layer_tc_supported(int cin, int cout) { return 27 * cin <= 32 && cout % 32 == 0 && cout <= 256; }
+
+int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
+                        int cout, __nv_bfloat16* wp, cudaStream_t st) {
+    const long long total = (long long)N * D * H * W * 4;
+    long long grid = (total + 255) / 256, cap = (long long)num_sms() * 32;
+    if (grid > cap) grid = cap;
+    B2_LAUNCH(patch_matrix_kernel, (int)grid, 256, 0, st, x, N, D, H, W, cin, x_pitch, P);
+    B2_LAUNCH(patch_weight_kernel, cdiv(cout * 32, 256), 256, 0, st, w_pt, cout, cin, wp);
+    return B2_OK;
+}
+
+static void first_wgrad_plan(int N, int D, int H, int W, int cout, int dz_pitch, TcWgradParams& p) {
+    ConvShape c;
+    c.n = N; c.d = D; c.h = H; c.w = W; c.cin = 32; c.cout = cout;
+    c.stride[0] = c.stride[1] = c.stride[2] = 1;
+    c.in_pitch = 32; c.out_pitch = dz_pitch;
+    wgrad_tc_plan(c, p, 1);
+    p.tap_off[0][0] = p.tap_off[0][1] = p.tap_off[0][2] = 0;
+}
+
+size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout) {
+    TcWgradParams p;
+    first_wgrad_plan(N, D, H, W, cout, cout, p);
+    return (size_t)p.nsplit * 32 * cout + 64;
+}
+
+int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
+                         float* part, float* dw, float* dbias, cudaStream_t st) {
+    TcWgradParams p;
+    first_wgrad_plan(N, D, H, W, cout, dz_pitch, p);
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, P, N, D, H, W, 32, 32, p.ci_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
+    if (rc) return rc;
+    rc = make_act_map(&tmB, dz, N, D, H, W, cout, dz_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
+    if (rc) return rc;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
+    static bool attr = false;
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part);
+    B2_LAUNCH(patch_wgrad_reduce_kernel, cdiv(32 * cout, 256), 256, 0, st, part, p.nsplit, cin, cout, dw);
+    if (dbias) B2_CUDA(cudaMemsetAsync(dbias, 0, cout * sizeof(float), st));   // bias feeds InstanceNorm: exactly zero
+    return B2_OK;
+}
+
 }  // namespace b2

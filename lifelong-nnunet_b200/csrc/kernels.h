@@ -75,6 +75,12 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
 bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W);
 int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
                         const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st);
+bool first_layer_tc_supported(int cin, int cout);
+int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
+                        int cout, __nv_bfloat16* wp, cudaStream_t st);
+size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);
+int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
+                         float* part, float* dw, float* dbias, cudaStream_t st);
 extern int g_use_halo;
 extern int g_wgrad_desc_mode, g_tc_wgrad;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only

@@ -94,7 +94,9 @@ struct b2_unet_plan {
     std::vector<ParamInfo> params;
     // execution order of conv modules for hooks: entries (kind, index): 0 conv block, 1 tconv
     std::vector<std::pair<int, int>> conv_modules;
-    Act x_in, dz_tmp;
+    Act x_in, dz_tmp, patch;          // patch: [voxels][32] im2col matrix of the first layer (bf16 tensor-core path)
+    bool first_tc = false;
+    size_t wp_off = 0;
     size_t act_elems = 0, grad_elems = 0, f32_floats = 0, scratch_floats = 0;
     size_t off_act = 0, off_grad = 0, off_f32 = 0, off_scratch = 0, total_bytes = 0;
     int esz = 4;
@@ -157,6 +159,13 @@ static int build_plan(b2_unet_plan* p) {
     }
     size_t ac = 0, gc = 0, fc = 0;
     p->x_in = alloc_act(ac, N, g.patch[0], g.patch[1], g.patch[2], g.in_channels);
+    p->first_tc = g.act_dtype == B2_BF16 && g_use_tc && g_tc_wgrad && first_layer_tc_supported(g.in_channels, p->feats[0]);
+    if (p->first_tc) {
+        p->patch = alloc_act(ac, N, g.patch[0], g.patch[1], g.patch[2], 32);
+        p->wp_off = fc; fc += ((size_t)p->feats[0] * 32 / 2 + 63) / 64 * 64;
+        p->scratch_floats = max_sz(p->scratch_floats, first_layer_wgrad_part_floats(N, g.patch[0], g.patch[1], g.patch[2], p->feats[0]));
+        p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, p->x_in.vox(), p->feats[0]));
+    }
     // concat buffers per encoder level 0..P-1 (activation + gradient)
     std::vector<Act> cat(P_), dcat(P_);
     for (int l = 0; l < P_; ++l) {
@@ -295,14 +304,34 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         float* stats = F32(ws, p, cb.stats_off);
         bool need_wf = true, need_wb = cb.din.c > 0;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            need_wf = !cb.tc_fwd;
+            need_wf = !cb.tc_fwd && !(p->first_tc && &cb == &p->convs[0]);
             need_wb = cb.din.c > 0 && !(cb.tc_dgrad || cb.tc_dgrad_strided);
         }
         int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, need_wf ? wf : nullptr, need_wb ? wb : nullptr, st);
         if (r) return r;
         bool done = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            if (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided) {
+            if (p->first_tc && &cb == &p->convs[0]) {
+                __nv_bfloat16* P_ = P<T>(ws, p, p->patch, false);
+                __nv_bfloat16* wp = (__nv_bfloat16*)F32(ws, p, p->wp_off);
+                r = first_layer_patches(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch, P_,
+                                        prm[cb.p_w], cb.shape.cout, wp, st);
+                if (r) return r;
+                TcGather tg;
+                memset(&tg, 0, sizeof(tg));
+                tg.src = P_; tg.N = g.batch; tg.Ds = cb.in.d; tg.Hs = cb.in.h; tg.Ws = cb.in.w; tg.K = 32; tg.src_pitch = 32;
+                tg.wmat = wp; tg.w_rows = cb.shape.cout; tg.rows_per_tap = cb.shape.cout; tg.Nout = cb.shape.cout; tg.bias = prm[cb.p_b];
+                tg.dst = P<T>(ws, p, cb.z, false); tg.Dd = cb.z.d; tg.Hd = cb.z.h; tg.Wd = cb.z.w; tg.dst_pitch = cb.z.pitch;
+                tg.LD = cb.z.d; tg.LH = cb.z.h; tg.LW = cb.z.w;
+                for (int a = 0; a < 3; ++a) { tg.stride[a] = 1; tg.os[a] = 1; tg.qk[a] = 1; }
+                tg.ntaps = 1;
+                r = conv_tc_gather(tg, st);
+                if (r) return r;
+                r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
+                if (r) return r;
+                done = true;
+            }
+            if (!done && (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided)) {
                 r = weight_shadow_bf16(prm[cb.p_w], cb.shape.cout, cb.shape.cin, (__nv_bfloat16*)F32(ws, p, cb.wk_off),
                                        (__nv_bfloat16*)F32(ws, p, cb.wd_off), st);
                 if (r) return r;
@@ -374,7 +403,13 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         s.out_pitch = cb.shape.cout;  // dz is dense
         bool wdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            if (cb.tc_wgrad) {
+            if (p->first_tc && &cb == &p->convs[0]) {
+                r = first_layer_wgrad_tc(P<T>(ws, p, p->patch, false), dz, g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.shape.cout,
+                                         cb.shape.cout, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+                if (r) return r;
+                wdone = true;
+            }
+            if (!wdone && cb.tc_wgrad) {
                 r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], true, st);
                 if (r) return r;
                 wdone = true;

@@ -241,7 +241,7 @@ int tconv_bwd(const TconvShape& s, const T* x, const T* dy, const float* w_pt, T
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int MAXCLS = 8;
 
-template <typename T>
+template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_fwd_kernel(const T* __restrict__ y, const float* __restrict__ w,
                                                           float* __restrict__ logits, int n, long long vox, int c,
                                                           int ncls, int y_pitch) {
@@ -254,11 +254,16 @@ __global__ void __launch_bounds__(256) seghead_fwd_kernel(const T* __restrict__ 
 #pragma unroll
         for (int k = 0; k < MAXCLS; ++k) acc[k] = 0.f;
         const T* p = y + v * y_pitch;
-        for (int cc = 0; cc < c; ++cc) {
-            const float a = to_f(p[cc]);
+        for (int cc = 0; cc < c; cc += VW) {
+            float a[VW];
+            if (VW == 8) load8(p + cc, *reinterpret_cast<float(*)[8]>(a));
+            else a[0] = to_f(p[cc]);
 #pragma unroll
             for (int k = 0; k < MAXCLS; ++k)
-                if (k < ncls) acc[k] = fmaf(a, ws[k * c + cc], acc[k]);
+                if (k < ncls) {
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) acc[k] = fmaf(a[j], ws[k * c + cc + j], acc[k]);
+                }
         }
         const int nn = (int)(v / vox);
         const long long vv = v % vox;
@@ -268,24 +273,41 @@ __global__ void __launch_bounds__(256) seghead_fwd_kernel(const T* __restrict__ 
     }
 }
 
-template <typename T>
+template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dl,
                                                             T* __restrict__ dy, int accumulate, int n, long long vox,
                                                             int c, int ncls, int dy_pitch) {
     extern __shared__ float ws[];
     for (int e = threadIdx.x; e < ncls * c; e += blockDim.x) ws[e] = w[e];
     __syncthreads();
-    const long long total = (long long)n * vox * c;
+    const int ncg = c / VW;
+    const long long total = (long long)n * vox * ncg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cc = (int)(i % c);
-        const long long v = i / c;
+        const int cg = (int)(i % ncg);
+        const long long v = i / ncg;
         const int nn = (int)(v / vox);
         const long long vv = v % vox;
-        float acc = 0.f;
-        for (int k = 0; k < ncls; ++k) acc = fmaf(dl[((long long)nn * ncls + k) * vox + vv], ws[k * c + cc], acc);
-        T* p = dy + v * dy_pitch + cc;
-        if (accumulate) acc += to_f(*p);
-        *p = from_f<T>(acc);
+        float acc[VW];
+#pragma unroll
+        for (int j = 0; j < VW; ++j) acc[j] = 0.f;
+        for (int k = 0; k < ncls; ++k) {
+            const float d = dl[((long long)nn * ncls + k) * vox + vv];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) acc[j] = fmaf(d, ws[k * c + cg * VW + j], acc[j]);
+        }
+        T* p = dy + v * dy_pitch + cg * VW;
+        if (VW == 8) {
+            if (accumulate) {
+                float o[8];
+                load8(p, o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += o[j];
+            }
+            store8(p, *reinterpret_cast<float(*)[8]>(acc));
+        } else {
+            if (accumulate) acc[0] += to_f(*p);
+            *p = from_f<T>(acc[0]);
+        }
     }
 }
 
@@ -341,7 +363,8 @@ int seghead_fwd(const T* y, const float* w, float* logits, int n, long long vox,
     int grid = (int)((total + 255) / 256);
     int cap = num_sms() * 16;
     if (grid > cap) grid = cap;
-    B2_LAUNCH(seghead_fwd_kernel<T>, grid, 256, (size_t)ncls * c * sizeof(float), st, y, w, logits, n, vox, c, ncls, y_pitch);
+    if (c % 8 == 0 && y_pitch % 8 == 0) B2_LAUNCH((seghead_fwd_kernel<T, 8>), grid, 256, (size_t)ncls * c * sizeof(float), st, y, w, logits, n, vox, c, ncls, y_pitch);
+    else B2_LAUNCH((seghead_fwd_kernel<T, 1>), grid, 256, (size_t)ncls * c * sizeof(float), st, y, w, logits, n, vox, c, ncls, y_pitch);
     return B2_OK;
 }
 
@@ -363,11 +386,13 @@ int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int acc
                 long long vox, int c, int ncls, int y_pitch, int dy_pitch, float* scratch, cudaStream_t st) {
     B2_CHECK_ARG(ncls <= MAXCLS && c <= 256);
     if (dy) {
-        long long total = (long long)n * vox * c;
+        const bool v8 = (c % 8 == 0) && (dy_pitch % 8 == 0);
+        long long total = (long long)n * vox * (v8 ? c / 8 : c);
         long long grid = (total + 255) / 256;
         long long cap = (long long)num_sms() * 16;
         if (grid > cap) grid = cap;
-        B2_LAUNCH(seghead_dgrad_kernel<T>, (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
+        if (v8) B2_LAUNCH((seghead_dgrad_kernel<T, 8>), (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
+        else B2_LAUNCH((seghead_dgrad_kernel<T, 1>), (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
     }
     if (dw) {
         int slabs = seghead_slabs(n, vox);
