@@ -65,7 +65,9 @@ struct TcConvParams {
     unsigned char tap_w[27];     // weight row-block of the tap
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_PRODUCERS = 4;                       // TMA producer warps (one stage each, round robin): the single-thread
+                                                      // issue latency (~300 cycles per stage) was the bottleneck of round-1 v1
+constexpr int TC_THREADS = 32 * (TC_PRODUCERS + 5);   // producers, 1 MMA warp, 4 epilogue warps
 constexpr int MAX_STAGES = 16;
 
 template <int KC>
@@ -89,7 +91,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    if (warp == TC_PRODUCERS) tmem_alloc(&tmem_base_smem, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -97,11 +99,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int kiters = p.ntaps * p.kchunks;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
+    if (warp < TC_PRODUCERS) {
+        // ===================== TMA producers: warp w issues the pipeline iterations with git % TC_PRODUCERS == w =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            uint32_t git = 0;   // global pipeline iteration (same sequence in every role)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int nb = t % p.nblk; t /= p.nblk;
@@ -110,7 +111,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int td = t % p.nt_d; t /= p.nt_d;
                 const int tn = t;
                 const int w0 = tw * p.TW * p.sw, h0 = th * p.TH * p.sh, d0 = td * p.TD * p.sd, n0 = tn * p.TN;
-                for (int it = 0; it < kiters; ++it) {
+                for (int it = 0; it < kiters; ++it, ++git) {
+                    if ((int)(git % TC_PRODUCERS) != warp) continue;
+                    const int stage = (int)(git % (uint32_t)p.stages);
+                    const uint32_t phase = (git / (uint32_t)p.stages) & 1;
                     const int tap = it / p.kchunks, kc = it % p.kchunks;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
@@ -119,28 +123,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
                                 d0 + p.tap_off[tap][0], n0);
                     tma_load_2d(&tmB, &full_bar[stage], sb, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-            for (int it = 0; it < kiters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+    } else if (warp == TC_PRODUCERS) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            uint32_t git = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int it = 0; it < kiters; ++it, ++git) {
+                    const int stage = (int)(git % (uint32_t)p.stages);
+                    const uint32_t phase = (git / (uint32_t)p.stages) & 1;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
                     const uint64_t adesc = umma_desc_kmajor<KC>(sa);
-                    const uint64_t bdesc = umma_desc_kmajor<KC>(sb);
+                    const uint64_t bdesc = umma_desc_kmajor<KC>(sa + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -149,11 +152,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     umma_commit(&empty_bar[stage]);
                     if (it == kiters - 1) umma_commit(&tfull_bar[acc]);
                 }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -211,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == TC_PRODUCERS) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }

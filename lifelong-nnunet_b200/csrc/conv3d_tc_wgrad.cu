@@ -55,7 +55,8 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t r
     return d;
 }
 
-constexpr int WG_THREADS = 192;
+constexpr int WG_PRODUCERS = 4;                        // A-operand TMA producer warps (round robin over group stages)
+constexpr int WG_THREADS = 32 * (WG_PRODUCERS + 6);    // + dz producer warp, MMA warp, 4 epilogue warps
 constexpr int WG_MAX_ASTAGES = 6;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -95,16 +96,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_init(&done_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    if (warp == WG_PRODUCERS + 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 0) {
+    if (warp < WG_PRODUCERS) {
+        // ---- shifted-operand producers: warp w issues the group stages with gg % WG_PRODUCERS == w ----
         if (lane == 0) {
-            int as = 0, bs = 0;
-            uint32_t aph = 0, bph = 0;
+            uint32_t gg = 0;
             for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
                 int t = vt;
                 const int tw = t % p.nt_w; t /= p.nt_w;
@@ -112,15 +113,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int td = t % p.nt_d; t /= p.nt_d;
                 const int tn = t;
                 const int w0 = tw * p.TW, h0 = th * p.TH, d0 = td * p.TD, n0 = tn * p.TN;
-                // dz tile
-                mbar_wait(&emptyB[bs], bph ^ 1);
-                mbar_expect_tx(&fullB[bs], B_BYTES);
-                for (int c = 0; c < p.b_chunks; ++c)
-                    tma_load_5d(&tmZ, &fullB[bs], smemB + (size_t)bs * B_BYTES + (size_t)c * b_chunk_bytes,
-                                cob * p.co_blk + c * p.co_sub, w0, h0, d0, n0);
-                if (++bs == 2) { bs = 0; bph ^= 1; }
-                // x tiles, one stage per group
-                for (int g = 0; g < my_groups; ++g) {
+                for (int g = 0; g < my_groups; ++g, ++gg) {
+                    if ((int)(gg % WG_PRODUCERS) != warp) continue;
+                    const int as = (int)(gg % (uint32_t)p.a_stages);
+                    const uint32_t aph = (gg / (uint32_t)p.a_stages) & 1;
                     mbar_wait(&emptyA[as], aph ^ 1);
                     mbar_expect_tx(&fullA[as], A_BYTES);
                     for (int c = 0; c < p.a_chunks; ++c) {
@@ -131,23 +127,44 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         tma_load_5d(&tmX, &fullA[as], smem + (size_t)as * A_BYTES + (size_t)c * a_chunk_bytes, cch,
                                     w0 * p.sw + p.tap_off[tap][2], h0 * p.sh + p.tap_off[tap][1], d0 * p.sd + p.tap_off[tap][0], n0);
                     }
-                    if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
-        bool first = true;
-        for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
-            mbar_wait(&fullB[bs], bph);
-            for (int g = 0; g < my_groups; ++g) {
-                mbar_wait(&fullA[as], aph);
-                tc_fence_after();
-                if (elect_one()) {
+    } else if (warp == WG_PRODUCERS) {
+        // ---- fixed-operand (dz) producer ----
+        if (lane == 0) {
+            int bs = 0;
+            uint32_t bph = 0;
+            for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+                int t = vt;
+                const int tw = t % p.nt_w; t /= p.nt_w;
+                const int th = t % p.nt_h; t /= p.nt_h;
+                const int td = t % p.nt_d; t /= p.nt_d;
+                const int tn = t;
+                mbar_wait(&emptyB[bs], bph ^ 1);
+                mbar_expect_tx(&fullB[bs], B_BYTES);
+                for (int c = 0; c < p.b_chunks; ++c)
+                    tma_load_5d(&tmZ, &fullB[bs], smemB + (size_t)bs * B_BYTES + (size_t)c * b_chunk_bytes,
+                                cob * p.co_blk + c * p.co_sub, tw * p.TW, th * p.TH, td * p.TD, tn * p.TN);
+                if (++bs == 2) { bs = 0; bph ^= 1; }
+            }
+        }
+    } else if (warp == WG_PRODUCERS + 1) {
+        if (lane == 0) {
+            uint32_t gg = 0;
+            int bs = 0;
+            uint32_t bph = 0;
+            bool first = true;
+            const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
+            for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+                mbar_wait(&fullB[bs], bph);
+                const uint32_t sb = smem_u32(smemB + (size_t)bs * B_BYTES);
+                for (int g = 0; g < my_groups; ++g, ++gg) {
+                    const int as = (int)(gg % (uint32_t)p.a_stages);
+                    const uint32_t aph = (gg / (uint32_t)p.a_stages) & 1;
+                    mbar_wait(&fullA[as], aph);
+                    tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)as * A_BYTES);
-                    const uint32_t sb = smem_u32(smemB + (size_t)bs * B_BYTES);
-                    const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {   // 128 voxels = 8 x K16
                         const uint64_t adesc = umma_desc_mnmajor(sa + k * 16 * a_row, a_row, p.a_lbo, p.a_sbo);
@@ -157,13 +174,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     umma_commit(&emptyA[as]);
                     if (g == my_groups - 1) umma_commit(&emptyB[bs]);
                 }
-                __syncwarp();
-                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                first = false;
+                if (++bs == 2) { bs = 0; bph ^= 1; }
             }
-            first = false;
-            if (++bs == 2) { bs = 0; bph ^= 1; }
+            umma_commit(&done_bar);
         }
-        if (elect_one()) umma_commit(&done_bar);
         __syncwarp();
     } else {
         const int q = warp & 3;
@@ -202,7 +217,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == WG_PRODUCERS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
