@@ -58,7 +58,9 @@ struct TcConvParams {
     int q_scatter, nblk_per_q, qk_h, qk_w;   // transposed-conv forward: column block -> (q, channel block)
     int ntaps;
     int stages;
-    int num_tiles;
+    int num_tiles;               // output tiles x ksplit
+    int nprod;                   // active TMA producer warps (<= stages, so that a producer can never lap the ring)
+    int ksplit;                  // > 1: the (tap, k-chunk) iterations of a tile are split over ksplit CTAs writing fp32 partials
     uint32_t idesc;
     uint32_t tmem_cols;
     signed char tap_off[27][3];  // source offset (d, h, w) per tap, padding included
@@ -73,7 +75,7 @@ constexpr int MAX_STAGES = 16;
 template <int KC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcConvParams p,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
@@ -100,19 +102,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kiters = p.ntaps * p.kchunks;
 
     if (warp < TC_PRODUCERS) {
+        // (warps >= p.nprod idle)
         // ===================== TMA producers: warp w issues the pipeline iterations with git % TC_PRODUCERS == w =====================
-        if (lane == 0) {
+        if (lane == 0 && warp < p.nprod) {
             uint32_t git = 0;   // global pipeline iteration (same sequence in every role)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int t = tile;
+                const int ks = t % p.ksplit; t /= p.ksplit;
                 const int nb = t % p.nblk; t /= p.nblk;
                 const int tw = t % p.nt_w; t /= p.nt_w;
                 const int th = t % p.nt_h; t /= p.nt_h;
                 const int td = t % p.nt_d; t /= p.nt_d;
                 const int tn = t;
                 const int w0 = tw * p.TW * p.sw, h0 = th * p.TH * p.sh, d0 = td * p.TD * p.sd, n0 = tn * p.TN;
-                for (int it = 0; it < kiters; ++it, ++git) {
-                    if ((int)(git % TC_PRODUCERS) != warp) continue;
+                const int it0 = (int)((long long)kiters * ks / p.ksplit), it1 = (int)((long long)kiters * (ks + 1) / p.ksplit);
+                for (int it = it0; it < it1; ++it, ++git) {
+                    if ((int)(git % (uint32_t)p.nprod) != warp) continue;
                     const int stage = (int)(git % (uint32_t)p.stages);
                     const uint32_t phase = (git / (uint32_t)p.stages) & 1;
                     const int tap = it / p.kchunks, kc = it % p.kchunks;
@@ -136,7 +141,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int it = 0; it < kiters; ++it, ++git) {
+                const int ks = tile % p.ksplit;
+                const int it0 = (int)((long long)kiters * ks / p.ksplit), it1 = (int)((long long)kiters * (ks + 1) / p.ksplit);
+                for (int it = it0; it < it1; ++it, ++git) {
                     const int stage = (int)(git % (uint32_t)p.stages);
                     const uint32_t phase = (git / (uint32_t)p.stages) & 1;
                     mbar_wait(&full_bar[stage], phase);
@@ -147,10 +154,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (it | k) != 0);
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, ((it - it0) | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (it == kiters - 1) umma_commit(&tfull_bar[acc]);
+                    if (it == it1 - 1) umma_commit(&tfull_bar[acc]);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -165,6 +172,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             int t = tile;
+            const int ks = t % p.ksplit; t /= p.ksplit;
+            const int otile = t;        // output tile (incl. column block)
             const int nb = t % p.nblk; t /= p.nblk;
             const int tw = t % p.nt_w; t /= p.nt_w;
             const int th = t % p.nt_h; t /= p.nt_h;
@@ -187,7 +196,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
-                if (valid) {
+                if (p.ksplit > 1) {
+                    // fp32 partial [ks][output tile][row][BN]; reduced in fixed order by splitk_reduce_kernel
+                    float* pp = partial + (((size_t)ks * (p.num_tiles / p.ksplit) + otile) * 128 + r) * p.BN + c0;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(pp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                         __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                } else if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float f[8];
@@ -216,6 +232,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == TC_PRODUCERS) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// split-K second stage: out = bf16( sum_ks partial[ks] + bias (+ out) ), same row -> voxel mapping as the epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(TcConvParams p, const float* __restrict__ partial, const float* __restrict__ bias,
+                                                            __nv_bfloat16* __restrict__ dst, int accumulate) {
+    const int otiles = p.num_tiles / p.ksplit;
+    const long long total = (long long)otiles * 128 * (p.BN / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % (p.BN / 8));
+        long long rr = i / (p.BN / 8);
+        const int r = (int)(rr % 128);
+        int t = (int)(rr / 128);
+        const int otile = t;
+        const int nb = t % p.nblk; t /= p.nblk;
+        const int tw = t % p.nt_w; t /= p.nt_w;
+        const int th = t % p.nt_h; t /= p.nt_h;
+        const int td = t % p.nt_d; t /= p.nt_d;
+        const int tn = t;
+        const int w_ = r % p.TW, h_ = (r / p.TW) % p.TH, d_ = (r / (p.TW * p.TH)) % p.TD, n_ = r / (p.TW * p.TH * p.TD);
+        const int lw = tw * p.TW + w_, lh = th * p.TH + h_, ld = td * p.TD + d_, on = tn * p.TN + n_;
+        int ow = lw * p.os_w + p.oo_w, oh = lh * p.os_h + p.oo_h, od = ld * p.os_d + p.oo_d;
+        int chan0 = nb * p.BN;
+        if (p.q_scatter) {
+            const int q = nb / p.nblk_per_q;
+            ow += q % p.qk_w; oh += (q / p.qk_w) % p.qk_h; od += q / (p.qk_w * p.qk_h);
+            chan0 = (nb % p.nblk_per_q) * p.BN;
+        }
+        if (!(lw < p.LW && lh < p.LH && ld < p.LD && on < p.N && ow < p.W && oh < p.H && od < p.D)) continue;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = bias ? bias[chan0 + cg * 8 + e] : 0.f;
+        for (int ks = 0; ks < p.ksplit; ++ks) {
+            const float* pp = partial + (((size_t)ks * otiles + otile) * 128 + r) * p.BN + cg * 8;
+            const float4 a = *reinterpret_cast<const float4*>(pp), b = *reinterpret_cast<const float4*>(pp + 4);
+            f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+        }
+        __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0 + cg * 8;
+        if (accumulate) {
+            float o[8];
+            load8(row, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += o[e];
+        }
+        store8(row, f);
     }
 }
 
@@ -333,7 +394,18 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
         for (int a = 0; a < 3; ++a) p.tap_off[t][a] = (signed char)g.tap_off[t][a];
         p.tap_w[t] = (unsigned char)g.tap_w[t];
     }
-    p.num_tiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n * nblk;
+    const int otiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n * nblk;
+    // split-K when the output tiles cannot fill the GPU (deep, small-volume layers)
+    int ksplit = 1;
+    const int kiters_total = g.ntaps * p.kchunks;
+    if (g.splitk_scratch && otiles * 2 <= num_sms()) {
+        ksplit = num_sms() / otiles;
+        if (ksplit > kiters_total / 4) ksplit = kiters_total / 4;
+        if (ksplit < 1) ksplit = 1;
+        while (ksplit > 1 && (size_t)ksplit * otiles * 128 * BN * sizeof(float) > g.splitk_scratch_bytes) --ksplit;
+    }
+    p.ksplit = ksplit;
+    p.num_tiles = otiles * ksplit;
     p.idesc = umma_idesc_bf16(128, BN);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * BN)) cols *= 2;
@@ -343,7 +415,11 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return fail(B2_EUNSUPPORTED, "conv_tc: tile does not fit shared memory%s", "");
+    // ring depth a multiple of the producer count: every stage is then always filled by the same producer warp, which
+    // keeps the 1-bit mbarrier phase parity unambiguous
+    if (stages >= TC_PRODUCERS) stages = stages / TC_PRODUCERS * TC_PRODUCERS;
     p.stages = stages;
+    p.nprod = stages < TC_PRODUCERS ? stages : TC_PRODUCERS;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
 
     CUtensorMap tmA, tmB;
@@ -356,10 +432,16 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     if (KC == 64) {
         if (!attr64) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr64 = true; }
-        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate);
+        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch);
     } else {
         if (!attr32) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr32 = true; }
-        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate);
+        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch);
+    }
+    if (p.ksplit > 1) {
+        const long long total = (long long)otiles * 128 * (BN / 8);
+        long long rg = (total + 255) / 256, cap = (long long)num_sms() * 8;
+        if (rg > cap) rg = cap;
+        B2_LAUNCH(splitk_reduce_kernel, (int)rg, 256, 0, st, p, g.splitk_scratch, g.bias, g.dst, g.accumulate);
     }
     return B2_OK;
 }
@@ -375,16 +457,26 @@ static void fill_common(TcGather& g, const __nv_bfloat16* src, int N, int Ds, in
     for (int a = 0; a < 3; ++a) { g.stride[a] = 1; g.os[a] = 1; g.oo[a] = 0; g.qk[a] = 1; }
 }
 
+// fp32 scratch that lets conv_tc_launch split K for a produced tensor of this size (0 when the tiles already fill the GPU)
+size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout) {
+    const long long vox = (long long)N * D * H * W;
+    const long long tiles = (vox + 127) / 128 + 8;
+    int nblk = cdiv(Nout, 256);
+    if (tiles * nblk * 2 > num_sms()) return 0;
+    return (size_t)num_sms() * 2 * 128 * 256;   // ksplit * otiles <= num_sms, BN <= 256 (x2 slack for ragged boxes)
+}
+
 // 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st) {
+                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes) {
     if (stride[0] == 1 && stride[1] == 1 && stride[2] == 1 && conv_tc_halo_supported(K, Nout, N, Dd, Hd, Wd))
         return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st);
     TcGather g;
     fill_common(g, src, N, Ds, Hs, Ws, K, src_pitch, wmat, Nout, bias, dst, Dd, Hd, Wd, dst_pitch, accumulate);
     for (int a = 0; a < 3; ++a) g.stride[a] = stride[a];
     g.ntaps = 27; g.w_rows = 27 * Nout;
+    g.splitk_scratch = scratch; g.splitk_scratch_bytes = scratch_bytes;
     for (int t = 0; t < 27; ++t) {
         g.tap_off[t][0] = t / 9 - 1; g.tap_off[t][1] = (t / 3) % 3 - 1; g.tap_off[t][2] = t % 3 - 1;
         g.tap_w[t] = t;

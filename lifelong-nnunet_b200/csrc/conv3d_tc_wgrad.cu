@@ -35,6 +35,7 @@ struct TcWgradParams {
     int nsplit;                  // CTAs per work item (split over voxel tiles)
     int num_vtiles;
     int a_stages;
+    int nprod;                   // active shifted-operand producer warps (<= a_stages)
     uint32_t idesc;
     uint32_t tmem_cols;
     // MN-major descriptor strides (bytes)
@@ -104,7 +105,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
     if (warp < WG_PRODUCERS) {
         // ---- shifted-operand producers: warp w issues the group stages with gg % WG_PRODUCERS == w ----
-        if (lane == 0) {
+        if (lane == 0 && warp < p.nprod) {
             uint32_t gg = 0;
             for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
                 int t = vt;
@@ -114,7 +115,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int tn = t;
                 const int w0 = tw * p.TW, h0 = th * p.TH, d0 = td * p.TD, n0 = tn * p.TN;
                 for (int g = 0; g < my_groups; ++g, ++gg) {
-                    if ((int)(gg % WG_PRODUCERS) != warp) continue;
+                    if ((int)(gg % (uint32_t)p.nprod) != warp) continue;
                     const int as = (int)(gg % (uint32_t)p.a_stages);
                     const uint32_t aph = (gg / (uint32_t)p.a_stages) & 1;
                     mbar_wait(&emptyA[as], aph ^ 1);
@@ -326,7 +327,9 @@ static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) 
     int st = (int)((200u * 1024 - 2 * B_BYTES) / A_BYTES);
     if (st > WG_MAX_ASTAGES) st = WG_MAX_ASTAGES;
     if (st < 2) st = 2;
+    if (st >= WG_PRODUCERS) st = st / WG_PRODUCERS * WG_PRODUCERS;   // see conv3d_tc.cu: ring depth % producers == 0
     p.a_stages = st;
+    p.nprod = st < WG_PRODUCERS ? st : WG_PRODUCERS;
 }
 
 size_t wgrad_tc_part_floats(const ConvShape& s) {

@@ -52,6 +52,7 @@ struct TcGather {
     int os[3], oo[3];                                               // produced = logical * os + oo
     int ntaps; int tap_off[27][3]; int tap_w[27];
     int q_scatter, q_channels, qk[3];                               // transposed-conv forward column->voxel scatter
+    float* splitk_scratch; size_t splitk_scratch_bytes;             // optional fp32 scratch enabling split-K for small volumes
 };
 int conv_tc_gather(const TcGather& g, cudaStream_t st);
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
@@ -64,7 +65,8 @@ int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout
 int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st);
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st);
+                   int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0);
+size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout);
 bool wgrad_tc_supported(int cin, int cout);
 size_t wgrad_tc_part_floats(const ConvShape& s);
 int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,

@@ -205,6 +205,8 @@ static int build_plan(b2_unet_plan* p) {
         cb.tc_wgrad = tc_ok && g_tc_wgrad && wgrad_tc_supported(in.c, cout) && (!strided || g_tc_strided);
         if (cb.tc_wgrad) p->scratch_floats = max_sz(p->scratch_floats, wgrad_tc_part_floats(cb.shape));
         if (tc_ok) {
+            p->scratch_floats = max_sz(p->scratch_floats, conv_tc_splitk_scratch_floats(N, od, oh, ow, cout));
+            p->scratch_floats = max_sz(p->scratch_floats, conv_tc_splitk_scratch_floats(N, in.d, in.h, in.w, in.c));
             cb.wk_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             cb.wd_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, (long long)od * oh * ow, cout));
@@ -339,7 +341,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
             if (cb.tc_fwd) {
                 r = conv_tc_launch(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch,
                                    (const __nv_bfloat16*)F32(ws, p, cb.wk_off), cb.shape.cout, prm[cb.p_b], P<T>(ws, p, cb.z, false),
-                                   cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st);
+                                   cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st, SCR(ws, p), p->scratch_floats * sizeof(float));
                 if (r) return r;
                 r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
                 if (r) return r;
@@ -426,7 +428,7 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                     const int one[3] = {1, 1, 1};
                     r = conv_tc_launch(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout,
                                        (const __nv_bfloat16*)F32(ws, p, cb.wd_off), cb.shape.cin, nullptr, P<T>(ws, p, cb.din, true),
-                                       cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, cb.din_accumulate, st);
+                                       cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, cb.din_accumulate, st, SCR(ws, p), p->scratch_floats * sizeof(float));
                     if (r) return r;
                     done = true;
                 } else if (cb.tc_dgrad_strided) {
@@ -615,6 +617,8 @@ extern "C" size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d) {
     if (wgrad_tc_supported(s.cin, s.cout)) { size_t t = wgrad_tc_part_floats(s); if (t > wg) wg = t; }
     size_t st2 = instnorm_stats_scratch_floats(s.n, (long long)s.d * s.h * s.w, s.cout);
     if (st2 > part) part = st2;
+    size_t sk = conv_tc_splitk_scratch_floats(s.n, s.d, s.h, s.w, s.cout > s.cin ? s.cout : s.cin);
+    if (sk > part) part = sk;
     return align_up((2 * w + (part > wg ? part : wg) + 64) * sizeof(float));
 }
 
@@ -636,8 +640,9 @@ extern "C" int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* 
         rc = weight_shadow_bf16(w_pt, s.cout, s.cin, wk, nullptr, st);
         if (rc) return rc;
         const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
+        const size_t part_bytes = b2_conv3d_scratch_bytes(d) - 2 * (size_t)27 * s.cin * s.cout * sizeof(float) - 256;
         rc = conv_tc_launch((const __nv_bfloat16*)x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, wk, s.cout, bias, (__nv_bfloat16*)z, od, oh, ow,
-                            s.out_pitch, s.stride, 0, st);
+                            s.out_pitch, s.stride, 0, st, part, part_bytes);
         if (rc) return rc;
         if (stats) return instnorm_stats<__nv_bfloat16>((const __nv_bfloat16*)z, s.n, (long long)od * oh * ow, s.cout, s.out_pitch, part, stats, eps, st);
         return B2_OK;
@@ -668,8 +673,9 @@ extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* d
             __nv_bfloat16* wd = (__nv_bfloat16*)wf;   // forward fp32 shadow is unused from here on
             if ((rc = weight_shadow_bf16(w_pt, s.cout, s.cin, nullptr, wd, st))) return rc;
             const int one[3] = {1, 1, 1};
+            const size_t part_bytes = b2_conv3d_scratch_bytes(d) - 2 * (size_t)27 * s.cin * s.cout * sizeof(float) - 256;
             if ((rc = conv_tc_launch((const __nv_bfloat16*)dz, s.n, s.d, s.h, s.w, s.cout, s.out_pitch, wd, s.cin, nullptr,
-                                     (__nv_bfloat16*)dx, s.d, s.h, s.w, s.in_pitch, one, accumulate_dx, st))) return rc;
+                                     (__nv_bfloat16*)dx, s.d, s.h, s.w, s.in_pitch, one, accumulate_dx, st, part, part_bytes))) return rc;
         } else if (dx && g_use_tc && strided && g_tc_strided && conv_tc_supported(s.cout, s.cin) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0) {
             __nv_bfloat16* wd = (__nv_bfloat16*)wf;
             if ((rc = weight_shadow_bf16(w_pt, s.cout, s.cin, nullptr, wd, st))) return rc;

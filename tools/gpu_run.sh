@@ -1,9 +1,9 @@
 #!/bin/bash
-# one GPU session: parity suite, bench, per-layer kernel timings, launch list
 mkdir -p gpurun_out
+timeout 120 tools/mma_probe > gpurun_out/mma_probe.txt 2>&1; cat gpurun_out/mma_probe.txt
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 tail -c 1100 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
 rm -f gpurun_out/kernels.txt
