@@ -105,7 +105,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // (warps >= p.nprod idle)
         // ===================== TMA producers: warp w issues the pipeline iterations with git % TC_PRODUCERS == w =====================
         if (lane == 0 && warp < p.nprod) {
-            uint32_t git = 0;   // global pipeline iteration (same sequence in every role)
+            // counters instead of divisions: gmod = git % nprod; (stage, phase) of this warp's next iteration
+            int gmod = 0, stage = warp;
+            uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int ks = t % p.ksplit; t /= p.ksplit;
@@ -116,48 +118,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tn = t;
                 const int w0 = tw * p.TW * p.sw, h0 = th * p.TH * p.sh, d0 = td * p.TD * p.sd, n0 = tn * p.TN;
                 const int it0 = (int)((long long)kiters * ks / p.ksplit), it1 = (int)((long long)kiters * (ks + 1) / p.ksplit);
-                for (int it = it0; it < it1; ++it, ++git) {
-                    if ((int)(git % (uint32_t)p.nprod) != warp) continue;
-                    const int stage = (int)(git % (uint32_t)p.stages);
-                    const uint32_t phase = (git / (uint32_t)p.stages) & 1;
-                    const int tap = it / p.kchunks, kc = it % p.kchunks;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-                    tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
-                                d0 + p.tap_off[tap][0], n0);
-                    tma_load_2d(&tmB, &full_bar[stage], sb, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
+                int tap = it0 / p.kchunks, kc = it0 % p.kchunks;
+                for (int it = it0; it < it1; ++it) {
+                    if (gmod == warp) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+                        tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
+                                    d0 + p.tap_off[tap][0], n0);
+                        tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
+                        stage += p.nprod;
+                        if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+                    }
+                    if (++gmod == p.nprod) gmod = 0;
+                    if (++kc == p.kchunks) { kc = 0; ++tap; }
                 }
             }
         }
     } else if (warp == TC_PRODUCERS) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            uint32_t git = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            constexpr uint32_t ROWB = KC * 2;
+            constexpr uint32_t DESC_HI = (uint32_t)(((uint64_t)((8 * ROWB) >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)(ROWB == 128 ? 2 : 4) << 61) >> 32);
+            auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
+            const uint32_t base_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | 0x10000u;
+            const uint32_t stage16 = STAGE_BYTES >> 4, a16 = A_BYTES >> 4;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, a_lo = base_lo;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 const int ks = tile % p.ksplit;
-                const int it0 = (int)((long long)kiters * ks / p.ksplit), it1 = (int)((long long)kiters * (ks + 1) / p.ksplit);
-                for (int it = it0; it < it1; ++it, ++git) {
-                    const int stage = (int)(git % (uint32_t)p.stages);
-                    const uint32_t phase = (git / (uint32_t)p.stages) & 1;
+                const int n_it = (int)((long long)kiters * (ks + 1) / p.ksplit) - (int)((long long)kiters * ks / p.ksplit);
+                for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_kmajor<KC>(sa);
-                    const uint64_t bdesc = umma_desc_kmajor<KC>(sa + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, ((it - it0) | k) != 0);
-                    }
+                    for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle atom per K16 step
+                        umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(a_lo + a16 + 2 * k), p.idesc, (it | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
-                    if (it == it1 - 1) umma_commit(&tfull_bar[acc]);
+                    if (it == n_it - 1) umma_commit(&tfull_bar[acc]);
+                    a_lo += stage16;
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }

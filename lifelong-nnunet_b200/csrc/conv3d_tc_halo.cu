@@ -106,79 +106,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 6) {
         // ===================== weight producer =====================
         if (lane == 0) {
-            if (p.b_resident) {
-                mbar_expect_tx(&wfull, 27 * B_TILE);
-                for (int t = 0; t < 27; ++t) tma_load_2d(&tmB, &wfull, wsm + (size_t)t * B_TILE, 0, t * p.BN);
-            } else {
-                int bs = 0;
-                uint32_t bph = 0;
-                for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                    int n, h0, w0, d0, d1;
-                    decode(item, n, h0, w0, d0, d1);
-                    for (int od = d0; od < d1; ++od)
-                        for (int t = 0; t < 27; ++t) {
-                            mbar_wait(&bempty[bs], bph ^ 1);
-                            mbar_expect_tx(&bfull[bs], B_TILE);
-                            tma_load_2d(&tmB, &bfull[bs], wsm + (size_t)bs * B_TILE, 0, t * p.BN);
-                            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-                        }
-                }
-            }
+            mbar_expect_tx(&wfull, 27 * B_TILE);
+            for (int t = 0; t < 27; ++t) tma_load_2d(&tmB, &wfull, wsm + (size_t)t * B_TILE, 0, t * p.BN);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        uint32_t jbase = 0;  // slab counter at the start of the current item
-        int acc = 0, bs = 0;
-        uint32_t acc_phase = 0, bph = 0;
-        if (p.b_resident) mbar_wait(&wfull, 0);
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            int n, h0, w0, d0, d1;
-            decode(item, n, h0, w0, d0, d1);
-            // slab index s (d0-1 .. d1) <-> counter jbase + (s - (d0 - 1))
-            uint32_t waited = 0;  // number of slabs of this item already waited for
-            for (int od = d0; od < d1; ++od) {
-                const uint32_t need = (uint32_t)(od + 1 - (d0 - 1)) + 1;  // slabs up to od+1 inclusive
-                while (waited < need) {
-                    const uint32_t j = jbase + waited;
-                    mbar_wait(&sfull[j % 3], (j / 3) & 1);
-                    ++waited;
-                }
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int t = 0; t < 27; ++t) {
-                    const int kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
-                    const uint32_t j = jbase + (uint32_t)(od + kd - 1 - (d0 - 1));
-                    const uint32_t sa = smem_u32(slabs + (j % 3) * SLAB_BYTES + kw * COPY_BYTES + kh * 8 * ROW);
-                    uint32_t sb;
-                    if (p.b_resident) sb = smem_u32(wsm + (size_t)t * B_TILE);
-                    else {
-                        mbar_wait(&bfull[bs], bph);
-                        sb = smem_u32(wsm + (size_t)bs * B_TILE);
+        // ===================== MMA issuer: ONE thread, straight-line code =====================
+        // The issuing thread is blocked ~45 cycles per tcgen05.mma (M128 x N<=64 x K16, measured with tools/mma_probe), and
+        // every scalar instruction between two MMAs adds to that: so descriptors are assembled from precomputed 32-bit
+        // halves and the 27 taps are fully unrolled (all offsets are immediates).
+        if (lane == 0) {
+            constexpr uint32_t DESC_HI = (uint32_t)(((uint64_t)((8 * ROW) >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)(ROW == 128 ? 2 : 4) << 61) >> 32);
+            auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
+            const uint32_t slab_lo0 = ((smem_u32(slabs) & 0x3FFFF) >> 4) | 0x10000u;
+            constexpr uint32_t SLAB16 = SLAB_BYTES >> 4;
+            const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFF) >> 4) | 0x10000u;
+            const uint32_t btile16 = B_TILE >> 4;
+            uint32_t jrel = 0;   // slab counter (mod 3) of slab (d0 - 1) of the current item
+            uint32_t jcnt = 0;   // absolute slab counter at the start of the item (for the barrier phases)
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            mbar_wait(&wfull, 0);
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int n, h0, w0, d0, d1;
+                decode(item, n, h0, w0, d0, d1);
+                uint32_t waited = 0;
+                uint32_t s0 = jrel;   // slot of slab (od - 1)
+                for (int od = d0; od < d1; ++od) {
+                    const uint32_t need = (uint32_t)(od - d0) + 3;
+                    while (waited < need) {
+                        const uint32_t j = jcnt + waited;
+                        mbar_wait(&sfull[j % 3], (j / 3) & 1);
+                        ++waited;
                     }
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t adesc = halo_desc<KC>(sa), bdesc = halo_desc<KC>(sb);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                    const uint32_t s1 = s0 == 2 ? 0 : s0 + 1, s2 = s1 == 2 ? 0 : s1 + 1;
+                    const uint32_t lo_kd0 = slab_lo0 + s0 * SLAB16, lo_kd1 = slab_lo0 + s1 * SLAB16, lo_kd2 = slab_lo0 + s2 * SLAB16;
+                    uint32_t b_lo = w_lo;
+#pragma unroll
+                    for (int t = 0; t < 27; ++t) {
+                        constexpr uint32_t C16 = COPY_BYTES >> 4, A16 = (8 * ROW) >> 4;
+                        const uint32_t a_lo = (t / 9 == 0 ? lo_kd0 : t / 9 == 1 ? lo_kd1 : lo_kd2) + (uint32_t)(t % 3) * C16 + (uint32_t)((t / 3) % 3) * A16;
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k)
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (t | k) != 0);
-                        if (!p.b_resident) umma_commit(&bempty[bs]);
-                        if (t == 8) umma_commit(&sempty[(jbase + (uint32_t)(od - d0)) % 3]);  // slab od-1: last use done
-                        if (t == 26) {
-                            umma_commit(&tfull[acc]);
-                            if (od == d1 - 1) {  // end of the strip segment: release the two remaining slabs
-                                umma_commit(&sempty[(jbase + (uint32_t)(od - d0) + 1) % 3]);
-                                umma_commit(&sempty[(jbase + (uint32_t)(od - d0) + 2) % 3]);
-                            }
-                        }
+                            umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc, (t | k) != 0 ? 1u : 0u);
+                        b_lo += btile16;
+                        if (t == 8) umma_commit(&sempty[s0]);          // slab od-1: last use issued
                     }
-                    __syncwarp();
-                    if (!p.b_resident) { if (++bs == p.b_stages) { bs = 0; bph ^= 1; } }
+                    umma_commit(&tfull[acc]);
+                    if (od == d1 - 1) { umma_commit(&sempty[s1]); umma_commit(&sempty[s2]); }
+                    s0 = s1;
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                const uint32_t used = (uint32_t)(d1 - d0 + 2);
+                jcnt += used;
+                jrel = (jrel + used) % 3;
             }
-            jbase += (uint32_t)(d1 - d0 + 2);
         }
+        __syncwarp();
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;
@@ -243,13 +229,10 @@ static bool halo_plan(int K, int Nout, int D, int H, int W, int N, HaloParams& p
     p.HB = cdiv(H, 16); p.WB = cdiv(W, 8);
     const uint32_t row = K * 2, slab = 3 * 144 * row, btile = (uint32_t)Nout * row;
     const size_t budget = 210 * 1024;
-    if (3ull * slab + 27ull * btile + 1024 <= budget) { p.b_resident = 1; p.b_stages = 0; smem = 3ull * slab + 27ull * btile + 1024; }
-    else {
-        int st = (int)((budget - 3ull * slab - 1024) / btile);
-        if (st > HALO_MAX_BSTAGES) st = HALO_MAX_BSTAGES;
-        if (st < 2) return false;
-        p.b_resident = 0; p.b_stages = st; smem = 3ull * slab + (size_t)st * btile + 1024;
-    }
+    // weights must be resident (27 taps): streaming them costs one mbarrier round trip per tap on the MMA thread, which is
+    // slower than the per-tap kernel of conv3d_tc.cu
+    if (3ull * slab + 27ull * btile + 1024 > budget) return false;
+    p.b_resident = 1; p.b_stages = 0; smem = 3ull * slab + 27ull * btile + 1024;
     // segment length: enough items for >= 4 waves when possible, at least 8 slabs per segment
     const int strips = N * p.HB * p.WB;
     int sd = D;

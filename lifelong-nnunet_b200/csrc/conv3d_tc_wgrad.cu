@@ -106,7 +106,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (warp < WG_PRODUCERS) {
         // ---- shifted-operand producers: warp w issues the group stages with gg % WG_PRODUCERS == w ----
         if (lane == 0 && warp < p.nprod) {
-            uint32_t gg = 0;
+            int gmod = 0, as = warp;
+            uint32_t aph = 0;
             for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
                 int t = vt;
                 const int tw = t % p.nt_w; t /= p.nt_w;
@@ -114,20 +115,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int td = t % p.nt_d; t /= p.nt_d;
                 const int tn = t;
                 const int w0 = tw * p.TW, h0 = th * p.TH, d0 = td * p.TD, n0 = tn * p.TN;
-                for (int g = 0; g < my_groups; ++g, ++gg) {
-                    if ((int)(gg % (uint32_t)p.nprod) != warp) continue;
-                    const int as = (int)(gg % (uint32_t)p.a_stages);
-                    const uint32_t aph = (gg / (uint32_t)p.a_stages) & 1;
-                    mbar_wait(&emptyA[as], aph ^ 1);
-                    mbar_expect_tx(&fullA[as], A_BYTES);
-                    for (int c = 0; c < p.a_chunks; ++c) {
-                        int tap, cch;
-                        if (p.stack_taps) { tap = tap0 + g * p.a_chunks + c; cch = 0; }
-                        else { tap = tap0 + g; cch = ci_item * 128 + c * p.ci_sub; }
-                        if (tap > p.ntaps - 1) tap = p.ntaps - 1;  // rows of non-existent taps are ignored by the epilogue
-                        tma_load_5d(&tmX, &fullA[as], smem + (size_t)as * A_BYTES + (size_t)c * a_chunk_bytes, cch,
-                                    w0 * p.sw + p.tap_off[tap][2], h0 * p.sh + p.tap_off[tap][1], d0 * p.sd + p.tap_off[tap][0], n0);
+                for (int g = 0; g < my_groups; ++g) {
+                    if (gmod == warp) {
+                        mbar_wait(&emptyA[as], aph ^ 1);
+                        mbar_expect_tx(&fullA[as], A_BYTES);
+                        for (int c = 0; c < p.a_chunks; ++c) {
+                            int tap, cch;
+                            if (p.stack_taps) { tap = tap0 + g * p.a_chunks + c; cch = 0; }
+                            else { tap = tap0 + g; cch = ci_item * 128 + c * p.ci_sub; }
+                            if (tap > p.ntaps - 1) tap = p.ntaps - 1;  // rows of non-existent taps are ignored by the epilogue
+                            tma_load_5d(&tmX, &fullA[as], smem + (size_t)as * A_BYTES + (size_t)c * a_chunk_bytes, cch,
+                                        w0 * p.sw + p.tap_off[tap][2], h0 * p.sh + p.tap_off[tap][1], d0 * p.sd + p.tap_off[tap][0], n0);
+                        }
+                        as += p.nprod;
+                        if (as >= p.a_stages) { as -= p.a_stages; aph ^= 1; }
                     }
+                    if (++gmod == p.nprod) gmod = 0;
                 }
             }
         }
@@ -152,28 +155,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
     } else if (warp == WG_PRODUCERS + 1) {
         if (lane == 0) {
-            uint32_t gg = 0;
-            int bs = 0;
-            uint32_t bph = 0;
-            bool first = true;
+            // one thread, counters instead of divisions, descriptors from precomputed halves (see conv3d_tc_halo.cu)
             const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
+            const uint64_t a_hi = umma_desc_mnmajor(0, a_row, p.a_lbo, p.a_sbo) & 0xFFFFFFFFFFFF0000ull;   // everything but the address
+            const uint64_t b_hi = umma_desc_mnmajor(0, b_row, p.b_lbo, p.b_sbo) & 0xFFFFFFFFFFFF0000ull;
+            const uint32_t a_base = (smem_u32(smem) & 0x3FFFF) >> 4, b_base = (smem_u32(smemB) & 0x3FFFF) >> 4;
+            const uint32_t a_stage16 = A_BYTES >> 4, b_stage16 = B_BYTES >> 4, a_k16 = a_row, b_k16 = b_row;   // 16 rows * row_bytes / 16
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0, a_lo = a_base;
+            bool first = true;
             for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
                 mbar_wait(&fullB[bs], bph);
-                const uint32_t sb = smem_u32(smemB + (size_t)bs * B_BYTES);
-                for (int g = 0; g < my_groups; ++g, ++gg) {
-                    const int as = (int)(gg % (uint32_t)p.a_stages);
-                    const uint32_t aph = (gg / (uint32_t)p.a_stages) & 1;
+                const uint32_t b_lo = b_base + (uint32_t)bs * b_stage16;
+                uint32_t d_tmem = tmem_base;
+                for (int g = 0; g < my_groups; ++g) {
                     mbar_wait(&fullA[as], aph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)as * A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {   // 128 voxels = 8 x K16
-                        const uint64_t adesc = umma_desc_mnmajor(sa + k * 16 * a_row, a_row, p.a_lbo, p.a_sbo);
-                        const uint64_t bdesc = umma_desc_mnmajor(sb + k * 16 * b_row, b_row, p.b_lbo, p.b_sbo);
-                        umma_bf16(tmem_base + (uint32_t)(g * p.co_blk), adesc, bdesc, p.idesc, (!first || k != 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
+                        umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + k * a_k16), b_hi | (uint64_t)(b_lo + k * b_k16), p.idesc,
+                                  (!first || k != 0) ? 1u : 0u);
                     umma_commit(&emptyA[as]);
                     if (g == my_groups - 1) umma_commit(&emptyB[bs]);
+                    d_tmem += (uint32_t)p.co_blk;
+                    a_lo += a_stage16;
+                    if (++as == p.a_stages) { as = 0; aph ^= 1; a_lo = a_base; }
                 }
                 first = false;
                 if (++bs == 2) { bs = 0; bph ^= 1; }

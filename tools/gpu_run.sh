@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 tools/mma_probe > gpurun_out/mma_probe.txt 2>&1; cat gpurun_out/mma_probe.txt
+
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log

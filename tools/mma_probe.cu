@@ -2,6 +2,7 @@
 // independent TMEM accumulators that consecutive instructions rotate through.  Build: nvcc -gencode arch=compute_100a,code=sm_100a
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -18,8 +19,8 @@ __device__ __forceinline__ uint64_t desc(uint32_t saddr) {
     return d;
 }
 
-template <int ROWB>
-__global__ void probe(int N, int nacc, int iters, int same_operands, long long* out) {
+template <int ROWB, int N, int NACC>
+__global__ void probe(int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -37,18 +38,19 @@ __global__ void probe(int N, int nacc, int iters, int same_operands, long long* 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (threadIdx.x == 0) {
         const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 48 * 1024);
+        const uint64_t ad = desc<ROWB>(sa), bd = desc<ROWB>(sb);
         long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const int a = i % nacc;
-            const uint32_t off = same_operands ? 0 : (uint32_t)((i % 8) * 2048);
-            const uint64_t ad = desc<ROWB>(sa + off), bd = desc<ROWB>(sb + off);
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem + (uint32_t)(a * N)), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+        for (int i = 0; i < iters; i += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem + (uint32_t)((u % NACC) * N)), "l"(ad + (uint64_t)(2 * (u & 1))), "l"(bd + (uint64_t)(2 * (u & 1))), "r"(idesc), "r"(1u) : "memory");
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         long long t1 = clock64();
@@ -63,27 +65,29 @@ __global__ void probe(int N, int nacc, int iters, int same_operands, long long* 
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-int main() {
-    long long* d; long long h[2];
-    cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(probe<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(probe<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+template <int ROWB, int N, int NACC>
+void run(long long* d) {
+    long long h[2];
     const int iters = 512;
-    for (int rowb : {64, 128})
-        for (int N : {32, 64, 128, 256})
-            for (int nacc : {1, 2, 4, 8}) {
-                if (nacc * N > 512) continue;
-                for (int same : {1, 0}) {
-                    for (int rep = 0; rep < 2; ++rep) {
-                        if (rowb == 64) probe<64><<<1, 128, 100 * 1024>>>(N, nacc, iters, same, d);
-                        else probe<128><<<1, 128, 100 * 1024>>>(N, nacc, iters, same, d);
-                        cudaError_t e = cudaDeviceSynchronize();
-                        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-                    }
-                    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-                    printf("rowB %3d N %3d accumulators %d %s operands: issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d)\n", rowb, N, nacc,
-                           same ? "same" : "rotating", (double)h[0] / iters, (double)h[1] / iters, N / 2);
-                }
-            }
+    cudaFuncSetAttribute(probe<ROWB, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int rep = 0; rep < 2; ++rep) {
+        probe<ROWB, N, NACC><<<1, 128, 100 * 1024>>>(iters, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+    }
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("rowB %3d N %3d accumulators %d: issue %.1f cyc/mma, complete %.1f cyc/mma (ideal %d)\n", ROWB, N, NACC,
+           (double)h[0] / iters, (double)h[1] / iters, N / 2);
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 16);
+    run<64, 32, 1>(d); run<64, 32, 2>(d); run<64, 32, 4>(d);
+    run<64, 64, 1>(d); run<64, 64, 2>(d); run<64, 64, 4>(d);
+    run<128, 32, 1>(d); run<128, 32, 4>(d);
+    run<128, 64, 1>(d); run<128, 64, 4>(d);
+    run<128, 128, 1>(d); run<128, 128, 2>(d); run<128, 128, 4>(d);
+    run<128, 256, 1>(d); run<128, 256, 2>(d);
     return 0;
 }
