@@ -137,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == TC_PRODUCERS) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        {
             constexpr uint32_t ROWB = KC * 2;
             constexpr uint32_t DESC_HI = (uint32_t)(((uint64_t)((8 * ROWB) >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)(ROWB == 128 ? 2 : 4) << 61) >> 32);
             auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
@@ -154,11 +154,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle atom per K16 step
-                        umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(a_lo + a16 + 2 * k), p.idesc, (it | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (it == n_it - 1) umma_commit(&tfull_bar[acc]);
+                        for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle atom per K16 step
+                            umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(a_lo + a16 + 2 * k), p.idesc, (it | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (it == n_it - 1) umma_commit(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
                     a_lo += stage16;
                     if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
                 }

@@ -114,7 +114,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // The issuing thread is blocked ~45 cycles per tcgen05.mma (M128 x N<=64 x K16, measured with tools/mma_probe), and
         // every scalar instruction between two MMAs adds to that: so descriptors are assembled from precomputed 32-bit
         // halves and the 27 taps are fully unrolled (all offsets are immediates).
-        if (lane == 0) {
+        {
             constexpr uint32_t DESC_HI = (uint32_t)(((uint64_t)((8 * ROW) >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)(ROW == 128 ? 2 : 4) << 61) >> 32);
             auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
             const uint32_t slab_lo0 = ((smem_u32(slabs) & 0x3FFFF) >> 4) | 0x10000u;
@@ -144,6 +144,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t s1 = s0 == 2 ? 0 : s0 + 1, s2 = s1 == 2 ? 0 : s1 + 1;
                     const uint32_t lo_kd0 = slab_lo0 + s0 * SLAB16, lo_kd1 = slab_lo0 + s1 * SLAB16, lo_kd2 = slab_lo0 + s2 * SLAB16;
                     uint32_t b_lo = w_lo;
+                    if (elect_one()) {
 #pragma unroll
                     for (int t = 0; t < 27; ++t) {
                         constexpr uint32_t C16 = COPY_BYTES >> 4, A16 = (8 * ROW) >> 4;
@@ -156,6 +157,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     umma_commit(&tfull[acc]);
                     if (od == d1 - 1) { umma_commit(&sempty[s1]); umma_commit(&sempty[s2]); }
+                    }
+                    __syncwarp();
                     s0 = s1;
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }

@@ -154,8 +154,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
         }
     } else if (warp == WG_PRODUCERS + 1) {
-        if (lane == 0) {
-            // one thread, counters instead of divisions, descriptors from precomputed halves (see conv3d_tc_halo.cu)
+        {
+            // whole warp runs the control flow, one elected lane issues; counters instead of divisions, descriptors from precomputed halves (see conv3d_tc_halo.cu)
             const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
             const uint64_t a_hi = umma_desc_mnmajor(0, a_row, p.a_lbo, p.a_sbo) & 0xFFFFFFFFFFFF0000ull;   // everything but the address
             const uint64_t b_hi = umma_desc_mnmajor(0, b_row, p.b_lbo, p.b_sbo) & 0xFFFFFFFFFFFF0000ull;
@@ -171,12 +171,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 for (int g = 0; g < my_groups; ++g) {
                     mbar_wait(&fullA[as], aph);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
-                        umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + k * a_k16), b_hi | (uint64_t)(b_lo + k * b_k16), p.idesc,
-                                  (!first || k != 0) ? 1u : 0u);
-                    umma_commit(&emptyA[as]);
-                    if (g == my_groups - 1) umma_commit(&emptyB[bs]);
+                        for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
+                            umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + k * a_k16), b_hi | (uint64_t)(b_lo + k * b_k16), p.idesc,
+                                      (!first || k != 0) ? 1u : 0u);
+                        umma_commit(&emptyA[as]);
+                        if (g == my_groups - 1) umma_commit(&emptyB[bs]);
+                    }
+                    __syncwarp();
                     d_tmem += (uint32_t)p.co_blk;
                     a_lo += a_stage16;
                     if (++as == p.a_stages) { as = 0; aph ^= 1; a_lo = a_base; }
@@ -184,7 +187,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 first = false;
                 if (++bs == 2) { bs = 0; bph ^= 1; }
             }
-            umma_commit(&done_bar);
+            if (elect_one()) umma_commit(&done_bar);
         }
         __syncwarp();
     } else {
