@@ -371,7 +371,7 @@ int seghead_fwd(const T* y, const float* w, float* logits, int n, long long vox,
 static int seghead_slabs(int n, long long vox) {
     long long total = (long long)n * vox;
     long long s = 8LL * num_sms();
-    long long maxs = (total + 1023) / 1024;
+    long long maxs = (total + 63) / 64;
     if (s > maxs) s = maxs;
     if (s < 1) s = 1;
     return (int)s;
