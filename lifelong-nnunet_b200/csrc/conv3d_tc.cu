@@ -346,15 +346,20 @@ bool conv_tc_supported(int K, int Nout) {
 // PyTorch [Cout][Cin][27] fp32 -> Wk [27][Cout][Cin] bf16 (forward) and Wd [27 flipped][Cin][Cout] bf16 (stride-1 dgrad).
 // One block transposes a 32 (co) x 32 (ci) x 27 tile through shared memory: coalesced fp32 reads (runs of 32*27 floats),
 // 64-byte bf16 write runs in both output layouts.
+constexpr int WS_TCO = 16;   // output channels per block of the shadow transpose
 __global__ void __launch_bounds__(256) weight_shadow_bf16_kernel(const float* __restrict__ w, int Cout, int Cin,
                                                                  __nv_bfloat16* __restrict__ wk, __nv_bfloat16* __restrict__ wd) {
     extern __shared__ float tile_raw[];
     float (*tile)[32 * 27 + 1] = reinterpret_cast<float (*)[32 * 27 + 1]>(tile_raw);
-    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-    const int nci = Cin - ci0 < 32 ? Cin - ci0 : 32, nco = Cout - co0 < 32 ? Cout - co0 : 32;
-    for (int r = 0; r < nco; ++r) {
-        const float* src = w + ((long long)(co0 + r) * Cin + ci0) * 27;
-        for (int e = threadIdx.x; e < nci * 27; e += 256) tile[r][e] = src[e];
+    const int co0 = blockIdx.y * WS_TCO, ci0 = blockIdx.x * 32;
+    const int nci = Cin - ci0 < 32 ? Cin - ci0 : 32, nco = Cout - co0 < WS_TCO ? Cout - co0 : WS_TCO;
+    {   // all rows in one flat loop: many independent loads in flight per thread
+        const int row_elems = nci * 27, total = nco * row_elems;
+#pragma unroll 4
+        for (int e = threadIdx.x; e < total; e += 256) {
+            const int r = e / row_elems, c = e - r * row_elems;
+            tile[r][c] = w[((long long)(co0 + r) * Cin + ci0) * 27 + c];
+        }
     }
     __syncthreads();
     // wk[t][co][ci]: item = (t, co_local), 32 consecutive ci per item
@@ -363,17 +368,17 @@ __global__ void __launch_bounds__(256) weight_shadow_bf16_kernel(const float* __
             const int ci = e & 31, co = (e >> 5) % nco, t = (e >> 5) / nco;
             if (ci < nci) wk[((long long)t * Cout + co0 + co) * Cin + ci0 + ci] = __float2bfloat16_rn(tile[co][ci * 27 + t]);
         }
-    // wd[26 - t][ci][co]: item = (t, ci_local), 32 consecutive co per item
+    // wd[26 - t][ci][co]: item = (t, ci_local), WS_TCO consecutive co per item
     if (wd)
-        for (int e = threadIdx.x; e < 27 * nci * 32; e += 256) {
-            const int co = e & 31, ci = (e >> 5) % nci, t = (e >> 5) / nci;
+        for (int e = threadIdx.x; e < 27 * nci * WS_TCO; e += 256) {
+            const int co = e % WS_TCO, ci = (e / WS_TCO) % nci, t = (e / WS_TCO) / nci;
             if (co < nco) wd[((long long)(26 - t) * Cin + ci0 + ci) * Cout + co0 + co] = __float2bfloat16_rn(tile[co][ci * 27 + t]);
         }
 }
 
 int weight_shadow_bf16(const float* w, int cout, int cin, __nv_bfloat16* wk, __nv_bfloat16* wd, cudaStream_t st) {
-    dim3 grid(cdiv(cin, 32), cdiv(cout, 32));
-    const size_t sh = 32 * (32 * 27 + 1) * sizeof(float);
+    dim3 grid(cdiv(cin, 32), cdiv(cout, WS_TCO));
+    const size_t sh = WS_TCO * (32 * 27 + 1) * sizeof(float);
     static bool attr = false;
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(weight_shadow_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); attr = true; }
     B2_LAUNCH(weight_shadow_bf16_kernel, grid, 256, sh, st, w, cout, cin, wk, wd);
