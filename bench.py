@@ -203,6 +203,17 @@ def time_dominant_kernel(geom, precision, steps, warmup):
     return ms, flops
 
 
+def dominant_traffic(geom):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/dominant_kernel.json); null for workloads other than the profiled one."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+    if geom.name not in ("cfg2", "cfg5") or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"value": d["dram_bytes_read"] + d["dram_bytes_write"], "unit": "bytes/launch",
+            "algorithmic_bytes": d["algorithmic_bytes"], "source": d["source"]}
+
+
 def run_ours(args, geom):
     import torch.distributed as dist
     from b200unet import _lib, synth
@@ -291,7 +302,8 @@ def run_ours(args, geom):
             "roofline": {"bound": "tensor", "kernel": "conv3d 3x3x3 forward, %d->%d @ %dx%dx%d x B%d (conv_blocks_context.0.blocks.1)" %
                                   (geom.base_features, geom.base_features, geom.patch[0], geom.patch[1], geom.patch[2], geom.batch),
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "kernel_ms": kms, "traffic": None,
+                         "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "kernel_ms": kms,
+                         "traffic": dominant_traffic(geom),
                          "step_frac_of_sustained_peak": value / world * gflop_patch / 1e3 / peaks.get("bf16_tflops_sustained", peak_tf)}}
     if world == 1 and not args.no_cpu_baseline:
         ts = time_cpu(geom, geom.batch, 1, 1)
