@@ -210,6 +210,12 @@ size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d);
 /* z = conv3d(x, w, bias); stats[n][c] = {mean, rstd} of z over the spatial axes (for the InstanceNorm that follows) */
 int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* w_pt, const float* bias, void* z, float* stats,
                   float eps, void* scratch, b2_stream_t stream);
+/* prepared-weights forward (bf16 tensor-core path only): build the [27][Cout][Cin] bf16 weight shadow once with
+ * b2_conv3d_make_shadow, then b2_conv3d_fwd_shadow launches exactly one convolution kernel (no statistics). */
+size_t b2_conv3d_shadow_bytes(const b2_conv_desc* d);
+int b2_conv3d_make_shadow(const b2_conv_desc* d, const float* w_pt, void* shadow, b2_stream_t stream);
+int b2_conv3d_fwd_shadow(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
+                         b2_stream_t stream);
 /* dx (nullable) = conv_transpose3d(dz, w); dw, dbias = parameter gradients (PyTorch layouts, overwritten) */
 int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx, int accumulate_dx,
                   float* dw, float* dbias, void* scratch, b2_stream_t stream);

@@ -89,6 +89,9 @@ SIGNATURES = {
     "b2_online_eval": (_I, [_VP, _VP, _I, _I, _I64, _VP, _VP, _VP]),
     "b2_conv3d_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "b2_conv3d_fwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
+    "b2_conv3d_shadow_bytes": (_SZ, [C.POINTER(ConvDesc)]),
+    "b2_conv3d_make_shadow": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP]),
+    "b2_conv3d_fwd_shadow": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2_conv3d_bwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "b2_norm_scratch_bytes": (_SZ, [_I, _I64, _I]),
     "b2_norm_lrelu_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I64, _I, _I, _I, _I, _F, _VP]),

@@ -650,6 +650,27 @@ extern "C" int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* 
     return conv3d_fwd_simt<__nv_bfloat16>(s, (const __nv_bfloat16*)x, wf, bias, (__nv_bfloat16*)z, part, stats, eps, st);
 }
 
+// prepared-weights variant (bf16 tensor-core path): make the [27][Cout][Cin] bf16 shadow once, run the conv many times
+extern "C" size_t b2_conv3d_shadow_bytes(const b2_conv_desc* d) { return d ? align_up((size_t)27 * d->cin * d->cout * 2) : 0; }
+
+extern "C" int b2_conv3d_make_shadow(const b2_conv_desc* d, const float* w_pt, void* shadow, b2_stream_t stream) {
+    B2_CHECK_ARG(d && w_pt && shadow && d->dtype == B2_BF16);
+    return weight_shadow_bf16(w_pt, d->cout, d->cin, (__nv_bfloat16*)shadow, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b2_conv3d_fwd_shadow(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
+                                    b2_stream_t stream) {
+    B2_CHECK_ARG(d && x && shadow && z && d->dtype == B2_BF16);
+    ConvShape s = to_shape(d);
+    if (!conv_tc_supported(s.cin, s.cout) || s.in_pitch % 8 != 0 || s.out_pitch % 8 != 0)
+        return fail(B2_EUNSUPPORTED, "b2_conv3d_fwd_shadow: shape not covered by the tensor-core path%s", "");
+    const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
+    const size_t part_bytes = scratch ? b2_conv3d_scratch_bytes(d) - 2 * (size_t)27 * s.cin * s.cout * sizeof(float) - 256 : 0;
+    float* part = scratch ? (float*)scratch + 2 * (size_t)27 * s.cin * s.cout : nullptr;
+    return conv_tc_launch((const __nv_bfloat16*)x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, (const __nv_bfloat16*)shadow, s.cout, bias,
+                          (__nv_bfloat16*)z, od, oh, ow, s.out_pitch, s.stride, 0, (cudaStream_t)stream, part, part_bytes);
+}
+
 extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx,
                              int accumulate_dx, float* dw, float* dbias, void* scratch, b2_stream_t stream) {
     B2_CHECK_ARG(d && x && dz && w_pt && scratch);
