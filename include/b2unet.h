@@ -91,6 +91,24 @@ int b2_unet_forward(b2_unet_plan* plan, const float* const* params, const float*
 int b2_unet_backward(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
                      float* const* grads, int32_t* has_grad_host, b2_stream_t stream);
 
+/* Partial passes for Generic_ViT_UNet (generic_ViT_UNet.py:217-287): the host runs the encoder stages, hands the first
+ * skip to the ViT, writes the ViT result over the bottleneck activation (b2_unet_debug_view(2*num_pool+1, 1)) and
+ * runs the decoder.  `parts` is a mask of B2_PART_*.  Forward: B2_PART_ENCODER converts the input and runs stages
+ * 0..num_pool-1, B2_PART_BOTTLENECK the two bottleneck blocks (V1 discards their result, :230-253, so they may be
+ * skipped), B2_PART_DECODER everything from tu[0] on (logits required).  Backward: the B2_PART_DECODER call opens the
+ * pass (resets has_grad_host to 1, needs dlogits) and leaves d(bottleneck activation) in debug view (2*num_pool+1, 2);
+ * a later call with B2_PART_ENCODER but without B2_PART_BOTTLENECK zero-fills the bottleneck parameters' gradients and
+ * flags them has_grad = 0 (`param.grad is None`).  The host adds the ViT's input gradient into the first
+ * skip's gradient (debug view (1, 2)) between the two calls.  grads[] of parts not named are left untouched. */
+#define B2_PART_ENCODER 1
+#define B2_PART_BOTTLENECK 2
+#define B2_PART_DECODER 4
+#define B2_PART_ALL 7
+int b2_unet_forward_parts(b2_unet_plan* plan, const float* const* params, const float* input, void* workspace,
+                          float* const* logits, int parts, b2_stream_t stream);
+int b2_unet_backward_parts(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
+                           float* const* grads, int32_t* has_grad_host, int parts, b2_stream_t stream);
+
 /* Raw (pre-norm) output of conv module `conv_idx` kept by the last forward, as an NDHWC view into the workspace --
  * what the reference's forward hooks capture (plop:330-353: output.detach() of every conv.Conv* module).
  * conv_idx enumerates modules in named_modules() order of the reference tree; see b2_unet_num_convs/_conv_name. */
@@ -103,7 +121,7 @@ typedef struct b2_act_view {
 int b2_unet_num_convs(const b2_unet_plan* plan);
 int b2_unet_conv_name(const b2_unet_plan* plan, int conv_idx, char name[96]);
 int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx, b2_act_view* out);
-/* development aid: view of conv block `block_idx` (execution order of the 3x3x3 blocks): which = 0 raw output z,
+/* activation views (used by the ViT hand-over above and by the debug tools): view of conv block `block_idx` (execution order of the 3x3x3 blocks): which = 0 raw output z,
  * 1 activated output y, 2 gradient wrt y, 3 block input, 4 gradient wrt the block input */
 int b2_unet_debug_view(const b2_unet_plan* plan, void* workspace, int block_idx, int which, b2_act_view* out);
 

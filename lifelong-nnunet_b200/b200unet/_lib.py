@@ -67,6 +67,8 @@ SIGNATURES = {
     "b2_unet_output_shape": (_I, [_VP, _I, C.POINTER(C.c_int32 * 3)]),
     "b2_unet_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "b2_unet_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b2_unet_forward_parts": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "b2_unet_backward_parts": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "b2_unet_num_convs": (_I, [_VP]),
     "b2_unet_conv_name": (_I, [_VP, _I, C.c_char_p]),
     "b2_unet_conv_output": (_I, [_VP, _VP, _I, C.POINTER(ActView)]),

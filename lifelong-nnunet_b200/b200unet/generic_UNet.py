@@ -325,8 +325,15 @@ class Generic_UNet(nn.Module):
             with torch.no_grad():
                 outs = _UNetFunction.forward(_NullCtx(), self, plan, x, *params)
         self._last_plan = plan
-        # fire forward hooks of the conv modules with the raw conv outputs (reference plop:330-353)
-        # in execution order: encoder convs, then per decoder level tu.u, loc.u.0, loc.u.1, seg_outputs.u
+        self._fire_hooks(plan, outs)
+        outs = tuple(self.final_nonlin(o) for o in outs)
+        if self._deep_supervision and self.do_ds:
+            return outs
+        return outs[0]
+
+    def _fire_hooks(self, plan, outs):
+        """Fire forward hooks of the conv modules with the raw conv outputs (reference plop:330-353) in execution
+        order: encoder convs, then per decoder level tu.u, loc.u.0, loc.u.1, seg_outputs.u."""
         mods = self._conv_modules(plan)
         n_enc = 2 * (self.num_pool + 1)
         for i, m in enumerate(mods):
@@ -340,10 +347,6 @@ class Generic_UNet(nn.Module):
                 if sm._forward_hooks:
                     for hook in list(sm._forward_hooks.values()):
                         hook(sm, (None,), outs[self.num_pool - 1 - u])
-        outs = tuple(self.final_nonlin(o) for o in outs)
-        if self._deep_supervision and self.do_ds:
-            return outs
-        return outs[0]
 
 
 class _NullCtx:

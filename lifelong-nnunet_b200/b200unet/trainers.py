@@ -27,6 +27,7 @@ import torch
 
 from . import deep_supervision as ds
 from .generic_UNet import Generic_UNet
+from .generic_ViT_UNet import Generic_ViT_UNet
 from .optim import B2SGD, fisher_square, rw_update
 
 EPSILON = 1e-8  # reference rw/nnUNetTrainerRW.py module constant
@@ -70,8 +71,10 @@ class DataParallelGroup:
 
 class nnUNetTrainerMultiHead:
     def __init__(self, geometry, precision="bf16", batch_dice=False, device=None, ddp=None, initial_lr=1e-2,
-                 weight_decay=3e-5, max_num_epochs=1000, seed=0, task="task_A"):
+                 weight_decay=3e-5, max_num_epochs=1000, seed=0, task="task_A", use_vit=False, vit_version='V1',
+                 vit_type='base'):
         self.geometry = geometry
+        self.use_vit, self.vit_version, self.vit_type = use_vit, vit_version, vit_type   # run_training.py --use_vit
         self.precision = precision
         self.batch_dice = batch_dice
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -87,9 +90,14 @@ class nnUNetTrainerMultiHead:
     def initialize_network(self):
         g = self.geometry
         torch.manual_seed(self.seed)
-        self.network = Generic_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool,
-                                    pool_op_kernel_sizes=[list(k) for k in g.pool],
-                                    conv_kernel_sizes=[[3, 3, 3]] * (g.num_pool + 1), max_num_features=g.max_features)
+        kw = dict(pool_op_kernel_sizes=[list(k) for k in g.pool], conv_kernel_sizes=[[3, 3, 3]] * (g.num_pool + 1),
+                  max_num_features=g.max_features)
+        if self.use_vit:     # MultiHead:357 -> nnViTUNetTrainer.initialize_network (:117-125)
+            self.network = Generic_ViT_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool,
+                                            [int(s) for s in g.patch], vit_version=self.vit_version,
+                                            vit_type=self.vit_type, **kw)
+        else:
+            self.network = Generic_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool, **kw)
         self.network.precision = self.precision
         self.network.to(self.device)
         self.network.inference_apply_nonlin = lambda x: torch.softmax(x, 1)
@@ -129,10 +137,13 @@ class nnUNetTrainerMultiHead:
         plan = getattr(self.network, "_last_plan", None)
         flat = getattr(plan, "last_flat_grad", None)
         params = [p for p in self.network.parameters() if p.grad is not None]
-        if flat is not None and all(p.grad.data_ptr() >= flat.data_ptr() and
-                                    p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in params):
-            self.ddp.allreduce_mean_(flat)     # grads are views of the arena: one collective
-        else:
+        if flat is not None:
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            outside = [p for p in params if not (lo <= p.grad.data_ptr() < hi)]
+            if len(outside) < len(params):
+                self.ddp.allreduce_mean_(flat)     # U-Net grads are views of the plan's arena: one collective
+                params = outside                    # (ViT grads live in autograd-owned tensors: second bucket)
+        if params:
             buf = torch.cat([p.grad.reshape(-1) for p in params])
             self.ddp.allreduce_mean_(buf)
             o = 0

@@ -1,0 +1,158 @@
+"""``VisionTransformer`` -- host-side mirror of the reference's 3D ViT (reference
+nnunet_ext/network_architecture/vision_transformer.py:218-458) for the ``Generic_ViT_UNet`` V1 build: one 3D patch
+embedding, one head, no LSA / SPT / task-specific LayerNorms (those variants raise).
+
+Scope note: the ViT is ~17 % of cfg4's FLOPs and is plain library GEMM
+work; it runs on the GPU through ATen (cuBLAS GEMMs, fused SDPA attention), NOT through hand-written kernels.  The
+roofline claims of this repository cover the convolutional stack only.  The tensors handed over by the CUDA plan are
+consumed in place: the first skip arrives as a channels-last strided view of the plan's workspace and is patchified by
+one gather copy (the k = s = patch Conv3d of vision_transformer.py:50 is a GEMM over non-overlapping patches).
+
+state_dict keys / named_parameters() order are the reference's (cls_token, pos_embed_0, blocks.layer.N.{norm1,
+attn.{qkv,proj},norm2,mlp.{fc1,fc2}}, norm, patch_embeds.0.proj, heads.0) so checkpoints and name-keyed Fisher
+dictionaries (`'ViT'` / `'norm'` substring filters, ewc_ln/nnUNetTrainerEWCLN.py:49-50) keep working.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+VIT_TYPES = {'base': {'embed_size': 768, 'head': 12, 'layers': 12},
+             'large': {'embed_size': 1024, 'head': 16, 'layers': 24},
+             'huge': {'embed_size': 1280, 'head': 16, 'layers': 32}}   # generic_ViT_UNet.py:64-66
+
+
+class PatchEmbed(nn.Module):
+    """vision_transformer.py:16-79, 3D branch: cubic patches of edge `patch`, flattened in (d, h, w) raster order."""
+
+    def __init__(self, img_size, patch, in_chans, embed_dim):
+        super().__init__()
+        d, h, w = (int(s) for s in img_size)
+        self.img_size, self.patch_size = (d, h, w), (d, patch, patch)     # attribute quirk of :43-44 kept
+        self.patch = int(patch)
+        self.grid_size = (d // patch, h // patch, w // patch)
+        self.num_patches = (w // patch) * (h // patch) * (d // patch)     # :47
+        self.flatten, self.embed2D, self.task_specific_ln = True, False, False
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch, stride=patch)   # parameter container
+        self.norm = nn.Identity()
+
+    def forward(self, x, task_name=None):
+        B, Cc, D, H, W = x.shape
+        if H != self.img_size[1] or W != self.img_size[2]:
+            raise AssertionError("Input image size (%d,%d) doesn't match model (%d,%d)." % (H, W, self.img_size[1], self.img_size[2]))
+        p = self.patch
+        gd, gh, gw = D // p, H // p, W // p
+        if (gd * p, gh * p, gw * p) != (D, H, W):
+            x = x[:, :, :gd * p, :gh * p, :gw * p]                         # Conv3d floor semantics
+        tok = x.reshape(B, Cc, gd, p, gh, p, gw, p).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B, gd * gh * gw, Cc * p ** 3)
+        return F.linear(tok, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Attention(nn.Module):
+    """vision_transformer.py:136-150 (non-LSA branch).  The probabilities are only materialised when the owner asked
+    for them (``VisionTransformer.store_attn_weights``); otherwise the fused SDPA kernel is used."""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        self.LSA = False
+        self.store_weights = False
+
+    def forward(self, x):
+        B, N, Cc = x.shape
+        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, Cc // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        if self.store_weights:
+            w = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1)
+            o = w @ v
+        else:
+            w = None
+            o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
+        return self.proj(o.transpose(1, 2).reshape(B, N, Cc)), w
+
+
+class Block(nn.Module):
+    def __init__(self, dim, num_heads, eps):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
+        self.attn = Attention(dim, num_heads)
+        self.drop_path = nn.Identity()
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = Mlp(dim, 4 * dim)
+        self.task_specific_ln = False
+
+    def forward(self, x):
+        a, w = self.attn(self.norm1(x))
+        x = x + a
+        return x + self.mlp(self.norm2(x)), w
+
+
+class Encoder(nn.Module):
+    def __init__(self, depth, dim, num_heads, eps):
+        super().__init__()
+        self.layer = nn.ModuleList([Block(dim, num_heads, eps) for _ in range(depth)])
+
+    def forward(self, x):
+        ws = []
+        for blk in self.layer:
+            x, w = blk(x)
+            ws.append(w)
+        return x, ws
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, ViT_2d, img_size, patch_size, img_depth, in_chans, num_classes, embed_dim=768, depth=12,
+                 num_heads=12, mlp_ratio=4, qkv_bias=True, task_specific_ln=False, task_name=None, is_LSA=False,
+                 is_SPT=False, **ignored):
+        super().__init__()
+        if ViT_2d or task_specific_ln or is_LSA or is_SPT or mlp_ratio != 4 or not qkv_bias:
+            raise NotImplementedError("b200unet.VisionTransformer: only the 3D V1 build without LSA / SPT / task-specific "
+                                      "LayerNorms is implemented")
+        self.LSA, self.SPT, self.task_specific_ln = False, False, False
+        self.block_depth, self.embed_dim, self.num_features = depth, embed_dim, embed_dim
+        self.num_tokens, self.num_classes = 1, int(num_classes)
+        self.attn_weights = None
+        self.store_attn_weights = False
+        eps = 1e-6
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        pe = PatchEmbed((img_depth[0], img_size[1], img_size[2]) if len(img_size) == 3 else (img_depth[0],) + tuple(img_size),
+                        patch_size[0], in_chans, embed_dim)
+        self.pos_embed_0 = nn.Parameter(torch.zeros(1, pe.num_patches + 1, embed_dim))
+        self.pos_drop = nn.Identity()
+        self.blocks = Encoder(depth, embed_dim, num_heads, eps)
+        self.norm = nn.LayerNorm(embed_dim, eps=eps)
+        self.pre_logits = nn.Identity()
+        self.patch_embeds = nn.ModuleList([pe])
+        self.heads = nn.ModuleList([nn.Linear(embed_dim, self.num_classes)])
+        self.head_dists = None
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        nn.init.trunc_normal_(self.heads[0].weight, std=.02)
+        nn.init.zeros_(self.heads[0].bias)
+
+    def register_new_task(self, task_name):
+        raise NotImplementedError("task-specific LayerNorms (vision_transformer.py:380-416) are not built yet")
+
+    def use_task(self, task_name):
+        raise NotImplementedError("task-specific LayerNorms (vision_transformer.py:380-416) are not built yet")
+
+    def forward(self, x, idx=0, task_name=None):   # :418-458
+        for blk in self.blocks.layer:
+            blk.attn.store_weights = self.store_attn_weights
+        x = self.patch_embeds[idx](x, task_name)
+        cls = self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype)
+        x = torch.cat((cls, x), dim=1) + getattr(self, 'pos_embed_' + str(idx)).to(x.dtype)
+        x, ws = self.blocks(x)
+        self.attn_weights = ws if self.store_attn_weights else None
+        return self.heads[idx](self.pre_logits(self.norm(x)[:, 0]))

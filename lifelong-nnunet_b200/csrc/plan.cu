@@ -295,10 +295,11 @@ static int build_plan(b2_unet_plan* p) {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 static int forward_t(b2_unet_plan* p, const float* const* prm, const float* input, void* ws, float* const* logits,
-                     cudaStream_t st) {
+                     int parts, cudaStream_t st) {
     const b2_unet_geometry& g = p->g;
     int rc;
-    if ((rc = nchw_to_ndhwc<T>(input, P<T>(ws, p, p->x_in, false), g.batch, g.in_channels, p->x_in.vox(), p->x_in.pitch, st))) return rc;
+    if (parts & B2_PART_ENCODER)
+        if ((rc = nchw_to_ndhwc<T>(input, P<T>(ws, p, p->x_in, false), g.batch, g.in_channels, p->x_in.vox(), p->x_in.pitch, st))) return rc;
     size_t ci = 0, ti = 0;
     auto run_conv = [&](ConvBlock& cb) -> int {
         float* wf = F32(ws, p, cb.wf_off);
@@ -356,9 +357,12 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                                  cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, g.lrelu_slope, st);
     };
     for (int d = 0; d <= g.num_pool; ++d) {
+        const bool on = d < g.num_pool ? (parts & B2_PART_ENCODER) != 0 : (parts & B2_PART_BOTTLENECK) != 0;
+        if (!on) { ci += 2; continue; }
         if ((rc = run_conv(p->convs[ci++]))) return rc;
         if ((rc = run_conv(p->convs[ci++]))) return rc;
     }
+    if (!(parts & B2_PART_DECODER)) return B2_OK;
     for (int u = 0; u < g.num_pool; ++u) {
         Tconv& t = p->tconvs[ti++];
         float* wq = F32(ws, p, t.wq_off);
@@ -389,11 +393,12 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
 
 template <typename T>
 static int backward_t(b2_unet_plan* p, const float* const* prm, const float* const* dlogits, void* ws,
-                      float* const* grads, int32_t* has_grad, cudaStream_t st) {
+                      float* const* grads, int32_t* has_grad, int parts, cudaStream_t st) {
     const b2_unet_geometry& g = p->g;
     const int P_ = g.num_pool;
     int rc;
-    for (size_t i = 0; i < p->params.size(); ++i) if (has_grad) has_grad[i] = 1;
+    if (parts & B2_PART_DECODER)     // the decoder call opens a backward pass: every flag starts at 1
+        for (size_t i = 0; i < p->params.size(); ++i) if (has_grad) has_grad[i] = 1;
     T* dz = reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off;
     auto conv_bwd = [&](ConvBlock& cb) -> int {
         float* stats = F32(ws, p, cb.stats_off);
@@ -449,7 +454,7 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         return B2_OK;
     };
     // decoder, from full resolution (u = P-1) down to u = 0
-    for (int u = P_ - 1; u >= 0; --u) {
+    for (int u = (parts & B2_PART_DECODER) ? P_ - 1 : -1; u >= 0; --u) {
         Head& h = p->heads[u];
         const float* dl = dlogits[h.level];
         const bool first_writer = (u == P_ - 1);
@@ -487,6 +492,20 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                                    tdg ? (T*)nullptr : P<T>(ws, p, t.din, true), twg ? (float*)nullptr : grads[t.p_w], SCR(ws, p), st))) return rc;
     }
     for (int d = P_; d >= 0; --d) {
+        const bool on = d < P_ ? (parts & B2_PART_ENCODER) != 0 : (parts & B2_PART_BOTTLENECK) != 0;
+        if (!on) {
+            // bottleneck bypassed (Generic_ViT_UNet V1 discards its output, generic_ViT_UNet.py:230-253): its parameters
+            // receive no gradient (`param.grad is None`)
+            if (d == P_ && (parts & B2_PART_ENCODER))
+                for (int k = 0; k < 2; ++k) {
+                    ConvBlock& cb = p->convs[2 * d + k];
+                    for (int pi : {cb.p_w, cb.p_b, cb.p_g, cb.p_be}) {
+                        B2_CUDA(cudaMemsetAsync(grads[pi], 0, p->params[pi].numel * sizeof(float), st));
+                        if (has_grad) has_grad[pi] = 0;
+                    }
+                }
+            continue;
+        }
         if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;
         if ((rc = conv_bwd(p->convs[2 * d]))) return rc;
     }
@@ -555,16 +574,36 @@ extern "C" int b2_unet_forward(b2_unet_plan* plan, const float* const* params, c
     B2_CHECK_ARG(plan && params && input && workspace && logits);
     (void)keep_for_backward;
     cudaStream_t st = (cudaStream_t)stream;
-    if (plan->g.act_dtype == B2_F32) return forward_t<float>(plan, params, input, workspace, logits, st);
-    return forward_t<__nv_bfloat16>(plan, params, input, workspace, logits, st);
+    if (plan->g.act_dtype == B2_F32) return forward_t<float>(plan, params, input, workspace, logits, B2_PART_ALL, st);
+    return forward_t<__nv_bfloat16>(plan, params, input, workspace, logits, B2_PART_ALL, st);
+}
+
+extern "C" int b2_unet_forward_parts(b2_unet_plan* plan, const float* const* params, const float* input, void* workspace,
+                                     float* const* logits, int parts, b2_stream_t stream) {
+    B2_CHECK_ARG(plan && params && workspace && parts > 0 && parts <= B2_PART_ALL);
+    B2_CHECK_ARG(!(parts & B2_PART_ENCODER) || input);
+    B2_CHECK_ARG(!(parts & B2_PART_DECODER) || logits);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->g.act_dtype == B2_F32) return forward_t<float>(plan, params, input, workspace, logits, parts, st);
+    return forward_t<__nv_bfloat16>(plan, params, input, workspace, logits, parts, st);
 }
 
 extern "C" int b2_unet_backward(b2_unet_plan* plan, const float* const* params, const float* const* dlogits,
                                 void* workspace, float* const* grads, int32_t* has_grad_host, b2_stream_t stream) {
     B2_CHECK_ARG(plan && params && dlogits && workspace && grads);
     cudaStream_t st = (cudaStream_t)stream;
-    if (plan->g.act_dtype == B2_F32) return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, st);
-    return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, st);
+    if (plan->g.act_dtype == B2_F32) return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, B2_PART_ALL, st);
+    return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, B2_PART_ALL, st);
+}
+
+extern "C" int b2_unet_backward_parts(b2_unet_plan* plan, const float* const* params, const float* const* dlogits,
+                                      void* workspace, float* const* grads, int32_t* has_grad_host, int parts,
+                                      b2_stream_t stream) {
+    B2_CHECK_ARG(plan && params && workspace && grads && parts > 0 && parts <= B2_PART_ALL);
+    B2_CHECK_ARG(!(parts & B2_PART_DECODER) || dlogits);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->g.act_dtype == B2_F32) return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, parts, st);
+    return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, parts, st);
 }
 
 extern "C" int b2_unet_num_convs(const b2_unet_plan* plan) { return plan ? (int)plan->conv_modules.size() : B2_EINVAL; }

@@ -8,6 +8,9 @@ Fixtures:
   tests/golden/cl_losses.npz  -- EWC / RW / LwF / MiB / POD / PLOP-pseudo-label values (+ selected gradients) from
                                  reference nnunet_ext/training/loss_functions/{deep_supervision,embeddings,
                                  knowledge_distillation,crossentropy}.py
+  tests/golden/vit_unet_tiny.npz -- logits / gradient norms of the REFERENCE's own Generic_ViT_UNet (V1, ViT-base;
+                                 generic_ViT_UNet.py + vision_transformer.py, unmodified, on the nnunet/timm shims)
+                                 for the "tiny" geometry with oracle.vit_unet.fill_parameters(seed 3) weights
   tests/golden/unet_tiny.npz  -- logits / loss / gradient norms of the oracle network on the "tiny" geometry
                                  (nnunet boundary: parity unpinned by the reference, see oracle/__init__.py)
 """
@@ -128,6 +131,44 @@ def unet_tiny_values():
     return res
 
 
+VIT_SEED = 3
+
+
+def vit_case():
+    """Seeded input / upstream gradient shared by the generator and the tests."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 1, 16, 32, 32, generator=g)
+    up = [torch.randn(2, 3, 16, 32, 32, generator=g), torch.randn(2, 3, 8, 16, 16, generator=g)]
+    return x, up
+
+
+def vit_values(net):
+    """logits + gradient norms of `net` (reference class or oracle restatement) on vit_case()."""
+    x, up = vit_case()
+    out = net(x)
+    l = sum((o * u).sum() for o, u in zip(out, up)) / 1000.0
+    l.backward()
+    res = {"scalar": float(l.detach()), "logits_last": out[-1].detach().numpy().copy(),
+           "logits0_slice": out[0][:, :, ::4, ::8, ::8].detach().numpy().copy()}
+    for n, p in net.named_parameters():
+        res["gnorm/" + n] = float(p.grad.norm()) if p.grad is not None else -1.0
+    res["grad_cls_token"] = net.ViT.cls_token.grad.numpy().copy()
+    return res
+
+
+def reference_vit_unet():
+    """The reference's own class, built as nnViTUNetTrainer.py:117-125 does, on the tiny geometry."""
+    from torch import nn
+    from nnunet.network_architecture.initialization import InitWeights_He
+    from nnunet_ext.network_architecture.generic_ViT_UNet import Generic_ViT_UNet
+    from oracle import vit_unet
+    net = Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], 2, 2, nn.Conv3d, nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True},
+                           nn.Dropout3d, {'p': 0, 'inplace': True}, nn.LeakyReLU, {'negative_slope': 1e-2, 'inplace': True},
+                           True, False, lambda x: x, InitWeights_He(1e-2), [[2, 2, 2], [2, 2, 2]], [[3, 3, 3]] * 3,
+                           False, True, True, vit_version='V1', vit_type='base')
+    return vit_unet.fill_parameters(net, VIT_SEED)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "the reference is only mounted in the build container"
     torch.set_num_threads(4)
@@ -136,6 +177,7 @@ if __name__ == "__main__":
     vals = reference_values(seeded_case())
     np.savez_compressed(os.path.join(gold, "cl_losses.npz"), **vals)
     np.savez_compressed(os.path.join(gold, "unet_tiny.npz"), **unet_tiny_values())
+    np.savez_compressed(os.path.join(gold, "vit_unet_tiny.npz"), **vit_values(reference_vit_unet()))
     for k, v in vals.items():
         if np.ndim(v) == 0:
             print("%-18s %.8f" % (k, v))

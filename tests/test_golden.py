@@ -112,3 +112,15 @@ def test_ds_weights_and_hard_dice():
     lg[:, 1] = 1.0
     tg = torch.ones(1, 1, 2, 2, 2)
     assert abs(cl_losses.hard_dice(lg, tg) - 0.5) < 1e-6      # class 1 perfect, class 2 absent -> (1 + 0)/2
+
+
+def test_vit_unet_oracle_against_reference_fixture():
+    """oracle/vit_unet.py (the checker that travels to the GPU box) reproduces the values the reference's own
+    Generic_ViT_UNet gave in the build container (tests/golden/vit_unet_tiny.npz)."""
+    from oracle import gen_golden, vit_unet
+    gold = np.load(os.path.join(GOLD, "vit_unet_tiny.npz"))
+    net = vit_unet.fill_parameters(vit_unet.Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], [[2, 2, 2], [2, 2, 2]]), gen_golden.VIT_SEED)
+    vals = gen_golden.vit_values(net)
+    assert set(gold.files) == set(vals)
+    for k in gold.files:
+        np.testing.assert_allclose(gold[k], vals[k], rtol=2e-5, atol=2e-6, err_msg=k)

@@ -41,3 +41,27 @@ def test_reference_own_structural_test_passes_on_the_shim():
                         os.path.join(REF, "test", "network_architecture", "test_MultiHead_Module.py")],
                        env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_vit_unet_restatement_equals_reference_class():
+    """oracle/vit_unet.py == the reference's generic_ViT_UNet.py + vision_transformer.py (unmodified, on the nnunet /
+    timm shims): same state_dict keys and parameter order, identical logits and gradients, and the committed fixture
+    is what the reference produces today."""
+    for p in (os.path.join(util.ROOT, "oracle", "shim"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from oracle import gen_golden, vit_unet
+    ref = gen_golden.reference_vit_unet()
+    mine = vit_unet.Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], [[2, 2, 2], [2, 2, 2]])
+    assert [(n, tuple(q.shape)) for n, q in ref.named_parameters()] == [(n, tuple(q.shape)) for n, q in mine.named_parameters()]
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict())
+    a, b = gen_golden.vit_values(ref), gen_golden.vit_values(mine)
+    assert set(a) == set(b)
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-7, err_msg=k)
+    assert a["gnorm/conv_blocks_context.2.0.blocks.0.conv.weight"] == -1.0     # Q14: bottleneck gets no gradient
+    gold = np.load(os.path.join(util.ROOT, "tests", "golden", "vit_unet_tiny.npz"))
+    assert set(gold.files) == set(a)
+    for k in gold.files:
+        np.testing.assert_allclose(gold[k], a[k], rtol=1e-5, atol=1e-6, err_msg=k)
