@@ -187,27 +187,25 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(GatherGeom g, const
     }
 }
 
-// mean / rstd from per-tile partial sums; one block per (n, 32 channels); fixed summation order, double accumulation.
+// mean / rstd from per-tile partial sums.  grid = (n, ceil(C / 8)); one WARP per channel: lanes stride the tiles with
+// independent loads in flight, double accumulation, fixed xor-shuffle tree => bit-reproducible.
 __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ part, int tiles, int C,
                                                              double inv_count, float eps, float* __restrict__ stats) {
-    __shared__ double sh[8][32][2];
-    const int n = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+    const int n = blockIdx.x, c = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= C) return;
+    const float* p = part + ((long long)n * tiles * C + c) * 2;
     double s1 = 0.0, s2 = 0.0;
-    if (c < C) {
-        const float* p = part + ((long long)n * tiles) * C * 2;
-        for (int t = lane; t < tiles; t += 8) {
-            s1 += (double)p[((long long)t * C + c) * 2];
-            s2 += (double)p[((long long)t * C + c) * 2 + 1];
-        }
+#pragma unroll 4
+    for (int t = lane; t < tiles; t += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(p + (long long)t * C * 2);
+        s1 += (double)v.x;
+        s2 += (double)v.y;
     }
-    sh[lane][threadIdx.x & 31][0] = s1;
-    sh[lane][threadIdx.x & 31][1] = s2;
-    __syncthreads();
-    if (lane == 0 && c < C) {
-        double a = 0.0, b = 0.0;
-        for (int l = 0; l < 8; ++l) { a += sh[l][threadIdx.x][0]; b += sh[l][threadIdx.x][1]; }
-        double mean = a * inv_count;
-        double var = b * inv_count - mean * mean;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        double mean = s1 * inv_count;
+        double var = s2 * inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
         stats[((long long)n * C + c) * 2] = (float)mean;
         stats[((long long)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(256) stats_reduce_kernel(const T* __restrict__
 
 static int stats_slabs(int n, long long vox) {
     long long want = (4LL * num_sms() + n - 1) / n;
-    long long maxs = (vox + 255) / 256;
+    long long maxs = (vox + 63) / 64;   // small volumes: still several blocks (a single block is latency-bound)
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     return (int)want;
@@ -410,7 +408,7 @@ int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* pa
     dim3 grid(slabs, n);
     if (v8) B2_LAUNCH((stats_reduce_kernel<T, 8>), grid, 256, sh, st, z, slabs, vox, c, pitch, part);
     else B2_LAUNCH((stats_reduce_kernel<T, 1>), grid, 256, sh, st, z, slabs, vox, c, pitch, part);
-    dim3 g2(n, cdiv(c, 32));
+    dim3 g2(n, cdiv(c, 8));
     B2_LAUNCH(stats_finalize_kernel, g2, 256, 0, st, part, slabs, c, 1.0 / (double)vox, eps, stats);
     return B2_OK;
 }
@@ -524,7 +522,7 @@ int conv3d_fwd_simt(const ConvShape& s, const T* x, const float* wf, const float
     int rc = launch_gemm<T, 0>(g, x, wf, bias, z, 0, stats ? stat_part : nullptr, st);
     if (rc) return rc;
     if (stats) {
-        dim3 grid(s.n, cdiv(s.cout, 32));
+        dim3 grid(s.n, cdiv(s.cout, 8));
         B2_LAUNCH(stats_finalize_kernel, grid, 256, 0, st, stat_part, g.tiles_per_sample, s.cout, 1.0 / (double)Vd, eps, stats);
     }
     return B2_OK;
@@ -623,7 +621,60 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
     return B2_OK;
 }
 
+// Tiled ordered reduction for the tensor-core wgrad partials.  A block of 32 (co) x 8 (k lanes) threads owns one ci, 32
+// consecutive co and up to NT consecutive taps: every load is a coalesced 128-byte row of part[k][t][ci][co0..co0+31], the
+// tap loop is fully unrolled so a thread keeps NT (x4 over k) independent loads in flight; the 8 k-lanes are combined in a
+// fixed order through shared memory, and the result is written as runs of consecutive taps of dw_pt[co][ci][t].
+// (A thread-per-output kernel walks the partials serially and writes 4-byte elements with a 108-byte stride.)
+template <int NT>
+__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ part, int nsplit, int Cin, int Cout,
+                                                                 float* __restrict__ dw) {
+    __shared__ float sh[8][NT][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int cob = Cout >> 5;
+    const int ci = blockIdx.x / cob, co0 = (blockIdx.x % cob) << 5;
+    const int t0 = blockIdx.y * NT;
+    const long long tot = 27LL * Cin * Cout;
+    const float* src = part + ((long long)t0 * Cin + ci) * Cout + co0 + tx;
+    const long long tstride = (long long)Cin * Cout;
+    float acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+#pragma unroll 4
+    for (int k = ty; k < nsplit; k += 8) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if (t0 + t < 27) acc[t] += __ldcs(src + (long long)k * tot + t * tstride);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) sh[ty][t][tx] = acc[t];
+    __syncthreads();
+    const int nt = 27 - t0 < NT ? 27 - t0 : NT;
+    for (int i = threadIdx.x; i < 32 * nt; i += 256) {
+        const int col = i / nt, t = i - col * nt;
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += sh[q][t][col];
+        dw[((long long)(co0 + col) * Cin + ci) * 27 + t0 + t] = v;
+    }
+}
+
 int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, int cout, float* dw, float* db, cudaStream_t st) {
+    if (!db && cout % 32 == 0) {
+        const int xb = cin * (cout / 32);
+        // few (ci, co-block) pairs (thin layers, hundreds of partials): split the taps over grid.y for parallelism
+        if (xb * 3 >= 2 * num_sms()) {
+            dim3 grid(xb, 1);
+            B2_LAUNCH(wgrad_reduce_tiled_kernel<27>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+        } else if (xb * 9 >= 2 * num_sms()) {
+            dim3 grid(xb, 3);
+            B2_LAUNCH(wgrad_reduce_tiled_kernel<9>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+        } else {
+            dim3 grid(xb, 9);
+            B2_LAUNCH(wgrad_reduce_tiled_kernel<3>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+        }
+        return B2_OK;
+    }
     long long tot = 27LL * cin * cout + (db ? cout : 0);
     B2_LAUNCH(wgrad_reduce_kernel, cdiv(tot, 256), 256, 0, st, part_w, part_b, nsplit, cin, cout, dw, db);
     return B2_OK;

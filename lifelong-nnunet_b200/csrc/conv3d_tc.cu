@@ -65,7 +65,44 @@ struct TcConvParams {
     uint32_t tmem_cols;
     signed char tap_off[27][3];  // source offset (d, h, w) per tap, padding included
     unsigned char tap_w[27];     // weight row-block of the tap
+    // tile classes (strided dgrad: one class per output-parity lattice, all in ONE launch).  nclass <= 1: a single class
+    // described by the fields above.  Class c owns the tiles [cls_tile0[c], cls_tile0[c+1]), the taps
+    // [cls_tap0[c], +cls_ntaps[c]) of the tables above, its own lattice offset and logical extent.
+    int nclass;
+    int cls_tile0[9];
+    unsigned char cls_tap0[8], cls_ntaps[8];
+    signed char cls_oo[8][3];
+    short cls_L[8][3], cls_nt[8][3];
 };
+
+struct TileInfo {
+    int ks, nb, tw, th, td, tn, otile;
+    int tap0, ntaps;
+    int oo_d, oo_h, oo_w, LD, LH, LW;
+};
+
+__device__ __forceinline__ void decode_tile(const TcConvParams& p, int tile, TileInfo& ti) {
+    int t = tile, nt_w = p.nt_w, nt_h = p.nt_h, nt_d = p.nt_d;
+    ti.tap0 = 0; ti.ntaps = p.ntaps;
+    ti.oo_d = p.oo_d; ti.oo_h = p.oo_h; ti.oo_w = p.oo_w;
+    ti.LD = p.LD; ti.LH = p.LH; ti.LW = p.LW;
+    if (p.nclass > 1) {
+        int c = 0;
+        while (c + 1 < p.nclass && tile >= p.cls_tile0[c + 1]) ++c;
+        t = tile - p.cls_tile0[c];
+        ti.tap0 = p.cls_tap0[c]; ti.ntaps = p.cls_ntaps[c];
+        ti.oo_d = p.cls_oo[c][0]; ti.oo_h = p.cls_oo[c][1]; ti.oo_w = p.cls_oo[c][2];
+        ti.LD = p.cls_L[c][0]; ti.LH = p.cls_L[c][1]; ti.LW = p.cls_L[c][2];
+        nt_d = p.cls_nt[c][0]; nt_h = p.cls_nt[c][1]; nt_w = p.cls_nt[c][2];
+    }
+    ti.ks = t % p.ksplit; t /= p.ksplit;
+    ti.otile = t;
+    ti.nb = t % p.nblk; t /= p.nblk;
+    ti.tw = t % nt_w; t /= nt_w;
+    ti.th = t % nt_h; t /= nt_h;
+    ti.td = t % nt_d; t /= nt_d;
+    ti.tn = t;
+}
 
 constexpr int TC_PRODUCERS = 4;                       // TMA producer warps (one stage each, round robin): the single-thread
                                                       // issue latency (~300 cycles per stage) was the bottleneck of round-1 v1
@@ -99,8 +136,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int kiters = p.ntaps * p.kchunks;
-
     if (warp < TC_PRODUCERS) {
         // (warps >= p.nprod idle)
         // ===================== TMA producers: warp w issues the pipeline iterations with git % TC_PRODUCERS == w =====================
@@ -109,16 +144,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int gmod = 0, stage = warp;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int ks = t % p.ksplit; t /= p.ksplit;
-                const int nb = t % p.nblk; t /= p.nblk;
-                const int tw = t % p.nt_w; t /= p.nt_w;
-                const int th = t % p.nt_h; t /= p.nt_h;
-                const int td = t % p.nt_d; t /= p.nt_d;
-                const int tn = t;
-                const int w0 = tw * p.TW * p.sw, h0 = th * p.TH * p.sh, d0 = td * p.TD * p.sd, n0 = tn * p.TN;
-                const int it0 = (int)((long long)kiters * ks / p.ksplit), it1 = (int)((long long)kiters * (ks + 1) / p.ksplit);
-                int tap = it0 / p.kchunks, kc = it0 % p.kchunks;
+                TileInfo ti;
+                decode_tile(p, tile, ti);
+                const int nb = ti.nb;
+                const int w0 = ti.tw * p.TW * p.sw, h0 = ti.th * p.TH * p.sh, d0 = ti.td * p.TD * p.sd, n0 = ti.tn * p.TN;
+                const int kiters = ti.ntaps * p.kchunks;
+                const int it0 = (int)((long long)kiters * ti.ks / p.ksplit), it1 = (int)((long long)kiters * (ti.ks + 1) / p.ksplit);
+                int tap = ti.tap0 + it0 / p.kchunks, kc = it0 % p.kchunks;
                 for (int it = it0; it < it1; ++it) {
                     if (gmod == warp) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -149,8 +181,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                const int ks = tile % p.ksplit;
-                const int n_it = (int)((long long)kiters * (ks + 1) / p.ksplit) - (int)((long long)kiters * ks / p.ksplit);
+                TileInfo ti;
+                decode_tile(p, tile, ti);
+                const int kiters = ti.ntaps * p.kchunks;
+                const int n_it = (int)((long long)kiters * (ti.ks + 1) / p.ksplit) - (int)((long long)kiters * ti.ks / p.ksplit);
                 for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -177,23 +211,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            int t = tile;
-            const int ks = t % p.ksplit; t /= p.ksplit;
-            const int otile = t;        // output tile (incl. column block)
-            const int nb = t % p.nblk; t /= p.nblk;
-            const int tw = t % p.nt_w; t /= p.nt_w;
-            const int th = t % p.nt_h; t /= p.nt_h;
-            const int td = t % p.nt_d; t /= p.nt_d;
-            const int tn = t;
-            const int lw = tw * p.TW + w_, lh = th * p.TH + h_, ld = td * p.TD + d_, on = tn * p.TN + n_;
-            int ow = lw * p.os_w + p.oo_w, oh = lh * p.os_h + p.oo_h, od = ld * p.os_d + p.oo_d;
+            TileInfo ti;
+            decode_tile(p, tile, ti);
+            const int ks = ti.ks, otile = ti.otile, nb = ti.nb;
+            const int lw = ti.tw * p.TW + w_, lh = ti.th * p.TH + h_, ld = ti.td * p.TD + d_, on = ti.tn * p.TN + n_;
+            int ow = lw * p.os_w + ti.oo_w, oh = lh * p.os_h + ti.oo_h, od = ld * p.os_d + ti.oo_d;
             int chan0 = nb * p.BN;
             if (p.q_scatter) {
                 const int q = nb / p.nblk_per_q;
                 ow += q % p.qk_w; oh += (q / p.qk_w) % p.qk_h; od += q / (p.qk_w * p.qk_h);
                 chan0 = (nb % p.nblk_per_q) * p.BN;
             }
-            const bool valid = lw < p.LW && lh < p.LH && ld < p.LD && on < p.N && ow < p.W && oh < p.H && od < p.D;
+            const bool valid = lw < ti.LW && lh < ti.LH && ld < ti.LD && on < p.N && ow < p.W && oh < p.H && od < p.D;
             __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -344,8 +373,7 @@ bool conv_tc_supported(int K, int Nout) {
 }
 
 // PyTorch [Cout][Cin][27] fp32 -> Wk [27][Cout][Cin] bf16 (forward) and Wd [27 flipped][Cin][Cout] bf16 (stride-1 dgrad).
-// (A shared-memory tiled transpose was measured SLOWER than this plain scatter on B200 -- the weights are L2-resident and
-// the launch is latency-bound: 0.84 ms vs 0.54 ms per step over the 22 layers of cfg2.)
+// Plain scatter: used only for shapes the tiled multi-tensor kernel below does not cover (channel counts % 32 != 0).
 __global__ void weight_shadow_bf16_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wk,
                                           __nv_bfloat16* __restrict__ wd) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +387,104 @@ __global__ void weight_shadow_bf16_kernel(const float* __restrict__ w, int Cout,
     if (wd) wd[((long long)(26 - t) * Cin + ci) * Cout + co] = v;
 }
 
+// Multi-tensor tiled shadow kernel: ONE launch converts every weight tensor of a forward pass.  A job is a 3-D fp32 tensor
+// w[A][B][T] (conv: A = Cout, B = Cin, T = 27; transposed conv: A = Cin, B = Cout, T = kd*kh*kw) and up to two bf16 outputs
+//     oab[t][A][B]            (conv: forward shadow Wk;            tconv: dgrad shadow wqd)
+//     oba[flip ? T-1-t : t][B][A]   (conv: flipped dgrad shadow Wd, flip = 1;  tconv: forward shadow wq)
+// A CTA owns a 32 (A) x 32 (B) x T tile: coalesced fp32 reads (32 rows of 32*T contiguous floats), bf16 staging in shared
+// memory (odd word strides: conflict-free for both read patterns), 16-byte stores of 64-byte row segments on both outputs.
+// The per-layer scatter kernels this replaces ran at ~0.5 TB/s (2-byte stores with a 27-element stride): 0.57 ms per step.
+constexpr int SH_ROW = 34;                          // bf16 elements per (t, a) row: 17 words
+constexpr int SH_TSTRIDE = 32 * SH_ROW + 2;         // 545 words: odd, so consecutive taps hit consecutive banks
+constexpr int SH_MAXT = 27;
+constexpr int SHADOW_MAX_JOBS = 40;
+struct ShadowJobsDev {
+    const float* w[SHADOW_MAX_JOBS];
+    __nv_bfloat16* oab[SHADOW_MAX_JOBS];
+    __nv_bfloat16* oba[SHADOW_MAX_JOBS];
+    int A[SHADOW_MAX_JOBS], B[SHADOW_MAX_JOBS];
+    int tile0[SHADOW_MAX_JOBS + 1];                  // first tile of each job (prefix sum)
+    unsigned char T[SHADOW_MAX_JOBS], flip[SHADOW_MAX_JOBS];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) shadow_multi_kernel(const __grid_constant__ ShadowJobsDev jobs) {
+    extern __shared__ __align__(16) __nv_bfloat16 sh_w[];   // [T][32 a][SH_ROW] with tap stride SH_TSTRIDE
+    int j = 0;
+    while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.tile0[j + 1]) ++j;
+    const int tile = (int)blockIdx.x - jobs.tile0[j];
+    const int A = jobs.A[j], B = jobs.B[j], T = jobs.T[j];
+    const int tb = B >> 5;
+    const int a0 = (tile / tb) << 5, b0 = (tile % tb) << 5;
+    const float* __restrict__ w = jobs.w[j];
+    const int rowlen = 32 * T;
+    // load: 32 rows (a) of 32*T contiguous floats
+    for (int a = 0; a < 32; ++a) {
+        const float* src = w + ((long long)(a0 + a) * B + b0) * T;
+        for (int r = threadIdx.x; r < rowlen; r += 256) {
+            const int b = r / T, t = r - b * T;
+            sh_w[t * SH_TSTRIDE + a * SH_ROW + b] = __float2bfloat16_rn(src[r]);
+        }
+    }
+    __syncthreads();
+    const int chunks = T * 128;                      // (t, row, 8-element chunk)
+    __nv_bfloat16* __restrict__ oab = jobs.oab[j];
+    __nv_bfloat16* __restrict__ oba = jobs.oba[j];
+    if (oab) {
+        for (int i = threadIdx.x; i < chunks; i += 256) {
+            const int q = i & 3, a = (i >> 2) & 31, t = i >> 7;
+            const uint32_t* s = reinterpret_cast<const uint32_t*>(sh_w + t * SH_TSTRIDE + a * SH_ROW + q * 8);
+            uint4 v = make_uint4(s[0], s[1], s[2], s[3]);
+            *reinterpret_cast<uint4*>(oab + ((long long)t * A + a0 + a) * B + b0 + q * 8) = v;
+        }
+    }
+    if (oba) {
+        const int flip = jobs.flip[j];
+        for (int i = threadIdx.x; i < chunks; i += 256) {
+            const int q = i & 3, b = (i >> 2) & 31, t = i >> 7;
+            const unsigned short* s = reinterpret_cast<const unsigned short*>(sh_w + t * SH_TSTRIDE + (q * 8) * SH_ROW + b);
+            uint32_t r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                r[e] = (uint32_t)s[(2 * e) * SH_ROW] | ((uint32_t)s[(2 * e + 1) * SH_ROW] << 16);
+            const int tt = flip ? T - 1 - t : t;
+            *reinterpret_cast<uint4*>(oba + ((long long)tt * B + b0 + b) * A + a0 + q * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    }
+}
+
+bool shadow_job_supported(int A, int B, int T) { return A % 32 == 0 && B % 32 == 0 && T >= 1 && T <= SH_MAXT; }
+
+int shadow_multi(const ShadowJob* jobs, int n, cudaStream_t st) {
+    static bool attr = false;
+    const size_t smem = (size_t)SH_MAXT * SH_TSTRIDE * sizeof(__nv_bfloat16);
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(shadow_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    for (int base = 0; base < n; base += SHADOW_MAX_JOBS) {
+        ShadowJobsDev d;
+        memset(&d, 0, sizeof(d));
+        const int m = n - base < SHADOW_MAX_JOBS ? n - base : SHADOW_MAX_JOBS;
+        int tiles = 0;
+        for (int i = 0; i < m; ++i) {
+            const ShadowJob& jb = jobs[base + i];
+            B2_CHECK_ARG(shadow_job_supported(jb.A, jb.B, jb.T));
+            d.w[i] = jb.w; d.oab[i] = jb.oab; d.oba[i] = jb.oba; d.A[i] = jb.A; d.B[i] = jb.B;
+            d.T[i] = (unsigned char)jb.T; d.flip[i] = (unsigned char)jb.flip;
+            d.tile0[i] = tiles;
+            tiles += (jb.A / 32) * (jb.B / 32);
+        }
+        d.tile0[m] = tiles;
+        d.n = m;
+        if (tiles > 0) B2_LAUNCH(shadow_multi_kernel, tiles, 256, smem, st, d);
+    }
+    return B2_OK;
+}
+
 int weight_shadow_bf16(const float* w, int cout, int cin, __nv_bfloat16* wk, __nv_bfloat16* wd, cudaStream_t st) {
+    if (!wk && !wd) return B2_OK;
+    if (shadow_job_supported(cout, cin, 27)) {
+        ShadowJob jb{w, wk, wd, cout, cin, 27, 1};
+        return shadow_multi(&jb, 1, st);
+    }
     long long tot = (long long)cout * cin * 27;
     B2_LAUNCH(weight_shadow_bf16_kernel, cdiv(tot, 256), 256, 0, st, w, cout, cin, wk, wd);
     return B2_OK;
@@ -402,11 +527,27 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
         for (int a = 0; a < 3; ++a) p.tap_off[t][a] = (signed char)g.tap_off[t][a];
         p.tap_w[t] = (unsigned char)g.tap_w[t];
     }
-    const int otiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n * nblk;
+    int otiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n * nblk;
+    if (g.nclass > 1) {
+        // tile classes: same voxel box for all, tiles enumerated class after class
+        B2_CHECK_ARG(g.nclass <= 8 && !g.q_scatter);
+        p.nclass = g.nclass;
+        int acc = 0;
+        for (int c = 0; c < g.nclass; ++c) {
+            p.cls_tile0[c] = acc;
+            p.cls_tap0[c] = (unsigned char)g.cls_tap0[c]; p.cls_ntaps[c] = (unsigned char)g.cls_ntaps[c];
+            for (int a = 0; a < 3; ++a) { p.cls_oo[c][a] = (signed char)g.cls_oo[c][a]; p.cls_L[c][a] = (short)g.cls_L[c][a]; }
+            p.cls_nt[c][0] = (short)cdiv(g.cls_L[c][0], p.TD); p.cls_nt[c][1] = (short)cdiv(g.cls_L[c][1], p.TH);
+            p.cls_nt[c][2] = (short)cdiv(g.cls_L[c][2], p.TW);
+            acc += p.cls_nt[c][0] * p.cls_nt[c][1] * p.cls_nt[c][2] * p.nt_n * nblk;
+        }
+        p.cls_tile0[g.nclass] = acc;
+        otiles = acc;
+    }
     // split-K when the output tiles cannot fill the GPU (deep, small-volume layers)
     int ksplit = 1;
     const int kiters_total = g.ntaps * p.kchunks;
-    if (g.splitk_scratch && otiles * 2 <= num_sms()) {
+    if (g.splitk_scratch && g.nclass <= 1 && otiles * 2 <= num_sms()) {
         ksplit = num_sms() / otiles;
         if (ksplit > kiters_total / 4) ksplit = kiters_total / 4;
         if (ksplit < 1) ksplit = 1;
@@ -494,10 +635,19 @@ int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int 
 
 // dgrad of a STRIDED 3x3x3 conv: one launch per output-parity class; class p receives the taps t with (p - t + 1) even
 // and reads dz at j + (p - t + 1) / 2.  wd = flipped/transposed shadow [26 - t][ci][co] (weight_shadow_bf16).
+int g_dgrad_one_launch = 1;
+
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
                           int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
                           cudaStream_t st) {
     const int dims_in[3] = {Di, Hi, Wi};
+    // all parity classes in ONE launch (tile classes of conv_tc_kernel): the per-class launches of the deep layers were
+    // dominated by launch + pipeline fill (8 x 11..29 us for 0.3..4 GFLOP each)
+    TcGather m;
+    fill_common(m, dz, N, Do, Ho, Wo, Cout, dz_pitch, wd, Cin, nullptr, dx, Di, Hi, Wi, dx_pitch, accumulate);
+    m.w_rows = 27 * Cin;
+    m.ntaps = 0; m.nclass = 0;
+    for (int a = 0; a < 3; ++a) m.os[a] = stride[a];
     for (int pd = 0; pd < stride[0]; ++pd)
         for (int ph = 0; ph < stride[1]; ++ph)
             for (int pw = 0; pw < stride[2]; ++pw) {
@@ -523,6 +673,8 @@ int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo
                     }
                 }
                 g.ntaps = 0;
+                const int c = m.nclass;
+                m.cls_tap0[c] = m.ntaps;
                 for (int i = 0; i < cnt[0]; ++i)
                     for (int j = 0; j < cnt[1]; ++j)
                         for (int k = 0; k < cnt[2]; ++k) {
@@ -530,11 +682,29 @@ int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo
                             g.tap_off[g.ntaps][0] = off[0][i]; g.tap_off[g.ntaps][1] = off[1][j]; g.tap_off[g.ntaps][2] = off[2][k];
                             g.tap_w[g.ntaps] = 26 - t;
                             ++g.ntaps;
+                            if (m.ntaps < 27) {
+                                for (int a = 0; a < 3; ++a) m.tap_off[m.ntaps][a] = g.tap_off[g.ntaps - 1][a];
+                                m.tap_w[m.ntaps] = 26 - t;
+                                ++m.ntaps;
+                            }
                         }
-                int rc = conv_tc_gather(g, st);
-                if (rc) return rc;
+                m.cls_ntaps[c] = g.ntaps;
+                for (int a = 0; a < 3; ++a) { m.cls_oo[c][a] = par[a]; m.cls_L[c][a] = L[a]; }
+                ++m.nclass;
+                if (!g_dgrad_one_launch) {
+                    int rc = conv_tc_gather(g, st);
+                    if (rc) return rc;
+                }
             }
-    return B2_OK;
+    if (!g_dgrad_one_launch || m.nclass == 0) return B2_OK;
+    // the voxel box is sized for the smallest class lattice (the class extents differ by at most one voxel per axis)
+    m.LD = m.cls_L[m.nclass - 1][0]; m.LH = m.cls_L[m.nclass - 1][1]; m.LW = m.cls_L[m.nclass - 1][2];
+    for (int c = 0; c < m.nclass; ++c)
+        for (int a = 0; a < 3; ++a) {
+            int& L = a == 0 ? m.LD : a == 1 ? m.LH : m.LW;
+            if (m.cls_L[c][a] < L) L = m.cls_L[c][a];
+        }
+    return conv_tc_gather(m, st);
 }
 
 // transposed conv (kernel == stride) forward: out[(2v + q), co] = sum_ci x[v, ci] * W[ci][co][q]; wq: [(q, co)][ci] bf16
@@ -580,6 +750,10 @@ __global__ void tconv_shadow_bf16_kernel(const float* __restrict__ w, int Cin, i
     if (wqd) wqd[((long long)q * Cin + ci) * Cout + co] = v;
 }
 int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st) {
+    if (shadow_job_supported(cin, cout, k8)) {
+        ShadowJob jb{w_pt, wqd, wq, cin, cout, k8, 0};
+        return shadow_multi(&jb, 1, st);
+    }
     long long tot = (long long)cin * cout * k8;
     B2_LAUNCH(tconv_shadow_bf16_kernel, cdiv(tot, 256), 256, 0, st, w_pt, cin, cout, k8, wq, wqd);
     return B2_OK;

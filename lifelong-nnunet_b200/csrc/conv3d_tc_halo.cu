@@ -18,37 +18,35 @@ namespace b2 {
 struct HaloParams {
     int N, D, H, W;       // produced tensor == gathered tensor extent (stride 1, padding 1)
     int dst_pitch;
-    int BN;               // output channels (<= 256)
+    int BN;               // output channels per CTA (<= 128)
+    int NS, Ntot;         // column splits (CTA c owns columns [(c % NS) * BN, +BN) for its whole life) and total channels
     int HB, WB, DS, SD;   // strips per sample along h / w, segments along d and their length
     int num_items;
-    int b_resident;       // weights resident in shared memory
-    int b_stages;         // ring depth when streaming
-    uint32_t idesc;
+    int nslot;            // slab ring depth (2..6)
+    int nacc, nacc_log2;  // TMEM accumulator ring: nacc slots of BN columns
+    int merge;            // 1: the three kd taps of a (kh, kw) pair are ONE tcgen05.mma of N = 3*BN (see below)
+    uint32_t idesc, idesc2, idesc3;   // instruction descriptors for N = BN, 2*BN, 3*BN
     uint32_t tmem_cols;
 };
 
 constexpr int HALO_THREADS = 224;  // warp 0: slab producer, 1: MMA, 2..5: epilogue, 6: weight producer
+constexpr int HALO_MAX_SLOTS = 6;
+constexpr int HALO_MAX_ACC = 16;
 
-template <int KC>
-__device__ __forceinline__ uint64_t halo_desc(uint32_t saddr) {
-    constexpr uint32_t row_bytes = KC * 2;
-    constexpr uint64_t layout = row_bytes == 128 ? 2 : 4;
-    constexpr uint64_t sbo = (8 * row_bytes) >> 4;
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= sbo << 32;
-    d |= (uint64_t)1 << 46;
-    d |= layout << 61;
-    return d;
-}
-
+// kd-merged issue ("input-stationary along d").  Input slab s feeds the three output slabs s+1 (kd = 0), s (kd = 1) and
+// s-1 (kd = 2) with the SAME A operand per (kh, kw).  Their accumulators sit in consecutive TMEM slots of the ring and the
+// three weight tiles sit back to back in shared memory in the order kd = 2, 1, 0, so one instruction of N = 3*BN updates
+// all three:   D[:, (s-1 | s | s+1) x BN] += A(slab s, kh, kw) * [W(2,kh,kw); W(1,kh,kw); W(0,kh,kw)]^T.
+// An SS-mode M=128 tcgen05.mma costs max(~45, N/2) cycles (profiles/r01_mma_probe.txt): at BN = 32 three N=32 MMAs (135
+// cycles) become one N=96 MMA (48 cycles).  The very first MMA of a slab is split in two (N = 2*BN accumulate + N = BN
+// overwrite) because slot s+1 must be zero-initialised; slabs at a segment edge or where the three slots wrap around the
+// ring take the per-kd path.
 template <int KC>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloParams p,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t sfull[2], sempty[2], wfull, tfull[4], tempty[4];
+    __shared__ __align__(8) uint64_t sfull[HALO_MAX_SLOTS], sempty[HALO_MAX_SLOTS], wfull, tfull[HALO_MAX_ACC], tempty[HALO_MAX_ACC];
     __shared__ uint32_t tmem_base_smem;
 
     constexpr uint32_t ROW = KC * 2;
@@ -57,15 +55,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t B_TILE = (uint32_t)p.BN * ROW;    // one tap of weights [BN][KC]
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* slabs = smem;
-    uint8_t* wsm = smem + 2 * SLAB_BYTES;            // 27 resident weight tiles
+    uint8_t* wsm = smem + (size_t)p.nslot * SLAB_BYTES;   // 27 resident weight tiles, order (kh*3+kw, 2-kd)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < 2; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
+        for (int s = 0; s < p.nslot; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
         mbar_init(&wfull, 1);
-        for (int a = 0; a < 4; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < p.nacc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -73,6 +71,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t amask = (uint32_t)p.nacc - 1;
+    const int cs = (int)blockIdx.x % p.NS;                    // this CTA's column split
+    const int item0 = (int)blockIdx.x / p.NS, item_step = (int)gridDim.x / p.NS;
 
     // item -> (n, hb, wb, ds)
     auto decode = [&](int item, int& n, int& h0, int& w0, int& d0, int& d1) {
@@ -86,18 +87,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         // ===================== slab producer =====================
         if (lane == 0) {
-            uint32_t j = 0;  // running slab counter -> slot j & 1, phase (j >> 1) & 1
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int item = item0; item < p.num_items; item += item_step) {
                 int n, h0, w0, d0, d1;
                 decode(item, n, h0, w0, d0, d1);
-                for (int s = d0 - 1; s <= d1; ++s, ++j) {
-                    const uint32_t slot = j & 1, ph = (j >> 1) & 1;
+                for (int s = d0 - 1; s <= d1; ++s) {
                     mbar_wait(&sempty[slot], ph ^ 1);
                     mbar_expect_tx(&sfull[slot], SLAB_BYTES);
-                    uint8_t* base = slabs + slot * SLAB_BYTES;
+                    uint8_t* base = slabs + (size_t)slot * SLAB_BYTES;
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw)
                         tma_load_5d(&tmA, &sfull[slot], base + kw * COPY_BYTES, 0, w0 + kw - 1, h0 - 1, s, n);
+                    if (++slot == p.nslot) { slot = 0; ph ^= 1; }
                 }
             }
         }
@@ -105,13 +107,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== weight producer =====================
         if (lane == 0) {
             mbar_expect_tx(&wfull, 27 * B_TILE);
-            for (int t = 0; t < 27; ++t) tma_load_2d(&tmB, &wfull, wsm + (size_t)t * B_TILE, 0, t * p.BN);
+            for (int t = 0; t < 27; ++t) {
+                const int kd = t / 9, t9 = t % 9;
+                tma_load_2d(&tmB, &wfull, wsm + (size_t)(t9 * 3 + 2 - kd) * B_TILE, 0, t * p.Ntot + cs * p.BN);
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane, straight-line code per slab) =====================
-        // The issuing thread is blocked ~45 cycles per tcgen05.mma (M128 x N<=64 x K16, measured with tools/mma_probe) and every
-        // scalar instruction between two MMAs adds to that: descriptors are assembled from precomputed 32-bit halves and the
-        // 27 taps are fully unrolled (all offsets are immediates).
+        // The issuing thread is blocked per tcgen05.mma and every scalar instruction between two MMAs adds to that:
+        // descriptors are assembled from precomputed 32-bit halves and the taps are fully unrolled (offsets are immediates).
         {
             constexpr uint32_t DESC_HI = (uint32_t)(((uint64_t)((8 * ROW) >> 4) << 32 | (uint64_t)1 << 46 | (uint64_t)(ROW == 128 ? 2 : 4) << 61) >> 32);
             auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; };
@@ -119,42 +123,62 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t SLAB16 = SLAB_BYTES >> 4, C16 = COPY_BYTES >> 4, A16 = (8 * ROW) >> 4;
             const uint32_t w_lo = ((smem_u32(wsm) & 0x3FFFF) >> 4) | 0x10000u;
             const uint32_t btile16 = B_TILE >> 4;
-            uint32_t jc = 0;    // running slab counter
+            int slot = 0;
+            uint32_t sph = 0;
             uint32_t ocb = 0;   // running output counter at d0 of the current item
             mbar_wait(&wfull, 0);
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            for (int item = item0; item < p.num_items; item += item_step) {
                 int n, h0, w0, d0, d1;
                 decode(item, n, h0, w0, d0, d1);
-                for (int s = d0 - 1; s <= d1; ++s, ++jc) {
-                    const uint32_t slot = jc & 1;
-                    mbar_wait(&sfull[slot], (jc >> 1) & 1);
+                for (int s = d0 - 1; s <= d1; ++s) {
+                    mbar_wait(&sfull[slot], sph);
                     // output s+1 starts with this slab (kd = 0): its accumulator must have been drained
                     const bool v0 = (s + 1 >= d0) && (s + 1 < d1), v1 = (s >= d0) && (s < d1), v2 = (s - 1 >= d0) && (s - 1 < d1);
                     const uint32_t oc0 = ocb + (uint32_t)(s + 1 - d0), oc1 = oc0 - 1, oc2 = oc0 - 2;
-                    if (v0) mbar_wait(&tempty[oc0 & 3], ((oc0 >> 2) & 1) ^ 1);
+                    if (v0) mbar_wait(&tempty[oc0 & amask], ((oc0 >> p.nacc_log2) & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_base = slab_lo0 + slot * SLAB16;
+                        const uint32_t a_base = slab_lo0 + (uint32_t)slot * SLAB16;
+                        if (p.merge && v0 && v1 && v2 && (oc0 & amask) >= 2) {
+                            const uint32_t d2 = tmem_base + (oc2 & amask) * (uint32_t)p.BN;
+                            const uint32_t d0t = d2 + 2u * (uint32_t)p.BN;
 #pragma unroll
-                        for (int kd = 0; kd < 3; ++kd) {
-                            const bool valid = kd == 0 ? v0 : kd == 1 ? v1 : v2;
-                            if (valid) {
-                                const uint32_t oc = kd == 0 ? oc0 : kd == 1 ? oc1 : oc2;
-                                const uint32_t d_tmem = tmem_base + (oc & 3) * (uint32_t)p.BN;
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                const uint32_t a_lo = a_base + (uint32_t)(t9 % 3) * C16 + (uint32_t)(t9 / 3) * A16;
+                                const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3) * btile16;
 #pragma unroll
-                                for (int t9 = 0; t9 < 9; ++t9) {
-                                    const uint32_t a_lo = a_base + (uint32_t)(t9 % 3) * C16 + (uint32_t)(t9 / 3) * A16;
-                                    const uint32_t b_lo = w_lo + (uint32_t)(kd * 9 + t9) * btile16;
+                                for (int k = 0; k < KC / 16; ++k) {
+                                    if (t9 == 0 && k == 0) {
+                                        umma_bf16(d2, mk(a_lo), mk(b_lo), p.idesc2, 1u);                     // outputs s-1, s
+                                        umma_bf16(d0t, mk(a_lo), mk(b_lo + 2 * btile16), p.idesc, 0u);       // output s+1: first write
+                                    } else {
+                                        umma_bf16(d2, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc3, 1u);
+                                    }
+                                }
+                            }
+                        } else {
 #pragma unroll
-                                    for (int k = 0; k < KC / 16; ++k)
-                                        umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc, (kd | t9 | k) != 0 ? 1u : 0u);
+                            for (int kd = 0; kd < 3; ++kd) {
+                                const bool valid = kd == 0 ? v0 : kd == 1 ? v1 : v2;
+                                if (valid) {
+                                    const uint32_t oc = kd == 0 ? oc0 : kd == 1 ? oc1 : oc2;
+                                    const uint32_t d_tmem = tmem_base + (oc & amask) * (uint32_t)p.BN;
+#pragma unroll
+                                    for (int t9 = 0; t9 < 9; ++t9) {
+                                        const uint32_t a_lo = a_base + (uint32_t)(t9 % 3) * C16 + (uint32_t)(t9 / 3) * A16;
+                                        const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3 + 2 - kd) * btile16;
+#pragma unroll
+                                        for (int k = 0; k < KC / 16; ++k)
+                                            umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc, (kd | t9 | k) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
                         }
-                        umma_commit(&sempty[slot]);                      // slab fully consumed
-                        if (v2) umma_commit(&tfull[oc2 & 3]);            // output s-1 complete (its kd = 2 taps were the last)
+                        umma_commit(&sempty[slot]);                        // slab fully consumed
+                        if (v2) umma_commit(&tfull[oc2 & amask]);          // output s-1 complete (its kd = 2 taps were the last)
                     }
                     __syncwarp();
+                    if (++slot == p.nslot) { slot = 0; sph ^= 1; }
                 }
                 ocb += (uint32_t)(d1 - d0);
             }
@@ -164,18 +188,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int w_ = r & 7, h_ = r >> 3;
-        uint32_t oc = 0;   // running output counter: accumulator oc & 3, phase (oc >> 2) & 1
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        uint32_t oc = 0;   // running output counter: accumulator oc & amask, phase (oc >> nacc_log2) & 1
+        for (int item = item0; item < p.num_items; item += item_step) {
             int n, h0, w0, d0, d1;
             decode(item, n, h0, w0, d0, d1);
             const int oh = h0 + h_, ow = w0 + w_;
             const bool valid = oh < p.H && ow < p.W;
             for (int od = d0; od < d1; ++od, ++oc) {
-                const int acc = (int)(oc & 3);
-                __nv_bfloat16* row = dst + ((((long long)n * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch;
-                mbar_wait(&tfull[acc], (oc >> 2) & 1);
+                const uint32_t acc = oc & amask;
+                __nv_bfloat16* row = dst + ((((long long)n * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + cs * p.BN;
+                mbar_wait(&tfull[acc], (oc >> p.nacc_log2) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
                 for (int c0 = 0; c0 < p.BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
@@ -187,7 +211,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 f[e] = __uint_as_float(v[jj + e]);
-                                if (bias) f[e] += bias[c0 + jj + e];
+                                if (bias) f[e] += bias[cs * p.BN + c0 + jj + e];
                             }
                             if (accumulate) {
                                 float o[8];
@@ -214,27 +238,49 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int KC, int BN);
 
+int g_halo_merge = 1;
+int g_halo_nsplit = 1;   // allow splitting the output channels over CTA classes when the weights do not fit
+
 static bool halo_plan(int K, int Nout, int D, int H, int W, int N, HaloParams& p, size_t& smem) {
-    if (!(K == 32 || K == 64) || Nout % 32 != 0 || Nout > 128) return false;   // 4 accumulators of Nout columns in TMEM
+    if (!(K == 32 || K == 64) || Nout % 32 != 0 || Nout > 256) return false;
     if (H < 16 || W < 8) return false;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.D = D; p.H = H; p.W = W; p.BN = Nout;
+    p.N = N; p.D = D; p.H = H; p.W = W; p.Ntot = Nout;
     p.HB = cdiv(H, 16); p.WB = cdiv(W, 8);
-    const uint32_t row = K * 2, slab = 3 * 144 * row, btile = (uint32_t)Nout * row;
+    const uint32_t row = K * 2, slab = 3 * 144 * row;
     const size_t budget = 223 * 1024;
-    // weights must be resident (27 taps): streaming them costs one mbarrier round trip per tap on the MMA thread, which is
-    // slower than the per-tap kernel of conv3d_tc.cu
-    if (2ull * slab + 27ull * btile + 1024 > budget) return false;
-    p.b_resident = 1; p.b_stages = 0; smem = 2ull * slab + 27ull * btile + 1024;
+    // The 27 weight tiles of a CTA must be resident (streaming them costs one mbarrier round trip per tap on the MMA thread
+    // and 9x the slab bytes in L2 traffic).  When [27][Nout][K] does not fit next to >= 2 slabs the output channels are split
+    // over NS CTAs-classes of BN = Nout / NS columns: every class re-reads the slabs, but at BN = 32 the kd-merged MMA
+    // (N = 96) already runs at the full tensor rate and 2 x 55 KB per 3456 MMA cycles stays under the ~43 B/clk/SM L2 cap --
+    // against 27 x 24 KB per 128 voxels in the per-tap kernel of conv3d_tc.cu.
+    int ns = 1;
+    while (ns <= 8 && (Nout % ns != 0 || (Nout / ns) % 32 != 0 || Nout / ns > 128 ||
+                       2ull * slab + 27ull * (Nout / ns) * row + 1024 > budget)) ++ns;
+    if (ns > 8) return false;
+    if (ns > 1 && !g_halo_nsplit) return false;
+    p.NS = ns; p.BN = Nout / ns;
+    const uint32_t btile = (uint32_t)p.BN * row;
+    int nslot = (int)((budget - 27ull * btile - 1024) / slab);
+    if (nslot > HALO_MAX_SLOTS) nslot = HALO_MAX_SLOTS;
+    p.nslot = nslot;
+    smem = (size_t)nslot * slab + 27ull * btile + 1024;
     // segment length: enough items for >= 4 waves when possible, at least 8 slabs per segment
     const int strips = N * p.HB * p.WB;
     int sd = D;
-    while (sd > 8 && strips * cdiv(D, sd) < 4 * num_sms()) sd = (sd + 1) / 2;
+    while (sd > 8 && strips * cdiv(D, sd) * ns < 4 * num_sms()) sd = (sd + 1) / 2;
     p.SD = sd; p.DS = cdiv(D, sd);
     p.num_items = strips * p.DS;
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
+    p.idesc = idesc(p.BN); p.idesc2 = idesc(2 * p.BN); p.idesc3 = idesc(3 * p.BN);
+    p.merge = g_halo_merge && 3 * p.BN <= 256;
+    int nacc = 4;
+    while (nacc * 2 <= HALO_MAX_ACC && nacc * 2 * p.BN <= 512) nacc *= 2;
+    p.nacc = nacc;
+    p.nacc_log2 = 0;
+    while ((1 << p.nacc_log2) < nacc) ++p.nacc_log2;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(4 * Nout)) cols *= 2;
+    while (cols < (uint32_t)(nacc * p.BN)) cols *= 2;
     p.tmem_cols = cols;
     return true;
 }
@@ -258,9 +304,10 @@ int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, in
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, src, N, D, H, W, K, src_pitch, K, 1, 1, 18, 8, 1, 1, 1);
     if (rc) return rc;
-    rc = make_w_map(&tmB, wmat, 27 * Nout, K, K, Nout);
+    rc = make_w_map(&tmB, wmat, 27 * Nout, K, K, p.BN);
     if (rc) return rc;
-    const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+    int grid = p.num_items * p.NS < num_sms() ? p.num_items * p.NS : num_sms();
+    grid = grid / p.NS * p.NS;   // every column split gets the same number of CTAs
     static bool a32 = false, a64 = false;
     if (K == 32) {
         if (!a32) { B2_CUDA(cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); a32 = true; }

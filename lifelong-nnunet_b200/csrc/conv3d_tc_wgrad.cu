@@ -42,6 +42,14 @@ struct TcWgradParams {
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
     int ntaps;
     signed char tap_off[27][3];   // offset of the shifted operand per tap (padding included)
+    // d-merged mode (stride-1 3x3x3, Cin <= 64): the shifted operand only carries the 9 (kh, kw) taps and the fixed operand
+    // is THREE dz boxes shifted by +1, 0, -1 along d, side by side in N:  D[(kh,kw,ci), (kd,co)] = sum_u x[u+(0,kh-1,kw-1)][ci]
+    // * dz[u-(kd-1,0,0)][co] == dW[(kd,kh,kw)][ci][co].  N grows from co_blk to 3*co_blk (an SS-mode MMA costs
+    // max(~45, N/2) cycles, so N = 32 wastes 2/3 of the issue slots) and the TMA bytes per voxel tile drop from
+    // 27 x-boxes + 1 dz-box to 9 + 3 -- the kernel is bound by the ~43 B/clk/SM L2->SM throughput.
+    int dmerge;
+    int nper;                     // accumulator columns per group (co_blk, or 3 * co_blk when d-merged)
+    int out_taps;                 // taps of the partial tensor written by the epilogue (27 when d-merged, else ntaps)
 };
 
 // MN-major UMMA descriptor: `row_bytes` = bytes of one K row (one voxel's channel chunk: 64 or 128)
@@ -72,7 +80,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t a_chunk_bytes = 128u * p.ci_sub * 2;
     const uint32_t A_BYTES = a_chunk_bytes * p.a_chunks;          // 32 KB
     const uint32_t b_chunk_bytes = 128u * p.co_sub * 2;
-    const uint32_t B_BYTES = b_chunk_bytes * p.b_chunks;
+    const int nb_boxes = p.dmerge ? 3 * p.b_chunks : p.b_chunks;
+    const uint32_t B_BYTES = b_chunk_bytes * nb_boxes;
     uint8_t* smemB = smem + (size_t)p.a_stages * A_BYTES;
 
     // work item decode: blockIdx.x = ((item * nsplit) + split); item = (ci_item, co_blk, tapset)
@@ -147,9 +156,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int tn = t;
                 mbar_wait(&emptyB[bs], bph ^ 1);
                 mbar_expect_tx(&fullB[bs], B_BYTES);
-                for (int c = 0; c < p.b_chunks; ++c)
+                for (int c = 0; c < nb_boxes; ++c) {
+                    const int kd = c / p.b_chunks, cc = c - kd * p.b_chunks;
                     tma_load_5d(&tmZ, &fullB[bs], smemB + (size_t)bs * B_BYTES + (size_t)c * b_chunk_bytes,
-                                cob * p.co_blk + c * p.co_sub, tw * p.TW, th * p.TH, td * p.TD, tn * p.TN);
+                                cob * p.co_blk + cc * p.co_sub, tw * p.TW, th * p.TH, td * p.TD + (p.dmerge ? 1 - kd : 0), tn * p.TN);
+                }
                 if (++bs == 2) { bs = 0; bph ^= 1; }
             }
         }
@@ -180,7 +191,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         if (g == my_groups - 1) umma_commit(&emptyB[bs]);
                     }
                     __syncwarp();
-                    d_tmem += (uint32_t)p.co_blk;
+                    d_tmem += (uint32_t)p.nper;
                     a_lo += a_stage16;
                     if (++as == p.a_stages) { as = 0; aph ^= 1; a_lo = a_base; }
                 }
@@ -199,14 +210,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&done_bar, 0);
             tc_fence_after();
         }
-        float* out = part + (size_t)split * p.ntaps * p.Cin * p.Cout;
+        float* out = part + (size_t)split * p.out_taps * p.Cin * p.Cout;
         for (int g = 0; g < my_groups; ++g) {
             int tap, ci;
             if (p.stack_taps) { tap = tap0 + g * p.a_chunks + chunk; ci = cil; }
             else { tap = tap0 + g; ci = ci_item * 128 + chunk * p.ci_sub + cil; }
             const bool valid = tap < p.ntaps && ci < p.Cin;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.co_blk);
-            for (int c0 = 0; c0 < p.co_blk; c0 += 32) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.nper);
+            for (int c0 = 0; c0 < p.nper; c0 += 32) {
                 uint32_t v[32];
                 if (has_work) {
                     tmem_ld32(taddr + c0, v);
@@ -216,7 +227,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     for (int e = 0; e < 32; ++e) v[e] = 0u;
                 }
                 if (valid) {
-                    float* dstp = out + ((size_t)tap * p.Cin + ci) * p.Cout + cob * p.co_blk + c0;
+                    const int kd = c0 / p.co_blk, cc0 = c0 - kd * p.co_blk;    // d-merged: column block -> kd
+                    const int tap_out = p.dmerge ? kd * 9 + tap : tap;
+                    float* dstp = out + ((size_t)tap_out * p.Cin + ci) * p.Cout + cob * p.co_blk + cc0;
 #pragma unroll
                     for (int e = 0; e < 32; e += 4)
                         *reinterpret_cast<float4*>(dstp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
@@ -288,10 +301,18 @@ bool wgrad_tc_supported(int cin, int cout) {
     return true;
 }
 
+int g_wgrad_dmerge = 1;
+
 static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) {
     memset(&p, 0, sizeof(p));
+    const bool dmerge = g_wgrad_dmerge && ntaps == 27 && s.cin <= 64 && s.cout <= 64 && s.stride[0] == 1 && s.stride[1] == 1 &&
+                        s.stride[2] == 1;
+    p.dmerge = dmerge ? 1 : 0;
+    p.out_taps = ntaps;
+    if (dmerge) ntaps = 9;
     p.ntaps = ntaps;
     for (int t = 0; t < 27; ++t) { p.tap_off[t][0] = t / 9 - 1; p.tap_off[t][1] = (t / 3) % 3 - 1; p.tap_off[t][2] = t % 3 - 1; }
+    if (dmerge) for (int t = 0; t < 9; ++t) { p.tap_off[t][0] = 0; p.tap_off[t][1] = t / 3 - 1; p.tap_off[t][2] = t % 3 - 1; }
     p.N = s.n;
     p.Do = (s.d - 1) / s.stride[0] + 1; p.Ho = (s.h - 1) / s.stride[1] + 1; p.Wo = (s.w - 1) / s.stride[2] + 1;
     p.sd = s.stride[0]; p.sh = s.stride[1]; p.sw = s.stride[2];
@@ -311,28 +332,30 @@ static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) 
     p.co_blk = s.cout / p.co_blks;
     p.co_sub = p.co_blk % 64 == 0 ? 64 : 32;
     p.b_chunks = p.co_blk / p.co_sub;
+    p.nper = dmerge ? 3 * p.co_blk : p.co_blk;
     const int total_groups = cdiv(ntaps, p.taps_per_group);
-    int gmax = 512 / p.co_blk;
+    int gmax = 512 / p.nper;
     if (gmax > total_groups) gmax = total_groups;
     p.groups = gmax;
     p.tapsets = cdiv(total_groups, gmax);
     const int items = p.ci_items * p.co_blks * p.tapsets;
-    int ns = (2 * num_sms()) / items;
+    // one resident CTA per SM (200 KB of shared memory): more CTAs than SMs only add partials for the ordered reduction
+    int ns = items >= num_sms() ? 1 : (items * 2 > num_sms() ? (2 * num_sms()) / items : num_sms() / items);
     if (ns < 1) ns = 1;
     if (ns > p.num_vtiles) ns = p.num_vtiles;
     p.nsplit = ns;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(p.groups * p.co_blk)) cols *= 2;
+    while (cols < (uint32_t)(p.groups * p.nper)) cols *= 2;
     p.tmem_cols = cols;
-    // kind::f16, bf16 x bf16 -> f32, A and B MN-major (bits 15, 16), M = 128, N = co_blk
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.co_blk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // kind::f16, bf16 x bf16 -> f32, A and B MN-major (bits 15, 16), M = 128, N = nper
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nper >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a_row = p.ci_sub * 2, b_row = p.co_sub * 2;
     // canonical MN-major layout (cute::UMMA, see tc_common.cuh): LBO = distance between MN chunks (one TMA box each),
     // SBO = distance between 8-row K groups
     p.a_lbo = 128u * a_row; p.a_sbo = 8u * a_row;
     p.b_lbo = 128u * b_row; p.b_sbo = 8u * b_row;
     if (g_wgrad_desc_mode == 1) { uint32_t t = p.a_lbo; p.a_lbo = p.a_sbo; p.a_sbo = t; t = p.b_lbo; p.b_lbo = p.b_sbo; p.b_sbo = t; }
-    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.nper * 2;
     int st = (int)((200u * 1024 - 2 * B_BYTES) / A_BYTES);
     if (st > WG_MAX_ASTAGES) st = WG_MAX_ASTAGES;
     if (st < 2) st = 2;
@@ -361,7 +384,7 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     if (rc) return rc;
     rc = make_act_map(&tmZ, dz, s.n, p.Do, p.Ho, p.Wo, s.cout, s.out_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
     if (rc) return rc;
-    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.nper * 2;
     const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
     if (smem > 220 * 1024) return fail(B2_EUNSUPPORTED, "wgrad_tc: tile does not fit shared memory%s", "");
     static bool attr = false;
@@ -441,7 +464,7 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     if (rc) return rc;
     rc = make_act_map(&tmB, x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
     if (rc) return rc;
-    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.nper * 2;
     const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
     if (smem > 220 * 1024) return fail(B2_EUNSUPPORTED, "tconv_wgrad_tc: tile does not fit shared memory%s", "");
     static bool attr = false;
@@ -461,29 +484,28 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patch_matrix_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int cin,
                                                            int x_pitch, __nv_bfloat16* __restrict__ P) {
-    // thread = (voxel, 8-wide group of the 32 patch columns): 16-byte stores
-    const long long total = (long long)N * D * H * W * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i & 3);
-        long long v = i >> 2;
+    // thread = voxel: gathers its 27*cin neighbours (L1-resident: adjacent threads share them) and writes the 64-byte row
+    // with four 16-byte stores -- a warp writes 2 KB contiguous.  (The first version used a thread per 8 columns with a
+    // div/mod chain per element: 286 us for 134 MB; this one is store-bound.)
+    const long long total = (long long)N * D * H * W;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
         const int w = (int)(v % W); long long r = v / W;
         const int h = (int)(r % H); r /= H;
         const int d = (int)(r % D);
         const int n = (int)(r / D);
-        float o[8];
+        uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float val = 0.f;
-            if (k < 27 * cin) {
-                const int t = k / cin, ci = k % cin;
-                const int id = d + t / 9 - 1, ih = h + (t / 3) % 3 - 1, iw = w + t % 3 - 1;
-                if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
-                    val = __bfloat162float(x[((((long long)n * D + id) * H + ih) * W + iw) * x_pitch + ci]);
-            }
-            o[j] = val;
+        for (int j = 0; j < 16; ++j) packed[j] = 0u;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {   // cin == 1 (27 * cin <= 32): column k == tap t
+            const int id = d + t / 9 - 1, ih = h + (t / 3) % 3 - 1, iw = w + t % 3 - 1;
+            const bool in = id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W;
+            const unsigned short u = in ? __bfloat16_as_ushort(x[((((long long)n * D + id) * H + ih) * W + iw) * x_pitch]) : (unsigned short)0;
+            packed[t >> 1] |= (uint32_t)u << ((t & 1) * 16);
         }
-        store8(P + v * 32 + g * 8, o);
+        uint4* dst = reinterpret_cast<uint4*>(P + v * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
 }
 
@@ -512,7 +534,8 @@ bool first_layer_tc_supported(int cin, int cout) { return 27 * cin <= 32 && cout
 
 int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
                         int cout, __nv_bfloat16* wp, cudaStream_t st) {
-    const long long total = (long long)N * D * H * W * 4;
+    B2_CHECK_ARG(cin == 1);
+    const long long total = (long long)N * D * H * W;
     long long grid = (total + 255) / 256, cap = (long long)num_sms() * 32;
     if (grid > cap) grid = cap;
     B2_LAUNCH(patch_matrix_kernel, (int)grid, 256, 0, st, x, N, D, H, W, cin, x_pitch, P);
@@ -544,7 +567,7 @@ int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N,
     if (rc) return rc;
     rc = make_act_map(&tmB, dz, N, D, H, W, cout, dz_pitch, p.co_sub, p.TN, p.TD, p.TH, p.TW, 1, 1, 1);
     if (rc) return rc;
-    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.co_blk * 2;
+    const uint32_t A_BYTES = 128u * p.ci_sub * 2 * p.a_chunks, B_BYTES = 128u * p.nper * 2;
     const size_t smem = (size_t)p.a_stages * A_BYTES + 2 * (size_t)B_BYTES + 1024;
     static bool attr = false;
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }

@@ -42,6 +42,10 @@ int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* pa
 // ---- conv3d_tc.cu (tcgen05 / TMA path, bf16) ----------------------------------------------------------------------
 bool conv_tc_supported(int K, int Nout);
 int weight_shadow_bf16(const float* w_pt, int cout, int cin, __nv_bfloat16* wk, __nv_bfloat16* wd, cudaStream_t st);
+// multi-tensor bf16 shadow: w[A][B][T] fp32 -> oab[t][A][B], oba[flip ? T-1-t : t][B][A] (either may be null)
+struct ShadowJob { const float* w; __nv_bfloat16* oab; __nv_bfloat16* oba; int A, B, T, flip; };
+bool shadow_job_supported(int A, int B, int T);
+int shadow_multi(const ShadowJob* jobs, int n, cudaStream_t st);
 struct TcGather {
     const __nv_bfloat16* src; int N, Ds, Hs, Ws, K, src_pitch;     // gathered tensor (NDHWC) and its channel count (GEMM K)
     const __nv_bfloat16* wmat; int w_rows, rows_per_tap, Nout;      // weight matrix [w_rows][K]; GEMM N
@@ -53,6 +57,9 @@ struct TcGather {
     int ntaps; int tap_off[27][3]; int tap_w[27];
     int q_scatter, q_channels, qk[3];                               // transposed-conv forward column->voxel scatter
     float* splitk_scratch; size_t splitk_scratch_bytes;             // optional fp32 scratch enabling split-K for small volumes
+    // tile classes (strided dgrad: one class per output-parity lattice, one launch): class c uses the taps
+    // [cls_tap0[c], +cls_ntaps[c]) of the tables above, lattice offset cls_oo[c] and logical extent cls_L[c]
+    int nclass; int cls_tap0[8], cls_ntaps[8], cls_oo[8][3], cls_L[8][3];
 };
 int conv_tc_gather(const TcGather& g, cudaStream_t st);
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
@@ -83,8 +90,8 @@ int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int 
 size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);
 int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
                          float* part, float* dw, float* dbias, cudaStream_t st);
-extern int g_use_halo;
-extern int g_wgrad_desc_mode, g_tc_wgrad;
+extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch;
+extern int g_wgrad_desc_mode, g_tc_wgrad, g_wgrad_dmerge;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 
 // ---- norm.cu ----------------------------------------------------------------------------------------------------
@@ -95,8 +102,8 @@ int norm_lrelu_fwd(const T* z, const float* stats, const float* gamma, const flo
 size_t norm_bwd_scratch_floats(int n, long long vox, int c);
 // dz = d(loss)/dz given dy; dgamma/dbeta overwritten. scratch: norm_bwd_scratch_floats floats.
 template <typename T>
-int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, T* dz, float* dgamma,
-                   float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
+int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, const float* beta, T* dz,
+                   float* dgamma, float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
                    float slope, float* scratch, cudaStream_t st);
 
 // ---- updown.cu --------------------------------------------------------------------------------------------------

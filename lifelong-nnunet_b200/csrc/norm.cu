@@ -48,9 +48,46 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, 
     }
 }
 
-template <typename T, int VW>
+// sums[n][c] = {S1, S2} from the per-slab partials; dgamma[c] = sum_n S2; dbeta[c] = sum_n S1.
+// One WARP per channel (8 channels per block): lanes stride the slabs with independent loads in flight, double
+// accumulation, fixed xor-shuffle tree => bit-reproducible.  (The first version gave a channel 8 serial lanes inside a
+// single block per 32 channels: 17 us of pure load latency per layer.)
+__global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, int n, int slabs, int c,
+                                                                float* __restrict__ sums, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+    const int cc = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (cc >= c) return;
+    double g = 0.0, b = 0.0;
+    for (int nn = 0; nn < n; ++nn) {
+        double s1 = 0.0, s2 = 0.0;
+        const float* p = part + ((long long)nn * slabs * c + cc) * 2;
+#pragma unroll 4
+        for (int t = lane; t < slabs; t += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(p + (long long)t * c * 2);
+            s1 += (double)v.x;
+            s2 += (double)v.y;
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            sums[((long long)nn * c + cc) * 2] = (float)s1;
+            sums[((long long)nn * c + cc) * 2 + 1] = (float)s2;
+        }
+        b += s1;
+        g += s2;
+    }
+    if (lane == 0) {
+        if (dgamma) dgamma[cc] = (float)g;
+        if (dbeta) dbeta[cc] = (float)b;
+    }
+}
+
+// RECOMPUTE: the sign of the pre-activation u = gamma*zhat + beta is recomputed from z (same fp32 expression as the
+// forward kernel) instead of reading y: one tensor read less in both backward sweeps.
+template <typename T, int VW, bool RECOMPUTE>
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restrict__ z, const T* __restrict__ y,
                                                               const T* __restrict__ dy, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               int slabs, long long vox, int c, int z_pitch, int y_pitch,
                                                               int dy_pitch, float slope, float* __restrict__ part) {
     extern __shared__ float sh[];  // [R][c][2]
@@ -60,7 +97,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restric
     const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
     const long long per = (vox + slabs - 1) / slabs;
     const long long v0 = (long long)slab * per, v1 = (v0 + per < vox) ? v0 + per : vox;
-    float s1[VW], s2[VW], mean[VW], rstd[VW];
+    float s1[VW], s2[VW], mean[VW], rstd[VW], ga[VW], be[VW];
     const int c0 = cg * VW;
     if (r < R) {
 #pragma unroll
@@ -68,18 +105,22 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restric
             s1[j] = 0.f; s2[j] = 0.f;
             mean[j] = stats[((long long)n * c + c0 + j) * 2];
             rstd[j] = stats[((long long)n * c + c0 + j) * 2 + 1];
+            ga[j] = RECOMPUTE ? gamma[c0 + j] : 0.f;
+            be[j] = RECOMPUTE ? beta[c0 + j] : 0.f;
         }
         for (long long v = v0 + r; v < v1; v += R) {
             const long long row = (long long)n * vox + v;
             float a[VW], b[VW], g[VW];
             Vec<T, VW>::ld(z + row * z_pitch + c0, a);
-            Vec<T, VW>::ld(y + row * y_pitch + c0, b);
+            if (!RECOMPUTE) Vec<T, VW>::ld(y + row * y_pitch + c0, b);
             Vec<T, VW>::ld(dy + row * dy_pitch + c0, g);
 #pragma unroll
             for (int j = 0; j < VW; ++j) {
-                const float du = b[j] > 0.f ? g[j] : g[j] * slope;
+                const float zh = (a[j] - mean[j]) * rstd[j];
+                const float u = RECOMPUTE ? ga[j] * zh + be[j] : b[j];
+                const float du = u > 0.f ? g[j] : g[j] * slope;
                 s1[j] += du;
-                s2[j] += du * ((a[j] - mean[j]) * rstd[j]);
+                s2[j] += du * zh;
             }
         }
 #pragma unroll
@@ -96,43 +137,10 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restric
     }
 }
 
-// sums[n][c] = {S1, S2}; dgamma[c] = sum_n S2; dbeta[c] = sum_n S1   (block = 32 channels x 8 slab lanes)
-__global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, int n, int slabs, int c,
-                                                                float* __restrict__ sums, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta) {
-    __shared__ double sh[8][32][2];
-    const int cc = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
-    double g = 0.0, b = 0.0;
-    for (int nn = 0; nn < n; ++nn) {
-        double s1 = 0.0, s2 = 0.0;
-        if (cc < c)
-            for (int t = lane; t < slabs; t += 8) {
-                s1 += (double)part[(((long long)nn * slabs + t) * c + cc) * 2];
-                s2 += (double)part[(((long long)nn * slabs + t) * c + cc) * 2 + 1];
-            }
-        __syncthreads();
-        sh[lane][threadIdx.x & 31][0] = s1;
-        sh[lane][threadIdx.x & 31][1] = s2;
-        __syncthreads();
-        if (lane == 0 && cc < c) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int l = 0; l < 8; ++l) { a1 += sh[l][threadIdx.x][0]; a2 += sh[l][threadIdx.x][1]; }
-            sums[((long long)nn * c + cc) * 2] = (float)a1;
-            sums[((long long)nn * c + cc) * 2 + 1] = (float)a2;
-            b += a1;
-            g += a2;
-        }
-    }
-    if (lane == 0 && cc < c) {
-        if (dgamma) dgamma[cc] = (float)g;
-        if (dbeta) dbeta[cc] = (float)b;
-    }
-}
-
-template <typename T, int VW>
+template <typename T, int VW, bool RECOMPUTE>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ y,
                                                              const T* __restrict__ dy, const float* __restrict__ stats,
-                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ sums, T* __restrict__ dz, int n,
                                                              long long vox, int c, int z_pitch, int y_pitch, int dy_pitch,
                                                              int dz_pitch, float slope, float inv_v) {
@@ -145,14 +153,15 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
         const int c0 = cg * VW;
         float a[VW], b[VW], g[VW], o[VW];
         Vec<T, VW>::ld(z + row * z_pitch + c0, a);
-        Vec<T, VW>::ld(y + row * y_pitch + c0, b);
+        if (!RECOMPUTE) Vec<T, VW>::ld(y + row * y_pitch + c0, b);
         Vec<T, VW>::ld(dy + row * dy_pitch + c0, g);
 #pragma unroll
         for (int j = 0; j < VW; ++j) {
             const long long sc = (long long)nn * c + c0 + j;
             const float mean = stats[sc * 2], rstd = stats[sc * 2 + 1];
             const float zh = (a[j] - mean) * rstd;
-            const float du = b[j] > 0.f ? g[j] : g[j] * slope;
+            const float u = RECOMPUTE ? gamma[c0 + j] * zh + beta[c0 + j] : b[j];
+            const float du = u > 0.f ? g[j] : g[j] * slope;
             o[j] = gamma[c0 + j] * rstd * (du - sums[sc * 2] * inv_v - zh * sums[sc * 2 + 1] * inv_v);
         }
         Vec<T, VW>::st(dz + row * dz_pitch + c0, o);
@@ -199,35 +208,45 @@ size_t norm_bwd_scratch_floats(int n, long long vox, int c) {
     return (size_t)n * norm_slabs(n, vox) * c * 2 + (size_t)n * c * 2;
 }
 
+template <typename T, int VW, bool RC>
+static int norm_bwd_launch(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, const float* beta, T* dz,
+                           float* dgamma, float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch,
+                           int dz_pitch, float slope, float* scratch, cudaStream_t st) {
+    const int slabs = norm_slabs(n, vox);
+    float* part = scratch;
+    float* sums = scratch + (size_t)n * slabs * c * 2;
+    const int ncg = c / VW, R = 256 / ncg;
+    const size_t sh = (size_t)R * c * 2 * sizeof(float);
+    dim3 grid(slabs, n);
+    B2_LAUNCH((norm_bwd_reduce_kernel<T, VW, RC>), grid, 256, sh, st, z, y, dy, stats, gamma, beta, slabs, vox, c, z_pitch, y_pitch,
+              dy_pitch, slope, part);
+    B2_LAUNCH(norm_bwd_finalize_kernel, cdiv(c, 8), 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
+    const long long total = (long long)n * vox * (c / VW);
+    const int g2 = stream_grid(total);
+    const float inv_v = (float)(1.0 / (double)vox);
+    B2_LAUNCH((norm_bwd_apply_kernel<T, VW, RC>), g2, 256, 0, st, z, y, dy, stats, gamma, beta, sums, dz, n, vox, c, z_pitch, y_pitch,
+              dy_pitch, dz_pitch, slope, inv_v);
+    return B2_OK;
+}
+
+// beta != nullptr: the activation sign is recomputed from z (y is not read); beta == nullptr: read y.
 template <typename T>
-int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, T* dz, float* dgamma,
-                   float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
+int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, const float* beta, T* dz,
+                   float* dgamma, float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
                    float slope, float* scratch, cudaStream_t st) {
     B2_CHECK_ARG(c <= 1024);
     int vw = pick_vw(c, z_pitch, y_pitch, dy_pitch, dz_pitch, sizeof(T));
     B2_CHECK_ARG(c / vw <= 256);
-    const int slabs = norm_slabs(n, vox);
-    float* part = scratch;
-    float* sums = scratch + (size_t)n * slabs * c * 2;
-    const int ncg = c / vw, R = 256 / ncg;
-    const size_t sh = (size_t)R * c * 2 * sizeof(float);
-    dim3 grid(slabs, n);
-    if (vw == 8) B2_LAUNCH((norm_bwd_reduce_kernel<T, 8>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
-    else if (vw == 4) B2_LAUNCH((norm_bwd_reduce_kernel<T, 4>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
-    else B2_LAUNCH((norm_bwd_reduce_kernel<T, 1>), grid, 256, sh, st, z, y, dy, stats, slabs, vox, c, z_pitch, y_pitch, dy_pitch, slope, part);
-    B2_LAUNCH(norm_bwd_finalize_kernel, cdiv(c, 32), 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
-    const long long total = (long long)n * vox * (c / vw);
-    const int g2 = stream_grid(total);
-    const float inv_v = (float)(1.0 / (double)vox);
-    if (vw == 8) B2_LAUNCH((norm_bwd_apply_kernel<T, 8>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
-    else if (vw == 4) B2_LAUNCH((norm_bwd_apply_kernel<T, 4>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
-    else B2_LAUNCH((norm_bwd_apply_kernel<T, 1>), g2, 256, 0, st, z, y, dy, stats, gamma, sums, dz, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope, inv_v);
-    return B2_OK;
+#define B2_NB(VW_, RC_) norm_bwd_launch<T, VW_, RC_>(z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, \
+                                                    dy_pitch, dz_pitch, slope, scratch, st)
+    if (beta) return vw == 8 ? B2_NB(8, true) : vw == 4 ? B2_NB(4, true) : B2_NB(1, true);
+    return vw == 8 ? B2_NB(8, false) : vw == 4 ? B2_NB(4, false) : B2_NB(1, false);
+#undef B2_NB
 }
 
 template int norm_lrelu_fwd<float>(const float*, const float*, const float*, const float*, float*, int, long long, int, int, int, float, cudaStream_t);
 template int norm_lrelu_fwd<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, const float*, __nv_bfloat16*, int, long long, int, int, int, float, cudaStream_t);
-template int norm_lrelu_bwd<float>(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
-template int norm_lrelu_bwd<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
+template int norm_lrelu_bwd<float>(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
+template int norm_lrelu_bwd<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*, const float*, __nv_bfloat16*, float*, float*, int, long long, int, int, int, int, int, float, float*, cudaStream_t);
 
 }  // namespace b2

@@ -31,6 +31,7 @@ std::atomic<long long> g_launches{0};
 int g_use_tc = 1;
 int g_tc_strided = 1;
 int g_tc_wgrad = 1;
+int g_norm_recompute = 1;   // norm backward recomputes the activation sign from z instead of reading y
 
 int num_sms() {
     static int n = 0;
@@ -301,6 +302,42 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
     if (parts & B2_PART_ENCODER)
         if ((rc = nchw_to_ndhwc<T>(input, P<T>(ws, p, p->x_in, false), g.batch, g.in_channels, p->x_in.vox(), p->x_in.pitch, st))) return rc;
     size_t ci = 0, ti = 0;
+    // bf16 weight shadows of every layer this call runs: ONE multi-tensor launch (tiled transposes) instead of one
+    // scatter kernel per layer
+    bool shadows_batched = false;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        std::vector<ShadowJob> jobs;
+        bool all_ok = true;
+        auto add_conv_job = [&](ConvBlock& cb) {
+            if (p->first_tc && &cb == &p->convs[0]) return;
+            if (!(cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided)) return;
+            if (!shadow_job_supported(cb.shape.cout, cb.shape.cin, 27)) { all_ok = false; return; }
+            jobs.push_back(ShadowJob{prm[cb.p_w], (__nv_bfloat16*)F32(ws, p, cb.wk_off), (__nv_bfloat16*)F32(ws, p, cb.wd_off),
+                                     cb.shape.cout, cb.shape.cin, 27, 1});
+        };
+        for (int d = 0; d <= g.num_pool; ++d) {
+            const bool on = d < g.num_pool ? (parts & B2_PART_ENCODER) != 0 : (parts & B2_PART_BOTTLENECK) != 0;
+            if (!on) continue;
+            add_conv_job(p->convs[2 * d]);
+            add_conv_job(p->convs[2 * d + 1]);
+        }
+        if (parts & B2_PART_DECODER)
+            for (int u = 0; u < g.num_pool; ++u) {
+                Tconv& t = p->tconvs[u];
+                const int k8 = t.shape.k[0] * t.shape.k[1] * t.shape.k[2];
+                if (t.tc) {
+                    if (!shadow_job_supported(t.shape.cin, t.shape.cout, k8)) all_ok = false;
+                    else jobs.push_back(ShadowJob{prm[t.p_w], (__nv_bfloat16*)F32(ws, p, t.wqd_off), (__nv_bfloat16*)F32(ws, p, t.wqb_off),
+                                                  t.shape.cin, t.shape.cout, k8, 0});
+                }
+                add_conv_job(p->convs[2 * (g.num_pool + 1) + 2 * u]);
+                add_conv_job(p->convs[2 * (g.num_pool + 1) + 2 * u + 1]);
+            }
+        if (all_ok && !jobs.empty()) {
+            if ((rc = shadow_multi(jobs.data(), (int)jobs.size(), st))) return rc;
+            shadows_batched = true;
+        }
+    }
     auto run_conv = [&](ConvBlock& cb) -> int {
         float* wf = F32(ws, p, cb.wf_off);
         float* wb = F32(ws, p, cb.wb_off);
@@ -334,7 +371,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 if (r) return r;
                 done = true;
             }
-            if (!done && (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided)) {
+            if (!done && !shadows_batched && (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided)) {
                 r = weight_shadow_bf16(prm[cb.p_w], cb.shape.cout, cb.shape.cin, (__nv_bfloat16*)F32(ws, p, cb.wk_off),
                                        (__nv_bfloat16*)F32(ws, p, cb.wd_off), st);
                 if (r) return r;
@@ -370,8 +407,9 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         bool tdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (t.tc) {
-                if ((rc = tconv_shadow_bf16(prm[t.p_w], t.shape.cin, t.shape.cout, k8, (__nv_bfloat16*)F32(ws, p, t.wqb_off),
-                                            (__nv_bfloat16*)F32(ws, p, t.wqd_off), st))) return rc;
+                if (!shadows_batched)
+                    if ((rc = tconv_shadow_bf16(prm[t.p_w], t.shape.cin, t.shape.cout, k8, (__nv_bfloat16*)F32(ws, p, t.wqb_off),
+                                                (__nv_bfloat16*)F32(ws, p, t.wqd_off), st))) return rc;
                 if ((rc = tconv_tc_fwd(P<T>(ws, p, t.in, false), g.batch, t.in.d, t.in.h, t.in.w, t.shape.cin, t.in.pitch,
                                        (const __nv_bfloat16*)F32(ws, p, t.wqb_off), t.shape.cout, t.shape.k, P<T>(ws, p, t.out, false),
                                        t.out.pitch, st))) return rc;
@@ -402,7 +440,8 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
     T* dz = reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off;
     auto conv_bwd = [&](ConvBlock& cb) -> int {
         float* stats = F32(ws, p, cb.stats_off);
-        int r = norm_lrelu_bwd<T>(P<T>(ws, p, cb.z, false), P<T>(ws, p, cb.y, false), P<T>(ws, p, cb.dy, true), stats, prm[cb.p_g], dz,
+        int r = norm_lrelu_bwd<T>(P<T>(ws, p, cb.z, false), P<T>(ws, p, cb.y, false), P<T>(ws, p, cb.dy, true), stats, prm[cb.p_g],
+                                  g_norm_recompute ? prm[cb.p_be] : nullptr, dz,
                                   grads[cb.p_g], grads[cb.p_be], g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch,
                                   cb.dy.pitch, cb.shape.cout, g.lrelu_slope, SCR(ws, p), st);
         if (r) return r;
@@ -524,6 +563,11 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "tc_strided")) { g_tc_strided = value; return B2_OK; }
     if (!strcmp(name, "tc_wgrad")) { g_tc_wgrad = value; return B2_OK; }
     if (!strcmp(name, "tc_halo")) { g_use_halo = value; return B2_OK; }
+    if (!strcmp(name, "dgrad_one_launch")) { g_dgrad_one_launch = value; return B2_OK; }
+    if (!strcmp(name, "wgrad_dmerge")) { g_wgrad_dmerge = value; return B2_OK; }
+    if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
+    if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
+    if (!strcmp(name, "norm_recompute")) { g_norm_recompute = value; return B2_OK; }
     if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
     return fail(B2_EINVAL, "unknown option %s", name);
 }
@@ -763,9 +807,9 @@ extern "C" int b2_norm_lrelu_bwd(const void* z, const void* y, const void* dy, c
     B2_CHECK_ARG(z && y && dy && stats && gamma && dz && scratch);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == B2_F32)
-        return norm_lrelu_bwd<float>((const float*)z, (const float*)y, (const float*)dy, stats, gamma, (float*)dz, dgamma, dbeta, n, vox, c,
+        return norm_lrelu_bwd<float>((const float*)z, (const float*)y, (const float*)dy, stats, gamma, nullptr, (float*)dz, dgamma, dbeta, n, vox, c,
                                      z_pitch, y_pitch, dy_pitch, dz_pitch, slope, (float*)scratch, st);
     return norm_lrelu_bwd<__nv_bfloat16>((const __nv_bfloat16*)z, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, stats, gamma,
-                                         (__nv_bfloat16*)dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope,
+                                         nullptr, (__nv_bfloat16*)dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch, slope,
                                          (float*)scratch, st);
 }

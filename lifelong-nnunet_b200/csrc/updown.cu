@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(256) seghead_dgrad_kernel(const float* __restr
     }
 }
 
-// dw[k][c] partial per slab: thread = (channel group of VW, row lane); VW-wide vector loads of y
+// dw[k][c] partial per (slab, sample): thread = (channel group of VW, row lane); VW-wide vector loads of y.
+// grid = (slabs, n): a slab never straddles two samples, so the loop carries no 64-bit division.
 template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_wgrad_kernel(const T* __restrict__ y, const float* __restrict__ dl,
                                                             int slabs, int n, long long vox, int c, int ncls,
@@ -320,39 +321,56 @@ __global__ void __launch_bounds__(256) seghead_wgrad_kernel(const T* __restrict_
     const int ncg = c / VW;
     const int R = 256 / ncg;
     const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
-    const long long total = (long long)n * vox;
-    const long long per = (total + slabs - 1) / slabs;
-    const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < total ? v0 + per : total;
+    const int nn = blockIdx.y;
+    const long long per = (vox + slabs - 1) / slabs;
+    const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < vox ? v0 + per : vox;
     float acc[MAXCLS][VW];
 #pragma unroll
     for (int k = 0; k < MAXCLS; ++k)
 #pragma unroll
         for (int j = 0; j < VW; ++j) acc[k][j] = 0.f;
     if (r < R) {
+        const T* yp = y + (long long)nn * vox * y_pitch + cg * VW;
+        const float* dp = dl + (long long)nn * ncls * vox;
+#pragma unroll 2
         for (long long v = v0 + r; v < v1; v += R) {
             float a[VW];
-            if (VW == 8) load8(y + v * y_pitch + cg * VW, *reinterpret_cast<float(*)[8]>(a));
-            else a[0] = to_f(y[v * y_pitch + cg]);
-            const int nn = (int)(v / vox);
-            const long long vv = v % vox;
+            if (VW == 8) load8(yp + v * y_pitch, *reinterpret_cast<float(*)[8]>(a));
+            else a[0] = to_f(yp[v * y_pitch]);
 #pragma unroll
             for (int k = 0; k < MAXCLS; ++k)
                 if (k < ncls) {
-                    const float d = dl[((long long)nn * ncls + k) * vox + vv];
+                    const float d = dp[(long long)k * vox + v];
 #pragma unroll
                     for (int j = 0; j < VW; ++j) acc[k][j] = fmaf(a[j], d, acc[k][j]);
                 }
         }
-        for (int k = 0; k < ncls; ++k)
 #pragma unroll
-            for (int j = 0; j < VW; ++j) sh[((size_t)r * ncls + k) * c + cg * VW + j] = acc[k][j];
+        for (int k = 0; k < MAXCLS; ++k)   // fully unrolled: a runtime-indexed acc[k] would live in local memory
+            if (k < ncls) {
+#pragma unroll
+                for (int j = 0; j < VW; ++j) sh[((size_t)r * ncls + k) * c + cg * VW + j] = acc[k][j];
+            }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < ncls * c; e += 256) {
         float s = 0.f;
         for (int q = 0; q < R; ++q) s += sh[(size_t)q * ncls * c + e];
-        part[(long long)blockIdx.x * ncls * c + e] = s;
+        part[((long long)nn * slabs + blockIdx.x) * ncls * c + e] = s;
     }
+}
+
+// out[i] = sum_k part[k][i] for MANY partials of FEW outputs: one warp per output, lanes stride the partials, fixed
+// shuffle tree (bit-reproducible).  (The thread-per-output kernel walks the partials serially: 76 us for 1184 x 96.)
+__global__ void __launch_bounds__(256) ordered_reduce_wide_kernel(const float* __restrict__ part, int nsplit, long long tot,
+                                                                  float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= tot) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int k = lane; k < nsplit; k += 32) s += part[(long long)k * tot + i];
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
 }
 
 template <typename T>
@@ -368,17 +386,17 @@ int seghead_fwd(const T* y, const float* w, float* logits, int n, long long vox,
     return B2_OK;
 }
 
+// slabs per sample
 static int seghead_slabs(int n, long long vox) {
-    long long total = (long long)n * vox;
-    long long s = 8LL * num_sms();
-    long long maxs = (total + 63) / 64;
+    long long s = (8LL * num_sms() + n - 1) / n;
+    long long maxs = (vox + 63) / 64;
     if (s > maxs) s = maxs;
     if (s < 1) s = 1;
     return (int)s;
 }
 
 size_t seghead_bwd_scratch_floats(int n, long long vox, int c, int ncls) {
-    return (size_t)seghead_slabs(n, vox) * ncls * c;
+    return (size_t)n * seghead_slabs(n, vox) * ncls * c;
 }
 
 template <typename T>
@@ -401,10 +419,12 @@ int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int acc
         const int R = 256 / ncg;
         size_t sh = (size_t)R * ncls * c * sizeof(float);
         B2_CHECK_ARG(sh <= 48 * 1024);
-        if (v8) B2_LAUNCH((seghead_wgrad_kernel<T, 8>), slabs, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
-        else B2_LAUNCH((seghead_wgrad_kernel<T, 1>), slabs, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
+        dim3 grid(slabs, n);
+        if (v8) B2_LAUNCH((seghead_wgrad_kernel<T, 8>), grid, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
+        else B2_LAUNCH((seghead_wgrad_kernel<T, 1>), grid, 256, sh, st, y, dlogits, slabs, n, vox, c, ncls, y_pitch, scratch);
         long long tot = (long long)ncls * c;
-        B2_LAUNCH(ordered_reduce_kernel, cdiv(tot, 256), 256, 0, st, scratch, slabs, tot, dw);
+        if (slabs * n >= 64) B2_LAUNCH(ordered_reduce_wide_kernel, cdiv(tot, 8), 256, 0, st, scratch, slabs * n, tot, dw);
+        else B2_LAUNCH(ordered_reduce_kernel, cdiv(tot, 256), 256, 0, st, scratch, slabs * n, tot, dw);
     }
     return B2_OK;
 }

@@ -1,8 +1,9 @@
 #!/bin/bash
+# one GPU-box call: GPU test-suite, bench line, per-launch ncu list of one step
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -6 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-tail -c 1300 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_tc.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_tc.log 2>&1
+tail -15 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+tail -c 900 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
