@@ -412,6 +412,11 @@ int instnorm_stats(const T* z, int n, long long vox, int c, int pitch, float* pa
     B2_LAUNCH(stats_finalize_kernel, g2, 256, 0, st, part, slabs, c, 1.0 / (double)vox, eps, stats);
     return B2_OK;
 }
+int stats_finalize(const float* part, int slots, int n, long long vox, int c, float eps, float* stats, cudaStream_t st) {
+    dim3 g2(n, cdiv(c, 8));
+    B2_LAUNCH(stats_finalize_kernel, g2, 256, 0, st, part, slots, c, 1.0 / (double)vox, eps, stats);
+    return B2_OK;
+}
 template int instnorm_stats<float>(const float*, int, long long, int, int, float*, float*, float, cudaStream_t);
 template int instnorm_stats<__nv_bfloat16>(const __nv_bfloat16*, int, long long, int, int, float*, float*, float, cudaStream_t);
 

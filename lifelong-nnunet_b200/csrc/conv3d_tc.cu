@@ -112,7 +112,8 @@ constexpr int MAX_STAGES = 16;
 template <int KC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcConvParams p,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, float* __restrict__ partial) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, float* __restrict__ partial,
+               EpiStats es) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
@@ -210,10 +211,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w_ = r % p.TW, h_ = (r / p.TW) % p.TH, d_ = (r / (p.TW * p.TH)) % p.TD, n_ = r / (p.TW * p.TH * p.TD);
         int acc = 0;
         uint32_t acc_phase = 0;
+        // InstanceNorm statistics from the fp32 accumulators (host enables this only for TN == 1, one column block, no split-K):
+        // lane = column of each 32-column chunk; flushed whenever the CTA moves on to the next sample
+        float st1[8], st2[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
+        int n_cur = -1, n_done = 0;
+        const int st_slot = (int)blockIdx.x * 4 + q;
+        auto st_write = [&](int nn, bool zero) {
+            for (int ch = 0; ch < p.BN / 32; ++ch) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k == ch && !zero) { a1 = st1[k]; a2 = st2[k]; }
+                *reinterpret_cast<float2*>(es.part + (((long long)nn * es.slots + st_slot) * es.C + ch * 32 + lane) * 2) = make_float2(a1, a2);
+            }
+        };
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             TileInfo ti;
             decode_tile(p, tile, ti);
             const int ks = ti.ks, otile = ti.otile, nb = ti.nb;
+            if (es.part && ti.tn != n_cur) {
+                if (n_cur >= 0) { st_write(n_cur, false); n_done = n_cur + 1; }
+                for (int nz = n_done; nz < ti.tn; ++nz) st_write(nz, true);
+                n_done = ti.tn; n_cur = ti.tn;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
+            }
             const int lw = ti.tw * p.TW + w_, lh = ti.th * p.TH + h_, ld = ti.td * p.TD + d_, on = ti.tn * p.TN + n_;
             int ow = lw * p.os_w + ti.oo_w, oh = lh * p.os_h + ti.oo_h, od = ld * p.os_d + ti.oo_d;
             int chan0 = nb * p.BN;
@@ -238,28 +262,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 32; e += 4)
                         *reinterpret_cast<float4*>(pp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
                                                                          __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-                } else if (valid) {
+                } else {
+                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float f[8];
+                    for (int e = 0; e < 32; ++e) {
+                        f[e] = __uint_as_float(v[e]);
+                        if (bias) f[e] += bias[chan0 + c0 + e];
+                    }
+                    if (valid) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            f[e] = __uint_as_float(v[j + e]);
-                            if (bias) f[e] += bias[chan0 + c0 + j + e];
+                        for (int j = 0; j < 32; j += 8) {
+                            float o8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o8[e] = f[j + e];
+                            if (accumulate) {
+                                float o[8];
+                                load8(row + c0 + j, o);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) o8[e] += o[e];
+                            }
+                            store8(row + c0 + j, o8);
                         }
-                        if (accumulate) {
-                            float o[8];
-                            load8(row + c0 + j, o);
+                    }
+                    if (es.part) {
+                        float sq[32];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] += o[e];
+                        for (int e = 0; e < 32; ++e) {
+                            f[e] = valid ? f[e] : 0.f;
+                            sq[e] = f[e] * f[e];
                         }
-                        store8(row + c0 + j, f);
+                        const float a1 = transpose_reduce32(f, lane), a2 = transpose_reduce32(sq, lane);
+                        const int ch = c0 >> 5;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k == ch) { st1[k] += a1; st2[k] += a2; }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (es.part) {
+            if (n_cur >= 0) { st_write(n_cur, false); n_done = n_cur + 1; }
+            for (int nz = n_done; nz < es.N; ++nz) st_write(nz, true);
         }
     }
     tc_fence_before();
@@ -579,12 +625,18 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
 
     static bool attr64 = false, attr32 = false;
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    EpiStats es{nullptr, 0, g.Nout, g.N};
+    if (g.stat_slots) *g.stat_slots = 0;
+    if (g.stat_part && g.stat_slots && g_epi_stats && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256) {
+        es.slots = grid * 4;
+        if ((size_t)g.N * es.slots * g.Nout * 2 <= g.stat_part_floats) { es.part = g.stat_part; *g.stat_slots = es.slots; }
+    }
     if (KC == 64) {
         if (!attr64) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr64 = true; }
-        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch);
+        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch, es);
     } else {
         if (!attr32) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr32 = true; }
-        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch);
+        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch, es);
     }
     if (p.ksplit > 1) {
         const long long total = (long long)otiles * 128 * (BN / 8);
@@ -618,14 +670,19 @@ size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout) {
 // 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes) {
+                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes, int* stat_slots) {
+    // stat_slots != nullptr: the caller wants InstanceNorm partials in `scratch` ([N][*stat_slots][Nout][2], see EpiStats);
+    // *stat_slots == 0 on return means the chosen kernel could not produce them (split-K, batch-spanning boxes, ...)
+    if (stat_slots) *stat_slots = 0;
     if (stride[0] == 1 && stride[1] == 1 && stride[2] == 1 && conv_tc_halo_supported(K, Nout, N, Dd, Hd, Wd))
-        return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st);
+        return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st,
+                                   stat_slots ? scratch : nullptr, scratch_bytes / sizeof(float), stat_slots);
     TcGather g;
     fill_common(g, src, N, Ds, Hs, Ws, K, src_pitch, wmat, Nout, bias, dst, Dd, Hd, Wd, dst_pitch, accumulate);
     for (int a = 0; a < 3; ++a) g.stride[a] = stride[a];
     g.ntaps = 27; g.w_rows = 27 * Nout;
     g.splitk_scratch = scratch; g.splitk_scratch_bytes = scratch_bytes;
+    g.stat_part = stat_slots ? scratch : nullptr; g.stat_part_floats = scratch_bytes / sizeof(float); g.stat_slots = stat_slots;
     for (int t = 0; t < 27; ++t) {
         g.tap_off[t][0] = t / 9 - 1; g.tap_off[t][1] = (t / 3) % 3 - 1; g.tap_off[t][2] = t % 3 - 1;
         g.tap_w[t] = t;

@@ -44,7 +44,7 @@ constexpr int HALO_MAX_ACC = 16;
 template <int KC>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloParams p,
-                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate) {
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, EpiStats es) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t sfull[HALO_MAX_SLOTS], sempty[HALO_MAX_SLOTS], wfull, tfull[HALO_MAX_ACC], tempty[HALO_MAX_ACC];
     __shared__ uint32_t tmem_base_smem;
@@ -189,9 +189,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = q * 32 + lane;
         const int w_ = r & 7, h_ = r >> 3;
         uint32_t oc = 0;   // running output counter: accumulator oc & amask, phase (oc >> nacc_log2) & 1
+        // InstanceNorm statistics of the produced tensor (fp32 accumulator values, before the bf16 rounding): lane = column
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+        int n_cur = -1, n_done = 0;
+        const int st_slot = ((int)blockIdx.x / p.NS) * 4 + q;
+        auto st_write = [&](int nn, bool zero) {
+            for (int ch = 0; ch < p.BN / 32; ++ch) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // (select instead of a runtime index: keeps st1 / st2 in registers)
+                    if (k == ch && !zero) { a1 = st1[k]; a2 = st2[k]; }
+                *reinterpret_cast<float2*>(es.part + (((long long)nn * es.slots + st_slot) * es.C + cs * p.BN + ch * 32 + lane) * 2) = make_float2(a1, a2);
+            }
+        };
         for (int item = item0; item < p.num_items; item += item_step) {
             int n, h0, w0, d0, d1;
             decode(item, n, h0, w0, d0, d1);
+            if (es.part && n != n_cur) {
+                if (n_cur >= 0) { st_write(n_cur, false); n_done = n_cur + 1; }
+                for (int nz = n_done; nz < n; ++nz) st_write(nz, true);
+                n_done = n; n_cur = n;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
+            }
             const int oh = h0 + h_, ow = w0 + w_;
             const bool valid = oh < p.H && ow < p.W;
             for (int od = d0; od < d1; ++od, ++oc) {
@@ -200,32 +220,53 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tfull[acc], (oc >> p.nacc_log2) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+#pragma unroll 1
                 for (int c0 = 0; c0 < p.BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        f[e] = __uint_as_float(v[e]);
+                        if (bias) f[e] += bias[cs * p.BN + c0 + e];
+                    }
                     if (valid) {
 #pragma unroll
                         for (int jj = 0; jj < 32; jj += 8) {
-                            float f[8];
+                            float o8[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                f[e] = __uint_as_float(v[jj + e]);
-                                if (bias) f[e] += bias[cs * p.BN + c0 + jj + e];
-                            }
+                            for (int e = 0; e < 8; ++e) o8[e] = f[jj + e];
                             if (accumulate) {
                                 float o[8];
                                 load8(row + c0 + jj, o);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] += o[e];
+                                for (int e = 0; e < 8; ++e) o8[e] += o[e];
                             }
-                            store8(row + c0 + jj, f);
+                            store8(row + c0 + jj, o8);
                         }
+                    }
+                    if (es.part) {
+                        float sq[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            f[e] = valid ? f[e] : 0.f;
+                            sq[e] = f[e] * f[e];
+                        }
+                        const float a1 = transpose_reduce32(f, lane), a2 = transpose_reduce32(sq, lane);
+                        const int ch = c0 >> 5;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k == ch) { st1[k] += a1; st2[k] += a2; }
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty[acc]);
             }
+        }
+        if (es.part) {
+            if (n_cur >= 0) { st_write(n_cur, false); n_done = n_cur + 1; }
+            for (int nz = n_done; nz < es.N; ++nz) st_write(nz, true);
         }
     }
     tc_fence_before();
@@ -239,6 +280,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int KC, int BN);
 
 int g_halo_merge = 1;
+int g_epi_stats = 1;      // InstanceNorm statistics from the convolution epilogues (no second pass over z)
 int g_halo_nsplit = 1;   // allow splitting the output channels over CTA classes when the weights do not fit
 
 static bool halo_plan(int K, int Nout, int D, int H, int W, int N, HaloParams& p, size_t& smem) {
@@ -295,7 +337,8 @@ bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W) {
 
 // src / dst: NDHWC bf16 of identical spatial extent; wmat: [27][Nout][K] bf16 (forward shadow, or the flipped shadow for dgrad)
 int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
-                        const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st) {
+                        const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st, float* stat_part,
+                        size_t stat_part_floats, int* stat_slots) {
     HaloParams p;
     size_t smem;
     if (!halo_plan(K, Nout, D, H, W, N, p, smem)) return fail(B2_EUNSUPPORTED, "conv_tc_halo: unsupported shape%s", "");
@@ -308,13 +351,19 @@ int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, in
     if (rc) return rc;
     int grid = p.num_items * p.NS < num_sms() ? p.num_items * p.NS : num_sms();
     grid = grid / p.NS * p.NS;   // every column split gets the same number of CTAs
+    EpiStats es{nullptr, 0, Nout, N};
+    if (stat_slots) *stat_slots = 0;
+    if (stat_part && stat_slots && g_epi_stats) {
+        es.slots = grid / p.NS * 4;
+        if ((size_t)N * es.slots * Nout * 2 <= stat_part_floats) { es.part = stat_part; *stat_slots = es.slots; }
+    }
     static bool a32 = false, a64 = false;
     if (K == 32) {
         if (!a32) { B2_CUDA(cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); a32 = true; }
-        B2_LAUNCH(conv_halo_kernel<32>, grid, HALO_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate);
+        B2_LAUNCH(conv_halo_kernel<32>, grid, HALO_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate, es);
     } else {
         if (!a64) { B2_CUDA(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); a64 = true; }
-        B2_LAUNCH(conv_halo_kernel<64>, grid, HALO_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate);
+        B2_LAUNCH(conv_halo_kernel<64>, grid, HALO_THREADS, smem, st, tmA, tmB, p, bias, dst, accumulate, es);
     }
     return B2_OK;
 }

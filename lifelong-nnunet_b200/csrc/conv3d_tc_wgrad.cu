@@ -305,7 +305,7 @@ int g_wgrad_dmerge = 1;
 
 static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) {
     memset(&p, 0, sizeof(p));
-    const bool dmerge = g_wgrad_dmerge && ntaps == 27 && s.cin <= 64 && s.cout <= 64 && s.stride[0] == 1 && s.stride[1] == 1 &&
+    const bool dmerge = g_wgrad_dmerge && ntaps == 27 && s.cin <= 128 && s.cout <= 64 && s.stride[0] == 1 && s.stride[1] == 1 &&
                         s.stride[2] == 1;
     p.dmerge = dmerge ? 1 : 0;
     p.out_taps = ntaps;

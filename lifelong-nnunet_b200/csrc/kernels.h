@@ -60,6 +60,8 @@ struct TcGather {
     // tile classes (strided dgrad: one class per output-parity lattice, one launch): class c uses the taps
     // [cls_tap0[c], +cls_ntaps[c]) of the tables above, lattice offset cls_oo[c] and logical extent cls_L[c]
     int nclass; int cls_tap0[8], cls_ntaps[8], cls_oo[8][3], cls_L[8][3];
+    // optional InstanceNorm partials from the epilogue: part[N][*stat_slots][Nout][2] (see EpiStats in tc_common.cuh)
+    float* stat_part; size_t stat_part_floats; int* stat_slots;
 };
 int conv_tc_gather(const TcGather& g, cudaStream_t st);
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
@@ -72,7 +74,9 @@ int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout
 int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st);
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0);
+                   int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0, int* stat_slots = nullptr);
+// mean / rstd from epilogue partials part[n][slots][c][2]
+int stats_finalize(const float* part, int slots, int n, long long vox, int c, float eps, float* stats, cudaStream_t st);
 size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout);
 bool wgrad_tc_supported(int cin, int cout);
 size_t wgrad_tc_part_floats(const ConvShape& s);
@@ -83,14 +87,15 @@ size_t tconv_wgrad_tc_part_floats(const TconvShape& s);
 int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* part, float* dw, cudaStream_t st);
 bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W);
 int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
-                        const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st);
+                        const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st, float* stat_part = nullptr,
+                        size_t stat_part_floats = 0, int* stat_slots = nullptr);
 bool first_layer_tc_supported(int cin, int cout);
 int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
                         int cout, __nv_bfloat16* wp, cudaStream_t st);
 size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);
 int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
                          float* part, float* dw, float* dbias, cudaStream_t st);
-extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch;
+extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch, g_epi_stats;
 extern int g_wgrad_desc_mode, g_tc_wgrad, g_wgrad_dmerge;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 
@@ -99,6 +104,12 @@ extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (de
 template <typename T>
 int norm_lrelu_fwd(const T* z, const float* stats, const float* gamma, const float* beta, T* y, int n, long long vox,
                    int c, int z_pitch, int y_pitch, float slope, cudaStream_t st);
+// small tensors (deep stages): statistics + apply in ONE launch; also writes stats [n][c]{mean, rstd}
+bool norm_small_supported(long long vox, int c, int p0, int p1, int p2, int p3);
+template <typename T>
+int norm_lrelu_fwd_small(const T* z, const float* gamma, const float* beta, T* y, float* stats, int n, long long vox, int c,
+                         int z_pitch, int y_pitch, float slope, float eps, cudaStream_t st);
+extern int g_norm_small;
 size_t norm_bwd_scratch_floats(int n, long long vox, int c);
 // dz = d(loss)/dz given dy; dgamma/dbeta overwritten. scratch: norm_bwd_scratch_floats floats.
 template <typename T>

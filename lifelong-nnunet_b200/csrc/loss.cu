@@ -93,24 +93,20 @@ __global__ void dsloss_finalize_kernel(const float* __restrict__ part, int B, in
                                        int batch_dice, float smooth, int do_bg, int with_dice, float* __restrict__ coef,
                                        float* __restrict__ loss_out) {
     constexpr int NV = 3 * MAXC + 2;
-    // 32 lanes sum strided subsets of the slabs (fixed order), thread 0 combines the lanes in order
-    extern __shared__ double lane_sum_raw[];   // [lanes][Bc*3*MAXC + 2]
-    const int NL = blockDim.x, LS = (B < 16 ? B : 16) * 3 * MAXC + 2;
+    // stage 1 (256 threads): lane = value index inside a partial row (coalesced 104-byte rows), warp = slab lane; every
+    // thread keeps several independent loads in flight; stage 2: thread 0 combines the 8 warps in order.
+    __shared__ double wsum[8][16][NV];
     const int Bc = B < 16 ? B : 16;
     {
-        double* mine = lane_sum_raw + (size_t)threadIdx.x * LS;
-        for (int i = 0; i < LS; ++i) mine[i] = 0.0;
-        for (int b = 0; b < Bc; ++b)
-            for (int s = threadIdx.x; s < slabs; s += NL) {
-                const float* p = part + ((long long)b * slabs + s) * NV;
-                for (int c = 0; c < C; ++c) {
-                    mine[(b * 3 + 0) * MAXC + c] += p[c];
-                    mine[(b * 3 + 1) * MAXC + c] += p[MAXC + c];
-                    mine[(b * 3 + 2) * MAXC + c] += p[2 * MAXC + c];
-                }
-                mine[LS - 2] += p[3 * MAXC];
-                mine[LS - 1] += p[3 * MAXC + 1];
+        const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int b = 0; b < Bc; ++b) {
+            double a = 0.0;
+            if (j < NV) {
+#pragma unroll 8
+                for (int sl = w; sl < slabs; sl += 8) a += (double)part[((long long)b * slabs + sl) * NV + j];
+                wsum[w][b][j] = a;
             }
+        }
     }
     __syncthreads();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -118,17 +114,16 @@ __global__ void dsloss_finalize_kernel(const float* __restrict__ part, int B, in
     double ce = 0.0, cnt = 0.0;
     for (int b = 0; b < Bc; ++b)
         for (int c = 0; c < MAXC; ++c) { sp[b][c] = 0; spy[b][c] = 0; sy[b][c] = 0; }
-    for (int l = 0; l < NL; ++l) {
-        const double* ls = lane_sum_raw + (size_t)l * LS;
-        for (int b = 0; b < Bc; ++b)
+    for (int b = 0; b < Bc; ++b)
+        for (int w = 0; w < 8; ++w) {
             for (int c = 0; c < C; ++c) {
-                sp[b][c] += ls[(b * 3 + 0) * MAXC + c];
-                spy[b][c] += ls[(b * 3 + 1) * MAXC + c];
-                sy[b][c] += ls[(b * 3 + 2) * MAXC + c];
+                sp[b][c] += wsum[w][b][c];
+                spy[b][c] += wsum[w][b][MAXC + c];
+                sy[b][c] += wsum[w][b][2 * MAXC + c];
             }
-        ce += ls[LS - 2];
-        cnt += ls[LS - 1];
-    }
+            ce += wsum[w][b][3 * MAXC];
+            cnt += wsum[w][b][3 * MAXC + 1];
+        }
     double loss = ce / cnt;  // NaN when every voxel is ignored, like torch
     coef[(long long)B * C * 2] = (float)(1.0 / cnt);
     for (int i = 0; i < B * C * 2; ++i) coef[i] = 0.f;
@@ -464,9 +459,7 @@ extern "C" int b2_dsloss_fwd_bwd(const float* logits, const float* target, int B
     float* coef = part + (size_t)B * slabs * (3 * MAXC + 2);
     dim3 grid(slabs, B);
     B2_LAUNCH(dsloss_reduce_kernel, grid, 256, 0, st, logits, target, C, (long long)V, slabs, ignore_index, part);
-    const int fin_lanes = B <= 4 ? 32 : 8;
-    const size_t fin_sh = (size_t)fin_lanes * ((B < 16 ? B : 16) * 3 * MAXC + 2) * sizeof(double);
-    B2_LAUNCH(dsloss_finalize_kernel, 1, fin_lanes, fin_sh, st, part, B, C, slabs, weight, batch_dice, smooth, do_bg, with_dice, coef, loss_out);
+    B2_LAUNCH(dsloss_finalize_kernel, 1, 256, 0, st, part, B, C, slabs, weight, batch_dice, smooth, do_bg, with_dice, coef, loss_out);
     if (dlogits) {
         long long total = (long long)B * V;
         long long g = (total + 255) / 256, cap = (long long)num_sms() * 16;

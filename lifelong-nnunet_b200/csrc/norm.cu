@@ -168,6 +168,169 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small tensors (the deep, low-resolution stages: <= 4096 voxels per sample).  There the three-launch sequences
+// (statistics partials -> finalize -> apply) are pure launch / latency cost -- the whole tensor is L2-resident -- so one
+// block per (8 channels, sample) does everything in two sweeps over its [vox][8] column strip.
+//   forward : sweep 1 sum z, sum z^2 -> mean, rstd (written to `stats` for the backward); sweep 2 y = lrelu(gamma*zhat+beta)
+//   backward: block per 8 channels, loops the samples: sweep 1 S1 = sum du, S2 = sum du*zhat; sweep 2 dz; dgamma, dbeta
+// All block reductions use a fixed tree (warp shuffles, then the 8 warps in order) => bit-reproducible.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_sum_vec(float (&v)[NV], float (*sh)[NV] /*[8][NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[warp][i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][i];
+        v[i] = t;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) norm_small_fwd_kernel(const T* __restrict__ z, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, T* __restrict__ y,
+                                                             float* __restrict__ stats, int vox, int c, int z_pitch, int y_pitch,
+                                                             float slope, float eps) {
+    __shared__ float sh[8][16];
+    const int c0 = blockIdx.x * 8, n = blockIdx.y;
+    const T* zp = z + (long long)n * vox * z_pitch + c0;
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = 0.f;
+    for (int v = threadIdx.x; v < vox; v += 256) {
+        float a[8];
+        load8(zp + (long long)v * z_pitch, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += a[j]; s[8 + j] += a[j] * a[j]; }
+    }
+    block_sum_vec<16>(s, sh);
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double m = (double)s[j] * (1.0 / (double)vox);
+        double var = (double)s[8 + j] * (1.0 / (double)vox) - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[j] = (float)m;
+        rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+        ga[j] = gamma[c0 + j];
+        be[j] = beta[c0 + j];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            stats[((long long)n * c + c0 + j) * 2] = mean[j];
+            stats[((long long)n * c + c0 + j) * 2 + 1] = rstd[j];
+        }
+    }
+    T* yp = y + (long long)n * vox * y_pitch + c0;
+    for (int v = threadIdx.x; v < vox; v += 256) {
+        float a[8], o[8];
+        load8(zp + (long long)v * z_pitch, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = ga[j] * ((a[j] - mean[j]) * rstd[j]) + be[j];
+            o[j] = u > 0.f ? u : u * slope;
+        }
+        store8(yp + (long long)v * y_pitch, o);
+    }
+}
+
+template <typename T, bool RECOMPUTE>
+__global__ void __launch_bounds__(256) norm_small_bwd_kernel(const T* __restrict__ z, const T* __restrict__ y, const T* __restrict__ dy,
+                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, T* __restrict__ dz,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int n, int vox,
+                                                             int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch, float slope) {
+    __shared__ float sh[8][16];
+    const int c0 = blockIdx.x * 8;
+    float ga[8], be[8], dg[8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga[j] = gamma[c0 + j]; be[j] = RECOMPUTE ? beta[c0 + j] : 0.f; dg[j] = 0.f; db[j] = 0.f; }
+    const float inv_v = (float)(1.0 / (double)vox);
+    for (int nn = 0; nn < n; ++nn) {
+        float mean[8], rstd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mean[j] = stats[((long long)nn * c + c0 + j) * 2];
+            rstd[j] = stats[((long long)nn * c + c0 + j) * 2 + 1];
+        }
+        const T* zp = z + (long long)nn * vox * z_pitch + c0;
+        const T* yp = y + (long long)nn * vox * y_pitch + c0;
+        const T* gp = dy + (long long)nn * vox * dy_pitch + c0;
+        T* op = dz + (long long)nn * vox * dz_pitch + c0;
+        float s[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = 0.f;
+        for (int v = threadIdx.x; v < vox; v += 256) {
+            float a[8], b[8], g[8];
+            load8(zp + (long long)v * z_pitch, a);
+            if (!RECOMPUTE) load8(yp + (long long)v * y_pitch, b);
+            load8(gp + (long long)v * dy_pitch, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float zh = (a[j] - mean[j]) * rstd[j];
+                const float u = RECOMPUTE ? ga[j] * zh + be[j] : b[j];
+                const float du = u > 0.f ? g[j] : g[j] * slope;
+                s[j] += du;
+                s[8 + j] += du * zh;
+            }
+        }
+        block_sum_vec<16>(s, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { db[j] += s[j]; dg[j] += s[8 + j]; }
+        for (int v = threadIdx.x; v < vox; v += 256) {
+            float a[8], b[8], g[8], o[8];
+            load8(zp + (long long)v * z_pitch, a);
+            if (!RECOMPUTE) load8(yp + (long long)v * y_pitch, b);
+            load8(gp + (long long)v * dy_pitch, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float zh = (a[j] - mean[j]) * rstd[j];
+                const float u = RECOMPUTE ? ga[j] * zh + be[j] : b[j];
+                const float du = u > 0.f ? g[j] : g[j] * slope;
+                o[j] = ga[j] * rstd[j] * (du - s[j] * inv_v - zh * s[8 + j] * inv_v);
+            }
+            store8(op + (long long)v * dz_pitch, o);
+        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (dgamma) dgamma[c0 + j] = dg[j];
+            if (dbeta) dbeta[c0 + j] = db[j];
+        }
+    }
+}
+
+int g_norm_small = 1;
+constexpr long long NORM_SMALL_VOX = 4096;
+
+bool norm_small_supported(long long vox, int c, int p0, int p1, int p2, int p3) {
+    return g_norm_small && vox <= NORM_SMALL_VOX && c % 8 == 0 && p0 % 8 == 0 && p1 % 8 == 0 && p2 % 8 == 0 && p3 % 8 == 0;
+}
+
+// statistics + apply in one launch (small tensors); writes `stats` like instnorm_stats would
+template <typename T>
+int norm_lrelu_fwd_small(const T* z, const float* gamma, const float* beta, T* y, float* stats, int n, long long vox, int c,
+                         int z_pitch, int y_pitch, float slope, float eps, cudaStream_t st) {
+    B2_CHECK_ARG(norm_small_supported(vox, c, z_pitch, y_pitch, 8, 8));
+    dim3 grid(c / 8, n);
+    B2_LAUNCH((norm_small_fwd_kernel<T>), grid, 256, 0, st, z, gamma, beta, y, stats, (int)vox, c, z_pitch, y_pitch, slope, eps);
+    return B2_OK;
+}
+template int norm_lrelu_fwd_small<float>(const float*, const float*, const float*, float*, float*, int, long long, int, int, int, float, float, cudaStream_t);
+template int norm_lrelu_fwd_small<__nv_bfloat16>(const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, float*, int, long long, int, int, int, float, float, cudaStream_t);
+
 static int pick_vw(int c, int p0, int p1, int p2, int p3, size_t esz) {
     auto ok = [&](int vw) {
         return c % vw == 0 && p0 % vw == 0 && p1 % vw == 0 && p2 % vw == 0 && p3 % vw == 0;
@@ -235,6 +398,13 @@ int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, cons
                    float* dgamma, float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch,
                    float slope, float* scratch, cudaStream_t st) {
     B2_CHECK_ARG(c <= 1024);
+    if (norm_small_supported(vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch)) {
+        if (beta) B2_LAUNCH((norm_small_bwd_kernel<T, true>), c / 8, 256, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
+                            z_pitch, y_pitch, dy_pitch, dz_pitch, slope);
+        else B2_LAUNCH((norm_small_bwd_kernel<T, false>), c / 8, 256, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
+                       z_pitch, y_pitch, dy_pitch, dz_pitch, slope);
+        return B2_OK;
+    }
     int vw = pick_vw(c, z_pitch, y_pitch, dy_pitch, dz_pitch, sizeof(T));
     B2_CHECK_ARG(c / vw <= 256);
 #define B2_NB(VW_, RC_) norm_bwd_launch<T, VW_, RC_>(z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, \

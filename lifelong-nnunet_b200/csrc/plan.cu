@@ -211,6 +211,7 @@ static int build_plan(b2_unet_plan* p) {
             cb.wk_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             cb.wd_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, (long long)od * oh * ow, cout));
+            p->scratch_floats = max_sz(p->scratch_floats, (size_t)N * num_sms() * 4 * cout * 2);   // epilogue statistics partials
         }
         max_z = max_sz(max_z, cb.z.elems());
         p->scratch_floats = max_sz(p->scratch_floats, conv_stat_part_floats(cb.shape));
@@ -350,6 +351,8 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, need_wf ? wf : nullptr, need_wb ? wb : nullptr, st);
         if (r) return r;
         bool done = false;
+        // deep stages: statistics + normalisation + activation in one launch (norm.cu, small tensors)
+        const bool small = norm_small_supported(cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, 8, 8);
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (p->first_tc && &cb == &p->convs[0]) {
                 __nv_bfloat16* P_ = P<T>(ws, p, p->patch, false);
@@ -365,9 +368,12 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 tg.LD = cb.z.d; tg.LH = cb.z.h; tg.LW = cb.z.w;
                 for (int a = 0; a < 3; ++a) { tg.stride[a] = 1; tg.os[a] = 1; tg.qk[a] = 1; }
                 tg.ntaps = 1;
+                int stat_slots = 0;
+                if (!small) { tg.stat_part = SCR(ws, p); tg.stat_part_floats = p->scratch_floats; tg.stat_slots = &stat_slots; }
                 r = conv_tc_gather(tg, st);
                 if (r) return r;
-                r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
+                if (stat_slots > 0) r = stats_finalize(SCR(ws, p), stat_slots, g.batch, cb.z.vox(), cb.shape.cout, g.norm_eps, stats, st);
+                else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
                 if (r) return r;
                 done = true;
             }
@@ -377,15 +383,21 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 if (r) return r;
             }
             if (cb.tc_fwd) {
+                int stat_slots = 0;
                 r = conv_tc_launch(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch,
                                    (const __nv_bfloat16*)F32(ws, p, cb.wk_off), cb.shape.cout, prm[cb.p_b], P<T>(ws, p, cb.z, false),
-                                   cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st, SCR(ws, p), p->scratch_floats * sizeof(float));
+                                   cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st, SCR(ws, p), p->scratch_floats * sizeof(float),
+                                   small ? nullptr : &stat_slots);
                 if (r) return r;
-                r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
+                if (stat_slots > 0) r = stats_finalize(SCR(ws, p), stat_slots, g.batch, cb.z.vox(), cb.shape.cout, g.norm_eps, stats, st);
+                else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
                 if (r) return r;
                 done = true;
             }
         }
+        if (done && small)
+            return norm_lrelu_fwd_small<T>(P<T>(ws, p, cb.z, false), prm[cb.p_g], prm[cb.p_be], P<T>(ws, p, cb.y, false), stats, g.batch,
+                                           cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, g.lrelu_slope, g.norm_eps, st);
         if (!done) {
             r = conv3d_fwd_simt<T>(cb.shape, P<T>(ws, p, cb.in, false), wf, prm[cb.p_b], P<T>(ws, p, cb.z, false), SCR(ws, p), stats, g.norm_eps, st);
             if (r) return r;
@@ -567,6 +579,8 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "wgrad_dmerge")) { g_wgrad_dmerge = value; return B2_OK; }
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
+    if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
+    if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }
     if (!strcmp(name, "norm_recompute")) { g_norm_recompute = value; return B2_OK; }
     if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
     return fail(B2_EINVAL, "unknown option %s", name);
@@ -702,6 +716,8 @@ extern "C" size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d) {
     if (st2 > part) part = st2;
     size_t sk = conv_tc_splitk_scratch_floats(s.n, s.d, s.h, s.w, s.cout > s.cin ? s.cout : s.cin);
     if (sk > part) part = sk;
+    size_t es = (size_t)s.n * num_sms() * 4 * s.cout * 2;   // InstanceNorm partials from the convolution epilogue
+    if (es > part) part = es;
     return align_up((2 * w + (part > wg ? part : wg) + 64) * sizeof(float));
 }
 
@@ -724,9 +740,11 @@ extern "C" int b2_conv3d_fwd(const b2_conv_desc* d, const void* x, const float* 
         if (rc) return rc;
         const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
         const size_t part_bytes = b2_conv3d_scratch_bytes(d) - 2 * (size_t)27 * s.cin * s.cout * sizeof(float) - 256;
+        int stat_slots = 0;
         rc = conv_tc_launch((const __nv_bfloat16*)x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, wk, s.cout, bias, (__nv_bfloat16*)z, od, oh, ow,
-                            s.out_pitch, s.stride, 0, st, part, part_bytes);
+                            s.out_pitch, s.stride, 0, st, part, part_bytes, stats ? &stat_slots : nullptr);
         if (rc) return rc;
+        if (stats && stat_slots > 0) return stats_finalize(part, stat_slots, s.n, (long long)od * oh * ow, s.cout, eps, stats, st);
         if (stats) return instnorm_stats<__nv_bfloat16>((const __nv_bfloat16*)z, s.n, (long long)od * oh * ow, s.cout, s.out_pitch, part, stats, eps, st);
         return B2_OK;
     }

@@ -98,6 +98,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// Column sums of a 32 x 32 tile held one row per lane (v[j] = element (lane, j)): 31 shuffles instead of 32 x 5.
+// Afterwards the return value of lane l is the sum over all lanes of column l.  Fixed tree => bit-reproducible.  v is clobbered.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const bool hi = (lane & off) != 0;
+            const float send = hi ? v[i] : v[i + off];
+            const float keep = hi ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// Per-(sample, channel) sum / sum-of-squares partials produced inside a convolution epilogue (InstanceNorm statistics
+// without a second pass over z).  Layout: part[n][slot][C][2]; a slot is one epilogue warp of one CTA; every (n, slot) row
+// of the channels the warp owns is written exactly once (zeros for samples the CTA never touched).
+struct EpiStats {
+    float* part;      // nullptr: disabled
+    int slots, C, N;
+};
+
 // host: cuTensorMapEncodeTiled via the runtime's driver entry point (no -lcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
