@@ -643,18 +643,34 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __
     const float* src = part + ((long long)t0 * Cin + ci) * Cout + co0 + tx;
     const long long tstride = (long long)Cin * Cout;
     float acc[NT];
+    const int nt = 27 - t0 < NT ? 27 - t0 : NT;
+    long long toff[NT];          // taps beyond the 27th re-read tap 0 of the block (branch-free loads; their sums are never stored)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
-#pragma unroll 4
-    for (int k = ty; k < nsplit; k += 8) {
+    for (int t = 0; t < NT; ++t) { acc[t] = 0.f; toff[t] = (t < nt ? t : 0) * tstride; }
+    // explicit load batches: all loads of a batch are issued before the first add (a predicated `acc += load` compiled to
+    // one exposed L2 round trip per element: 80 us for 32 MB)
+    int k = ty;
+    for (; k + 24 < nsplit; k += 32) {
+        float tmp[4][NT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
-            if (t0 + t < 27) acc[t] += __ldcs(src + (long long)k * tot + t * tstride);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) tmp[u][t] = __ldcs(src + (long long)(k + 8 * u) * tot + toff[t]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t] += tmp[u][t];
+    }
+    for (; k < nsplit; k += 8) {
+        float tmp[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) tmp[t] = __ldcs(src + (long long)k * tot + toff[t]);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] += tmp[t];
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) sh[ty][t][tx] = acc[t];
     __syncthreads();
-    const int nt = 27 - t0 < NT ? 27 - t0 : NT;
     for (int i = threadIdx.x; i < 32 * nt; i += 256) {
         const int col = i / nt, t = i - col * nt;
         float v = 0.f;

@@ -262,8 +262,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 32; e += 4)
                         *reinterpret_cast<float4*>(pp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
                                                                          __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-                } else {
-                    float f[32];
+                } else if (es.part) {
+                    // store + InstanceNorm partial sums of the fp32 values
+                    float f[32], sq[32];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         f[e] = __uint_as_float(v[e]);
@@ -275,27 +276,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float o8[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) o8[e] = f[j + e];
-                            if (accumulate) {
-                                float o[8];
-                                load8(row + c0 + j, o);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) o8[e] += o[e];
-                            }
                             store8(row + c0 + j, o8);
                         }
                     }
-                    if (es.part) {
-                        float sq[32];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            f[e] = valid ? f[e] : 0.f;
-                            sq[e] = f[e] * f[e];
+                    for (int e = 0; e < 32; ++e) {
+                        f[e] = valid ? f[e] : 0.f;
+                        sq[e] = f[e] * f[e];
+                    }
+                    const float a1 = transpose_reduce32(f, lane), a2 = transpose_reduce32(sq, lane);
+                    const int ch = c0 >> 5;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k == ch) { st1[k] += a1; st2[k] += a2; }
+                } else if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            f[e] = __uint_as_float(v[j + e]);
+                            if (bias) f[e] += bias[chan0 + c0 + j + e];
                         }
-                        const float a1 = transpose_reduce32(f, lane), a2 = transpose_reduce32(sq, lane);
-                        const int ch = c0 >> 5;
+                        if (accumulate) {
+                            float o[8];
+                            load8(row + c0 + j, o);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (k == ch) { st1[k] += a1; st2[k] += a2; }
+                            for (int e = 0; e < 8; ++e) f[e] += o[e];
+                        }
+                        store8(row + c0 + j, f);
                     }
                 }
             }
@@ -627,7 +636,9 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     EpiStats es{nullptr, 0, g.Nout, g.N};
     if (g.stat_slots) *g.stat_slots = 0;
-    if (g.stat_part && g.stat_slots && g_epi_stats && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256) {
+    // (few K iterations per tile = epilogue-bound kernel: a separate streaming pass over z is cheaper there)
+    if (g.stat_part && g.stat_slots && g_epi_stats && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256 &&
+        !g.accumulate && kiters_total >= 8) {
         es.slots = grid * 4;
         if ((size_t)g.N * es.slots * g.Nout * 2 <= g.stat_part_floats) { es.part = g.stat_part; *g.stat_slots = es.slots; }
     }

@@ -70,7 +70,7 @@ constexpr int WG_MAX_ASTAGES = 6;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, TcWgradParams p,
-                float* __restrict__ part) {
+                float* __restrict__ part, float* __restrict__ dw_direct) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t fullA[WG_MAX_ASTAGES], emptyA[WG_MAX_ASTAGES], fullB[2], emptyB[2], done_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -226,7 +226,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = 0u;
                 }
-                if (valid) {
+                if (valid && dw_direct) {
+                    // single split (deep layers: a handful of voxel tiles): this CTA holds the complete sums of its rows, so
+                    // it writes dW in the PyTorch layout [co][ci][taps] itself -- no partial tensor, no reduction launch
+                    const int kd = c0 / p.co_blk, cc0 = c0 - kd * p.co_blk;
+                    const int tap_out = p.dmerge ? kd * 9 + tap : tap;
+                    float* dstp = dw_direct + ((size_t)(cob * p.co_blk + cc0) * p.Cin + ci) * p.out_taps + tap_out;
+                    const size_t cstride = (size_t)p.Cin * p.out_taps;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dstp[e * cstride] = __uint_as_float(v[e]);
+                } else if (valid) {
                     const int kd = c0 / p.co_blk, cc0 = c0 - kd * p.co_blk;    // d-merged: column block -> kd
                     const int tap_out = p.dmerge ? kd * 9 + tap : tap;
                     float* dstp = out + ((size_t)tap_out * p.Cin + ci) * p.Cout + cob * p.co_blk + cc0;
@@ -302,6 +311,7 @@ bool wgrad_tc_supported(int cin, int cout) {
 }
 
 int g_wgrad_dmerge = 1;
+int g_wgrad_direct = 1;   // single-split layers write dW directly from the wgrad epilogue
 
 static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) {
     memset(&p, 0, sizeof(p));
@@ -340,7 +350,7 @@ static void wgrad_tc_plan(const ConvShape& s, TcWgradParams& p, int ntaps = 27) 
     p.tapsets = cdiv(total_groups, gmax);
     const int items = p.ci_items * p.co_blks * p.tapsets;
     // one resident CTA per SM (200 KB of shared memory): more CTAs than SMs only add partials for the ordered reduction
-    int ns = items >= num_sms() ? 1 : (items * 2 > num_sms() ? (2 * num_sms()) / items : num_sms() / items);
+    int ns = num_sms() / items;
     if (ns < 1) ns = 1;
     if (ns > p.num_vtiles) ns = p.num_vtiles;
     p.nsplit = ns;
@@ -390,7 +400,8 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     static bool attr = false;
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
-    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part);
+    const bool direct = g_wgrad_direct && p.nsplit == 1;
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part, direct ? dw : (float*)nullptr);
     // The bias of a conv that feeds InstanceNorm has an exactly-zero gradient in exact arithmetic (the norm removes the
     // per-channel mean); PyTorch's value there is pure rounding noise, so the network plan asks for the exact value.
     if (dbias && bias_feeds_norm) {
@@ -409,8 +420,10 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
         B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
     }
     // ordered reduction over the split CTAs, written in PyTorch layout [co][ci][27]
-    rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
-    if (rc) return rc;
+    if (!direct) {
+        rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
+        if (rc) return rc;
+    }
     return B2_OK;
 }
 
@@ -470,7 +483,7 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     static bool attr = false;
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
-    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part);
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part, (float*)nullptr);
     const long long tot = (long long)p.ntaps * s.cin * s.cout;
     B2_LAUNCH(tconv_wgrad_reduce_kernel, cdiv(tot, 256), 256, 0, st, part, p.nsplit, p.ntaps, s.cin, s.cout, dw);
     return B2_OK;
@@ -572,7 +585,7 @@ int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N,
     static bool attr = false;
     if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
-    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part);
+    B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmA, tmB, p, part, (float*)nullptr);
     B2_LAUNCH(patch_wgrad_reduce_kernel, cdiv(32 * cout, 256), 256, 0, st, part, p.nsplit, cin, cout, dw);
     if (dbias) B2_CUDA(cudaMemsetAsync(dbias, 0, cout * sizeof(float), st));   // bias feeds InstanceNorm: exactly zero
     return B2_OK;
