@@ -55,7 +55,7 @@ struct TcConvParams {
     int sd, sh, sw;              // source coordinate = logical * s + tap_off
     int os_d, os_h, os_w;        // produced coordinate = logical * os + oo (+ q offset when q_scatter)
     int oo_d, oo_h, oo_w;
-    int q_scatter, nblk_per_q, qk_h, qk_w;   // transposed-conv forward: column block -> (q, channel block)
+    int q_scatter, q_channels, qk_h, qk_w;   // transposed-conv forward: GEMM column -> (q = col / q_channels, channel = col % q_channels)
     int ntaps;
     int stages;
     int num_tiles;               // output tiles x ksplit
@@ -239,19 +239,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int ch = 0; ch < 8; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
             }
             const int lw = ti.tw * p.TW + w_, lh = ti.th * p.TH + h_, ld = ti.td * p.TD + d_, on = ti.tn * p.TN + n_;
-            int ow = lw * p.os_w + ti.oo_w, oh = lh * p.os_h + ti.oo_h, od = ld * p.os_d + ti.oo_d;
-            int chan0 = nb * p.BN;
-            if (p.q_scatter) {
-                const int q = nb / p.nblk_per_q;
-                ow += q % p.qk_w; oh += (q / p.qk_w) % p.qk_h; od += q / (p.qk_w * p.qk_h);
-                chan0 = (nb % p.nblk_per_q) * p.BN;
-            }
-            const bool valid = lw < ti.LW && lh < ti.LH && ld < ti.LD && on < p.N && ow < p.W && oh < p.H && od < p.D;
-            __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
+            const int ow0 = lw * p.os_w + ti.oo_w, oh0 = lh * p.os_h + ti.oo_h, od0 = ld * p.os_d + ti.oo_d;
+            const bool in_grid = lw < ti.LW && lh < ti.LH && ld < ti.LD && on < p.N;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                // column chunk -> produced voxel / channel (transposed conv: a tile spans several q, one per chunk group)
+                int ow = ow0, oh = oh0, od = od0, chan0 = nb * p.BN;
+                if (p.q_scatter) {
+                    const int col = nb * p.BN + c0, qq = col / p.q_channels;
+                    chan0 = col - qq * p.q_channels - c0;
+                    ow += qq % p.qk_w; oh += (qq / p.qk_w) % p.qk_h; od += qq / (p.qk_w * p.qk_h);
+                }
+                const bool valid = in_grid && ow < p.W && oh < p.H && od < p.D;
+                __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld_wait();
@@ -346,9 +348,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(TcConvParams p, cons
         int ow = lw * p.os_w + p.oo_w, oh = lh * p.os_h + p.oo_h, od = ld * p.os_d + p.oo_d;
         int chan0 = nb * p.BN;
         if (p.q_scatter) {
-            const int q = nb / p.nblk_per_q;
-            ow += q % p.qk_w; oh += (q / p.qk_w) % p.qk_h; od += q / (p.qk_w * p.qk_h);
-            chan0 = (nb % p.nblk_per_q) * p.BN;
+            const int col = nb * p.BN + cg * 8, qq = col / p.q_channels;
+            ow += qq % p.qk_w; oh += (qq / p.qk_w) % p.qk_h; od += qq / (p.qk_w * p.qk_h);
+            chan0 = col - qq * p.q_channels - cg * 8;
         }
         if (!(lw < p.LW && lh < p.LH && ld < p.LD && on < p.N && ow < p.W && oh < p.H && od < p.D)) continue;
         float f[8];
@@ -553,10 +555,18 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     const int KC = (g.K % 64 == 0) ? 64 : 32;
     int nblk, BN;
     if (g.q_scatter) {
-        // column blocks must not straddle q: block the per-q channel count
-        int per = cdiv(g.q_channels, 256);
-        while (g.q_channels % per != 0 || (g.q_channels / per) % 32 != 0) ++per;
-        BN = g.q_channels / per;
+        // 32-column chunks must not straddle q (q_channels % 32 == 0).  Narrow layers: one tile spans several q (BN = 256)
+        // -- a tile per q made Cout = 32 layers run as 8x more (K-iteration-free, epilogue-bound) tiles; wide layers: block
+        // the per-q channel count
+        B2_CHECK_ARG(g.q_channels % 32 == 0);
+        if (g.q_channels <= 256 && 256 % g.q_channels == 0) {
+            BN = g.Nout < 256 ? g.Nout : 256;
+            while (g.Nout % BN != 0) BN -= g.q_channels;
+        } else {
+            int per = cdiv(g.q_channels, 256);
+            while (g.q_channels % per != 0 || (g.q_channels / per) % 32 != 0) ++per;
+            BN = g.q_channels / per;
+        }
         nblk = g.Nout / BN;
     } else {
         nblk = cdiv(g.Nout, 256);
@@ -576,7 +586,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     p.sd = g.stride[0]; p.sh = g.stride[1]; p.sw = g.stride[2];
     p.os_d = g.os[0]; p.os_h = g.os[1]; p.os_w = g.os[2];
     p.oo_d = g.oo[0]; p.oo_h = g.oo[1]; p.oo_w = g.oo[2];
-    p.q_scatter = g.q_scatter; p.nblk_per_q = g.q_scatter ? g.q_channels / BN : 1; p.qk_h = g.qk[1]; p.qk_w = g.qk[2];
+    p.q_scatter = g.q_scatter; p.q_channels = g.q_scatter ? g.q_channels : 1; p.qk_h = g.qk[1]; p.qk_w = g.qk[2];
     p.ntaps = g.ntaps;
     for (int t = 0; t < g.ntaps; ++t) {
         for (int a = 0; a < 3; ++a) p.tap_off[t][a] = (signed char)g.tap_off[t][a];
