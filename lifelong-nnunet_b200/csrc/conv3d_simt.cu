@@ -195,11 +195,16 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __rest
     if (c >= C) return;
     const float* p = part + ((long long)n * tiles * C + c) * 2;
     double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-    for (int t = lane; t < tiles; t += 32) {
-        const float2 v = *reinterpret_cast<const float2*>(p + (long long)t * C * 2);
-        s1 += (double)v.x;
-        s2 += (double)v.y;
+    // batches of 8 independent loads (a plain `s += load` loop compiles to one exposed L2 round trip per element)
+    for (int t0 = lane; t0 < tiles; t0 += 256) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = t0 + 32 * u;
+            v[u] = t < tiles ? *reinterpret_cast<const float2*>(p + (long long)t * C * 2) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
@@ -684,10 +689,10 @@ int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, 
     if (!db && cout % 32 == 0) {
         const int xb = cin * (cout / 32);
         // few (ci, co-block) pairs (thin layers, hundreds of partials): split the taps over grid.y for parallelism
-        if (xb * 3 >= 2 * num_sms()) {
+        if (xb >= 4 * num_sms()) {
             dim3 grid(xb, 1);
             B2_LAUNCH(wgrad_reduce_tiled_kernel<27>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
-        } else if (xb * 9 >= 2 * num_sms()) {
+        } else if (xb * 3 >= 4 * num_sms()) {
             dim3 grid(xb, 3);
             B2_LAUNCH(wgrad_reduce_tiled_kernel<9>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
         } else {

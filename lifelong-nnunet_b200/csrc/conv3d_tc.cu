@@ -241,6 +241,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int lw = ti.tw * p.TW + w_, lh = ti.th * p.TH + h_, ld = ti.td * p.TD + d_, on = ti.tn * p.TN + n_;
             const int ow0 = lw * p.os_w + ti.oo_w, oh0 = lh * p.os_h + ti.oo_h, od0 = ld * p.os_d + ti.oo_d;
             const bool in_grid = lw < ti.LW && lh < ti.LH && ld < ti.LD && on < p.N;
+            // accumulate mode (skip-connection gradients): the read of the destination row is issued BEFORE waiting for the
+            // accumulator (and for the next chunk before the current one is consumed), so its latency overlaps the MMAs
+            const bool pf = accumulate && !p.q_scatter && p.ksplit == 1 && in_grid && ow0 < p.W && oh0 < p.H && od0 < p.D;
+            const __nv_bfloat16* row_pf = dst + ((((long long)on * p.D + od0) * p.H + oh0) * p.W + ow0) * p.dst_pitch + nb * p.BN;
+            uint4 pre[4];
+            if (pf) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pre[j] = *reinterpret_cast<const uint4*>(row_pf + 8 * j);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -256,6 +265,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
+                uint4 cur[4];
+                if (pf) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cur[j] = pre[j];
+                    if (c0 + 32 < p.BN) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pre[j] = *reinterpret_cast<const uint4*>(row_pf + c0 + 32 + 8 * j);
+                    }
+                }
                 tmem_ld_wait();
                 if (p.ksplit > 1) {
                     // fp32 partial [ks][output tile][row][BN]; reduced in fixed order by splitk_reduce_kernel
@@ -300,7 +318,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             f[e] = __uint_as_float(v[j + e]);
                             if (bias) f[e] += bias[chan0 + c0 + j + e];
                         }
-                        if (accumulate) {
+                        if (pf) {
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[j >> 3]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 o2 = __bfloat1622float2(h[e]);
+                                f[2 * e] += o2.x; f[2 * e + 1] += o2.y;
+                            }
+                        } else if (accumulate) {
                             float o[8];
                             load8(row + c0 + j, o);
 #pragma unroll
@@ -474,13 +499,41 @@ __global__ void __launch_bounds__(256) shadow_multi_kernel(const __grid_constant
     const int tb = B >> 5;
     const int a0 = (tile / tb) << 5, b0 = (tile % tb) << 5;
     const float* __restrict__ w = jobs.w[j];
-    const int rowlen = 32 * T;
-    // load: 32 rows (a) of 32*T contiguous floats
-    for (int a = 0; a < 32; ++a) {
-        const float* src = w + ((long long)(a0 + a) * B + b0) * T;
-        for (int r = threadIdx.x; r < rowlen; r += 256) {
-            const int b = r / T, t = r - b * T;
-            sh_w[t * SH_TSTRIDE + a * SH_ROW + b] = __float2bfloat16_rn(src[r]);
+    // load: 32 rows (a) of 32*T contiguous floats (16-byte aligned: b0 % 32 == 0), as float4 in batches of 4 independent loads
+    const int row4 = 8 * T, n4 = 32 * row4;
+    if (!(jobs.flip[j] & 2)) {
+        // source not 16-byte aligned (a view at an odd offset): scalar loads
+        const int rowlen = 32 * T;
+        for (int a = 0; a < 32; ++a) {
+            const float* src = w + ((long long)(a0 + a) * B + b0) * T;
+            for (int r = threadIdx.x; r < rowlen; r += 256) {
+                const int b = r / T, t = r - b * T;
+                sh_w[t * SH_TSTRIDE + a * SH_ROW + b] = __float2bfloat16_rn(src[r]);
+            }
+        }
+    } else
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 256 * u;
+            if (i < n4) {
+                const int a = i / row4, r4 = i - a * row4;
+                v[u] = *reinterpret_cast<const float4*>(w + ((long long)(a0 + a) * B + b0) * T + 4 * r4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 256 * u;
+            if (i < n4) {
+                const int a = i / row4, r4 = i - a * row4;
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = 4 * r4 + q, b = r / T, t = r - b * T;
+                    sh_w[t * SH_TSTRIDE + a * SH_ROW + b] = __float2bfloat16_rn(e[q]);
+                }
+            }
         }
     }
     __syncthreads();
@@ -496,7 +549,7 @@ __global__ void __launch_bounds__(256) shadow_multi_kernel(const __grid_constant
         }
     }
     if (oba) {
-        const int flip = jobs.flip[j];
+        const int flip = jobs.flip[j] & 1;
         for (int i = threadIdx.x; i < chunks; i += 256) {
             const int q = i & 3, b = (i >> 2) & 31, t = i >> 7;
             const unsigned short* s = reinterpret_cast<const unsigned short*>(sh_w + t * SH_TSTRIDE + (q * 8) * SH_ROW + b);
@@ -525,7 +578,8 @@ int shadow_multi(const ShadowJob* jobs, int n, cudaStream_t st) {
             const ShadowJob& jb = jobs[base + i];
             B2_CHECK_ARG(shadow_job_supported(jb.A, jb.B, jb.T));
             d.w[i] = jb.w; d.oab[i] = jb.oab; d.oba[i] = jb.oba; d.A[i] = jb.A; d.B[i] = jb.B;
-            d.T[i] = (unsigned char)jb.T; d.flip[i] = (unsigned char)jb.flip;
+            d.T[i] = (unsigned char)jb.T;
+            d.flip[i] = (unsigned char)((jb.flip ? 1 : 0) | (((uintptr_t)jb.w & 15) == 0 ? 2 : 0));   // bit 1: 16-byte aligned source
             d.tile0[i] = tiles;
             tiles += (jb.A / 32) * (jb.B / 32);
         }

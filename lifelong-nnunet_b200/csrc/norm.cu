@@ -88,11 +88,16 @@ __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __r
     for (int nn = 0; nn < n; ++nn) {
         double s1 = 0.0, s2 = 0.0;
         const float* p = part + ((long long)nn * slabs * c + cc) * 2;
-#pragma unroll 4
-        for (int t = lane; t < slabs; t += 32) {
-            const float2 v = *reinterpret_cast<const float2*>(p + (long long)t * c * 2);
-            s1 += (double)v.x;
-            s2 += (double)v.y;
+        // batches of 8 independent loads (a plain `s += load` loop compiles to one exposed L2 round trip per element)
+        for (int t0 = lane; t0 < slabs; t0 += 256) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + 32 * u;
+                v[u] = t < slabs ? *reinterpret_cast<const float2*>(p + (long long)t * c * 2) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
         }
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __r
 // RECOMPUTE: the sign of the pre-activation u = gamma*zhat + beta is recomputed from z (same fp32 expression as the
 // forward kernel) instead of reading y: one tensor read less in both backward sweeps.
 template <typename T, int VW, bool RECOMPUTE>
-__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const T* __restrict__ z, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const T* __restrict__ z, const T* __restrict__ y,
                                                               const T* __restrict__ dy, const float* __restrict__ stats,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               int slabs, long long vox, int c, int z_pitch, int y_pitch,
