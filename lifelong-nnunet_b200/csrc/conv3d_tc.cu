@@ -73,6 +73,9 @@ struct TcConvParams {
     unsigned char cls_tap0[8], cls_ntaps[8];
     signed char cls_oo[8][3];
     short cls_L[8][3], cls_nt[8][3];
+    // magic numbers for the index decode (FastDiv, tc_common.cuh)
+    FastDiv fd_ksplit, fd_nblk, fd_ntw, fd_nth, fd_ntd, fd_qch, fd_qkw, fd_qkh;
+    FastDiv cls_fd[8][3];        // per class: nt_d, nt_h, nt_w
 };
 
 struct TileInfo {
@@ -81,27 +84,38 @@ struct TileInfo {
     int oo_d, oo_h, oo_w, LD, LH, LW;
 };
 
+// class of a tile (tile classes only) and its tap count -- all the MMA warp needs
+__device__ __forceinline__ int tile_class(const TcConvParams& p, int tile) {
+    int c = 0;
+    while (c + 1 < p.nclass && tile >= p.cls_tile0[c + 1]) ++c;
+    return c;
+}
+
 __device__ __forceinline__ void decode_tile(const TcConvParams& p, int tile, TileInfo& ti) {
-    int t = tile, nt_w = p.nt_w, nt_h = p.nt_h, nt_d = p.nt_d;
+    int t = tile;
     ti.tap0 = 0; ti.ntaps = p.ntaps;
     ti.oo_d = p.oo_d; ti.oo_h = p.oo_h; ti.oo_w = p.oo_w;
     ti.LD = p.LD; ti.LH = p.LH; ti.LW = p.LW;
     if (p.nclass > 1) {
-        int c = 0;
-        while (c + 1 < p.nclass && tile >= p.cls_tile0[c + 1]) ++c;
+        const int c = tile_class(p, tile);
         t = tile - p.cls_tile0[c];
         ti.tap0 = p.cls_tap0[c]; ti.ntaps = p.cls_ntaps[c];
         ti.oo_d = p.cls_oo[c][0]; ti.oo_h = p.cls_oo[c][1]; ti.oo_w = p.cls_oo[c][2];
         ti.LD = p.cls_L[c][0]; ti.LH = p.cls_L[c][1]; ti.LW = p.cls_L[c][2];
-        nt_d = p.cls_nt[c][0]; nt_h = p.cls_nt[c][1]; nt_w = p.cls_nt[c][2];
+        ti.ks = 0;                                   // (no split-K with tile classes)
+        ti.otile = t;
+        t = fd_divmod(t, p.fd_nblk, ti.nb);
+        t = fd_divmod(t, p.cls_fd[c][2], ti.tw);
+        t = fd_divmod(t, p.cls_fd[c][1], ti.th);
+        ti.tn = fd_divmod(t, p.cls_fd[c][0], ti.td);
+        return;
     }
-    ti.ks = t % p.ksplit; t /= p.ksplit;
+    t = fd_divmod(t, p.fd_ksplit, ti.ks);
     ti.otile = t;
-    ti.nb = t % p.nblk; t /= p.nblk;
-    ti.tw = t % nt_w; t /= nt_w;
-    ti.th = t % nt_h; t /= nt_h;
-    ti.td = t % nt_d; t /= nt_d;
-    ti.tn = t;
+    t = fd_divmod(t, p.fd_nblk, ti.nb);
+    t = fd_divmod(t, p.fd_ntw, ti.tw);
+    t = fd_divmod(t, p.fd_nth, ti.th);
+    ti.tn = fd_divmod(t, p.fd_ntd, ti.td);
 }
 
 constexpr int TC_PRODUCERS = 4;                       // TMA producer warps (one stage each, round robin): the single-thread
@@ -150,8 +164,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int nb = ti.nb;
                 const int w0 = ti.tw * p.TW * p.sw, h0 = ti.th * p.TH * p.sh, d0 = ti.td * p.TD * p.sd, n0 = ti.tn * p.TN;
                 const int kiters = ti.ntaps * p.kchunks;
-                const int it0 = (int)((long long)kiters * ti.ks / p.ksplit), it1 = (int)((long long)kiters * (ti.ks + 1) / p.ksplit);
-                int tap = ti.tap0 + it0 / p.kchunks, kc = it0 % p.kchunks;
+                int it0 = 0, it1 = kiters, tap = ti.tap0, kc = 0;
+                if (p.ksplit > 1) {
+                    it0 = (int)((long long)kiters * ti.ks / p.ksplit); it1 = (int)((long long)kiters * (ti.ks + 1) / p.ksplit);
+                    tap = ti.tap0 + it0 / p.kchunks; kc = it0 % p.kchunks;
+                }
                 for (int it = it0; it < it1; ++it) {
                     if (gmod == warp) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -182,10 +199,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                TileInfo ti;
-                decode_tile(p, tile, ti);
-                const int kiters = ti.ntaps * p.kchunks;
-                const int n_it = (int)((long long)kiters * (ti.ks + 1) / p.ksplit) - (int)((long long)kiters * ti.ks / p.ksplit);
+                int n_it = p.ntaps * p.kchunks;            // (the MMA warp only needs the iteration count of the tile)
+                if (p.nclass > 1) n_it = p.cls_ntaps[tile_class(p, tile)] * p.kchunks;
+                else if (p.ksplit > 1) {
+                    int ks;
+                    fd_divmod(tile, p.fd_ksplit, ks);
+                    n_it = (int)((long long)n_it * (ks + 1) / p.ksplit) - (int)((long long)n_it * ks / p.ksplit);
+                }
                 for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -241,15 +261,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int lw = ti.tw * p.TW + w_, lh = ti.th * p.TH + h_, ld = ti.td * p.TD + d_, on = ti.tn * p.TN + n_;
             const int ow0 = lw * p.os_w + ti.oo_w, oh0 = lh * p.os_h + ti.oo_h, od0 = ld * p.os_d + ti.oo_d;
             const bool in_grid = lw < ti.LW && lh < ti.LH && ld < ti.LD && on < p.N;
-            // accumulate mode (skip-connection gradients): the read of the destination row is issued BEFORE waiting for the
-            // accumulator (and for the next chunk before the current one is consumed), so its latency overlaps the MMAs
-            const bool pf = accumulate && !p.q_scatter && p.ksplit == 1 && in_grid && ow0 < p.W && oh0 < p.H && od0 < p.D;
-            const __nv_bfloat16* row_pf = dst + ((((long long)on * p.D + od0) * p.H + oh0) * p.W + ow0) * p.dst_pitch + nb * p.BN;
-            uint4 pre[4];
-            if (pf) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pre[j] = *reinterpret_cast<const uint4*>(row_pf + 8 * j);
-            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -257,23 +268,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // column chunk -> produced voxel / channel (transposed conv: a tile spans several q, one per chunk group)
                 int ow = ow0, oh = oh0, od = od0, chan0 = nb * p.BN;
                 if (p.q_scatter) {
-                    const int col = nb * p.BN + c0, qq = col / p.q_channels;
-                    chan0 = col - qq * p.q_channels - c0;
-                    ow += qq % p.qk_w; oh += (qq / p.qk_w) % p.qk_h; od += qq / (p.qk_w * p.qk_h);
+                    int chq, qw, qh;
+                    const int col = nb * p.BN + c0, qq = fd_divmod(col, p.fd_qch, chq);
+                    chan0 = chq - c0;
+                    const int qd = fd_divmod(fd_divmod(qq, p.fd_qkw, qw), p.fd_qkh, qh);
+                    ow += qw; oh += qh; od += qd;
                 }
                 const bool valid = in_grid && ow < p.W && oh < p.H && od < p.D;
                 __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
-                uint4 cur[4];
-                if (pf) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cur[j] = pre[j];
-                    if (c0 + 32 < p.BN) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) pre[j] = *reinterpret_cast<const uint4*>(row_pf + c0 + 32 + 8 * j);
-                    }
-                }
                 tmem_ld_wait();
                 if (p.ksplit > 1) {
                     // fp32 partial [ks][output tile][row][BN]; reduced in fixed order by splitk_reduce_kernel
@@ -318,14 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             f[e] = __uint_as_float(v[j + e]);
                             if (bias) f[e] += bias[chan0 + c0 + j + e];
                         }
-                        if (pf) {
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[j >> 3]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 o2 = __bfloat1622float2(h[e]);
-                                f[2 * e] += o2.x; f[2 * e + 1] += o2.y;
-                            }
-                        } else if (accumulate) {
+                        if (accumulate) {
                             float o[8];
                             load8(row + c0 + j, o);
 #pragma unroll
@@ -641,6 +638,8 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     p.os_d = g.os[0]; p.os_h = g.os[1]; p.os_w = g.os[2];
     p.oo_d = g.oo[0]; p.oo_h = g.oo[1]; p.oo_w = g.oo[2];
     p.q_scatter = g.q_scatter; p.q_channels = g.q_scatter ? g.q_channels : 1; p.qk_h = g.qk[1]; p.qk_w = g.qk[2];
+    p.fd_qch = make_fastdiv(p.q_channels); p.fd_qkw = make_fastdiv(p.qk_w); p.fd_qkh = make_fastdiv(p.qk_h);
+    p.fd_nblk = make_fastdiv(nblk); p.fd_ntw = make_fastdiv(p.nt_w); p.fd_nth = make_fastdiv(p.nt_h); p.fd_ntd = make_fastdiv(p.nt_d);
     p.ntaps = g.ntaps;
     for (int t = 0; t < g.ntaps; ++t) {
         for (int a = 0; a < 3; ++a) p.tap_off[t][a] = (signed char)g.tap_off[t][a];
@@ -658,6 +657,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
             for (int a = 0; a < 3; ++a) { p.cls_oo[c][a] = (signed char)g.cls_oo[c][a]; p.cls_L[c][a] = (short)g.cls_L[c][a]; }
             p.cls_nt[c][0] = (short)cdiv(g.cls_L[c][0], p.TD); p.cls_nt[c][1] = (short)cdiv(g.cls_L[c][1], p.TH);
             p.cls_nt[c][2] = (short)cdiv(g.cls_L[c][2], p.TW);
+            for (int a = 0; a < 3; ++a) p.cls_fd[c][a] = make_fastdiv(p.cls_nt[c][a]);
             acc += p.cls_nt[c][0] * p.cls_nt[c][1] * p.cls_nt[c][2] * p.nt_n * nblk;
         }
         p.cls_tile0[g.nclass] = acc;
@@ -673,6 +673,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
         while (ksplit > 1 && (size_t)ksplit * otiles * 128 * BN * sizeof(float) > g.splitk_scratch_bytes) --ksplit;
     }
     p.ksplit = ksplit;
+    p.fd_ksplit = make_fastdiv(ksplit);
     p.num_tiles = otiles * ksplit;
     p.idesc = umma_idesc_bf16(128, BN);
     uint32_t cols = 32;

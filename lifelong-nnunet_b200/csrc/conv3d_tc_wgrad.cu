@@ -378,15 +378,24 @@ size_t wgrad_tc_part_floats(const ConvShape& s) {
     TcWgradParams p;
     wgrad_tc_plan(s, p);
     size_t colsum = (size_t)(2 * num_sms()) * s.cout;
-    return (size_t)p.nsplit * 27 * s.cin * s.cout + colsum + 64;
+    int nsplit = p.nsplit;
+    if (nsplit < num_sms() && (s.cin == 32 || s.cin == 64) && (s.cout == 32 || s.cout == 64)) nsplit = num_sms();   // halo-reuse plan
+    return (size_t)nsplit * 27 * s.cin * s.cout + colsum + 64;
 }
 
 // wgrad_reduce_kernel lives in conv3d_simt.cu
 int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, int cout, float* dw, float* db, cudaStream_t st);
 
+static int wgrad_bias(const ConvShape& s, const __nv_bfloat16* dz, float* part_b, float* dbias, bool bias_feeds_norm, cudaStream_t st);
+static bool wgrad_halo_plan(const ConvShape& s, struct WgHaloParams& p, size_t& smem);
+static int conv3d_wgrad_halo(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
+                             bool bias_feeds_norm, cudaStream_t st);
+static bool wgrad_halo_ok(const ConvShape& s);
+
 int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
                     bool bias_feeds_norm, cudaStream_t st) {
     B2_CHECK_ARG(wgrad_tc_supported(s.cin, s.cout) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0);
+    if (wgrad_halo_ok(s)) return conv3d_wgrad_halo(s, x, dz, part, dw, dbias, bias_feeds_norm, st);
     TcWgradParams p;
     wgrad_tc_plan(s, p);
     CUtensorMap tmX, tmZ;
@@ -402,23 +411,8 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     const int grid = p.ci_items * p.co_blks * p.tapsets * p.nsplit;
     const bool direct = g_wgrad_direct && p.nsplit == 1;
     B2_LAUNCH(wgrad_tc_kernel, grid, WG_THREADS, smem, st, tmX, tmZ, p, part, direct ? dw : (float*)nullptr);
-    // The bias of a conv that feeds InstanceNorm has an exactly-zero gradient in exact arithmetic (the norm removes the
-    // per-channel mean); PyTorch's value there is pure rounding noise, so the network plan asks for the exact value.
-    if (dbias && bias_feeds_norm) {
-        B2_CUDA(cudaMemsetAsync(dbias, 0, s.cout * sizeof(float), st));
-    } else if (dbias) {
-        float* part_b = part + (size_t)p.nsplit * 27 * s.cin * s.cout;
-        const long long rows = (long long)s.n * p.Do * p.Ho * p.Wo;
-        int slabs = 2 * num_sms();
-        if (slabs > rows) slabs = (int)rows;
-        if (s.cout <= 256) {
-            const int lanes = 256 / s.cout;
-            B2_LAUNCH(colsum_part_kernel, slabs, 256, (size_t)lanes * s.cout * sizeof(float), st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
-        } else {
-            B2_LAUNCH(colsum_wide_kernel, slabs, 256, 0, st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
-        }
-        B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
-    }
+    rc = wgrad_bias(s, dz, part + (size_t)p.nsplit * 27 * s.cin * s.cout, dbias, bias_feeds_norm, st);
+    if (rc) return rc;
     // ordered reduction over the split CTAs, written in PyTorch layout [co][ci][27]
     if (!direct) {
         rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
@@ -427,6 +421,291 @@ int conv3d_wgrad_tc(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloa
     return B2_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Halo-reuse weight gradient for the thin stride-1 layers (Cin, Cout in {32, 64}): the layers that carry half of the FLOPs.
+// wgrad_tc_kernel re-fetches the 128-voxel x box once per tap (9 boxes per voxel tile even when d-merged) and is bound by the
+// ~43 B/clk/SM L2->SM throughput.  Here a voxel tile (2 d x 8 h x 8 w) loads
+//     A: three w-shifted copies (w0-1, w0, w0+1) of the x box [2 d][10 h][8 w]   (rows = voxels, Cin channels per row)
+//     B: ONE dz box [4 d = d0-1 .. d0+2][8 h][8 w]
+// and every operand of the d-merged formulation is a swizzle-atom-aligned sub-view of those:
+//     tap (kh, kw)  ->  copy kw, rows d*80 + (kh + hh)*8 + ww          (kh shifts by whole 8-row atoms)
+//     kd            ->  dz rows (dd + 2 - kd)*64 + hh*8 + ww           (three overlapping 128-row windows, 64 rows apart)
+//     D[(kh, kw, ci), (kd, co)] += sum_u x[u + (0, kh-1, kw-1)][ci] * dz[u - (kd-1, 0, 0)][co]  ==  dW[(kd,kh,kw)][ci][co].
+// Bytes per voxel tile: 3*160*Cin*2 + 256*Cout*2 = 46 KB at 32->32 (d-merged per-tap kernel: 120 KB; original: 232 KB).
+// MN-major UMMA operands as in wgrad_tc_kernel: M = (tap chunk, ci) with the chunk stride (LBO) chosen per accumulator group
+// (kh step = 8 rows, or kw step = one copy), N = (kd, co) with LBO = 64 rows; K = 16 voxels per instruction.
+// Same partial layout / ordered reduction as wgrad_tc_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgHaloParams {
+    int N, D, H, W, Cin, Cout;
+    int nt_n, nt_d, nt_h, nt_w, num_vtiles;
+    int ngroups;                 // accumulator groups in total (3 for Cin = 32, 5 for Cin = 64)
+    int groups;                  // groups per CTA (groups * 3 * Cout <= 512 TMEM columns)
+    int tapsets, nsplit, stages;
+    uint32_t a_off[5], a_lbo[5]; // per group: byte offset of chunk 0 inside the A stage, chunk stride
+    signed char grp_tap[5][4];   // (kh*3 + kw) of each chunk of the group, -1 = unused rows
+    uint32_t idesc, tmem_cols;
+};
+
+constexpr int WH_THREADS = 32 * 6;   // warp 0: TMA producer, 1: MMA issuer + TMEM owner, 2..5: epilogue
+constexpr int WH_MAX_STAGES = 4;
+
+__global__ void __launch_bounds__(WH_THREADS, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, WgHaloParams p,
+                  float* __restrict__ part, float* __restrict__ dw_direct) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full[WH_MAX_STAGES], empty[WH_MAX_STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t ROWA = (uint32_t)p.Cin * 2, ROWB = (uint32_t)p.Cout * 2;
+    const uint32_t COPY = 160u * ROWA, A_BYTES = 3u * COPY, B_BYTES = 256u * ROWB, STAGE = A_BYTES + B_BYTES;
+    const int nper = 3 * p.Cout;
+
+    const int split = blockIdx.x % p.nsplit, tapset = blockIdx.x / p.nsplit;
+    const int g0 = tapset * p.groups;
+    const int my_groups = p.ngroups - g0 < p.groups ? p.ngroups - g0 : p.groups;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmZ);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+                int t = vt;
+                const int tw = t % p.nt_w; t /= p.nt_w;
+                const int th = t % p.nt_h; t /= p.nt_h;
+                const int td = t % p.nt_d; t /= p.nt_d;
+                const int n = t, w0 = tw * 8, h0 = th * 8, d0 = td * 2;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], STAGE);
+                uint8_t* base = smem + (size_t)st * STAGE;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) tma_load_5d(&tmX, &full[st], base + kw * COPY, 0, w0 + kw - 1, h0 - 1, d0, n);
+                tma_load_5d(&tmZ, &full[st], base + A_BYTES, 0, w0, h0, d0 - 1, n);
+                if (++st == p.stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint64_t b_hi = umma_desc_mnmajor(0, ROWB, 64u * ROWB, 8u * ROWB) & 0xFFFFFFFFFFFF0000ull;
+        uint64_t a_hi[5];
+        uint32_t a_off16[5];
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+            const int gg = g0 + g < 5 ? g0 + g : 4;
+            a_hi[g] = umma_desc_mnmajor(0, ROWA, p.a_lbo[gg], 8u * ROWA) & 0xFFFFFFFFFFFF0000ull;
+            a_off16[g] = p.a_off[gg] >> 4;
+        }
+        const uint32_t base16 = (smem_u32(smem) & 0x3FFFF) >> 4, stage16 = STAGE >> 4, ab16 = A_BYTES >> 4;
+        const uint32_t a_d16 = (80u * ROWA) >> 4, a_k16 = (16u * ROWA) >> 4, b_k16 = (16u * ROWB) >> 4;
+        int st = 0;
+        uint32_t ph = 0;
+        bool first = true;
+        for (int vt = split; vt < p.num_vtiles; vt += p.nsplit) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t s16 = base16 + (uint32_t)st * stage16;
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    if (g < my_groups) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(g * nper);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {   // k = (d, ks): 16 voxels of slab d
+                            const uint32_t a_lo = s16 + a_off16[g] + (uint32_t)(k >> 2) * a_d16 + (uint32_t)(k & 3) * a_k16;
+                            const uint32_t b_lo = s16 + ab16 + (uint32_t)k * b_k16;
+                            umma_bf16(d_tmem, a_hi[g] | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, p.idesc, (!first || k != 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(&empty[st]);
+            }
+            __syncwarp();
+            first = false;
+            if (++st == p.stages) { st = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(&done_bar);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int chunk = r / p.Cin, cil = r % p.Cin;
+        const bool has_work = split < p.num_vtiles;
+        if (has_work) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+        }
+        float* out = part + (size_t)split * 27 * p.Cin * p.Cout;
+        for (int g = 0; g < my_groups; ++g) {
+            const int tap9 = p.grp_tap[g0 + g][chunk];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * nper);
+            for (int c0 = 0; c0 < nper; c0 += 32) {
+                uint32_t v[32];
+                if (has_work) {
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = 0u;
+                }
+                if (tap9 >= 0) {
+                    const int kdi = c0 / p.Cout, cc0 = c0 - kdi * p.Cout;
+                    const int tap = (2 - kdi) * 9 + tap9;       // column block kdi holds kd = 2 - kdi
+                    if (dw_direct) {
+                        float* dstp = dw_direct + ((size_t)cc0 * p.Cin + cil) * 27 + tap;
+                        const size_t cstride = (size_t)p.Cin * 27;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) dstp[e * cstride] = __uint_as_float(v[e]);
+                    } else {
+                        float* dstp = out + ((size_t)tap * p.Cin + cil) * p.Cout + cc0;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dstp + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+int g_wgrad_halo = 1;
+
+static bool wgrad_halo_plan(const ConvShape& s, WgHaloParams& p, size_t& smem) {
+    if (!g_wgrad_halo) return false;
+    if (!(s.cin == 32 || s.cin == 64) || !(s.cout == 32 || s.cout == 64)) return false;
+    if (s.stride[0] != 1 || s.stride[1] != 1 || s.stride[2] != 1) return false;
+    if (s.h < 8 || s.w < 8 || s.d < 2) return false;
+    memset(&p, 0, sizeof(p));
+    p.N = s.n; p.D = s.d; p.H = s.h; p.W = s.w; p.Cin = s.cin; p.Cout = s.cout;
+    p.nt_w = cdiv(s.w, 8); p.nt_h = cdiv(s.h, 8); p.nt_d = cdiv(s.d, 2); p.nt_n = s.n;
+    p.num_vtiles = p.nt_w * p.nt_h * p.nt_d * p.nt_n;
+    const uint32_t ROWA = s.cin * 2, COPY = 160u * ROWA;
+    for (int g = 0; g < 5; ++g)
+        for (int c = 0; c < 4; ++c) p.grp_tap[g][c] = -1;
+    if (s.cin == 32) {
+        // one group per kw: chunks kh = 0, 1, 2 (8 rows apart) + one unused chunk
+        p.ngroups = 3;
+        for (int kw = 0; kw < 3; ++kw) {
+            p.a_off[kw] = kw * COPY; p.a_lbo[kw] = 8u * ROWA;
+            for (int kh = 0; kh < 3; ++kh) p.grp_tap[kw][kh] = (signed char)(kh * 3 + kw);
+        }
+    } else {
+        // two chunks per group: (kh 0, kh 1) of each kw; (kw 0, kw 1) of kh 2 (one copy apart); (kh 2, kw 2) + unused
+        p.ngroups = 5;
+        for (int kw = 0; kw < 3; ++kw) {
+            p.a_off[kw] = kw * COPY; p.a_lbo[kw] = 8u * ROWA;
+            p.grp_tap[kw][0] = (signed char)kw; p.grp_tap[kw][1] = (signed char)(3 + kw);
+        }
+        p.a_off[3] = 16u * ROWA; p.a_lbo[3] = COPY;
+        p.grp_tap[3][0] = 6; p.grp_tap[3][1] = 7;
+        p.a_off[4] = 2u * COPY + 16u * ROWA; p.a_lbo[4] = 8u * ROWA;
+        p.grp_tap[4][0] = 8;
+    }
+    const int nper = 3 * s.cout;
+    p.groups = 512 / nper < p.ngroups ? 512 / nper : p.ngroups;
+    p.tapsets = cdiv(p.ngroups, p.groups);
+    int ns = num_sms() / p.tapsets;
+    if (ns < 1) ns = 1;
+    if (ns > p.num_vtiles) ns = p.num_vtiles;
+    p.nsplit = ns;
+    const size_t stage = 3ull * COPY + 256ull * s.cout * 2;
+    int st = (int)((200ull * 1024) / stage);
+    if (st > WH_MAX_STAGES) st = WH_MAX_STAGES;
+    if (st < 2) return false;
+    p.stages = st;
+    smem = (size_t)st * stage + 1024;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.groups * nper)) cols *= 2;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nper >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    return true;
+}
+
+// 5D activation map with an explicit box (channels, w, h, d, n)
+static int make_box_map(CUtensorMap* m, const void* ptr, int N, int D, int H, int W, int C, int pitch, int bc, int bw, int bh, int bd) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return fail(B2_ECUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2, (cuuint64_t)D * H * W * pitch * 2};
+    cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     bc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B2_ECUDA, "cuTensorMapEncodeTiled(box) failed: code %s%lld", "", (long long)r);
+    return B2_OK;
+}
+
+// The bias of a conv that feeds InstanceNorm has an exactly-zero gradient in exact arithmetic (the norm removes the
+// per-channel mean); PyTorch's value there is pure rounding noise, so the network plan asks for the exact value.
+static int wgrad_bias(const ConvShape& s, const __nv_bfloat16* dz, float* part_b, float* dbias, bool bias_feeds_norm, cudaStream_t st) {
+    if (!dbias) return B2_OK;
+    if (bias_feeds_norm) {
+        B2_CUDA(cudaMemsetAsync(dbias, 0, s.cout * sizeof(float), st));
+        return B2_OK;
+    }
+    const int Do = (s.d - 1) / s.stride[0] + 1, Ho = (s.h - 1) / s.stride[1] + 1, Wo = (s.w - 1) / s.stride[2] + 1;
+    const long long rows = (long long)s.n * Do * Ho * Wo;
+    int slabs = 2 * num_sms();
+    if (slabs > rows) slabs = (int)rows;
+    if (s.cout <= 256) {
+        const int lanes = 256 / s.cout;
+        B2_LAUNCH(colsum_part_kernel, slabs, 256, (size_t)lanes * s.cout * sizeof(float), st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+    } else {
+        B2_LAUNCH(colsum_wide_kernel, slabs, 256, 0, st, dz, rows, s.cout, s.out_pitch, slabs, part_b);
+    }
+    B2_LAUNCH(colsum_final_kernel, cdiv(s.cout, 128), 128, 0, st, part_b, slabs, s.cout, dbias);
+    return B2_OK;
+}
+
+static bool wgrad_halo_ok(const ConvShape& s) {
+    WgHaloParams p;
+    size_t smem;
+    return wgrad_halo_plan(s, p, smem) && s.in_pitch % 8 == 0 && s.out_pitch % 8 == 0;
+}
+
+static int conv3d_wgrad_halo(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* dz, float* part, float* dw, float* dbias,
+                             bool bias_feeds_norm, cudaStream_t st) {
+    WgHaloParams p;
+    size_t smem;
+    if (!wgrad_halo_plan(s, p, smem)) return fail(B2_EUNSUPPORTED, "wgrad_halo: unsupported shape%s", "");
+    CUtensorMap tmX, tmZ;
+    int rc = make_box_map(&tmX, x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, s.cin, 8, 10, 2);
+    if (rc) return rc;
+    rc = make_box_map(&tmZ, dz, s.n, s.d, s.h, s.w, s.cout, s.out_pitch, s.cout, 8, 8, 4);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) { B2_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    const bool direct = g_wgrad_direct && p.nsplit == 1;
+    B2_LAUNCH(wgrad_halo_kernel, p.tapsets * p.nsplit, WH_THREADS, smem, st, tmX, tmZ, p, part, direct ? dw : (float*)nullptr);
+    rc = wgrad_bias(s, dz, part + (size_t)p.nsplit * 27 * s.cin * s.cout, dbias, bias_feeds_norm, st);
+    if (rc) return rc;
+    if (!direct) {
+        rc = wgrad_reduce(part, nullptr, p.nsplit, s.cin, s.cout, dw, nullptr, st);
+        if (rc) return rc;
+    }
+    return B2_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // transposed-conv (kernel == stride) weight gradient on the same kernel: dW[ci][co][q] = sum_v x[v][ci] * dy[k*v + q][co].

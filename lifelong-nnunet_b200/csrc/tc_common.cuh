@@ -98,6 +98,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// Division of a non-negative int (< 2^31) by a run-time constant without the ~25-instruction software sequence:
+// q = umulhi(n, m) >> sh with m = ceil(2^(31+s) / d), s = ceil(log2 d), sh = s - 1 (exact for n < 2^31; d == 1 passes through).
+// The per-tile index decode of the persistent kernels ran a dozen such divisions per tile in EVERY role warp; for tiles with
+// few K iterations that scalar stream (790 instructions per tile in the epilogue warps) was the critical path.
+struct FastDiv { uint32_t m, sh, d; };
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f{0u, 0u, (uint32_t)(d < 1 ? 1 : d)};
+    if (f.d > 1) {
+        uint32_t s = 0;
+        while ((1ull << s) < f.d) ++s;
+        f.m = (uint32_t)(((1ull << (31 + s)) + f.d - 1) / f.d);
+        f.sh = s - 1;
+    }
+    return f;
+}
+__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
+    return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.m) >> f.sh);
+}
+// n -> (n / d, n % d)
+__device__ __forceinline__ int fd_divmod(int n, const FastDiv& f, int& rem) {
+    const int q = fd_div(n, f);
+    rem = n - q * (int)f.d;
+    return q;
+}
+
 // Column sums of a 32 x 32 tile held one row per lane (v[j] = element (lane, j)): 31 shuffles instead of 32 x 5.
 // Afterwards the return value of lane l is the sum over all lanes of column l.  Fixed tree => bit-reproducible.  v is clobbered.
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {

@@ -147,7 +147,8 @@ def test_halo_kernel_variants_agree_on_large_volumes(shape):
 
 
 @pytest.mark.parametrize("shape", BIG[:4])
-def test_wgrad_dmerge_agrees_with_per_tap_plan(shape):
+def test_wgrad_variants_agree_on_large_volumes(shape):
+    """halo-reuse wgrad kernel == d-merged per-tap plan == plain per-tap plan (fp32 sums of the same bf16 products)"""
     from b200unet import ops
     N, D, H, W, cin, cout = shape
     x, w, b = _case(N, D, H, W, cin, cout, 6)
@@ -155,10 +156,14 @@ def test_wgrad_dmerge_agrees_with_per_tap_plan(shape):
     dz = torch.randn((N, cout, D, H, W), generator=g)
     xd, dzd, wd_ = _ndhwc(x, torch.bfloat16), _ndhwc(dz, torch.bfloat16), w.cuda()
     try:
+        _, dw_halo, _ = ops.conv3d_bwd(xd, dzd, wd_, (1, 1, 1))
+        ops.set_option("wgrad_halo", 0)
         _, dw1, _ = ops.conv3d_bwd(xd, dzd, wd_, (1, 1, 1))
         ops.set_option("wgrad_dmerge", 0)
         _, dw0, _ = ops.conv3d_bwd(xd, dzd, wd_, (1, 1, 1))
         torch.cuda.synchronize()
     finally:
         ops.set_option("wgrad_dmerge", 1)
-    assert rel_err(dw1, dw0) < 1e-4, rel_err(dw1, dw0)   # fp32 outputs of the same bf16 products
+        ops.set_option("wgrad_halo", 1)
+    assert rel_err(dw1, dw0) < 1e-4, rel_err(dw1, dw0)
+    assert rel_err(dw_halo, dw0) < 1e-4, rel_err(dw_halo, dw0)
