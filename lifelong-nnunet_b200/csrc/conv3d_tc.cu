@@ -120,7 +120,9 @@ __device__ __forceinline__ void decode_tile(const TcConvParams& p, int tile, Til
 
 constexpr int TC_PRODUCERS = 4;                       // TMA producer warps (one stage each, round robin): the single-thread
                                                       // issue latency (~300 cycles per stage) was the bottleneck of round-1 v1
-constexpr int TC_THREADS = 32 * (TC_PRODUCERS + 5);   // producers, 1 MMA warp, 4 epilogue warps
+constexpr int TC_EPI_SETS = 2;                        // epilogue warp sets: set s drains TMEM accumulator s (tiles alternate), so
+                                                      // the scalar-heavy epilogue of short-K tiles runs two tiles at a time
+constexpr int TC_THREADS = 32 * (TC_PRODUCERS + 1 + 4 * TC_EPI_SETS);   // producers, 1 MMA warp, 2 x 4 epilogue warps
 constexpr int MAX_STAGES = 16;
 
 template <int KC>
@@ -226,18 +228,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global =====================
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access (4 consecutive warps: 4 quadrants)
+        const int ew = warp - (TC_PRODUCERS + 1), set = ew >> 2;
         const int r = q * 32 + lane;            // accumulator row == voxel inside the box
         const int w_ = r % p.TW, h_ = (r / p.TW) % p.TH, d_ = (r / (p.TW * p.TH)) % p.TD, n_ = r / (p.TW * p.TH * p.TD);
-        int acc = 0;
+        const int acc = set;                    // tile i of this CTA uses accumulator i & 1 and is drained by set i & 1
         uint32_t acc_phase = 0;
+        int tile_it = 0;
         // InstanceNorm statistics from the fp32 accumulators (host enables this only for TN == 1, one column block, no split-K):
         // lane = column of each 32-column chunk; flushed whenever the CTA moves on to the next sample
         float st1[8], st2[8];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
         int n_cur = -1, n_done = 0;
-        const int st_slot = (int)blockIdx.x * 4 + q;
+        const int st_slot = (int)blockIdx.x * (4 * TC_EPI_SETS) + ew;
         auto st_write = [&](int nn, bool zero) {
             for (int ch = 0; ch < p.BN / 32; ++ch) {
                 float a1 = 0.f, a2 = 0.f;
@@ -247,7 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<float2*>(es.part + (((long long)nn * es.slots + st_slot) * es.C + ch * 32 + lane) * 2) = make_float2(a1, a2);
             }
         };
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_it) {
+            if ((tile_it & 1) != set) continue;
             TileInfo ti;
             decode_tile(p, tile, ti);
             const int ks = ti.ks, otile = ti.otile, nb = ti.nb;
@@ -334,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
         }
         if (es.part) {
             if (n_cur >= 0) { st_write(n_cur, false); n_done = n_cur + 1; }
@@ -704,7 +709,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     // (few K iterations per tile = epilogue-bound kernel: a separate streaming pass over z is cheaper there)
     if (g.stat_part && g.stat_slots && g_epi_stats && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256 &&
         !g.accumulate && kiters_total >= 8) {
-        es.slots = grid * 4;
+        es.slots = grid * 4 * TC_EPI_SETS;
         if ((size_t)g.N * es.slots * g.Nout * 2 <= g.stat_part_floats) { es.part = g.stat_part; *g.stat_slots = es.slots; }
     }
     if (KC == 64) {

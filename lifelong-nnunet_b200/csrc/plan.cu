@@ -211,7 +211,7 @@ static int build_plan(b2_unet_plan* p) {
             cb.wk_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             cb.wd_off = fc; fc += ((size_t)27 * in.c * cout / 2 + 63) / 64 * 64;
             p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, (long long)od * oh * ow, cout));
-            p->scratch_floats = max_sz(p->scratch_floats, (size_t)N * num_sms() * 4 * cout * 2);   // epilogue statistics partials
+            p->scratch_floats = max_sz(p->scratch_floats, (size_t)N * num_sms() * 8 * cout * 2);   // epilogue statistics partials (8 epilogue warps per CTA)
         }
         max_z = max_sz(max_z, cb.z.elems());
         p->scratch_floats = max_sz(p->scratch_floats, conv_stat_part_floats(cb.shape));
@@ -718,7 +718,7 @@ extern "C" size_t b2_conv3d_scratch_bytes(const b2_conv_desc* d) {
     if (st2 > part) part = st2;
     size_t sk = conv_tc_splitk_scratch_floats(s.n, s.d, s.h, s.w, s.cout > s.cin ? s.cout : s.cin);
     if (sk > part) part = sk;
-    size_t es = (size_t)s.n * num_sms() * 4 * s.cout * 2;   // InstanceNorm partials from the convolution epilogue
+    size_t es = (size_t)s.n * num_sms() * 8 * s.cout * 2;   // InstanceNorm partials from the convolution epilogue
     if (es > part) part = es;
     return align_up((2 * w + (part > wg ? part : wg) + 64) * sizeof(float));
 }
