@@ -118,6 +118,12 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # tuning switches for experiments: B2_OPTIONS="name=value,name=value" (see b2_set_option in csrc/plan.cu)
+    for kv in filter(None, os.environ.get("B2_OPTIONS", "").split(",")):
+        name, _, val = kv.partition("=")
+        rc = lib.b2_set_option(name.strip().encode(), int(val))
+        if rc != 0:
+            raise B2Error("B2_OPTIONS: %s" % lib.b2_last_error().decode())
     return lib
 
 

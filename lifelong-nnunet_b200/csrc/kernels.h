@@ -109,7 +109,7 @@ bool norm_small_supported(long long vox, int c, int p0, int p1, int p2, int p3);
 template <typename T>
 int norm_lrelu_fwd_small(const T* z, const float* gamma, const float* beta, T* y, float* stats, int n, long long vox, int c,
                          int z_pitch, int y_pitch, float slope, float eps, cudaStream_t st);
-extern int g_norm_small;
+extern int g_norm_small, g_norm_cfg;
 size_t norm_bwd_scratch_floats(int n, long long vox, int c);
 // dz = d(loss)/dz given dy; dgamma/dbeta overwritten. scratch: norm_bwd_scratch_floats floats.
 template <typename T>

@@ -28,7 +28,7 @@ template <typename T> struct Vec<T, 1> {
 // for its whole life, so mean / rstd / gamma / beta are loaded once into registers (the first version re-read 4 x VW
 // scalars per 16 bytes of data and ran at ~55 % of the HBM peak); rows are walked two at a time so that every thread has
 // two independent vector loads per input tensor in flight.
-template <typename T, int VW>
+template <typename T, int VW, int ROWS>
 __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        T* __restrict__ y, int n, long long vox, int c, int z_pitch,
@@ -49,21 +49,22 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, 
     T* yp = y + (long long)nn * vox * y_pitch + c0;
     const long long step = (long long)gridDim.x * R;
     long long v = (long long)blockIdx.x * R + r;
-    for (; v + step < vox; v += 2 * step) {
-        float a0[VW], a1[VW], o0[VW], o1[VW];
-        Vec<T, VW>::ld(zp + v * z_pitch, a0);
-        Vec<T, VW>::ld(zp + (v + step) * z_pitch, a1);
+    for (; v + (ROWS - 1) * step < vox; v += ROWS * step) {
+        float a[ROWS][VW];
 #pragma unroll
-        for (int j = 0; j < VW; ++j) {
-            const float u0 = ga[j] * ((a0[j] - mean[j]) * rstd[j]) + be[j];
-            const float u1 = ga[j] * ((a1[j] - mean[j]) * rstd[j]) + be[j];
-            o0[j] = u0 > 0.f ? u0 : u0 * slope;
-            o1[j] = u1 > 0.f ? u1 : u1 * slope;
+        for (int i = 0; i < ROWS; ++i) Vec<T, VW>::ld(zp + (v + i * step) * z_pitch, a[i]);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            float o[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const float u = ga[j] * ((a[i][j] - mean[j]) * rstd[j]) + be[j];
+                o[j] = u > 0.f ? u : u * slope;
+            }
+            Vec<T, VW>::st(yp + (v + i * step) * y_pitch, o);
         }
-        Vec<T, VW>::st(yp + v * y_pitch, o0);
-        Vec<T, VW>::st(yp + (v + step) * y_pitch, o1);
     }
-    if (v < vox) {
+    for (; v < vox; v += step) {
         float a0[VW], o0[VW];
         Vec<T, VW>::ld(zp + v * z_pitch, a0);
 #pragma unroll
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __r
 
 // RECOMPUTE: the sign of the pre-activation u = gamma*zhat + beta is recomputed from z (same fp32 expression as the
 // forward kernel) instead of reading y: one tensor read less in both backward sweeps.
-template <typename T, int VW, bool RECOMPUTE>
+template <typename T, int VW, bool RECOMPUTE, int ROWS>
 __global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const T* __restrict__ z, const T* __restrict__ y,
                                                               const T* __restrict__ dy, const float* __restrict__ stats,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -140,32 +141,30 @@ __global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const T* __rest
             ga[j] = RECOMPUTE ? gamma[c0 + j] : 0.f;
             be[j] = RECOMPUTE ? beta[c0 + j] : 0.f;
         }
-        // two rows per iteration: two independent vector loads per tensor in flight (the summation order per thread stays
+        // ROWS rows per iteration: ROWS independent vector loads per tensor in flight (the summation order per thread stays
         // v0+r, v0+r+R, ... so the result does not depend on the unrolling)
         long long v = v0 + r;
-        for (; v + R < v1; v += 2 * R) {
-            const long long row0 = (long long)n * vox + v, row1 = row0 + R;
-            float a0[VW], b0[VW], g0[VW], a1[VW], b1[VW], g1[VW];
-            Vec<T, VW>::ld(z + row0 * z_pitch + c0, a0);
-            Vec<T, VW>::ld(z + row1 * z_pitch + c0, a1);
-            if (!RECOMPUTE) { Vec<T, VW>::ld(y + row0 * y_pitch + c0, b0); Vec<T, VW>::ld(y + row1 * y_pitch + c0, b1); }
-            Vec<T, VW>::ld(dy + row0 * dy_pitch + c0, g0);
-            Vec<T, VW>::ld(dy + row1 * dy_pitch + c0, g1);
+        for (; v + (ROWS - 1) * R < v1; v += ROWS * R) {
+            const long long row0 = (long long)n * vox + v;
+            float a[ROWS][VW], b[ROWS][VW], g[ROWS][VW];
 #pragma unroll
-            for (int j = 0; j < VW; ++j) {
-                const float zh0 = (a0[j] - mean[j]) * rstd[j];
-                const float u0 = RECOMPUTE ? ga[j] * zh0 + be[j] : b0[j];
-                const float du0 = u0 > 0.f ? g0[j] : g0[j] * slope;
-                s1[j] += du0;
-                s2[j] += du0 * zh0;
-                const float zh1 = (a1[j] - mean[j]) * rstd[j];
-                const float u1 = RECOMPUTE ? ga[j] * zh1 + be[j] : b1[j];
-                const float du1 = u1 > 0.f ? g1[j] : g1[j] * slope;
-                s1[j] += du1;
-                s2[j] += du1 * zh1;
+            for (int i = 0; i < ROWS; ++i) {
+                Vec<T, VW>::ld(z + (row0 + i * R) * z_pitch + c0, a[i]);
+                if (!RECOMPUTE) Vec<T, VW>::ld(y + (row0 + i * R) * y_pitch + c0, b[i]);
+                Vec<T, VW>::ld(dy + (row0 + i * R) * dy_pitch + c0, g[i]);
             }
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+                for (int j = 0; j < VW; ++j) {
+                    const float zh = (a[i][j] - mean[j]) * rstd[j];
+                    const float u = RECOMPUTE ? ga[j] * zh + be[j] : b[i][j];
+                    const float du = u > 0.f ? g[i][j] : g[i][j] * slope;
+                    s1[j] += du;
+                    s2[j] += du * zh;
+                }
         }
-        if (v < v1) {
+        for (; v < v1; v += R) {
             const long long row = (long long)n * vox + v;
             float a[VW], b[VW], g[VW];
             Vec<T, VW>::ld(z + row * z_pitch + c0, a);
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const T* __rest
     }
 }
 
-template <typename T, int VW, bool RECOMPUTE>
+template <typename T, int VW, bool RECOMPUTE, int ROWS>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ z, const T* __restrict__ y,
                                                              const T* __restrict__ dy, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -218,7 +217,31 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
     }
     const long long base = (long long)nn * vox;
     const long long step = (long long)gridDim.x * R;
-    auto one = [&](long long v) {
+    long long v = (long long)blockIdx.x * R + r;
+    for (; v + (ROWS - 1) * step < vox; v += ROWS * step) {
+        // ROWS independent rows: all loads issue before the first is consumed
+        float a[ROWS][VW], b[ROWS][VW], g[ROWS][VW];
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const long long row = base + v + i * step;
+            Vec<T, VW>::ld(z + row * z_pitch + c0, a[i]);
+            if (!RECOMPUTE) Vec<T, VW>::ld(y + row * y_pitch + c0, b[i]);
+            Vec<T, VW>::ld(dy + row * dy_pitch + c0, g[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            float o[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const float zh = (a[i][j] - mean[j]) * rstd[j];
+                const float u = RECOMPUTE ? ga[j] * zh + be[j] : b[i][j];
+                const float du = u > 0.f ? g[i][j] : g[i][j] * slope;
+                o[j] = ga[j] * rstd[j] * (du - k1[j] - zh * k2[j]);
+            }
+            Vec<T, VW>::st(dz + (base + v + i * step) * dz_pitch + c0, o);
+        }
+    }
+    for (; v < vox; v += step) {
         const long long row = base + v;
         float a[VW], b[VW], g[VW], o[VW];
         Vec<T, VW>::ld(z + row * z_pitch + c0, a);
@@ -232,29 +255,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
             o[j] = ga[j] * rstd[j] * (du - k1[j] - zh * k2[j]);
         }
         Vec<T, VW>::st(dz + row * dz_pitch + c0, o);
-    };
-    long long v = (long long)blockIdx.x * R + r;
-    for (; v + step < vox; v += 2 * step) {
-        // two independent rows: loads of both issue before either is consumed
-        const long long row0 = base + v, row1 = row0 + step;
-        float a0[VW], b0[VW], g0[VW], o0[VW], a1[VW], b1[VW], g1[VW], o1[VW];
-        Vec<T, VW>::ld(z + row0 * z_pitch + c0, a0);
-        Vec<T, VW>::ld(z + row1 * z_pitch + c0, a1);
-        if (!RECOMPUTE) { Vec<T, VW>::ld(y + row0 * y_pitch + c0, b0); Vec<T, VW>::ld(y + row1 * y_pitch + c0, b1); }
-        Vec<T, VW>::ld(dy + row0 * dy_pitch + c0, g0);
-        Vec<T, VW>::ld(dy + row1 * dy_pitch + c0, g1);
-#pragma unroll
-        for (int j = 0; j < VW; ++j) {
-            const float zh0 = (a0[j] - mean[j]) * rstd[j], zh1 = (a1[j] - mean[j]) * rstd[j];
-            const float u0 = RECOMPUTE ? ga[j] * zh0 + be[j] : b0[j], u1 = RECOMPUTE ? ga[j] * zh1 + be[j] : b1[j];
-            const float du0 = u0 > 0.f ? g0[j] : g0[j] * slope, du1 = u1 > 0.f ? g1[j] : g1[j] * slope;
-            o0[j] = ga[j] * rstd[j] * (du0 - k1[j] - zh0 * k2[j]);
-            o1[j] = ga[j] * rstd[j] * (du1 - k1[j] - zh1 * k2[j]);
-        }
-        Vec<T, VW>::st(dz + row0 * dz_pitch + c0, o0);
-        Vec<T, VW>::st(dz + row1 * dz_pitch + c0, o1);
     }
-    if (v < vox) one(v);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -440,15 +441,23 @@ static dim3 apply_grid(int n, long long vox, int ncg) {
     return dim3((unsigned)blocks, (unsigned)n);
 }
 
+// streaming configuration: bit 0 -> 4-wide vectors instead of 8-wide (half the per-thread state: more resident blocks),
+// bit 1 -> four rows in flight per thread instead of two
+int g_norm_cfg = 3;
+
 template <typename T>
 int norm_lrelu_fwd(const T* z, const float* stats, const float* gamma, const float* beta, T* y, int n, long long vox,
                    int c, int z_pitch, int y_pitch, float slope, cudaStream_t st) {
-    const int vw = pick_vw(c, z_pitch, y_pitch, 8, 8, sizeof(T));
+    int vw = pick_vw(c, z_pitch, y_pitch, 8, 8, sizeof(T));
+    if (vw == 8 && (g_norm_cfg & 1) && c / 4 <= 256) vw = 4;
     B2_CHECK_ARG(c / vw <= 256);
     const dim3 grid = apply_grid(n, vox, c / vw);
-    if (vw == 8) B2_LAUNCH((norm_fwd_kernel<T, 8>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
-    else if (vw == 4) B2_LAUNCH((norm_fwd_kernel<T, 4>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
-    else B2_LAUNCH((norm_fwd_kernel<T, 1>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope);
+    const bool r4 = (g_norm_cfg & 2) != 0;
+#define B2_NF(VW_, R_) B2_LAUNCH((norm_fwd_kernel<T, VW_, R_>), grid, 256, 0, st, z, stats, gamma, beta, y, n, vox, c, z_pitch, y_pitch, slope)
+    if (vw == 8) { if (r4) B2_NF(8, 4); else B2_NF(8, 2); }
+    else if (vw == 4) { if (r4) B2_NF(4, 4); else B2_NF(4, 2); }
+    else B2_NF(1, 2);
+#undef B2_NF
     return B2_OK;
 }
 
@@ -464,7 +473,7 @@ size_t norm_bwd_scratch_floats(int n, long long vox, int c) {
     return (size_t)n * norm_slabs(n, vox) * c * 2 + (size_t)n * c * 2;
 }
 
-template <typename T, int VW, bool RC>
+template <typename T, int VW, bool RC, int ROWS>
 static int norm_bwd_launch(const T* z, const T* y, const T* dy, const float* stats, const float* gamma, const float* beta, T* dz,
                            float* dgamma, float* dbeta, int n, long long vox, int c, int z_pitch, int y_pitch, int dy_pitch,
                            int dz_pitch, float slope, float* scratch, cudaStream_t st) {
@@ -474,12 +483,12 @@ static int norm_bwd_launch(const T* z, const T* y, const T* dy, const float* sta
     const int ncg = c / VW, R = 256 / ncg;
     const size_t sh = (size_t)R * c * 2 * sizeof(float);
     dim3 grid(slabs, n);
-    B2_LAUNCH((norm_bwd_reduce_kernel<T, VW, RC>), grid, 256, sh, st, z, y, dy, stats, gamma, beta, slabs, vox, c, z_pitch, y_pitch,
+    B2_LAUNCH((norm_bwd_reduce_kernel<T, VW, RC, ROWS>), grid, 256, sh, st, z, y, dy, stats, gamma, beta, slabs, vox, c, z_pitch, y_pitch,
               dy_pitch, slope, part);
     B2_LAUNCH(norm_bwd_finalize_kernel, cdiv(c, 8), 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
     const dim3 g2 = apply_grid(n, vox, c / VW);
     const float inv_v = (float)(1.0 / (double)vox);
-    B2_LAUNCH((norm_bwd_apply_kernel<T, VW, RC>), g2, 256, 0, st, z, y, dy, stats, gamma, beta, sums, dz, n, vox, c, z_pitch, y_pitch,
+    B2_LAUNCH((norm_bwd_apply_kernel<T, VW, RC, ROWS>), g2, 256, 0, st, z, y, dy, stats, gamma, beta, sums, dz, n, vox, c, z_pitch, y_pitch,
               dy_pitch, dz_pitch, slope, inv_v);
     return B2_OK;
 }
@@ -498,11 +507,19 @@ int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, cons
         return B2_OK;
     }
     int vw = pick_vw(c, z_pitch, y_pitch, dy_pitch, dz_pitch, sizeof(T));
+    if (vw == 8 && (g_norm_cfg & 1) && c / 4 <= 256) vw = 4;
     B2_CHECK_ARG(c / vw <= 256);
-#define B2_NB(VW_, RC_) norm_bwd_launch<T, VW_, RC_>(z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, \
-                                                    dy_pitch, dz_pitch, slope, scratch, st)
-    if (beta) return vw == 8 ? B2_NB(8, true) : vw == 4 ? B2_NB(4, true) : B2_NB(1, true);
-    return vw == 8 ? B2_NB(8, false) : vw == 4 ? B2_NB(4, false) : B2_NB(1, false);
+    const bool r4 = (g_norm_cfg & 2) != 0;
+#define B2_NB(VW_, RC_, R_) norm_bwd_launch<T, VW_, RC_, R_>(z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, vox, c, z_pitch, y_pitch, \
+                                                         dy_pitch, dz_pitch, slope, scratch, st)
+    if (beta) {
+        if (vw == 8) return r4 ? B2_NB(8, true, 4) : B2_NB(8, true, 2);
+        if (vw == 4) return r4 ? B2_NB(4, true, 4) : B2_NB(4, true, 2);
+        return B2_NB(1, true, 2);
+    }
+    if (vw == 8) return r4 ? B2_NB(8, false, 4) : B2_NB(8, false, 2);
+    if (vw == 4) return r4 ? B2_NB(4, false, 4) : B2_NB(4, false, 2);
+    return B2_NB(1, false, 2);
 #undef B2_NB
 }
 

@@ -582,6 +582,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
+    if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
     if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }
     if (!strcmp(name, "norm_recompute")) { g_norm_recompute = value; return B2_OK; }
     if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
