@@ -98,9 +98,23 @@ struct b2_unet_plan {
     Act x_in, dz_tmp, patch;          // patch: [voxels][32] im2col matrix of the first layer (bf16 tensor-core path)
     bool first_tc = false;
     size_t wp_off = 0;
-    size_t act_elems = 0, grad_elems = 0, f32_floats = 0, scratch_floats = 0;
-    size_t off_act = 0, off_grad = 0, off_f32 = 0, off_scratch = 0, total_bytes = 0;
+    size_t act_elems = 0, grad_elems = 0, f32_floats = 0, scratch_floats = 0, wg_scratch_floats = 0;
+    size_t off_act = 0, off_grad = 0, off_f32 = 0, off_scratch = 0, off_wg_scratch = 0, total_bytes = 0;
     int esz = 4;
+    // backward overlap: the weight-gradient kernels of a layer run on a side stream next to its data-gradient kernels
+    // (dz double-buffered, own scratch); created lazily, joined before b2_unet_backward returns to the caller's stream
+    Act dz_tmp2;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_misc = nullptr;
+    bool side_ok = false;
+    ~b2_unet_plan() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev_dz[i]) cudaEventDestroy(ev_dz[i]);
+            if (ev_wg[i]) cudaEventDestroy(ev_wg[i]);
+        }
+        if (ev_misc) cudaEventDestroy(ev_misc);
+        if (side) cudaStreamDestroy(side);
+    }
 };
 
 namespace b2 {
@@ -135,6 +149,21 @@ template <typename T> static inline T* P(void* ws, const b2_unet_plan* p, const 
 }
 static inline float* F32(void* ws, const b2_unet_plan* p, size_t off) { return reinterpret_cast<float*>((char*)ws + p->off_f32) + off; }
 static inline float* SCR(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_scratch); }
+static inline float* SCR_WG(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_wg_scratch); }
+
+int g_bwd_overlap = 1;
+
+static bool ensure_side_stream(b2_unet_plan* p) {
+    if (p->side_ok) return true;
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess) return false;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&p->ev_dz[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&p->ev_wg[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    if (cudaEventCreateWithFlags(&p->ev_misc, cudaEventDisableTiming) != cudaSuccess) return false;
+    p->side_ok = true;
+    return true;
+}
 
 static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
@@ -165,6 +194,7 @@ static int build_plan(b2_unet_plan* p) {
         p->patch = alloc_act(ac, N, g.patch[0], g.patch[1], g.patch[2], 32);
         p->wp_off = fc; fc += ((size_t)p->feats[0] * 32 / 2 + 63) / 64 * 64;
         p->scratch_floats = max_sz(p->scratch_floats, first_layer_wgrad_part_floats(N, g.patch[0], g.patch[1], g.patch[2], p->feats[0]));
+        p->wg_scratch_floats = max_sz(p->wg_scratch_floats, first_layer_wgrad_part_floats(N, g.patch[0], g.patch[1], g.patch[2], p->feats[0]));
         p->scratch_floats = max_sz(p->scratch_floats, instnorm_stats_scratch_floats(N, p->x_in.vox(), p->feats[0]));
     }
     // concat buffers per encoder level 0..P-1 (activation + gradient)
@@ -204,7 +234,10 @@ static int build_plan(b2_unet_plan* p) {
         cb.tc_dgrad = tc_ok && !strided && din.c > 0 && din.pitch % 8 == 0;
         cb.tc_dgrad_strided = tc_ok && strided && g_tc_strided && din.c > 0 && din.pitch % 8 == 0;
         cb.tc_wgrad = tc_ok && g_tc_wgrad && wgrad_tc_supported(in.c, cout) && (!strided || g_tc_strided);
-        if (cb.tc_wgrad) p->scratch_floats = max_sz(p->scratch_floats, wgrad_tc_part_floats(cb.shape));
+        if (cb.tc_wgrad) {
+            p->scratch_floats = max_sz(p->scratch_floats, wgrad_tc_part_floats(cb.shape));
+            p->wg_scratch_floats = max_sz(p->wg_scratch_floats, wgrad_tc_part_floats(cb.shape));
+        }
         if (tc_ok) {
             p->scratch_floats = max_sz(p->scratch_floats, conv_tc_splitk_scratch_floats(N, od, oh, ow, cout));
             p->scratch_floats = max_sz(p->scratch_floats, conv_tc_splitk_scratch_floats(N, in.d, in.h, in.w, in.c));
@@ -216,6 +249,7 @@ static int build_plan(b2_unet_plan* p) {
         max_z = max_sz(max_z, cb.z.elems());
         p->scratch_floats = max_sz(p->scratch_floats, conv_stat_part_floats(cb.shape));
         p->scratch_floats = max_sz(p->scratch_floats, conv_wgrad_part_floats(cb.shape));
+        p->wg_scratch_floats = max_sz(p->wg_scratch_floats, conv_wgrad_part_floats(cb.shape));
         p->scratch_floats = max_sz(p->scratch_floats, norm_bwd_scratch_floats(N, cb.z.vox(), cout));
         p->convs.push_back(cb);
         p->conv_modules.push_back({0, (int)p->convs.size() - 1});
@@ -261,7 +295,10 @@ static int build_plan(b2_unet_plan* p) {
         fc = (fc + 63) / 64 * 64;
         t.tc = g.act_dtype == B2_BF16 && g_use_tc && cur.c % 32 == 0 && fs % 32 == 0 && cur.pitch % 8 == 0 && dcur.pitch % 8 == 0;
         if (t.tc && g_tc_wgrad && tconv_wgrad_tc_supported(cur.c, fs))
+        {
             p->scratch_floats = max_sz(p->scratch_floats, tconv_wgrad_tc_part_floats(t.shape));
+            p->wg_scratch_floats = max_sz(p->wg_scratch_floats, tconv_wgrad_tc_part_floats(t.shape));
+        }
         if (t.tc) {
             t.wqb_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
             t.wqd_off = fc; fc += ((size_t)k8 * cur.c * fs / 2 + 63) / 64 * 64;
@@ -285,12 +322,15 @@ static int build_plan(b2_unet_plan* p) {
     }
     p->dz_tmp.off = gc;
     gc += (max_z + 63) / 64 * 64;
+    p->dz_tmp2.off = gc;
+    gc += (max_z + 63) / 64 * 64;
     p->act_elems = ac; p->grad_elems = gc; p->f32_floats = fc;
     p->off_act = 0;
     p->off_grad = align_up(ac * p->esz, 1024);
     p->off_f32 = p->off_grad + align_up(gc * p->esz, 1024);
     p->off_scratch = p->off_f32 + align_up(fc * 4, 1024);
-    p->total_bytes = p->off_scratch + align_up(p->scratch_floats * 4, 1024);
+    p->off_wg_scratch = p->off_scratch + align_up(p->scratch_floats * 4, 1024);
+    p->total_bytes = p->off_wg_scratch + align_up(p->wg_scratch_floats * 4, 1024);
     return B2_OK;
 }
 
@@ -449,33 +489,53 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
     int rc;
     if (parts & B2_PART_DECODER)     // the decoder call opens a backward pass: every flag starts at 1
         for (size_t i = 0; i < p->params.size(); ++i) if (has_grad) has_grad[i] = 1;
-    T* dz = reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off;
+    T* dzbuf[2] = {reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off,
+                   reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp2.off};
+    // weight-gradient kernels on the side stream (see b2_unet_plan): layer k uses dz buffer k & 1; the buffer is rewritten by
+    // layer k + 2 only after the side stream has finished reading it
+    const bool overlap = g_bwd_overlap && ensure_side_stream(p);
+    cudaStream_t wst = overlap ? p->side : st;
+    float* wscr = overlap ? SCR_WG(ws, p) : SCR(ws, p);
+    int layer_k = 0;
+    bool wg_pending[2] = {false, false};
     auto conv_bwd = [&](ConvBlock& cb) -> int {
+        const int buf = layer_k & 1;
+        ++layer_k;
+        T* dz = dzbuf[buf];
+        if (overlap && wg_pending[buf]) B2_CUDA(cudaStreamWaitEvent(st, p->ev_wg[buf], 0));
         float* stats = F32(ws, p, cb.stats_off);
         int r = norm_lrelu_bwd<T>(P<T>(ws, p, cb.z, false), P<T>(ws, p, cb.y, false), P<T>(ws, p, cb.dy, true), stats, prm[cb.p_g],
                                   g_norm_recompute ? prm[cb.p_be] : nullptr, dz,
                                   grads[cb.p_g], grads[cb.p_be], g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch,
                                   cb.dy.pitch, cb.shape.cout, g.lrelu_slope, SCR(ws, p), st);
         if (r) return r;
+        if (overlap) {
+            B2_CUDA(cudaEventRecord(p->ev_dz[buf], st));
+            B2_CUDA(cudaStreamWaitEvent(wst, p->ev_dz[buf], 0));
+        }
         ConvShape s = cb.shape;
         s.out_pitch = cb.shape.cout;  // dz is dense
         bool wdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (p->first_tc && &cb == &p->convs[0]) {
                 r = first_layer_wgrad_tc(P<T>(ws, p, p->patch, false), dz, g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.shape.cout,
-                                         cb.shape.cout, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+                                         cb.shape.cout, wscr, grads[cb.p_w], grads[cb.p_b], wst);
                 if (r) return r;
                 wdone = true;
             }
             if (!wdone && cb.tc_wgrad) {
-                r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], true, st);
+                r = conv3d_wgrad_tc(s, P<T>(ws, p, cb.in, false), dz, wscr, grads[cb.p_w], grads[cb.p_b], true, wst);
                 if (r) return r;
                 wdone = true;
             }
         }
         if (!wdone) {
-            r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, SCR(ws, p), grads[cb.p_w], grads[cb.p_b], st);
+            r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, wscr, grads[cb.p_w], grads[cb.p_b], wst);
             if (r) return r;
+        }
+        if (overlap) {
+            B2_CUDA(cudaEventRecord(p->ev_wg[buf], wst));
+            wg_pending[buf] = true;
         }
         if (cb.din.c > 0) {
             bool done = false;
@@ -534,7 +594,11 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         bool twg = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (t.tc && g_tc_wgrad && tconv_wgrad_tc_supported(t.shape.cin, t.shape.cout)) {
-                if ((rc = tconv_wgrad_tc(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), SCR(ws, p), grads[t.p_w], st))) return rc;
+                if (overlap) {   // dout is complete (the localization convs' dgrad ran on st): fork
+                    B2_CUDA(cudaEventRecord(p->ev_misc, st));
+                    B2_CUDA(cudaStreamWaitEvent(wst, p->ev_misc, 0));
+                }
+                if ((rc = tconv_wgrad_tc(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), wscr, grads[t.p_w], wst))) return rc;
                 twg = true;
             }
         }
@@ -560,6 +624,10 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;
         if ((rc = conv_bwd(p->convs[2 * d]))) return rc;
     }
+    if (overlap) {   // join: every gradient is complete in the caller's stream order
+        B2_CUDA(cudaEventRecord(p->ev_misc, wst));
+        B2_CUDA(cudaStreamWaitEvent(st, p->ev_misc, 0));
+    }
     return B2_OK;
 }
 
@@ -582,6 +650,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
+    if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
     if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }
     if (!strcmp(name, "norm_recompute")) { g_norm_recompute = value; return B2_OK; }
