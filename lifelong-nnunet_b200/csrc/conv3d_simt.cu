@@ -636,9 +636,11 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
 // tap loop is fully unrolled so a thread keeps NT (x4 over k) independent loads in flight; the 8 k-lanes are combined in a
 // fixed order through shared memory, and the result is written as runs of consecutive taps of dw_pt[co][ci][t].
 // (A thread-per-output kernel walks the partials serially and writes 4-byte elements with a 108-byte stride.)
-template <int NT>
-__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ part, int nsplit, int Cin, int Cout,
-                                                                 float* __restrict__ dw) {
+// KB = partials per load batch (4: hundreds of partials of a thin layer; 1: the <= 8 partials of a deep layer, where the
+// batch registers only cost occupancy -- the kernel is then bound by load latency x resident blocks)
+template <int NT, int KB>
+__global__ void __launch_bounds__(256, KB == 1 ? 3 : 1) wgrad_reduce_tiled_kernel(const float* __restrict__ part, int nsplit, int Cin, int Cout,
+                                                                                  float* __restrict__ dw) {
     __shared__ float sh[8][NT][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int cob = Cout >> 5;
@@ -655,16 +657,18 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __
     // explicit load batches: all loads of a batch are issued before the first add (a predicated `acc += load` compiled to
     // one exposed L2 round trip per element: 80 us for 32 MB)
     int k = ty;
-    for (; k + 24 < nsplit; k += 32) {
-        float tmp[4][NT];
+    if (KB == 4) {
+        for (; k + 24 < nsplit; k += 32) {
+            float tmp[4][NT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) tmp[u][t] = __ldcs(src + (long long)(k + 8 * u) * tot + toff[t]);
+                for (int t = 0; t < NT; ++t) tmp[u][t] = __ldcs(src + (long long)(k + 8 * u) * tot + toff[t]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) acc[t] += tmp[u][t];
+                for (int t = 0; t < NT; ++t) acc[t] += tmp[u][t];
+        }
     }
     for (; k < nsplit; k += 8) {
         float tmp[NT];
@@ -691,13 +695,14 @@ int wgrad_reduce(const float* part_w, const float* part_b, int nsplit, int cin, 
         // few (ci, co-block) pairs (thin layers, hundreds of partials): split the taps over grid.y for parallelism
         if (xb >= 4 * num_sms()) {
             dim3 grid(xb, 1);
-            B2_LAUNCH(wgrad_reduce_tiled_kernel<27>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+            if (nsplit > 8) B2_LAUNCH((wgrad_reduce_tiled_kernel<27, 4>), grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+            else B2_LAUNCH((wgrad_reduce_tiled_kernel<27, 1>), grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
         } else if (xb * 3 >= 4 * num_sms()) {
             dim3 grid(xb, 3);
-            B2_LAUNCH(wgrad_reduce_tiled_kernel<9>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+            B2_LAUNCH((wgrad_reduce_tiled_kernel<9, 4>), grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
         } else {
             dim3 grid(xb, 9);
-            B2_LAUNCH(wgrad_reduce_tiled_kernel<3>, grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
+            B2_LAUNCH((wgrad_reduce_tiled_kernel<3, 4>), grid, 256, 0, st, part_w, nsplit, cin, cout, dw);
         }
         return B2_OK;
     }
