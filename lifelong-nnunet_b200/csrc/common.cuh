@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 #include <string>
@@ -34,12 +35,36 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
             return ::b2::fail(B2_ECUDA, "CUDA error: %s (line %lld)", cudaGetErrorString(_e), __LINE__); \
     } while (0)
 
+// Programmatic dependent launch (PDL): every kernel is launched with programmaticStreamSerialization allowed and begins
+// with pdl_grid_sync(): `griddepcontrol.wait` blocks until the preceding grid in the stream has completed and its memory
+// is visible (so the semantics stay plain stream order), `griddepcontrol.launch_dependents` lets the NEXT grid's CTAs be
+// scheduled onto SMs as they drain instead of after the last CTA retires.  A step is ~250 dependent launches, many of
+// them 5-20 us long, so launch latency and tails are a measurable share of it.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_grid_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+extern int g_pdl;
+
 // every kernel launch goes through this so gpu_launches is an honest count
-#define B2_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+#define B2_LAUNCH(kernel, grid_, block_, smem_, stream_, ...)                                   \
     do {                                                                                    \
-        kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);           \
+        cudaLaunchConfig_t _cfg;                                                            \
+        memset(&_cfg, 0, sizeof(_cfg));                                                     \
+        _cfg.gridDim = dim3(grid_);                                                         \
+        _cfg.blockDim = dim3(block_);                                                        \
+        _cfg.dynamicSmemBytes = (smem_);                                                     \
+        _cfg.stream = (cudaStream_t)(stream_);                                               \
+        cudaLaunchAttribute _attr[1];                                                       \
+        _attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                   \
+        _attr[0].val.programmaticStreamSerializationAllowed = ::b2::g_pdl ? 1 : 0;          \
+        _cfg.attrs = _attr;                                                                 \
+        _cfg.numAttrs = 1;                                                                  \
+        cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                    \
         ::b2::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
-        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e == cudaSuccess) _e = cudaGetLastError();                                     \
         if (_e != cudaSuccess)                                                              \
             return ::b2::fail(B2_ECUDA, "launch failed: %s (line %lld)", cudaGetErrorString(_e), __LINE__); \
     } while (0)

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(GatherGeom g, const
                                                              const float* __restrict__ Wm,
                                                              const float* __restrict__ bias, T* __restrict__ dst,
                                                              int accumulate, float* __restrict__ stat_part) {
+    pdl_grid_sync();
     constexpr int TN = BN / 16;
     __shared__ __align__(16) float As[BK][BM];
     __shared__ __align__(16) float Bs[BK][BN];
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(GatherGeom g, const
 // independent loads in flight, double accumulation, fixed xor-shuffle tree => bit-reproducible.
 __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ part, int tiles, int C,
                                                              double inv_count, float eps, float* __restrict__ stats) {
+    pdl_grid_sync();
     const int n = blockIdx.x, c = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     const float* p = part + ((long long)n * tiles * C + c) * 2;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __rest
 // PyTorch [Cout][Cin][27] -> Wf [27][Cin][Cout] and Wb [27][Cout][Cin]
 __global__ void weight_shadow_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ wf,
                                      float* __restrict__ wb) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tot = (long long)Cout * Cin * 27;
     if (i >= tot) return;
@@ -246,6 +249,7 @@ struct WgradGeom {
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradGeom g, const T* __restrict__ x, const T* __restrict__ dz,
                                                     float* __restrict__ part_w, float* __restrict__ part_b) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) float smem[];
     const int halo_vox = g.hd * g.hh * g.hw;
     const int chunk_vox = g.cd * g.chh * g.cw;
@@ -335,6 +339,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradGeom g, const T* __rest
 // dW_pt[co][ci][t] = sum_split part[split][t][ci][co]  (ordered);  dbias likewise
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b, int nsplit,
                                     int Cin, int Cout, float* __restrict__ dw, float* __restrict__ db) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long tot = 27LL * Cin * Cout;
     if (i < tot) {
@@ -358,6 +363,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part_w, const floa
 template <typename T, int VW>
 __global__ void __launch_bounds__(256) stats_reduce_kernel(const T* __restrict__ z, int slabs, long long vox, int c, int pitch,
                                                            float* __restrict__ part) {
+    pdl_grid_sync();
     extern __shared__ float sh[];  // [R][c][2]
     const int ncg = c / VW;
     const int R = 256 / ncg;
@@ -434,6 +440,7 @@ static inline int out_dim_(int i, int s) { return (i + 2 - 3) / s + 1; }
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) wgrad_smallcin_kernel(WgradGeom g, const T* __restrict__ x, const T* __restrict__ dz,
                                                              float* __restrict__ part_w, float* __restrict__ part_b, int lanes) {
+    pdl_grid_sync();
     extern __shared__ float sh[];  // [lanes][27*CIN + 1][Cout]
     const int cout = g.Cout;
     const int co = threadIdx.x % cout, lane = threadIdx.x / cout;
@@ -641,6 +648,7 @@ int conv3d_wgrad_simt(const ConvShape& s, const T* x, const T* dz, float* part, 
 template <int NT, int KB>
 __global__ void __launch_bounds__(256, KB == 1 ? 3 : 1) wgrad_reduce_tiled_kernel(const float* __restrict__ part, int nsplit, int Cin, int Cout,
                                                                                   float* __restrict__ dw) {
+    pdl_grid_sync();
     __shared__ float sh[8][NT][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int cob = Cout >> 5;

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcConvParams p,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, float* __restrict__ partial,
                EpiStats es) {
+    pdl_grid_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
@@ -357,6 +358,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // split-K second stage: out = bf16( sum_ks partial[ks] + bias (+ out) ), same row -> voxel mapping as the epilogue
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(TcConvParams p, const float* __restrict__ partial, const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ dst, int accumulate) {
+    pdl_grid_sync();
     const int otiles = p.num_tiles / p.ksplit;
     const long long total = (long long)otiles * 128 * (p.BN / 8);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -460,6 +462,7 @@ bool conv_tc_supported(int K, int Nout) {
 // Plain scatter: used only for shapes the tiled multi-tensor kernel below does not cover (channel counts % 32 != 0).
 __global__ void weight_shadow_bf16_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wk,
                                           __nv_bfloat16* __restrict__ wd) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tot = (long long)Cout * Cin * 27;
     if (i >= tot) return;
@@ -493,6 +496,7 @@ struct ShadowJobsDev {
 };
 
 __global__ void __launch_bounds__(256) shadow_multi_kernel(const __grid_constant__ ShadowJobsDev jobs) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) __nv_bfloat16 sh_w[];   // [T][32 a][SH_ROW] with tap stride SH_TSTRIDE
     int j = 0;
     while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.tile0[j + 1]) ++j;
@@ -877,6 +881,7 @@ int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout
 // PyTorch ConvTranspose3d weight [Cin][Cout][K8] fp32 -> wq [(q, co)][ci] and wqd [q][ci][co] (bf16)
 __global__ void tconv_shadow_bf16_kernel(const float* __restrict__ w, int Cin, int Cout, int K8, __nv_bfloat16* __restrict__ wq,
                                          __nv_bfloat16* __restrict__ wqd) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tot = (long long)Cin * Cout * K8;
     if (i >= tot) return;

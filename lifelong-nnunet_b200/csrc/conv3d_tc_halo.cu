@@ -45,6 +45,7 @@ template <int KC>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloParams p,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, EpiStats es) {
+    pdl_grid_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t sfull[HALO_MAX_SLOTS], sempty[HALO_MAX_SLOTS], wfull, tfull[HALO_MAX_ACC], tempty[HALO_MAX_ACC];
     __shared__ uint32_t tmem_base_smem;

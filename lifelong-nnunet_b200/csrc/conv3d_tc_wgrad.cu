@@ -71,6 +71,7 @@ constexpr int WG_MAX_ASTAGES = 6;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, TcWgradParams p,
                 float* __restrict__ part, float* __restrict__ dw_direct) {
+    pdl_grid_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t fullA[WG_MAX_ASTAGES], emptyA[WG_MAX_ASTAGES], fullB[2], emptyB[2], done_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -258,6 +259,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // dbias[co] = sum over all voxels of dz: ordered two-stage column sum
 __global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* __restrict__ dz, long long rows, int c, int pitch,
                                                           int slabs, float* __restrict__ part) {
+    pdl_grid_sync();
     // thread = (column, lane); lanes stride rows
     const int lanes = 256 / c > 0 ? 256 / c : 1;
     const int col = threadIdx.x % c, ln = threadIdx.x / c;
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(256) colsum_part_kernel(const __nv_bfloat16* _
 // wide layers (c > 256): thread per column, rows sequential (their volumes are tiny)
 __global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* __restrict__ dz, long long rows, int c, int pitch,
                                                           int slabs, float* __restrict__ part) {
+    pdl_grid_sync();
     const long long per = (rows + slabs - 1) / slabs;
     const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
     for (int col = threadIdx.x; col < c; col += 256) {
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* _
     }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int slabs, int c, float* __restrict__ out) {
+    pdl_grid_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     float s = 0.f;
@@ -454,6 +458,7 @@ constexpr int WH_MAX_STAGES = 4;
 __global__ void __launch_bounds__(WH_THREADS, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ, WgHaloParams p,
                   float* __restrict__ part, float* __restrict__ dw_direct) {
+    pdl_grid_sync();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full[WH_MAX_STAGES], empty[WH_MAX_STAGES], done_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -712,6 +717,7 @@ static int conv3d_wgrad_halo(const ConvShape& s, const __nv_bfloat16* x, const _
 // The shifted operand is dy ("taps" = q, traversal stride k), the fixed operand is x: D[(q, co)][ci].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void tconv_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int k8, int Cin, int Cout, float* __restrict__ dw) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over [q][co][ci]
     const long long tot = (long long)k8 * Cout * Cin;
     if (i >= tot) return;
@@ -776,6 +782,7 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patch_matrix_kernel(const __nv_bfloat16* __restrict__ x, int N, int D, int H, int W, int cin,
                                                            int x_pitch, __nv_bfloat16* __restrict__ P) {
+    pdl_grid_sync();
     // thread = voxel: gathers its 27*cin neighbours (L1-resident: adjacent threads share them) and writes the 64-byte row
     // with four 16-byte stores -- a warp writes 2 KB contiguous.  (The first version used a thread per 8 columns with a
     // div/mod chain per element: 286 us for 134 MB; this one is store-bound.)
@@ -803,6 +810,7 @@ __global__ void __launch_bounds__(256) patch_matrix_kernel(const __nv_bfloat16* 
 
 // PyTorch [Cout][Cin][27] -> Wp [Cout][32] bf16 (k = t*Cin + ci, zero padded)
 __global__ void patch_weight_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ wp) {
+    pdl_grid_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cout * 32) return;
     const int k = i & 31, co = i >> 5;
@@ -812,6 +820,7 @@ __global__ void patch_weight_kernel(const float* __restrict__ w, int cout, int c
 }
 
 __global__ void patch_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int cin, int cout, float* __restrict__ dw) {
+    pdl_grid_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [k < 32][co]
     if (i >= 32 * cout) return;
     const int co = i % cout, k = i / cout;

@@ -50,6 +50,7 @@ __device__ __forceinline__ void block_reduce_store(const float (&vals)[NV], int 
 __global__ void __launch_bounds__(256) dsloss_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                             int C, long long V, int slabs, int ignore_index,
                                                             float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float sh[8 * (3 * MAXC + 2)];
     const int b = blockIdx.y, slab = blockIdx.x;
     const long long per = (V + slabs - 1) / slabs;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) dsloss_reduce_kernel(const float* __restr
 __global__ void dsloss_finalize_kernel(const float* __restrict__ part, int B, int C, int slabs, float weight,
                                        int batch_dice, float smooth, int do_bg, int with_dice, float* __restrict__ coef,
                                        float* __restrict__ loss_out) {
+    pdl_grid_sync();
     constexpr int NV = 3 * MAXC + 2;
     // stage 1 (256 threads): lane = value index inside a partial row (coalesced 104-byte rows), warp = slab lane; every
     // thread keeps several independent loads in flight; stage 2: thread 0 combines the 8 warps in order.
@@ -162,6 +164,7 @@ __global__ void dsloss_finalize_kernel(const float* __restrict__ part, int B, in
 __global__ void __launch_bounds__(256) dsloss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                           int B, int C, long long V, int ignore_index, float weight,
                                                           const float* __restrict__ coef, float* __restrict__ dlogits) {
+    pdl_grid_sync();
     const long long total = (long long)B * V;
     const float inv_cnt = coef[(long long)B * C * 2];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -208,6 +211,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) kd_kernel(const float* __restrict__ x, const float* __restrict__ t, int C,
                                                  long long V, int slabs, float a, float gscale,
                                                  float* __restrict__ dlogits, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float sh[8];
     const int b = blockIdx.y, slab = blockIdx.x;
     const long long per = (V + slabs - 1) / slabs;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(256) kd_kernel(const float* __restrict__ x, co
 }
 
 __global__ void scalar_finalize_kernel(const float* __restrict__ part, int n, double scale, float* __restrict__ out) {
+    pdl_grid_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s = 0.0;
     for (int i = 0; i < n; ++i) s += part[i];
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(256) plop_mask_kernel(const float* __restrict_
                                                         int C, int D, int H, int W, const float* __restrict__ thr,
                                                         float max_entropy, int8_t* __restrict__ code,
                                                         float* __restrict__ numden /*[B][W][2]*/) {
+    pdl_grid_sync();
     // one block per (b, w-chunk of 32 columns): threads x = w lane, y = row lanes; ordered reduce over (d,h)
     __shared__ float sh[8][32][2];
     const int b = blockIdx.y;
@@ -323,6 +329,7 @@ __global__ void __launch_bounds__(256) plop_mask_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) plop_ce_reduce_kernel(const float* __restrict__ x, const float* __restrict__ target,
                                                              const int8_t* __restrict__ code, int C, long long V,
                                                              int slabs, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float sh[8 * 4];
     const int b = blockIdx.y, slab = blockIdx.x;
     const long long per = (V + slabs - 1) / slabs;
@@ -356,6 +363,7 @@ __global__ void __launch_bounds__(256) plop_ce_reduce_kernel(const float* __rest
 // finalize: value = weight * mean_{b,w}(num/den) * (ce_p/cnt_p + ce_n/cnt_n); coef = {fbar/cnt_p, fbar/cnt_n} * weight
 __global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ numden, int B,
                                      int W, float weight, float* __restrict__ coef, float* __restrict__ loss_out) {
+    pdl_grid_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s[4] = {0, 0, 0, 0};
     for (int i = 0; i < nparts; ++i)
@@ -372,6 +380,7 @@ __global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts,
 __global__ void __launch_bounds__(256) plop_grad_kernel(const float* __restrict__ x, const float* __restrict__ target,
                                                         const int8_t* __restrict__ code, int B, int C, long long V,
                                                         const float* __restrict__ coef, float* __restrict__ dlogits) {
+    pdl_grid_sync();
     const long long total = (long long)B * V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / V);
@@ -400,6 +409,7 @@ __global__ void __launch_bounds__(256) plop_grad_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) eval_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                           int C, long long V, int slabs, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float sh[8 * 3 * MAXC];
     const int b = blockIdx.y, slab = blockIdx.x;
     const long long per = (V + slabs - 1) / slabs;
@@ -429,6 +439,7 @@ __global__ void __launch_bounds__(256) eval_reduce_kernel(const float* __restric
 }
 
 __global__ void eval_finalize_kernel(const float* __restrict__ part, int B, int C, int slabs, float* __restrict__ out) {
+    pdl_grid_sync();
     const int i = threadIdx.x;
     if (i >= B * (C - 1) * 3) return;
     const int k = i % 3, c = (i / 3) % (C - 1) + 1, b = i / (3 * (C - 1));

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        T* __restrict__ y, int n, long long vox, int c, int z_pitch,
                                                        int y_pitch, float slope) {
+    pdl_grid_sync();
     const int ncg = c / VW, R = 256 / ncg;
     const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
     if (r >= R) return;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, 
 __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, int n, int slabs, int c,
                                                                 float* __restrict__ sums, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta) {
+    pdl_grid_sync();
     const int cc = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (cc >= c) return;
     double g = 0.0, b = 0.0;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256, 3) norm_bwd_reduce_kernel(const T* __rest
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               int slabs, long long vox, int c, int z_pitch, int y_pitch,
                                                               int dy_pitch, float slope, float* __restrict__ part) {
+    pdl_grid_sync();
     extern __shared__ float sh[];  // [R][c][2]
     const int ncg = c / VW;
     const int R = 256 / ncg;
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
                                                              const float* __restrict__ sums, T* __restrict__ dz, int n,
                                                              long long vox, int c, int z_pitch, int y_pitch, int dy_pitch,
                                                              int dz_pitch, float slope, float inv_v) {
+    pdl_grid_sync();
     const int ncg = c / VW, R = 256 / ncg;
     const int cg = threadIdx.x % ncg, r = threadIdx.x / ncg;
     if (r >= R) return;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(256) norm_small_fwd_kernel(const T* __restrict
                                                              const float* __restrict__ beta, T* __restrict__ y,
                                                              float* __restrict__ stats, int vox, int c, int z_pitch, int y_pitch,
                                                              float slope, float eps) {
+    pdl_grid_sync();
     __shared__ float sh[8][16];
     const int c0 = blockIdx.x * 8, n = blockIdx.y;
     const T* zp = z + (long long)n * vox * z_pitch + c0;
@@ -341,6 +346,7 @@ __global__ void __launch_bounds__(256) norm_small_bwd_kernel(const T* __restrict
                                                              const float* __restrict__ beta, T* __restrict__ dz,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int n, int vox,
                                                              int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch, float slope) {
+    pdl_grid_sync();
     __shared__ float sh[8][16];
     const int c0 = blockIdx.x * 8;
     float ga[8], be[8], dg[8], db[8];

@@ -68,6 +68,7 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (((uintptr_t)p
 // ordered final sum of `n` partials by one block
 __global__ void __launch_bounds__(256) ordered_sum_kernel(const float* __restrict__ part, int n, float scale,
                                                           float* __restrict__ out, int accumulate) {
+    pdl_grid_sync();
     __shared__ double red[32];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += (double)part[i];
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) ordered_sum_kernel(const float* __restric
 __global__ void __launch_bounds__(MT_THREADS) quadpen_kernel(const int* __restrict__ prefix, const long long* __restrict__ numel,
                                                              const b2_pen_entry* __restrict__ ent, int n_tensors,
                                                              float coef, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float red[32];
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const b2_pen_entry e = ent[l.tensor];
@@ -129,6 +131,7 @@ struct SqEntry { const float* grad; float* fisher; long long numel; };
 
 __global__ void __launch_bounds__(MT_THREADS) fisher_square_kernel(const int* __restrict__ prefix, const long long* __restrict__ numel,
                                                                    const SqEntry* __restrict__ ent, int n_tensors) {
+    pdl_grid_sync();
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const SqEntry e = ent[l.tensor];
     for (long long i = threadIdx.x; i < l.n; i += MT_THREADS) {
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(MT_THREADS) fisher_square_kernel(const int* __
 __global__ void __launch_bounds__(MT_THREADS) rw_update_kernel(const int* __restrict__ prefix, const long long* __restrict__ numel,
                                                                const b2_rw_entry* __restrict__ ent, int n_tensors,
                                                                float alpha, float eps, int have_prev) {
+    pdl_grid_sync();
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const b2_rw_entry e = ent[l.tensor];
     for (long long i = threadIdx.x; i < l.n; i += MT_THREADS) {
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(MT_THREADS) rw_update_kernel(const int* __rest
 __global__ void __launch_bounds__(MT_THREADS) gradnorm_kernel(const int* __restrict__ prefix, const long long* __restrict__ numel,
                                                               const b2_sgd_entry* __restrict__ ent, int n_tensors,
                                                               float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float red[32];
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const float* g = ent[l.tensor].grad + l.off;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(MT_THREADS) gradnorm_kernel(const int* __restr
 // norm = sqrt(sum); clip = min(1, max_norm/(norm+1e-6))  -> out[0] = norm, out[1] = clip
 __global__ void __launch_bounds__(256) clipcoef_kernel(const float* __restrict__ part, int n, float max_norm,
                                                        float* __restrict__ out) {
+    pdl_grid_sync();
     __shared__ double red[32];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += (double)part[i];
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(MT_THREADS) sgd_kernel(const int* __restrict__
                                                          const b2_sgd_entry* __restrict__ ent, int n_tensors, float lr,
                                                          float momentum, float wd, int nesterov, int first_step,
                                                          const float* __restrict__ clip) {
+    pdl_grid_sync();
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const b2_sgd_entry e = ent[l.tensor];
     const float c = clip[1];

@@ -31,6 +31,7 @@ std::atomic<long long> g_launches{0};
 int g_use_tc = 1;
 int g_tc_strided = 1;
 int g_tc_wgrad = 1;
+int g_pdl = 1;              // programmatic dependent launch for every kernel (common.cuh)
 int g_norm_recompute = 1;   // norm backward recomputes the activation sign from z instead of reading y
 
 int num_sms() {
@@ -650,6 +651,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
+    if (!strcmp(name, "pdl")) { g_pdl = value; return B2_OK; }
     if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
     if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }

@@ -26,6 +26,7 @@ struct PodGeom {
 template <typename T>
 __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict__ a, const T* __restrict__ b,
                                                   float* __restrict__ out) {
+    pdl_grid_sync();
     __shared__ float sh[8][32][2];
     const int bd = blockIdx.x;
     const int c = blockIdx.y * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict
 
 __global__ void __launch_bounds__(256) pod_finalize_kernel(const float* __restrict__ part, long long n, double scale,
                                                            float* __restrict__ out) {
+    pdl_grid_sync();
     __shared__ double red[32];
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += 256) s += (double)part[i];

@@ -16,6 +16,7 @@ namespace b2 {
 // ---------------------------------------------------------------------------------------------------------------
 // PyTorch [Cin][Cout][K8] -> Wq [K8][Cin][Cout]
 __global__ void tconv_shadow_kernel(const float* __restrict__ w, int Cin, int Cout, int K8, float* __restrict__ wq) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tot = (long long)Cin * Cout * K8;
     if (i >= tot) return;
@@ -34,6 +35,7 @@ constexpr int TI = 16;  // input voxels per CTA
 template <typename T>
 __global__ void __launch_bounds__(256) tconv_fwd_kernel(TG g, const T* __restrict__ x, const float* __restrict__ wq,
                                                         T* __restrict__ y) {
+    pdl_grid_sync();
     extern __shared__ float xs[];  // [TI][Cin]
     const long long Vin = (long long)g.N * g.D * g.H * g.W;
     const long long v0 = (long long)blockIdx.x * TI;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(256) tconv_fwd_kernel(TG g, const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) tconv_dgrad_kernel(TG g, const T* __restrict__ dy, const float* __restrict__ w_pt,
                                                           T* __restrict__ dx) {
+    pdl_grid_sync();
     extern __shared__ float ds[];  // [TI][K8][Cout]
     const long long Vin = (long long)g.N * g.D * g.H * g.W;
     const long long v0 = (long long)blockIdx.x * TI;
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(256) tconv_dgrad_kernel(TG g, const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) tconv_wgrad_kernel(TG g, const T* __restrict__ x, const T* __restrict__ dy,
                                                           int nsplit, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float xs[32][33];
     __shared__ __align__(16) float zs[32][32];
     const int cob = blockIdx.z / g.K8, q = blockIdx.z % g.K8;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(256) tconv_wgrad_kernel(TG g, const T* __restr
 }
 
 __global__ void ordered_reduce_kernel(const float* __restrict__ part, int nsplit, long long tot, float* __restrict__ out) {
+    pdl_grid_sync();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= tot) return;
     float s = 0.f;
@@ -245,6 +250,7 @@ template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_fwd_kernel(const T* __restrict__ y, const float* __restrict__ w,
                                                           float* __restrict__ logits, int n, long long vox, int c,
                                                           int ncls, int y_pitch) {
+    pdl_grid_sync();
     extern __shared__ float ws[];  // [ncls][c]
     for (int e = threadIdx.x; e < ncls * c; e += blockDim.x) ws[e] = w[e];
     __syncthreads();
@@ -277,6 +283,7 @@ template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dl,
                                                             T* __restrict__ dy, int accumulate, int n, long long vox,
                                                             int c, int ncls, int dy_pitch) {
+    pdl_grid_sync();
     extern __shared__ float ws[];
     for (int e = threadIdx.x; e < ncls * c; e += blockDim.x) ws[e] = w[e];
     __syncthreads();
@@ -317,6 +324,7 @@ template <typename T, int VW>
 __global__ void __launch_bounds__(256) seghead_wgrad_kernel(const T* __restrict__ y, const float* __restrict__ dl,
                                                             int slabs, int n, long long vox, int c, int ncls,
                                                             int y_pitch, float* __restrict__ part) {
+    pdl_grid_sync();
     extern __shared__ float sh[];  // [R][ncls][c]
     const int ncg = c / VW;
     const int R = 256 / ncg;
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__(256) seghead_wgrad_kernel(const T* __restrict_
 template <typename T, int NC>
 __global__ void __launch_bounds__(256) seghead_wgrad32_kernel(const T* __restrict__ y, const float* __restrict__ dl, int slabs,
                                                               long long vox, int c, int ncls, int y_pitch, float* __restrict__ part) {
+    pdl_grid_sync();
     __shared__ float sh[8][NC * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nn = blockIdx.y, c0 = blockIdx.z * 32;
@@ -421,6 +430,7 @@ __global__ void __launch_bounds__(256) seghead_wgrad32_kernel(const T* __restric
 // shuffle tree (bit-reproducible).  (The thread-per-output kernel walks the partials serially: 76 us for 1184 x 96.)
 __global__ void __launch_bounds__(256) ordered_reduce_wide_kernel(const float* __restrict__ part, int nsplit, long long tot,
                                                                   float* __restrict__ out) {
+    pdl_grid_sync();
     const long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= tot) return;
     const int lane = threadIdx.x & 31;
@@ -497,6 +507,7 @@ int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int acc
 template <typename T>
 __global__ void nchw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int n, int c, long long vox,
                                      int dst_pitch) {
+    pdl_grid_sync();
     const long long total = (long long)n * c * vox;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long v = i % vox;
