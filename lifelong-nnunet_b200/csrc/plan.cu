@@ -31,7 +31,7 @@ std::atomic<long long> g_launches{0};
 int g_use_tc = 1;
 int g_tc_strided = 1;
 int g_tc_wgrad = 1;
-int g_pdl = 1;              // programmatic dependent launch for every kernel (common.cuh)
+int g_pdl = 0;              // programmatic dependent launch (common.cuh); measured: no gain on the step (293 vs 296 patches/s), off by default
 int g_norm_recompute = 1;   // norm backward recomputes the activation sign from z instead of reading y
 
 int num_sms() {
@@ -105,6 +105,7 @@ struct b2_unet_plan {
     // backward overlap: the weight-gradient kernels of a layer run on a side stream next to its data-gradient kernels
     // (dz double-buffered, own scratch); created lazily, joined before b2_unet_backward returns to the caller's stream
     Act dz_tmp2;
+    bool patch_valid = false;   // the first layer's patch matrix matches the current input (built by the GEMM forward or lazily in backward)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_misc = nullptr;
     bool side_ok = false;
@@ -153,6 +154,7 @@ static inline float* SCR(void* ws, const b2_unet_plan* p) { return reinterpret_c
 static inline float* SCR_WG(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_wg_scratch); }
 
 int g_bwd_overlap = 1;
+int g_first_simt = 1;       // first layer forward: direct SIMT convolution instead of patch matrix + GEMM
 
 static bool ensure_side_stream(b2_unet_plan* p) {
     if (p->side_ok) return true;
@@ -395,7 +397,19 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         // deep stages: statistics + normalisation + activation in one launch (norm.cu, small tensors)
         const bool small = norm_small_supported(cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, 8, 8);
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            if (p->first_tc && &cb == &p->convs[0]) {
+            if (p->first_tc && &cb == &p->convs[0] && g_first_simt && first_layer_simt_supported(cb.shape.cin, cb.shape.cout)) {
+                // direct SIMT convolution + statistics; the patch matrix for the weight gradient is built in the backward pass
+                int stat_slots = 0;
+                r = first_layer_fwd_simt(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.in.pitch, prm[cb.p_w], prm[cb.p_b],
+                                         P<T>(ws, p, cb.z, false), cb.z.pitch, small ? nullptr : SCR(ws, p), p->scratch_floats, &stat_slots, st);
+                if (r) return r;
+                if (stat_slots > 0) r = stats_finalize(SCR(ws, p), stat_slots, g.batch, cb.z.vox(), cb.shape.cout, g.norm_eps, stats, st);
+                else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
+                if (r) return r;
+                p->patch_valid = false;
+                done = true;
+            } else if (p->first_tc && &cb == &p->convs[0]) {
+                p->patch_valid = true;
                 __nv_bfloat16* P_ = P<T>(ws, p, p->patch, false);
                 __nv_bfloat16* wp = (__nv_bfloat16*)F32(ws, p, p->wp_off);
                 r = first_layer_patches(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch, P_,
@@ -519,6 +533,12 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         bool wdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (p->first_tc && &cb == &p->convs[0]) {
+                if (!p->patch_valid) {   // forward ran the direct kernel: build the patch matrix now (side stream)
+                    r = first_layer_patches(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch,
+                                            P<T>(ws, p, p->patch, false), prm[cb.p_w], cb.shape.cout, nullptr, wst);
+                    if (r) return r;
+                    p->patch_valid = true;
+                }
                 r = first_layer_wgrad_tc(P<T>(ws, p, p->patch, false), dz, g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.shape.cout,
                                          cb.shape.cout, wscr, grads[cb.p_w], grads[cb.p_b], wst);
                 if (r) return r;
@@ -651,6 +671,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
+    if (!strcmp(name, "first_simt")) { g_first_simt = value; return B2_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value; return B2_OK; }
     if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
