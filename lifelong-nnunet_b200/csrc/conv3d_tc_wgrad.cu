@@ -831,110 +831,6 @@ __global__ void patch_wgrad_reduce_kernel(const float* __restrict__ part, int ns
     dw[((long long)co * cin + ci) * 27 + t] = s;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// First layer, forward: direct 27-tap convolution of the 1-channel input on the CUDA cores (3.6 GFLOP at cfg2 -- K = 27 is
-// too thin for the tensor cores, and going through the patch matrix costs a 134 MB write + read on the critical path of the
-// forward pass).  A block owns a 16 (h) x 32 (w) tile of one d-plane: the 3 x 18 x 34 input halo and the 27 x 32 weights
-// sit in shared memory as fp32; a thread computes 2 voxels (w, w + 16 ... see mapping) x 32 output channels with the
-// weights read as broadcast float4.  The InstanceNorm partial sums come out of the same pass (transpose-reduce over the
-// lanes, lane = channel).  The patch matrix is still built for the weight gradient -- in the backward pass, on the side
-// stream (plan.cu).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int FL_TH = 16, FL_TW = 32;
-__global__ void __launch_bounds__(256) first_conv_simt_kernel(const __nv_bfloat16* __restrict__ x, int D, int H, int W, int x_pitch,
-                                                              const float* __restrict__ w_pt, const float* __restrict__ bias,
-                                                              __nv_bfloat16* __restrict__ z, int z_pitch, float* __restrict__ stat_part,
-                                                              int slots) {
-    pdl_grid_sync();
-    __shared__ float xs[3][FL_TH + 2][FL_TW + 2];
-    __shared__ __align__(16) float ws[27][32];
-    __shared__ float red[8][64];
-    const int tw = blockIdx.x % ((W + FL_TW - 1) / FL_TW), th = blockIdx.x / ((W + FL_TW - 1) / FL_TW);
-    const int d = blockIdx.y, n = blockIdx.z;
-    const int h0 = th * FL_TH, w0 = tw * FL_TW;
-    for (int i = threadIdx.x; i < 27 * 32; i += 256) {
-        const int t = i >> 5, co = i & 31;
-        ws[t][co] = w_pt[co * 27 + t];          // PyTorch [Cout][1][27]
-    }
-    for (int i = threadIdx.x; i < 3 * (FL_TH + 2) * (FL_TW + 2); i += 256) {
-        const int ww = i % (FL_TW + 2), r = i / (FL_TW + 2), hh = r % (FL_TH + 2), dd = r / (FL_TH + 2);
-        const int id = d + dd - 1, ih = h0 + hh - 1, iw = w0 + ww - 1;
-        float v = 0.f;
-        if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
-            v = __bfloat162float(x[((((long long)n * D + id) * H + ih) * W + iw) * x_pitch]);
-        xs[dd][hh][ww] = v;
-    }
-    __syncthreads();
-    // thread -> voxels (hl, wl) and (hl + 8, wl): a warp covers one 32-wide row of each half
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int hl = warp, wl = lane;
-    float acc0[32], acc1[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) { const float b = bias ? bias[c] : 0.f; acc0[c] = b; acc1[c] = b; }
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        const int kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
-        const float x0 = xs[kd][hl + kh][wl + kw], x1 = xs[kd][hl + 8 + kh][wl + kw];
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 wv = *reinterpret_cast<const float4*>(&ws[t][c4 * 4]);
-            acc0[c4 * 4 + 0] = fmaf(x0, wv.x, acc0[c4 * 4 + 0]); acc1[c4 * 4 + 0] = fmaf(x1, wv.x, acc1[c4 * 4 + 0]);
-            acc0[c4 * 4 + 1] = fmaf(x0, wv.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(x1, wv.y, acc1[c4 * 4 + 1]);
-            acc0[c4 * 4 + 2] = fmaf(x0, wv.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(x1, wv.z, acc1[c4 * 4 + 2]);
-            acc0[c4 * 4 + 3] = fmaf(x0, wv.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(x1, wv.w, acc1[c4 * 4 + 3]);
-        }
-    }
-    const int oh0 = h0 + hl, oh1 = h0 + hl + 8, ow = w0 + wl;
-    const bool v0 = oh0 < H && ow < W, v1 = oh1 < H && ow < W;
-    if (v0) {
-        __nv_bfloat16* row = z + ((((long long)n * D + d) * H + oh0) * W + ow) * z_pitch;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store8(row + j, *reinterpret_cast<float(*)[8]>(&acc0[j]));
-    }
-    if (v1) {
-        __nv_bfloat16* row = z + ((((long long)n * D + d) * H + oh1) * W + ow) * z_pitch;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) store8(row + j, *reinterpret_cast<float(*)[8]>(&acc1[j]));
-    }
-    if (stat_part) {
-        float s[32], q[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float a = v0 ? acc0[c] : 0.f, b = v1 ? acc1[c] : 0.f;
-            s[c] = a + b;
-            q[c] = a * a + b * b;
-        }
-        const float s1 = transpose_reduce32(s, lane), s2 = transpose_reduce32(q, lane);
-        red[warp][lane] = s1;
-        red[warp][32 + lane] = s2;
-        __syncthreads();
-        if (threadIdx.x < 64) {
-            float t = 0.f;
-#pragma unroll
-            for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
-            const int slot = blockIdx.y * gridDim.x + blockIdx.x;
-            const int c = threadIdx.x & 31, which = threadIdx.x >> 5;
-            stat_part[(((long long)n * slots + slot) * 32 + c) * 2 + which] = t;
-        }
-    }
-}
-
-bool first_layer_simt_supported(int cin, int cout) { return cin == 1 && cout == 32; }
-
-// z = conv(x) + bias (bf16 NDHWC); stat_part != nullptr: InstanceNorm partials part[n][*slots][32][2] (see EpiStats)
-int first_layer_fwd_simt(const __nv_bfloat16* x, int N, int D, int H, int W, int x_pitch, const float* w_pt, const float* bias,
-                         __nv_bfloat16* z, int z_pitch, float* stat_part, size_t stat_part_floats, int* slots, cudaStream_t st) {
-    B2_CHECK_ARG(z_pitch % 8 == 0);
-    const int gx = cdiv(W, FL_TW) * cdiv(H, FL_TH);
-    dim3 grid(gx, D, N);
-    int nslots = gx * D;
-    if (slots) *slots = 0;
-    if (stat_part && slots && (size_t)N * nslots * 32 * 2 <= stat_part_floats) *slots = nslots;
-    else stat_part = nullptr;
-    B2_LAUNCH(first_conv_simt_kernel, grid, 256, 0, st, x, D, H, W, x_pitch, w_pt, bias, z, z_pitch, stat_part, nslots);
-    return B2_OK;
-}
-
 bool first_layer_tc_supported(int cin, int cout) { return 27 * cin <= 32 && cout % 32 == 0 && cout <= 256; }
 
 int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,

@@ -90,9 +90,6 @@ int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, in
                         const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st, float* stat_part = nullptr,
                         size_t stat_part_floats = 0, int* stat_slots = nullptr);
 bool first_layer_tc_supported(int cin, int cout);
-bool first_layer_simt_supported(int cin, int cout);
-int first_layer_fwd_simt(const __nv_bfloat16* x, int N, int D, int H, int W, int x_pitch, const float* w_pt, const float* bias,
-                         __nv_bfloat16* z, int z_pitch, float* stat_part, size_t stat_part_floats, int* slots, cudaStream_t st);
 int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
                         int cout, __nv_bfloat16* wp, cudaStream_t st);
 size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);

@@ -154,7 +154,6 @@ static inline float* SCR(void* ws, const b2_unet_plan* p) { return reinterpret_c
 static inline float* SCR_WG(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_wg_scratch); }
 
 int g_bwd_overlap = 1;
-int g_first_simt = 1;       // first layer forward: direct SIMT convolution instead of patch matrix + GEMM
 
 static bool ensure_side_stream(b2_unet_plan* p) {
     if (p->side_ok) return true;
@@ -348,7 +347,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
     size_t ci = 0, ti = 0;
     // bf16 weight shadows of every layer this call runs: ONE multi-tensor launch (tiled transposes) instead of one
     // scatter kernel per layer
-    bool shadows_batched = false;
+    bool shadows_batched = false, fwd_side = false, shadows_pending = false, heads_on_side = false;
     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
         std::vector<ShadowJob> jobs;
         bool all_ok = true;
@@ -378,7 +377,14 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 add_conv_job(p->convs[2 * (g.num_pool + 1) + 2 * u + 1]);
             }
         if (all_ok && !jobs.empty()) {
-            if ((rc = shadow_multi(jobs.data(), (int)jobs.size(), st))) return rc;
+            // on the side stream: the input layout conversion and the first layer do not need the shadows
+            fwd_side = g_bwd_overlap && ensure_side_stream(p);
+            if (fwd_side) {
+                B2_CUDA(cudaEventRecord(p->ev_misc, st));          // (orders the shadow writes after everything already queued on st)
+                B2_CUDA(cudaStreamWaitEvent(p->side, p->ev_misc, 0));
+            }
+            if ((rc = shadow_multi(jobs.data(), (int)jobs.size(), fwd_side ? p->side : st))) return rc;
+            if (fwd_side) { B2_CUDA(cudaEventRecord(p->ev_dz[0], p->side)); shadows_pending = true; }
             shadows_batched = true;
         }
     }
@@ -397,18 +403,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         // deep stages: statistics + normalisation + activation in one launch (norm.cu, small tensors)
         const bool small = norm_small_supported(cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, 8, 8);
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-            if (p->first_tc && &cb == &p->convs[0] && g_first_simt && first_layer_simt_supported(cb.shape.cin, cb.shape.cout)) {
-                // direct SIMT convolution + statistics; the patch matrix for the weight gradient is built in the backward pass
-                int stat_slots = 0;
-                r = first_layer_fwd_simt(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.in.pitch, prm[cb.p_w], prm[cb.p_b],
-                                         P<T>(ws, p, cb.z, false), cb.z.pitch, small ? nullptr : SCR(ws, p), p->scratch_floats, &stat_slots, st);
-                if (r) return r;
-                if (stat_slots > 0) r = stats_finalize(SCR(ws, p), stat_slots, g.batch, cb.z.vox(), cb.shape.cout, g.norm_eps, stats, st);
-                else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
-                if (r) return r;
-                p->patch_valid = false;
-                done = true;
-            } else if (p->first_tc && &cb == &p->convs[0]) {
+            if (p->first_tc && &cb == &p->convs[0]) {
                 p->patch_valid = true;
                 __nv_bfloat16* P_ = P<T>(ws, p, p->patch, false);
                 __nv_bfloat16* wp = (__nv_bfloat16*)F32(ws, p, p->wp_off);
@@ -431,6 +426,10 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
                 if (r) return r;
                 done = true;
+            }
+            if (!done && shadows_pending) {   // first consumer of the batched shadows: join the side stream
+                B2_CUDA(cudaStreamWaitEvent(st, p->ev_dz[0], 0));
+                shadows_pending = false;
             }
             if (!done && !shadows_batched && (cb.tc_fwd || cb.tc_dgrad || cb.tc_dgrad_strided)) {
                 r = weight_shadow_bf16(prm[cb.p_w], cb.shape.cout, cb.shape.cin, (__nv_bfloat16*)F32(ws, p, cb.wk_off),
@@ -474,6 +473,7 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         bool tdone = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
             if (t.tc) {
+                if (shadows_pending) { B2_CUDA(cudaStreamWaitEvent(st, p->ev_dz[0], 0)); shadows_pending = false; }
                 if (!shadows_batched)
                     if ((rc = tconv_shadow_bf16(prm[t.p_w], t.shape.cin, t.shape.cout, k8, (__nv_bfloat16*)F32(ws, p, t.wqb_off),
                                                 (__nv_bfloat16*)F32(ws, p, t.wqd_off), st))) return rc;
@@ -490,8 +490,22 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         if ((rc = run_conv(p->convs[ci++]))) return rc;
         if ((rc = run_conv(p->convs[ci++]))) return rc;
         Head& h = p->heads[u];
-        if (logits[h.level])
-            if ((rc = seghead_fwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], logits[h.level], g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, st))) return rc;
+        if (logits[h.level]) {
+            // the heads of the lower-resolution levels run next to the rest of the decoder; the last one stays on st
+            cudaStream_t hs = st;
+            if (fwd_side && u + 1 < g.num_pool) {
+                B2_CUDA(cudaEventRecord(p->ev_misc, st));
+                B2_CUDA(cudaStreamWaitEvent(p->side, p->ev_misc, 0));
+                hs = p->side;
+                heads_on_side = true;
+            }
+            if ((rc = seghead_fwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], logits[h.level], g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, hs))) return rc;
+        }
+    }
+    if (shadows_pending) { B2_CUDA(cudaStreamWaitEvent(st, p->ev_dz[0], 0)); shadows_pending = false; }
+    if (heads_on_side) {   // join: every logits tensor is complete in the caller's stream order
+        B2_CUDA(cudaEventRecord(p->ev_misc, p->side));
+        B2_CUDA(cudaStreamWaitEvent(st, p->ev_misc, 0));
     }
     return B2_OK;
 }
@@ -671,7 +685,6 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
-    if (!strcmp(name, "first_simt")) { g_first_simt = value; return B2_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value; return B2_OK; }
     if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
