@@ -29,6 +29,10 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / unset in some images
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 WORKLOAD = "cfg2"

@@ -69,3 +69,34 @@ def test_invalid_geometry_is_rejected():
     h = ctypes.c_void_p()
     assert lib.b2_unet_plan_create(ctypes.byref(g), ctypes.byref(h)) != 0
     assert b"invalid argument" in lib.b2_last_error()
+
+
+def test_every_kernel_is_pdl_safe():
+    """b2_set_option("pdl", 1) launches every kernel with programmatic stream serialization: that is only correct if every
+    __global__ function starts with pdl_grid_sync() (griddepcontrol.wait) -- checked on the sources."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lifelong-nnunet_b200", "csrc")
+    missing = []
+    for path in sorted(glob.glob(os.path.join(root, "*.cu"))):
+        src = open(path).read()
+        for m in re.finditer(r"__global__", src):
+            i, depth = m.end(), 0
+            while True:
+                ch = src[i]
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                elif ch == "{" and depth == 0:
+                    break
+                elif ch == ";" and depth == 0:
+                    i = -1
+                    break
+                i += 1
+            if i < 0:
+                continue
+            if not src[i + 1:i + 60].lstrip().startswith("pdl_grid_sync();"):
+                missing.append("%s: %s" % (os.path.basename(path), src[m.start():m.start() + 120].split("(")[0].replace("\n", " ")))
+    assert not missing, missing
