@@ -320,6 +320,7 @@ static int build_plan(b2_unet_plan* p) {
         hd.in = cur; hd.din = dcur; hd.c = fs; hd.level = lvl;
         hd.p_w = add_param(p, hd.prefix + ".weight", {g.num_classes, fs, 1, 1, 1});
         p->scratch_floats = max_sz(p->scratch_floats, seghead_bwd_scratch_floats(N, cur.vox(), fs, g.num_classes));
+        p->wg_scratch_floats = max_sz(p->wg_scratch_floats, seghead_bwd_scratch_floats(N, cur.vox(), fs, g.num_classes));
         p->heads.push_back(hd);
     }
     p->dz_tmp.off = gc;
@@ -605,8 +606,15 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         const float* dl = dlogits[h.level];
         const bool first_writer = (u == P_ - 1);
         if (dl) {
-            if ((rc = seghead_bwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], dl, P<T>(ws, p, h.din, true), first_writer ? 0 : 1, grads[h.p_w],
+            // data gradient on the main stream, weight gradient (+ its ordered reduce) on the side stream
+            if ((rc = seghead_bwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], dl, P<T>(ws, p, h.din, true), first_writer ? 0 : 1, (float*)nullptr,
                                      g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, h.din.pitch, SCR(ws, p), st))) return rc;
+            if (overlap) {
+                B2_CUDA(cudaEventRecord(p->ev_misc, st));       // dlogits were produced on st before this call
+                B2_CUDA(cudaStreamWaitEvent(wst, p->ev_misc, 0));
+            }
+            if ((rc = seghead_bwd<T>(P<T>(ws, p, h.in, false), prm[h.p_w], dl, (T*)nullptr, 0, grads[h.p_w],
+                                     g.batch, h.in.vox(), h.c, g.num_classes, h.in.pitch, h.din.pitch, wscr, wst))) return rc;
         } else {
             B2_CUDA(cudaMemsetAsync(grads[h.p_w], 0, p->params[h.p_w].numel * sizeof(float), st));
             if (has_grad) has_grad[h.p_w] = 0;
