@@ -89,5 +89,7 @@ int main() {
     run<128, 64, 1>(d); run<128, 64, 4>(d);
     run<128, 128, 1>(d); run<128, 128, 2>(d); run<128, 128, 4>(d);
     run<128, 256, 1>(d); run<128, 256, 2>(d);
+    // kd-merged widths of the halo / wgrad kernels
+    run<64, 96, 1>(d); run<64, 96, 3>(d); run<128, 96, 3>(d); run<64, 160, 1>(d); run<64, 192, 2>(d); run<128, 192, 2>(d);
     return 0;
 }
