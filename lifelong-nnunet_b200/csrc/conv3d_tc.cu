@@ -73,6 +73,14 @@ struct TcConvParams {
     unsigned char cls_tap0[8], cls_ntaps[8];
     signed char cls_oo[8][3];
     short cls_L[8][3], cls_nt[8][3];
+    // shared-A stages (merged-class strided dgrad): a pipeline stage is ONE source tile (a shift of the dz box) plus the weight
+    // blocks of every (parity class, tap) pair that reads it; block j of stage s accumulates into the column block of its
+    // class.  A tile of the coarse lattice then produces all parity classes at once: 8 source tiles per output tile instead
+    // of 27 (the per-class launches were L2-bound on re-fetching dz), and the epilogue scatters column block -> class
+    // lattice with the q_scatter mapping.
+    int mes, mes_nst, mes_blk_rows;
+    unsigned char mes_nb[12], mes_blk0[13];
+    unsigned char mes_wrow[27], mes_cls[27], mes_first[27];
     // magic numbers for the index decode (FastDiv, tc_common.cuh)
     FastDiv fd_ksplit, fd_nblk, fd_ntw, fd_nth, fd_ntd, fd_qch, fd_qkw, fd_qkh;
     FastDiv cls_fd[8][3];        // per class: nt_d, nt_h, nt_w
@@ -166,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 decode_tile(p, tile, ti);
                 const int nb = ti.nb;
                 const int w0 = ti.tw * p.TW * p.sw, h0 = ti.th * p.TH * p.sh, d0 = ti.td * p.TD * p.sd, n0 = ti.tn * p.TN;
-                const int kiters = ti.ntaps * p.kchunks;
+                const int kiters = (p.mes ? p.mes_nst : ti.ntaps) * p.kchunks;
                 int it0 = 0, it1 = kiters, tap = ti.tap0, kc = 0;
                 if (p.ksplit > 1) {
                     it0 = (int)((long long)kiters * ti.ks / p.ksplit); it1 = (int)((long long)kiters * (ti.ks + 1) / p.ksplit);
@@ -176,10 +184,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (gmod == warp) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                        if (p.mes) {
+                            const int nbk = p.mes_nb[tap], b0 = p.mes_blk0[tap];
+                            const uint32_t blk_bytes = (uint32_t)p.mes_blk_rows * KC * 2;
+                            mbar_expect_tx(&full_bar[stage], A_BYTES + (uint32_t)nbk * blk_bytes);
+                            tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
+                                        d0 + p.tap_off[tap][0], n0);
+                            for (int j = 0; j < nbk; ++j)
+                                tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES + (size_t)j * blk_bytes, kc * KC,
+                                            (int)p.mes_wrow[b0 + j] * p.rows_per_tap);
+                        } else {
                         mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
                         tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
                                     d0 + p.tap_off[tap][0], n0);
                         tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
+                        }
                         stage += p.nprod;
                         if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
                     }
@@ -203,25 +222,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 int n_it = p.ntaps * p.kchunks;            // (the MMA warp only needs the iteration count of the tile)
-                if (p.nclass > 1) n_it = p.cls_ntaps[tile_class(p, tile)] * p.kchunks;
+                if (p.mes) n_it = p.mes_nst * p.kchunks;
+                else if (p.nclass > 1) n_it = p.cls_ntaps[tile_class(p, tile)] * p.kchunks;
                 else if (p.ksplit > 1) {
                     int ks;
                     fd_divmod(tile, p.fd_ksplit, ks);
                     n_it = (int)((long long)n_it * (ks + 1) / p.ksplit) - (int)((long long)n_it * ks / p.ksplit);
                 }
+                int mes_s = 0, mes_kc = 0;
                 for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
+                        if (p.mes) {
+                            const int nbk = p.mes_nb[mes_s], b0 = p.mes_blk0[mes_s];
+                            const uint32_t blk16 = ((uint32_t)p.mes_blk_rows * KC * 2) >> 4;
+                            for (int j = 0; j < nbk; ++j) {
+                                const uint32_t dj = d_tmem + (uint32_t)p.mes_cls[b0 + j] * (uint32_t)p.mes_blk_rows;
+                                const uint32_t fresh = (p.mes_first[b0 + j] && mes_kc == 0) ? 1u : 0u;
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k)
+                                    umma_bf16(dj, mk(a_lo + 2 * k), mk(a_lo + a16 + (uint32_t)j * blk16 + 2 * k), p.idesc,
+                                              (fresh && k == 0) ? 0u : 1u);
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle atom per K16 step
                             umma_bf16(d_tmem, mk(a_lo + 2 * k), mk(a_lo + a16 + 2 * k), p.idesc, (it | k) != 0 ? 1u : 0u);
+                        }
                         umma_commit(&empty_bar[stage]);
                         if (it == n_it - 1) umma_commit(&tfull_bar[acc]);
                     }
                     __syncwarp();
                     a_lo += stage16;
                     if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
+                    if (++mes_kc == p.kchunks) { mes_kc = 0; ++mes_s; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -614,7 +649,10 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     B2_CHECK_ARG(g.src_pitch % 8 == 0 && g.dst_pitch % 8 == 0 && g.ntaps >= 1 && g.ntaps <= 27);
     const int KC = (g.K % 64 == 0) ? 64 : 32;
     int nblk, BN;
-    if (g.q_scatter) {
+    if (g.mes) {
+        BN = g.Nout; nblk = 1;          // all parity classes side by side: Nout = nclass * channels, <= 256
+        B2_CHECK_ARG(BN <= 256 && g.q_scatter && g.q_channels == g.mes_blk_rows && g.mes_nst <= 12);
+    } else if (g.q_scatter) {
         // 32-column chunks must not straddle q (q_channels % 32 == 0).  Narrow layers: one tile spans several q (BN = 256)
         // -- a tile per q made Cout = 32 layers run as 8x more (K-iteration-free, epilogue-bound) tiles; wide layers: block
         // the per-q channel count
@@ -675,7 +713,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     // split-K when the output tiles cannot fill the GPU (deep, small-volume layers)
     int ksplit = 1;
     const int kiters_total = g.ntaps * p.kchunks;
-    if (g.splitk_scratch && g.nclass <= 1 && otiles * 2 <= num_sms()) {
+    if (g.splitk_scratch && g.nclass <= 1 && !g.mes && otiles * 2 <= num_sms()) {
         ksplit = num_sms() / otiles;
         if (ksplit > kiters_total / 4) ksplit = kiters_total / 4;
         if (ksplit < 1) ksplit = 1;
@@ -684,7 +722,15 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     p.ksplit = ksplit;
     p.fd_ksplit = make_fastdiv(ksplit);
     p.num_tiles = otiles * ksplit;
-    p.idesc = umma_idesc_bf16(128, BN);
+    p.idesc = umma_idesc_bf16(128, g.mes ? g.mes_blk_rows : BN);
+    if (g.mes) {
+        p.mes = 1; p.mes_nst = g.mes_nst; p.mes_blk_rows = g.mes_blk_rows;
+        for (int i = 0; i < 12; ++i) p.mes_nb[i] = (unsigned char)g.mes_nb[i];
+        for (int i = 0; i < 13; ++i) p.mes_blk0[i] = (unsigned char)g.mes_blk0[i];
+        for (int i = 0; i < 27; ++i) {
+            p.mes_wrow[i] = (unsigned char)g.mes_wrow[i]; p.mes_cls[i] = (unsigned char)g.mes_cls[i]; p.mes_first[i] = (unsigned char)g.mes_first[i];
+        }
+    }
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * BN)) cols *= 2;
     p.tmem_cols = cols;
@@ -703,7 +749,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, g.src, g.N, g.Ds, g.Hs, g.Ws, g.K, g.src_pitch, KC, p.TN, p.TD, p.TH, p.TW, p.sd, p.sh, p.sw);
     if (rc) return rc;
-    rc = make_w_map(&tmB, g.wmat, g.w_rows, g.K, KC, BN);
+    rc = make_w_map(&tmB, g.wmat, g.w_rows, g.K, KC, g.mes ? g.mes_blk_rows : BN);
     if (rc) return rc;
 
     static bool attr64 = false, attr32 = false;
@@ -778,11 +824,81 @@ int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int 
 // dgrad of a STRIDED 3x3x3 conv: one launch per output-parity class; class p receives the taps t with (p - t + 1) even
 // and reads dz at j + (p - t + 1) / 2.  wd = flipped/transposed shadow [26 - t][ci][co] (weight_shadow_bf16).
 int g_dgrad_one_launch = 1;
+int g_dgrad_mes = 1;        // merged-class strided dgrad (shared-A stages) when all classes fit one accumulator (nclass * Cin <= 256)
+
+// dx[j*s + p] for ALL parity classes p of a coarse-lattice tile j in one accumulator set (columns = (class, ci)).
+static int conv_tc_dgrad_strided_mes(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
+                                     int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
+                                     cudaStream_t st) {
+    const int nclass = stride[0] * stride[1] * stride[2];
+    TcGather g;
+    fill_common(g, dz, N, Do, Ho, Wo, Cout, dz_pitch, wd, nclass * Cin, nullptr, dx, Di, Hi, Wi, dx_pitch, accumulate);
+    g.w_rows = 27 * Cin; g.rows_per_tap = Cin;
+    // logical grid = coarse lattice of the largest class (class 0): ceil(dim / stride)
+    g.LD = (Di + stride[0] - 1) / stride[0]; g.LH = (Hi + stride[1] - 1) / stride[1]; g.LW = (Wi + stride[2] - 1) / stride[2];
+    for (int a = 0; a < 3; ++a) { g.os[a] = stride[a]; g.oo[a] = 0; g.qk[a] = stride[a]; }
+    g.q_scatter = 1; g.q_channels = Cin;
+    g.mes = 1; g.mes_blk_rows = Cin; g.mes_nst = 0;
+    // enumerate (class, tap) pairs and group them by source shift
+    struct Pair { int cls, t, off[3]; };
+    Pair pairs[27];
+    int np = 0;
+    for (int pd = 0; pd < stride[0]; ++pd)
+        for (int ph = 0; ph < stride[1]; ++ph)
+            for (int pw = 0; pw < stride[2]; ++pw) {
+                const int par[3] = {pd, ph, pw};
+                const int cls = (pd * stride[1] + ph) * stride[2] + pw;     // == q of the scatter mapping (w fastest)
+                int cnt[3], tt[3][3], off[3][3];
+                for (int a = 0; a < 3; ++a) {
+                    cnt[a] = 0;
+                    for (int t = 0; t < 3; ++t) {
+                        const int num = par[a] - t + 1;
+                        if (stride[a] == 1) { tt[a][cnt[a]] = t; off[a][cnt[a]] = 1 - t; ++cnt[a]; }
+                        else if ((num & 1) == 0) { tt[a][cnt[a]] = t; off[a][cnt[a]] = num / 2; ++cnt[a]; }
+                    }
+                }
+                for (int i = 0; i < cnt[0]; ++i)
+                    for (int j = 0; j < cnt[1]; ++j)
+                        for (int k = 0; k < cnt[2]; ++k) {
+                            if (np >= 27) return fail(B2_EINVAL, "dgrad_mes: more than 27 (class, tap) pairs%s", "");
+                            pairs[np].cls = cls; pairs[np].t = tt[0][i] * 9 + tt[1][j] * 3 + tt[2][k];
+                            pairs[np].off[0] = off[0][i]; pairs[np].off[1] = off[1][j]; pairs[np].off[2] = off[2][k];
+                            ++np;
+                        }
+            }
+    bool used[27] = {false}, seen_cls[64] = {false};
+    int nblk_total = 0;
+    for (int i = 0; i < np; ++i) {
+        if (used[i]) continue;
+        if (g.mes_nst >= 12) return fail(B2_EUNSUPPORTED, "dgrad_mes: more than 12 source shifts%s", "");
+        const int s_ = g.mes_nst++;
+        for (int a = 0; a < 3; ++a) g.tap_off[s_][a] = pairs[i].off[a];
+        g.mes_blk0[s_] = nblk_total;
+        int nb = 0;
+        for (int j = i; j < np; ++j) {     // pairs are enumerated class-major: blocks of a stage come out class-ascending
+            if (used[j] || pairs[j].off[0] != pairs[i].off[0] || pairs[j].off[1] != pairs[i].off[1] || pairs[j].off[2] != pairs[i].off[2]) continue;
+            used[j] = true;
+            g.mes_wrow[nblk_total] = 26 - pairs[j].t;
+            g.mes_cls[nblk_total] = pairs[j].cls;
+            g.mes_first[nblk_total] = seen_cls[pairs[j].cls] ? 0 : 1;
+            seen_cls[pairs[j].cls] = true;
+            ++nblk_total; ++nb;
+        }
+        g.mes_nb[s_] = nb;
+        if (nb > nclass) return fail(B2_EINVAL, "dgrad_mes: stage with more blocks than classes%s", "");
+    }
+    g.mes_blk0[g.mes_nst] = nblk_total;
+    g.ntaps = g.mes_nst;
+    for (int t = 0; t < g.ntaps; ++t) g.tap_w[t] = 0;
+    return conv_tc_gather(g, st);
+}
 
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
                           int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
                           cudaStream_t st) {
     const int dims_in[3] = {Di, Hi, Wi};
+    if (g_dgrad_mes && g_dgrad_one_launch && Cin % 32 == 0 && stride[0] * stride[1] * stride[2] * Cin <= 256)
+        return conv_tc_dgrad_strided_mes(dz, N, Do, Ho, Wo, Cout, dz_pitch, wd, Cin, dx, Di, Hi, Wi, dx_pitch, stride, accumulate, st);
     // all parity classes in ONE launch (tile classes of conv_tc_kernel): the per-class launches of the deep layers were
     // dominated by launch + pipeline fill (8 x 11..29 us for 0.3..4 GFLOP each)
     TcGather m;

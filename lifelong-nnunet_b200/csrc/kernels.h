@@ -60,6 +60,9 @@ struct TcGather {
     // tile classes (strided dgrad: one class per output-parity lattice, one launch): class c uses the taps
     // [cls_tap0[c], +cls_ntaps[c]) of the tables above, lattice offset cls_oo[c] and logical extent cls_L[c]
     int nclass; int cls_tap0[8], cls_ntaps[8], cls_oo[8][3], cls_L[8][3];
+    // shared-A stages (merged-class strided dgrad, see TcConvParams in conv3d_tc.cu): stage s = shift tap_off[s] + blocks
+    // [mes_blk0[s], +mes_nb[s]) of (weight row-block, class column block, first-contribution flag)
+    int mes, mes_nst, mes_blk_rows, mes_nb[12], mes_blk0[13], mes_wrow[27], mes_cls[27], mes_first[27];
     // optional InstanceNorm partials from the epilogue: part[N][*stat_slots][Nout][2] (see EpiStats in tc_common.cuh)
     float* stat_part; size_t stat_part_floats; int* stat_slots;
 };
@@ -95,7 +98,7 @@ int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int 
 size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);
 int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
                          float* part, float* dw, float* dbias, cudaStream_t st);
-extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch, g_epi_stats;
+extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch, g_dgrad_mes, g_epi_stats;
 extern int g_wgrad_desc_mode, g_tc_wgrad, g_wgrad_dmerge, g_wgrad_direct, g_wgrad_halo;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only
 

@@ -203,17 +203,37 @@ __global__ void __launch_bounds__(MT_THREADS) sgd_kernel(const int* __restrict__
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const b2_sgd_entry e = ent[l.tensor];
     const float c = clip[1];
-    float* gw = const_cast<float*>(e.grad);
-    for (long long i = threadIdx.x; i < l.n; i += MT_THREADS) {
-        const long long k = l.off + i;
-        const float g = e.grad[k] * c;   // clip_grad_norm_ scales .grad in place (RW reads it afterwards, rw:223-225)
-        gw[k] = g;
-        const float p = e.theta[k];
+    float* gw = const_cast<float*>(e.grad) + l.off;
+    float* th = e.theta + l.off;
+    float* mo = e.momentum + l.off;
+    auto upd = [&](float g0, float p, float m, float& g_out, float& p_out, float& m_out) {
+        const float g = g0 * c;   // clip_grad_norm_ scales .grad in place (RW reads it afterwards, rw:223-225)
+        g_out = g;
         float d = g + wd * p;
-        float buf = first_step ? d : momentum * e.momentum[k] + d;
-        e.momentum[k] = buf;
+        const float buf = first_step ? d : momentum * m + d;
+        m_out = buf;
         d = nesterov ? d + momentum * buf : buf;
-        e.theta[k] = p - lr * d;
+        p_out = p - lr * d;
+    };
+    // 16-byte accesses (3 reads + 3 writes per element: the step is pure HBM traffic)
+    const bool vec = aligned16(gw) && aligned16(th) && aligned16(mo);
+    const long long nv = vec ? (l.n / 4) * 4 : 0;
+    for (long long i = (long long)threadIdx.x * 4; i < nv; i += MT_THREADS * 4) {
+        float4 g = *reinterpret_cast<const float4*>(gw + i);
+        float4 p = *reinterpret_cast<const float4*>(th + i);
+        float4 m = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(mo + i);
+        upd(g.x, p.x, m.x, g.x, p.x, m.x);
+        upd(g.y, p.y, m.y, g.y, p.y, m.y);
+        upd(g.z, p.z, m.z, g.z, p.z, m.z);
+        upd(g.w, p.w, m.w, g.w, p.w, m.w);
+        *reinterpret_cast<float4*>(gw + i) = g;
+        *reinterpret_cast<float4*>(mo + i) = m;
+        *reinterpret_cast<float4*>(th + i) = p;
+    }
+    for (long long i = nv + threadIdx.x; i < l.n; i += MT_THREADS) {
+        float g, p, m;
+        upd(gw[i], th[i], first_step ? 0.f : mo[i], g, p, m);
+        gw[i] = g; mo[i] = m; th[i] = p;
     }
 }
 

@@ -686,6 +686,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "tc_strided")) { g_tc_strided = value; return B2_OK; }
     if (!strcmp(name, "tc_wgrad")) { g_tc_wgrad = value; return B2_OK; }
     if (!strcmp(name, "tc_halo")) { g_use_halo = value; return B2_OK; }
+    if (!strcmp(name, "dgrad_mes")) { g_dgrad_mes = value; return B2_OK; }
     if (!strcmp(name, "dgrad_one_launch")) { g_dgrad_one_launch = value; return B2_OK; }
     if (!strcmp(name, "wgrad_halo")) { g_wgrad_halo = value; return B2_OK; }
     if (!strcmp(name, "wgrad_direct")) { g_wgrad_direct = value; return B2_OK; }

@@ -167,3 +167,36 @@ def test_wgrad_variants_agree_on_large_volumes(shape):
         ops.set_option("wgrad_halo", 1)
     assert rel_err(dw1, dw0) < 1e-4, rel_err(dw1, dw0)
     assert rel_err(dw_halo, dw0) < 1e-4, rel_err(dw_halo, dw0)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 48, 64, 32, 64, (2, 2, 2)), (2, 8, 32, 32, 64, 128, (1, 2, 2)), (1, 9, 30, 36, 32, 64, (2, 2, 2))])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_strided_dgrad_merged_classes_agree_with_class_tiles(shape, accumulate):
+    """merged-class strided dgrad (all parity classes of a coarse tile in one accumulator set) == one tile class per parity
+    class == one launch per class; many tiles per CTA, odd extents"""
+    from b200unet import ops
+    N, D, H, W, cin, cout, stride = shape
+    x, w, b = _case(N, D, H, W, cin, cout, 8)
+    od, oh, ow = [(s - 1) // st + 1 for s, st in zip((D, H, W), stride)]
+    g = torch.Generator().manual_seed(9)
+    dz = torch.randn((N, cout, od, oh, ow), generator=g)
+    base = torch.randn((N, cin, D, H, W), generator=g)
+    xd, dzd, wd_ = _ndhwc(x, torch.bfloat16), _ndhwc(dz, torch.bfloat16), w.cuda()
+
+    def run():
+        acc = _ndhwc(base, torch.bfloat16).clone() if accumulate else None
+        dx, _, _ = ops.conv3d_bwd(xd, dzd, wd_, stride, accumulate_into=acc)
+        return (acc if accumulate else dx).float()
+    try:
+        a = run()
+        ops.set_option("dgrad_mes", 0)
+        b1 = run()
+        ops.set_option("dgrad_one_launch", 0)
+        c = run()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("dgrad_mes", 1)
+        ops.set_option("dgrad_one_launch", 1)
+    assert rel_err(b1, c) < 1e-2
+    assert rel_err(a, c) < 1e-2
+    assert (a == c).float().mean().item() > 0.9
