@@ -133,7 +133,7 @@ constexpr int TC_EPI_SETS = 2;                        // epilogue warp sets: set
 constexpr int TC_THREADS = 32 * (TC_PRODUCERS + 1 + 4 * TC_EPI_SETS);   // producers, 1 MMA warp, 2 x 4 epilogue warps
 constexpr int MAX_STAGES = 16;
 
-template <int KC>
+template <int KC, bool MES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcConvParams p,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, int accumulate, float* __restrict__ partial,
@@ -174,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 decode_tile(p, tile, ti);
                 const int nb = ti.nb;
                 const int w0 = ti.tw * p.TW * p.sw, h0 = ti.th * p.TH * p.sh, d0 = ti.td * p.TD * p.sd, n0 = ti.tn * p.TN;
-                const int kiters = (p.mes ? p.mes_nst : ti.ntaps) * p.kchunks;
+                const int kiters = (MES ? p.mes_nst : ti.ntaps) * p.kchunks;
                 int it0 = 0, it1 = kiters, tap = ti.tap0, kc = 0;
                 if (p.ksplit > 1) {
                     it0 = (int)((long long)kiters * ti.ks / p.ksplit); it1 = (int)((long long)kiters * (ti.ks + 1) / p.ksplit);
@@ -184,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (gmod == warp) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-                        if (p.mes) {
+                        if (MES) {
                             const int nbk = p.mes_nb[tap], b0 = p.mes_blk0[tap];
                             const uint32_t blk_bytes = (uint32_t)p.mes_blk_rows * KC * 2;
                             mbar_expect_tx(&full_bar[stage], A_BYTES + (uint32_t)nbk * blk_bytes);
@@ -222,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 int n_it = p.ntaps * p.kchunks;            // (the MMA warp only needs the iteration count of the tile)
-                if (p.mes) n_it = p.mes_nst * p.kchunks;
+                if (MES) n_it = p.mes_nst * p.kchunks;
                 else if (p.nclass > 1) n_it = p.cls_ntaps[tile_class(p, tile)] * p.kchunks;
                 else if (p.ksplit > 1) {
                     int ks;
@@ -234,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        if (p.mes) {
+                        if (MES) {
                             const int nbk = p.mes_nb[mes_s], b0 = p.mes_blk0[mes_s];
                             const uint32_t blk16 = ((uint32_t)p.mes_blk_rows * KC * 2) >> 4;
                             for (int j = 0; j < nbk; ++j) {
@@ -256,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     a_lo += stage16;
                     if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = base_lo; }
-                    if (++mes_kc == p.kchunks) { mes_kc = 0; ++mes_s; }
+                    if (MES) { if (++mes_kc == p.kchunks) { mes_kc = 0; ++mes_s; } }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -752,7 +752,6 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     rc = make_w_map(&tmB, g.wmat, g.w_rows, g.K, KC, g.mes ? g.mes_blk_rows : BN);
     if (rc) return rc;
 
-    static bool attr64 = false, attr32 = false;
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     EpiStats es{nullptr, 0, g.Nout, g.N};
     if (g.stat_slots) *g.stat_slots = 0;
@@ -762,13 +761,18 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
         es.slots = grid * 4 * TC_EPI_SETS;
         if ((size_t)g.N * es.slots * g.Nout * 2 <= g.stat_part_floats) { es.part = g.stat_part; *g.stat_slots = es.slots; }
     }
-    if (KC == 64) {
-        if (!attr64) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr64 = true; }
-        B2_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch, es);
-    } else {
-        if (!attr32) { B2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr32 = true; }
-        B2_LAUNCH(conv_tc_kernel<32>, grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch, es);
-    }
+    static bool attr_set[4] = {false, false, false, false};
+#define B2_TC_LAUNCH(KC_, MES_, IDX_)                                                                                              \
+    do {                                                                                                                         \
+        if (!attr_set[IDX_]) {                                                                                                   \
+            B2_CUDA(cudaFuncSetAttribute((conv_tc_kernel<KC_, MES_>), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));   \
+            attr_set[IDX_] = true;                                                                                               \
+        }                                                                                                                        \
+        B2_LAUNCH((conv_tc_kernel<KC_, MES_>), grid, TC_THREADS, smem, st, tmA, tmB, p, g.bias, g.dst, g.accumulate, g.splitk_scratch, es); \
+    } while (0)
+    if (KC == 64) { if (g.mes) B2_TC_LAUNCH(64, true, 0); else B2_TC_LAUNCH(64, false, 1); }
+    else { if (g.mes) B2_TC_LAUNCH(32, true, 2); else B2_TC_LAUNCH(32, false, 3); }
+#undef B2_TC_LAUNCH
     if (p.ksplit > 1) {
         const long long total = (long long)otiles * 128 * (BN / 8);
         long long rg = (total + 255) / 256, cap = (long long)num_sms() * 8;
