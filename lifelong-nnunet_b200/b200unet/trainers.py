@@ -85,6 +85,11 @@ class nnUNetTrainerMultiHead:
         self.epoch = 0
         self.online_eval_tp, self.online_eval_fp, self.online_eval_fn = [], [], []
         self.was_initialized = False
+        # opt-in input pipelining (not in the reference, whose `to_cuda(non_blocking=True)` is stream-ordered with the
+        # compute): the H2D copy of batch i+1 is issued on a copy stream before the kernels of batch i are launched.
+        # It consumes the generator one batch ahead, so it is off by default (LwF draws several batches per iteration).
+        self.prefetch_inputs = False
+        self._prefetched, self._copy_stream = None, None
 
     # -- reference MultiHead:337-456 / nnViTUNetTrainer.py:101-138 ---------------------------------------------------
     def initialize_network(self):
@@ -161,11 +166,7 @@ class nnUNetTrainerMultiHead:
 
     # -- reference MultiHead:598-656 (fp32 branch; bf16 needs no loss scaling) ----------------------------------------
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
-        data_dict = next(data_generator)
-        data = maybe_to_torch(data_dict['data'])
-        target = maybe_to_torch(data_dict['target'])
-        data = to_cuda(data, gpu_id=self.device.index)
-        target = to_cuda(target, gpu_id=self.device.index)
+        data, target = self._next_batch(data_generator)
 
         self.optimizer.zero_grad()
         l = None
@@ -186,6 +187,39 @@ class nnUNetTrainerMultiHead:
             if detach:
                 l = l.detach().cpu().numpy()
             return l
+
+    def _fetch(self, data_generator, stream=None):
+        data_dict = next(data_generator)
+        data = maybe_to_torch(data_dict['data'])
+        target = maybe_to_torch(data_dict['target'])
+        if stream is None:
+            return to_cuda(data, gpu_id=self.device.index), to_cuda(target, gpu_id=self.device.index), None
+        with torch.cuda.stream(stream):
+            data = to_cuda(data, gpu_id=self.device.index)
+            target = to_cuda(target, gpu_id=self.device.index)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return data, target, ev
+
+    def _next_batch(self, data_generator):
+        """reference MultiHead:606-615 (next / maybe_to_torch / to_cuda); with `prefetch_inputs` the copy of the NEXT
+        batch is started on a side stream right away so that it overlaps this iteration's kernels"""
+        if not self.prefetch_inputs:
+            self._prefetched = None
+            data, target, _ = self._fetch(data_generator)
+            return data, target
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        if self._prefetched is not None and self._prefetched[0] is data_generator:
+            _, data, target, ev = self._prefetched
+        else:
+            data, target, ev = self._fetch(data_generator, self._copy_stream)
+        cur.wait_event(ev)
+        for t in ([data] if torch.is_tensor(data) else list(data)) + ([target] if torch.is_tensor(target) else list(target)):
+            t.record_stream(cur)
+        self._prefetched = (data_generator,) + self._fetch(data_generator, self._copy_stream)
+        return data, target
 
     def update_after_iteration(self):
         """reference MultiHead_Module.update_after_iteration (MultiHead_Module.py:139-157) re-splits the model and
