@@ -26,14 +26,28 @@ def _scratch(nbytes, dev):
 # --------------------------------------------------------------------------------------------------------------------
 # base: MultipleOutputLoss2(DC_and_CE_loss) in two sweeps per level (value + dlogits)
 # --------------------------------------------------------------------------------------------------------------------
+_LEVEL_STREAMS = {}
+
+
+def _level_stream(dev, i):
+    """side streams for the deep-supervision levels >= 1 (a level is three short dependent launches: the low-resolution
+    levels run next to the full-resolution one instead of after it)"""
+    key = (dev.index, i)
+    if key not in _LEVEL_STREAMS:
+        _LEVEL_STREAMS[key] = torch.cuda.Stream(dev)
+    return _LEVEL_STREAMS[key]
+
+
 class _DSLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, targets, *logits):
         lib = _lib.load()
         dev = logits[0].device
-        loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        dls = []
+        dls, parts, events = [], [], []
         need_grad = any(l.requires_grad for l in logits)
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
         for i, (x, y) in enumerate(zip(logits, targets)):
             w = float(cfg['weights'][i])
             if w == 0 and i > 0:
@@ -45,15 +59,33 @@ class _DSLossFunction(torch.autograd.Function):
             V = x[0, 0].numel()
             if y.numel() != B * V:
                 raise ValueError("target %d has %d elements, expected %d" % (i, y.numel(), B * V))
-            dl = torch.empty_like(x) if need_grad else None
-            scr = _scratch(lib.b2_dsloss_scratch_bytes(B, Cc, V), dev)
-            _lib.check(lib.b2_dsloss_fwd_bwd(x.data_ptr(), y.data_ptr(), B, Cc, V, w, int(cfg['batch_dice']),
-                                             float(cfg['smooth']), int(cfg['do_bg']), int(cfg['ignore_index']),
-                                             int(cfg['with_dice']), None if dl is None else dl.data_ptr(),
-                                             loss.data_ptr(), scr.data_ptr(), _stream(dev)))
+            stream = cur if i == 0 else _level_stream(dev, i)
+            if i > 0:
+                stream.wait_event(start)
+            with torch.cuda.stream(stream):
+                part = torch.zeros(1, dtype=torch.float32, device=dev)
+                dl = torch.empty_like(x) if need_grad else None
+                scr = _scratch(lib.b2_dsloss_scratch_bytes(B, Cc, V), dev)
+                _lib.check(lib.b2_dsloss_fwd_bwd(x.data_ptr(), y.data_ptr(), B, Cc, V, w, int(cfg['batch_dice']),
+                                                 float(cfg['smooth']), int(cfg['do_bg']), int(cfg['ignore_index']),
+                                                 int(cfg['with_dice']), None if dl is None else dl.data_ptr(),
+                                                 part.data_ptr(), scr.data_ptr(), _stream(dev)))
+                if i > 0:
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    events.append(ev)
+                    for t in (part, dl, scr, x, y):
+                        if t is not None:
+                            t.record_stream(stream)
+            parts.append(part)
             dls.append(dl)
+        for ev in events:
+            cur.wait_event(ev)
+        for t in parts + [d for d in dls if d is not None]:
+            t.record_stream(cur)
         ctx.dls = dls
-        return loss[0]
+        # fixed summation order (level 0 first), one launch
+        return torch.cat(parts).sum() if len(parts) > 1 else parts[0][0]
 
     @staticmethod
     def backward(ctx, g):

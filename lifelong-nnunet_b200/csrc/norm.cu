@@ -270,8 +270,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
 //   backward: block per 8 channels, loops the samples: sweep 1 S1 = sum du, S2 = sum du*zhat; sweep 2 dz; dgamma, dbeta
 // All block reductions use a fixed tree (warp shuffles, then the 8 warps in order) => bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int NS_THREADS = 512, NS_WARPS = NS_THREADS / 32;   // small-tensor kernels: 16 warps per block (rows in flight)
 template <int NV>
-__device__ __forceinline__ void block_sum_vec(float (&v)[NV], float (*sh)[NV] /*[8][NV]*/) {
+__device__ __forceinline__ void block_sum_vec(float (&v)[NV], float (*sh)[NV] /*[NS_WARPS][NV]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
@@ -285,24 +286,24 @@ __device__ __forceinline__ void block_sum_vec(float (&v)[NV], float (*sh)[NV] /*
     for (int i = 0; i < NV; ++i) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sh[w][i];
+        for (int w = 0; w < NS_WARPS; ++w) t += sh[w][i];
         v[i] = t;
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) norm_small_fwd_kernel(const T* __restrict__ z, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(NS_THREADS) norm_small_fwd_kernel(const T* __restrict__ z, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, T* __restrict__ y,
                                                              float* __restrict__ stats, int vox, int c, int z_pitch, int y_pitch,
                                                              float slope, float eps) {
     pdl_grid_sync();
-    __shared__ float sh[8][16];
+    __shared__ float sh[NS_WARPS][16];
     const int c0 = blockIdx.x * 8, n = blockIdx.y;
     const T* zp = z + (long long)n * vox * z_pitch + c0;
     float s[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) s[j] = 0.f;
-    for (int v = threadIdx.x; v < vox; v += 256) {
+    for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
         float a[8];
         load8(zp + (long long)v * z_pitch, a);
 #pragma unroll
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(256) norm_small_fwd_kernel(const T* __restrict
         }
     }
     T* yp = y + (long long)n * vox * y_pitch + c0;
-    for (int v = threadIdx.x; v < vox; v += 256) {
+    for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
         float a[8], o[8];
         load8(zp + (long long)v * z_pitch, a);
 #pragma unroll
@@ -341,13 +342,13 @@ __global__ void __launch_bounds__(256) norm_small_fwd_kernel(const T* __restrict
 }
 
 template <typename T, bool RECOMPUTE>
-__global__ void __launch_bounds__(256) norm_small_bwd_kernel(const T* __restrict__ z, const T* __restrict__ y, const T* __restrict__ dy,
+__global__ void __launch_bounds__(NS_THREADS) norm_small_bwd_kernel(const T* __restrict__ z, const T* __restrict__ y, const T* __restrict__ dy,
                                                              const float* __restrict__ stats, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, T* __restrict__ dz,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int n, int vox,
                                                              int c, int z_pitch, int y_pitch, int dy_pitch, int dz_pitch, float slope) {
     pdl_grid_sync();
-    __shared__ float sh[8][16];
+    __shared__ float sh[NS_WARPS][16];
     const int c0 = blockIdx.x * 8;
     float ga[8], be[8], dg[8], db[8];
 #pragma unroll
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) norm_small_bwd_kernel(const T* __restrict
         float s[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) s[j] = 0.f;
-        for (int v = threadIdx.x; v < vox; v += 256) {
+        for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
             float a[8], b[8], g[8];
             load8(zp + (long long)v * z_pitch, a);
             if (!RECOMPUTE) load8(yp + (long long)v * y_pitch, b);
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(256) norm_small_bwd_kernel(const T* __restrict
         block_sum_vec<16>(s, sh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { db[j] += s[j]; dg[j] += s[8 + j]; }
-        for (int v = threadIdx.x; v < vox; v += 256) {
+        for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
             float a[8], b[8], g[8], o[8];
             load8(zp + (long long)v * z_pitch, a);
             if (!RECOMPUTE) load8(yp + (long long)v * y_pitch, b);
@@ -421,7 +422,7 @@ int norm_lrelu_fwd_small(const T* z, const float* gamma, const float* beta, T* y
                          int z_pitch, int y_pitch, float slope, float eps, cudaStream_t st) {
     B2_CHECK_ARG(norm_small_supported(vox, c, z_pitch, y_pitch, 8, 8));
     dim3 grid(c / 8, n);
-    B2_LAUNCH((norm_small_fwd_kernel<T>), grid, 256, 0, st, z, gamma, beta, y, stats, (int)vox, c, z_pitch, y_pitch, slope, eps);
+    B2_LAUNCH((norm_small_fwd_kernel<T>), grid, NS_THREADS, 0, st, z, gamma, beta, y, stats, (int)vox, c, z_pitch, y_pitch, slope, eps);
     return B2_OK;
 }
 template int norm_lrelu_fwd_small<float>(const float*, const float*, const float*, float*, float*, int, long long, int, int, int, float, float, cudaStream_t);
@@ -506,9 +507,9 @@ int norm_lrelu_bwd(const T* z, const T* y, const T* dy, const float* stats, cons
                    float slope, float* scratch, cudaStream_t st) {
     B2_CHECK_ARG(c <= 1024);
     if (norm_small_supported(vox, c, z_pitch, y_pitch, dy_pitch, dz_pitch)) {
-        if (beta) B2_LAUNCH((norm_small_bwd_kernel<T, true>), c / 8, 256, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
+        if (beta) B2_LAUNCH((norm_small_bwd_kernel<T, true>), c / 8, NS_THREADS, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
                             z_pitch, y_pitch, dy_pitch, dz_pitch, slope);
-        else B2_LAUNCH((norm_small_bwd_kernel<T, false>), c / 8, 256, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
+        else B2_LAUNCH((norm_small_bwd_kernel<T, false>), c / 8, NS_THREADS, 0, st, z, y, dy, stats, gamma, beta, dz, dgamma, dbeta, n, (int)vox, c,
                        z_pitch, y_pitch, dy_pitch, dz_pitch, slope);
         return B2_OK;
     }
