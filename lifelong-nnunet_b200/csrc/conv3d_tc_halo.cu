@@ -157,6 +157,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     }
                                 }
                             }
+                        } else if (p.merge && v0 && v1 && !v2 && (oc0 & amask) >= 1) {
+                            // second slab of a segment: outputs s (accumulate) and s+1 (first write) -- two-wide merge
+                            const uint32_t d1t = tmem_base + (oc1 & amask) * (uint32_t)p.BN;
+                            const uint32_t d0t = d1t + (uint32_t)p.BN;
+#pragma unroll
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                const uint32_t a_lo = a_base + (uint32_t)(t9 % 3) * C16 + (uint32_t)(t9 / 3) * A16;
+                                const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3 + 1) * btile16;      // tiles kd = 1, kd = 0
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k) {
+                                    if (t9 == 0 && k == 0) {
+                                        umma_bf16(d1t, mk(a_lo), mk(b_lo), p.idesc, 1u);
+                                        umma_bf16(d0t, mk(a_lo), mk(b_lo + btile16), p.idesc, 0u);
+                                    } else {
+                                        umma_bf16(d1t, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc2, 1u);
+                                    }
+                                }
+                            }
+                        } else if (p.merge && !v0 && v1 && v2 && (oc1 & amask) >= 1) {
+                            // last-but-one slab of a segment: outputs s-1 and s, both accumulate -- two-wide merge
+                            const uint32_t d2 = tmem_base + (oc2 & amask) * (uint32_t)p.BN;
+#pragma unroll
+                            for (int t9 = 0; t9 < 9; ++t9) {
+                                const uint32_t a_lo = a_base + (uint32_t)(t9 % 3) * C16 + (uint32_t)(t9 / 3) * A16;
+                                const uint32_t b_lo = w_lo + (uint32_t)(t9 * 3) * btile16;          // tiles kd = 2, kd = 1
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k)
+                                    umma_bf16(d2, mk(a_lo + 2 * k), mk(b_lo + 2 * k), p.idesc2, 1u);
+                            }
                         } else {
 #pragma unroll
                             for (int kd = 0; kd < 3; ++kd) {
@@ -316,7 +345,7 @@ static bool halo_plan(int K, int Nout, int D, int H, int W, int N, HaloParams& p
     p.num_items = strips * p.DS;
     auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
     p.idesc = idesc(p.BN); p.idesc2 = idesc(2 * p.BN); p.idesc3 = idesc(3 * p.BN);
-    p.merge = g_halo_merge && 3 * p.BN <= 256;
+    p.merge = g_halo_merge && 3 * p.BN <= 256;   // (the two-wide edge merges need 2 * BN <= 256 only, implied)
     int nacc = 4;
     while (nacc * 2 <= HALO_MAX_ACC && nacc * 2 * p.BN <= 512) nacc *= 2;
     p.nacc = nacc;
