@@ -32,6 +32,7 @@ for p in (ROOT, PKG):
 # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / unset in some images
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 

@@ -8,6 +8,7 @@ reproduced: Q1/Q2 (the ``network_params`` generator is consumed by the first sto
 the POD accumulation), Q6 (POD tiling), Q10 (PLOP adaptive factor axes).
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -27,6 +28,7 @@ def _scratch(nbytes, dev):
 # base: MultipleOutputLoss2(DC_and_CE_loss) in two sweeps per level (value + dlogits)
 # --------------------------------------------------------------------------------------------------------------------
 _LEVEL_STREAMS = {}
+_USE_LEVEL_STREAMS = os.environ.get("B2_LOSS_STREAMS", "1") != "0"
 
 
 def _level_stream(dev, i):
@@ -59,8 +61,9 @@ class _DSLossFunction(torch.autograd.Function):
             V = x[0, 0].numel()
             if y.numel() != B * V:
                 raise ValueError("target %d has %d elements, expected %d" % (i, y.numel(), B * V))
-            stream = cur if i == 0 else _level_stream(dev, i)
-            if i > 0:
+            side = i > 0 and _USE_LEVEL_STREAMS
+            stream = _level_stream(dev, i) if side else cur
+            if side:
                 stream.wait_event(start)
             with torch.cuda.stream(stream):
                 part = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -70,7 +73,7 @@ class _DSLossFunction(torch.autograd.Function):
                                                  float(cfg['smooth']), int(cfg['do_bg']), int(cfg['ignore_index']),
                                                  int(cfg['with_dice']), None if dl is None else dl.data_ptr(),
                                                  part.data_ptr(), scr.data_ptr(), _stream(dev)))
-                if i > 0:
+                if side:
                     ev = torch.cuda.Event()
                     ev.record(stream)
                     events.append(ev)

@@ -65,6 +65,10 @@ class DataParallelGroup:
         self.rank = dist.get_rank()
 
     def allreduce_mean_(self, flat):
+        # NCCL averages inside the collective (one pass less over the 123 MB arena); gloo (CPU tests) has no AVG
+        if flat.is_cuda and self.dist.get_backend() == "nccl":
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.AVG)
+            return
         self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
         flat.mul_(1.0 / self.world)
 
