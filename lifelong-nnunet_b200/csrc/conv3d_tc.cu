@@ -52,6 +52,7 @@ struct TcConvParams {
     int nblk, BN;                // output-column blocks and their width
     int kchunks;                 // K / KC
     int rows_per_tap;            // rows of the weight matrix per tap block
+    int w_row0;                  // first row of the computed output-channel window inside a tap block
     int sd, sh, sw;              // source coordinate = logical * s + tap_off
     int os_d, os_h, os_w;        // produced coordinate = logical * os + oo (+ q offset when q_scatter)
     int oo_d, oo_h, oo_w;
@@ -197,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
                         tma_load_5d(&tmA, &full_bar[stage], sa, kc * KC, w0 + p.tap_off[tap][2], h0 + p.tap_off[tap][1],
                                     d0 + p.tap_off[tap][0], n0);
-                        tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + nb * p.BN);
+                        tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kc * KC, (int)p.tap_w[tap] * p.rows_per_tap + p.w_row0 + nb * p.BN);
                         }
                         stage += p.nprod;
                         if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
@@ -680,7 +681,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     p.TD = pow2_le(g.LD, 128 / (p.TW * p.TH));
     p.TN = 128 / (p.TW * p.TH * p.TD);
     p.nt_w = cdiv(g.LW, p.TW); p.nt_h = cdiv(g.LH, p.TH); p.nt_d = cdiv(g.LD, p.TD); p.nt_n = cdiv(g.N, p.TN);
-    p.nblk = nblk; p.BN = BN; p.kchunks = g.K / KC; p.rows_per_tap = g.rows_per_tap;
+    p.nblk = nblk; p.BN = BN; p.kchunks = g.K / KC; p.rows_per_tap = g.rows_per_tap; p.w_row0 = g.w_row0;
     p.sd = g.stride[0]; p.sh = g.stride[1]; p.sw = g.stride[2];
     p.os_d = g.os[0]; p.os_h = g.os[1]; p.os_w = g.os[2];
     p.oo_d = g.oo[0]; p.oo_h = g.oo[1]; p.oo_w = g.oo[2];
@@ -805,17 +806,18 @@ size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout) {
 // 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes, int* stat_slots) {
+                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes, int* stat_slots, int w_pitch, int w_row0) {
     // stat_slots != nullptr: the caller wants InstanceNorm partials in `scratch` ([N][*stat_slots][Nout][2], see EpiStats);
     // *stat_slots == 0 on return means the chosen kernel could not produce them (split-K, batch-spanning boxes, ...)
     if (stat_slots) *stat_slots = 0;
     if (stride[0] == 1 && stride[1] == 1 && stride[2] == 1 && conv_tc_halo_supported(K, Nout, N, Dd, Hd, Wd))
         return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st,
-                                   stat_slots ? scratch : nullptr, scratch_bytes / sizeof(float), stat_slots);
+                                   stat_slots ? scratch : nullptr, scratch_bytes / sizeof(float), stat_slots, w_pitch, w_row0);
     TcGather g;
     fill_common(g, src, N, Ds, Hs, Ws, K, src_pitch, wmat, Nout, bias, dst, Dd, Hd, Wd, dst_pitch, accumulate);
     for (int a = 0; a < 3; ++a) g.stride[a] = stride[a];
     g.ntaps = 27; g.w_rows = 27 * Nout;
+    if (w_pitch > 0) { g.w_rows = 27 * w_pitch; g.rows_per_tap = w_pitch; g.w_row0 = w_row0; }   // output-channel window
     g.splitk_scratch = scratch; g.splitk_scratch_bytes = scratch_bytes;
     g.stat_part = stat_slots ? scratch : nullptr; g.stat_part_floats = scratch_bytes / sizeof(float); g.stat_slots = stat_slots;
     for (int t = 0; t < 27; ++t) {

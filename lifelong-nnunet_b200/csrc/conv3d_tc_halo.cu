@@ -20,6 +20,7 @@ struct HaloParams {
     int dst_pitch;
     int BN;               // output channels per CTA (<= 128)
     int NS, Ntot;         // column splits (CTA c owns columns [(c % NS) * BN, +BN) for its whole life) and total channels
+    int w_pitch, w_row0;  // rows per tap of the weight matrix and first row of the computed column window (w_pitch >= Ntot)
     int HB, WB, DS, SD;   // strips per sample along h / w, segments along d and their length
     int num_items;
     int nslot;            // slab ring depth (2..6)
@@ -110,7 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(&wfull, 27 * B_TILE);
             for (int t = 0; t < 27; ++t) {
                 const int kd = t / 9, t9 = t % 9;
-                tma_load_2d(&tmB, &wfull, wsm + (size_t)(t9 * 3 + 2 - kd) * B_TILE, 0, t * p.Ntot + cs * p.BN);
+                tma_load_2d(&tmB, &wfull, wsm + (size_t)(t9 * 3 + 2 - kd) * B_TILE, 0, t * p.w_pitch + p.w_row0 + cs * p.BN);
             }
         }
     } else if (warp == 1) {
@@ -368,16 +369,20 @@ bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W) {
 // src / dst: NDHWC bf16 of identical spatial extent; wmat: [27][Nout][K] bf16 (forward shadow, or the flipped shadow for dgrad)
 int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
                         const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st, float* stat_part,
-                        size_t stat_part_floats, int* stat_slots) {
+                        size_t stat_part_floats, int* stat_slots, int w_pitch, int w_row0) {
+    // (w_pitch, w_row0): compute only the output-channel window [w_row0, w_row0 + Nout) of a weight matrix with w_pitch rows per
+    // tap -- the caller offsets dst / bias itself.  Used to split the data gradient of a concat input into its two halves.
+    if (w_pitch <= 0) { w_pitch = Nout; w_row0 = 0; }
     HaloParams p;
     size_t smem;
     if (!halo_plan(K, Nout, D, H, W, N, p, smem)) return fail(B2_EUNSUPPORTED, "conv_tc_halo: unsupported shape%s", "");
     B2_CHECK_ARG(src_pitch % 8 == 0 && dst_pitch % 8 == 0);
     p.dst_pitch = dst_pitch;
+    p.w_pitch = w_pitch; p.w_row0 = w_row0;
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, src, N, D, H, W, K, src_pitch, K, 1, 1, 18, 8, 1, 1, 1);
     if (rc) return rc;
-    rc = make_w_map(&tmB, wmat, 27 * Nout, K, K, p.BN);
+    rc = make_w_map(&tmB, wmat, 27 * w_pitch, K, K, p.BN);
     if (rc) return rc;
     int grid = p.num_items * p.NS < num_sms() ? p.num_items * p.NS : num_sms();
     grid = grid / p.NS * p.NS;   // every column split gets the same number of CTAs

@@ -49,6 +49,7 @@ int shadow_multi(const ShadowJob* jobs, int n, cudaStream_t st);
 struct TcGather {
     const __nv_bfloat16* src; int N, Ds, Hs, Ws, K, src_pitch;     // gathered tensor (NDHWC) and its channel count (GEMM K)
     const __nv_bfloat16* wmat; int w_rows, rows_per_tap, Nout;      // weight matrix [w_rows][K]; GEMM N
+    int w_row0;                                                     // first row of the computed window inside a tap block
     const float* bias;
     __nv_bfloat16* dst; int Dd, Hd, Wd, dst_pitch, accumulate;      // produced tensor
     int LD, LH, LW;                                                 // logical grid tiled by the 128-voxel boxes
@@ -77,7 +78,8 @@ int tconv_tc_dgrad(const __nv_bfloat16* dy, int N, int D, int H, int W, int Cout
 int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat16* wq, __nv_bfloat16* wqd, cudaStream_t st);
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0, int* stat_slots = nullptr);
+                   int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0, int* stat_slots = nullptr,
+                   int w_pitch = 0, int w_row0 = 0);
 // mean / rstd from epilogue partials part[n][slots][c][2]
 int stats_finalize(const float* part, int slots, int n, long long vox, int c, float eps, float* stats, cudaStream_t st);
 size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout);
@@ -91,7 +93,7 @@ int tconv_wgrad_tc(const TconvShape& s, const __nv_bfloat16* x, const __nv_bfloa
 bool conv_tc_halo_supported(int K, int Nout, int N, int D, int H, int W);
 int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, int K, int src_pitch, const __nv_bfloat16* wmat, int Nout,
                         const float* bias, __nv_bfloat16* dst, int dst_pitch, int accumulate, cudaStream_t st, float* stat_part = nullptr,
-                        size_t stat_part_floats = 0, int* stat_slots = nullptr);
+                        size_t stat_part_floats = 0, int* stat_slots = nullptr, int w_pitch = 0, int w_row0 = 0);
 bool first_layer_tc_supported(int cin, int cout);
 int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int cin, int x_pitch, __nv_bfloat16* P, const float* w_pt,
                         int cout, __nv_bfloat16* wp, cudaStream_t st);

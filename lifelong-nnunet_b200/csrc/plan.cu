@@ -62,6 +62,8 @@ struct ConvBlock {
     size_t stats_off = 0, wf_off = 0, wb_off = 0;  // fp32 offsets
     size_t wk_off = 0, wd_off = 0;                 // bf16 shadows for the tensor-core path (offsets in floats)
     bool tc_fwd = false, tc_dgrad = false, tc_wgrad = false, tc_dgrad_strided = false;
+    int cat_level = -1;        // >= 0: the input is the concat buffer of that level (decoder): its data gradient can be split
+    int skip_wait_level = -1;  // >= 0: din (accumulate) / dy is the skip half of that level's concat gradient
 };
 
 struct Tconv {
@@ -107,7 +109,7 @@ struct b2_unet_plan {
     Act dz_tmp2;
     bool patch_valid = false;   // the first layer's patch matrix matches the current input (built by the GEMM forward or lazily in backward)
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_misc = nullptr;
+    cudaEvent_t ev_dz[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_misc = nullptr, ev_skip[8] = {};
     bool side_ok = false;
     ~b2_unet_plan() {
         for (int i = 0; i < 2; ++i) {
@@ -115,6 +117,7 @@ struct b2_unet_plan {
             if (ev_wg[i]) cudaEventDestroy(ev_wg[i]);
         }
         if (ev_misc) cudaEventDestroy(ev_misc);
+        for (int i = 0; i < 8; ++i) if (ev_skip[i]) cudaEventDestroy(ev_skip[i]);
         if (side) cudaStreamDestroy(side);
     }
 };
@@ -154,6 +157,7 @@ static inline float* SCR(void* ws, const b2_unet_plan* p) { return reinterpret_c
 static inline float* SCR_WG(void* ws, const b2_unet_plan* p) { return reinterpret_cast<float*>((char*)ws + p->off_wg_scratch); }
 
 int g_bwd_overlap = 1;
+int g_dgrad_split = 1;      // decoder convs on a concat input: the skip half of the data gradient runs on the side stream
 
 static bool ensure_side_stream(b2_unet_plan* p) {
     if (p->side_ok) return true;
@@ -163,6 +167,8 @@ static bool ensure_side_stream(b2_unet_plan* p) {
         if (cudaEventCreateWithFlags(&p->ev_wg[i], cudaEventDisableTiming) != cudaSuccess) return false;
     }
     if (cudaEventCreateWithFlags(&p->ev_misc, cudaEventDisableTiming) != cudaSuccess) return false;
+    for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&p->ev_skip[i], cudaEventDisableTiming) != cudaSuccess) return false;
     p->side_ok = true;
     return true;
 }
@@ -271,9 +277,11 @@ static int build_plan(b2_unet_plan* p) {
         // gradient wrt the stage input accumulates into the skip gradient of the previous level (already holding the
         // decoder's contribution)
         ConvBlock b0 = add_conv(buf, cur, dcur, d > 0 ? 1 : 0, fo, st0, nullptr, nullptr);
+        if (d > 0) p->convs.back().skip_wait_level = d - 1;     // accumulates into the skip gradient of level d-1
         if (d < P_) snprintf(buf, sizeof(buf), "conv_blocks_context.%d.blocks.1", d);
         else snprintf(buf, sizeof(buf), "conv_blocks_context.%d.1.blocks.0", d);
         ConvBlock b1 = add_conv(buf, b0.y, b0.dy, 0, fo, one, skip_level ? &ysk : nullptr, skip_level ? &dysk : nullptr);
+        if (skip_level) p->convs.back().skip_wait_level = d;    // its dy is the skip gradient of level d
         cur = b1.y;
         dcur = b1.dy;
     }
@@ -310,6 +318,8 @@ static int build_plan(b2_unet_plan* p) {
         p->conv_modules.push_back({1, (int)p->tconvs.size() - 1});
         snprintf(buf, sizeof(buf), "conv_blocks_localization.%d.0.blocks.0", u);
         ConvBlock l0 = add_conv(buf, cat[lvl], dcat[lvl], 0, fs, one, nullptr, nullptr);
+        p->convs.back().cat_level = lvl;
+        p->wg_scratch_floats = max_sz(p->wg_scratch_floats, conv_tc_splitk_scratch_floats(N, cat[lvl].d, cat[lvl].h, cat[lvl].w, fs));
         snprintf(buf, sizeof(buf), "conv_blocks_localization.%d.1.blocks.0", u);
         ConvBlock l1 = add_conv(buf, l0.y, l0.dy, 0, fs, one, nullptr, nullptr);
         cur = l1.y;
@@ -528,11 +538,22 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
     float* wscr = overlap ? SCR_WG(ws, p) : SCR(ws, p);
     int layer_k = 0;
     bool wg_pending[2] = {false, false};
+    bool skip_pending[8] = {false, false, false, false, false, false, false, false};
     auto conv_bwd = [&](ConvBlock& cb) -> int {
         const int buf = layer_k & 1;
         ++layer_k;
         T* dz = dzbuf[buf];
         if (overlap && wg_pending[buf]) B2_CUDA(cudaStreamWaitEvent(st, p->ev_wg[buf], 0));
+        // the skip half of a concat gradient may still be in flight on the side stream: join before its first consumer
+        // (conv_blocks_context.{l}.1 reads it as dy; conv_blocks_context.{l+1}.0 accumulates into it -- that one runs first)
+        auto join_skip = [&](int lvl) -> int {
+            if (lvl >= 0 && lvl < 8 && skip_pending[lvl]) {
+                B2_CUDA(cudaStreamWaitEvent(st, p->ev_skip[lvl], 0));
+                skip_pending[lvl] = false;
+            }
+            return B2_OK;
+        };
+        if (cb.skip_wait_level >= 0 && !cb.din_accumulate) { int rj = join_skip(cb.skip_wait_level); if (rj) return rj; }
         float* stats = F32(ws, p, cb.stats_off);
         int r = norm_lrelu_bwd<T>(P<T>(ws, p, cb.z, false), P<T>(ws, p, cb.y, false), P<T>(ws, p, cb.dy, true), stats, prm[cb.p_g],
                                   g_norm_recompute ? prm[cb.p_be] : nullptr, dz,
@@ -569,14 +590,29 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
             r = conv3d_wgrad_simt<T>(s, P<T>(ws, p, cb.in, false), dz, wscr, grads[cb.p_w], grads[cb.p_b], wst);
             if (r) return r;
         }
-        if (overlap) {
-            B2_CUDA(cudaEventRecord(p->ev_wg[buf], wst));
-            wg_pending[buf] = true;
-        }
         if (cb.din.c > 0) {
             bool done = false;
+            if (cb.din_accumulate && cb.skip_wait_level >= 0) { int rj = join_skip(cb.skip_wait_level); if (rj) return rj; }
             if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-                if (cb.tc_dgrad) {
+                if (cb.tc_dgrad && overlap && g_dgrad_split && cb.cat_level >= 0 && cb.cat_level < 8 && !cb.din_accumulate &&
+                    cb.shape.cin % 64 == 0) {
+                    // concat input [transposed-conv half | skip half]: the first half feeds the next link of the backward chain
+                    // (main stream); the skip half is only read when the encoder backward reaches this level (side stream)
+                    const int one[3] = {1, 1, 1};
+                    const int half = cb.shape.cin / 2;
+                    const __nv_bfloat16* wd = (const __nv_bfloat16*)F32(ws, p, cb.wd_off);
+                    r = conv_tc_launch(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout, wd, half, nullptr,
+                                       P<T>(ws, p, cb.din, true), cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, 0, st, SCR(ws, p),
+                                       p->scratch_floats * sizeof(float), nullptr, cb.shape.cin, 0);
+                    if (r) return r;
+                    r = conv_tc_launch(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout, wd, half, nullptr,
+                                       P<T>(ws, p, cb.din, true) + half, cb.in.d, cb.in.h, cb.in.w, cb.din.pitch, one, 0, wst, wscr,
+                                       p->wg_scratch_floats * sizeof(float), nullptr, cb.shape.cin, half);
+                    if (r) return r;
+                    B2_CUDA(cudaEventRecord(p->ev_skip[cb.cat_level], wst));
+                    skip_pending[cb.cat_level] = true;
+                    done = true;
+                } else if (cb.tc_dgrad) {
                     const int one[3] = {1, 1, 1};
                     r = conv_tc_launch(dz, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.shape.cout,
                                        (const __nv_bfloat16*)F32(ws, p, cb.wd_off), cb.shape.cin, nullptr, P<T>(ws, p, cb.din, true),
@@ -597,6 +633,10 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                 r = conv3d_dgrad_simt<T>(sd, dz, F32(ws, p, cb.wb_off), P<T>(ws, p, cb.din, true), cb.din_accumulate, st);
                 if (r) return r;
             }
+        }
+        if (overlap) {   // everything the side stream reads from this layer's dz is enqueued
+            B2_CUDA(cudaEventRecord(p->ev_wg[buf], wst));
+            wg_pending[buf] = true;
         }
         return B2_OK;
     };
@@ -695,6 +735,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value; return B2_OK; }
+    if (!strcmp(name, "dgrad_split")) { g_dgrad_split = value; return B2_OK; }
     if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
     if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }
