@@ -100,3 +100,20 @@ def test_every_kernel_is_pdl_safe():
             if not src[i + 1:i + 60].lstrip().startswith("pdl_grid_sync();"):
                 missing.append("%s: %s" % (os.path.basename(path), src[m.start():m.start() + 120].split("(")[0].replace("\n", " ")))
     assert not missing, missing
+
+
+def test_fastdiv_exact(tmp_path):
+    """the magic-number division of the kernels' tile decode (tc_common.cuh: make_fastdiv / fd_div) is exact for n < 2^31:
+    a host mirror of the device expression is checked on ~27 M (n, d) pairs (built with nvcc, no GPU needed)"""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        import pytest
+        pytest.skip("nvcc not available")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "fastdiv_host.cu")
+    exe = str(tmp_path / "fastdiv_host")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
