@@ -79,15 +79,23 @@ def cpu_reference_step_fn(geom, batch):
     return one
 
 
-def time_cpu(geom, batch, steps, warmup):
+def time_cpu(geom, batch, steps, warmup, budget_s=None):
+    """per-step wall times of the CPU arm; with `budget_s` the number of timed steps is cut so that the whole run stays
+    within about that many seconds (a CPU step of the full workload takes seconds to tens of seconds)"""
     one = cpu_reference_step_fn(geom, batch)
+    t_first = None
     for _ in range(warmup):
+        t0 = time.perf_counter()
         one()
+        t_first = time.perf_counter() - t0
     ts = []
-    for _ in range(steps):
+    for i in range(steps):
         t0 = time.perf_counter()
         one()
         ts.append(time.perf_counter() - t0)
+        est = t_first if t_first is not None else ts[0]
+        if budget_s is not None and (warmup + len(ts) + 1) * est > budget_s:
+            break
     return ts
 
 
@@ -96,7 +104,7 @@ def run_reference(args, geom):
     if rank != 0:
         return
     steps, warmup = args.steps, min(args.warmup, 1)   # bounded: every CPU step is seconds long
-    ts = time_cpu(geom, geom.batch, steps, warmup)
+    ts = time_cpu(geom, geom.batch, steps, warmup, budget_s=150.0)    # bounded sample: the run ends within a few minutes
     total = sum(ts)
     val = geom.batch * len(ts) / total
     sample = "%d timed + %d warm-up steps of the full workload batch (B=%d), oracle port (PyTorch CPU fp32, eager)" % (len(ts), warmup, geom.batch)
