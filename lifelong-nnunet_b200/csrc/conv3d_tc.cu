@@ -1,9 +1,11 @@
 // conv3d_tc.cu -- bf16 3x3x3 convolution (forward and stride-1 dgrad) as an implicit GEMM on the 5th-generation tensor
 // cores: TMA (cp.async.bulk.tensor) stages NDHWC activation boxes and K-major weight tiles into 128B/64B-swizzled shared
-// memory, one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in TMEM, and four
+// memory, one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in TMEM, and the
 // epilogue warps drain TMEM with tcgen05.ld, add the bias, convert to bf16 and store.  Persistent CTAs (one per SM),
-// warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue; the
-// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// warp-specialised: warps 0..3 = TMA producers (one pipeline stage each, round robin), warp 4 = MMA issuer (+ TMEM
+// allocation), warps 5..12 = two epilogue sets; the accumulator is double-buffered in TMEM (set s drains buffer s) so the
+// epilogue of tile i overlaps the MMAs of tile i+1 and the scalar-heavy epilogues of two short-K tiles overlap each other.
+// The thin stride-1 layers (K = 32 / 64) do not run here but in conv3d_tc_halo.cu (input-stationary, kd-merged).
 //
 // GEMM view:  D[m, n] = sum_{tap, c} A_tap[m, c] * W[tap][n][c]
 //   m   : 128 output voxels = one (TN,TD,TH,TW) box of the NDHWC tensor (rows in w-fastest order)

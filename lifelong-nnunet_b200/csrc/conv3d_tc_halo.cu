@@ -1,13 +1,15 @@
 // conv3d_tc_halo.cu -- stride-1 3x3x3 bf16 convolution for the thin layers (K = 32 or 64 input channels), where the
 // per-tap kernel of conv3d_tc.cu is bound by L2->SM traffic (every 128-voxel A tile is fetched 27 times: FLOP/byte of
-// L2 traffic == Cout).  Here a CTA walks a strip of 16 (h) x 8 (w) output voxels along d and keeps a ring of three input
+// L2 traffic == Cout).  Here a CTA walks a strip of 16 (h) x 8 (w) output voxels along d and keeps a ring of up to six input
 // d-slabs in shared memory; every slab is fetched ONCE as three w-shifted copies (w0-1, w0, w0+1) of an 18 (h) x 8 (w) box,
 // so that the A operand of every tap (kd, kh, kw) is a plain, swizzle-atom-aligned sub-view:
 //     slab (d + kd - 1) -> copy kw -> atom row kh .. kh + 15      (atom = 8 consecutive w voxels = 8 rows of KC*2 bytes)
-// i.e. no per-tap loads at all: L2->SM traffic drops from 27 to 3.4 fetches per input voxel.  Weights stay resident in
-// shared memory for the whole CTA when they fit (27 * N * K * 2 B <= 110 KB), otherwise they stream through a small ring.
-// tcgen05.mma M = 128 (16 h x 8 w), N = Nout, K = 16; accumulators double-buffered in TMEM; same warp roles as
-// conv3d_tc.cu plus an optional weight-producer warp.
+// i.e. no per-tap loads at all: L2->SM traffic drops from 27 to 3.4 fetches per input voxel.  The 27 weight tiles stay
+// resident in shared memory; when [27][Nout][K] does not fit, the output channels are split over CTA classes (halo_plan).
+// tcgen05.mma M = 128 (16 h x 8 w), K = 16, N = 3 * BN: the three kd taps of a (kh, kw) pair are ONE instruction that
+// updates the accumulators of the output slabs d-1, d, d+1 (consecutive slots of a 16-slot TMEM ring) -- see the comment
+// above conv_halo_kernel.  Warp roles: 0 slab producer, 1 MMA issuer, 2..5 epilogue (bias, bf16 store, InstanceNorm
+// partial sums), 6 weight producer.
 #include <string.h>
 
 #include "kernels.h"

@@ -9,7 +9,11 @@
 // columns of groups resident over its whole range of voxel tiles (split-K over voxels across CTAs), then writes one fp32
 // partial; the ordered reduction over CTAs (wgrad_reduce_kernel) makes the result bit-reproducible -- no atomics.
 //
-// Warp roles as in conv3d_tc.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// Stride-1 layers with Cin <= 128, Cout <= 64 use the d-merged formulation (TcWgradParams::dmerge); the thin layers
+// (Cin, Cout in {32, 64}) use wgrad_halo_kernel further down, which additionally fetches every input voxel once.
+// A layer that needs a single split writes dW directly from the epilogue (no partial tensor, no reduction launch).
+//
+// Warp roles: warps 0..3 shifted-operand TMA producers, 4 dz producer, 5 MMA issuer + TMEM owner, 6..9 epilogue.
 #include <string.h>
 
 #include "kernels.h"
