@@ -4,9 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched under torchrun)
     python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch path on the host CPU cores
 
-Workload (config.workload): BASELINE.json configs[1] -- nnUNetTrainerEWC, 5-stage 3D U-Net, 64x128x128 synthetic
-hippocampus-shaped patches, batch 2 per GPU, one stored EWC task, bf16 activations (fp32 accumulation, fp32 params).
-A "step" = zero_grad -> forward -> Dice+CE (+EWC) -> backward -> [grad all-reduce] -> clip(12) -> SGD-Nesterov.
+Workload (config.workload, default cfg2): BASELINE.json configs[1] -- nnUNetTrainerEWC, 5-stage 3D U-Net, 64x128x128
+synthetic hippocampus-shaped patches, batch 2 per GPU, one stored EWC task, bf16 activations (fp32 accumulation, fp32
+params).  A "step" = zero_grad -> forward -> Dice+CE (+EWC) -> backward -> [grad all-reduce] -> clip(12) -> SGD-Nesterov.
+--workload cfg3 | cfg4 | cfg5 run the other BASELINE.json configurations (parity-test cases, benched for the record):
+  cfg3  nnUNetTrainerLWF, 64x160x160, one finished task (its head evaluated on the shared body + KL term)
+  cfg4  nnUNetTrainerPLOP + Generic_ViT_UNet (V1, base), 48x192x192, teacher in the loop (pseudo labels + local POD)
+  cfg5  nnUNetTrainerRW, 64x128x128, third task of a sequence (two stored tasks penalised: documented math,
+        strict_reference=False -- under the reference's quirk Q2 the penalty would be off after the first iteration),
+        Fisher / score update every 10 iterations
 
   value        patches/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
   e2e          patches/s through trainer.run_iteration(generator) with pinned HOST buffers: H2D of data+targets and
@@ -37,6 +43,8 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import torch  # noqa: E402
 
 WORKLOAD = "cfg2"
+METRIC = {"cfg1": "3D patches/sec", "cfg2": "3D patches/sec (EWC on)", "cfg3": "3D patches/sec (LwF on)",
+          "cfg4": "3D patches/sec (PLOP + ViT)", "cfg5": "3D patches/sec (RW on)"}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
@@ -49,10 +57,19 @@ def load_peaks():
     return dict(FALLBACK_PEAKS)
 
 
+TRAINER_DESC = {
+    "cfg1": "nnUNetTrainerSequential",
+    "cfg2": "nnUNetTrainerEWC, EWC on (1 stored task, lambda 0.4)",
+    "cfg3": "nnUNetTrainerLWF, 1 finished task (old head on the shared body + KL, T=2)",
+    "cfg4": "nnUNetTrainerPLOP + Generic_ViT_UNet V1 base (ViT through ATen), frozen teacher in the loop, pod_lambda 1e-2, 3 scales",
+    "cfg5": "nnUNetTrainerRW, task 3 of 3 (2 stored tasks penalised every iteration: strict_reference=False), F/S update every 10 its",
+}
+
+
 def workload_desc(geom, precision, n_gpus):
-    return {"workload": "%s: nnUNetTrainerEWC, %d-stage 3D U-Net, %dx%dx%d synthetic 1-ch patches, batch %d/GPU, "
-                        "EWC on (1 stored task, lambda 0.4), %s activations" %
-                        (geom.name, geom.num_pool, geom.patch[0], geom.patch[1], geom.patch[2], geom.batch, precision),
+    return {"workload": "%s: %s, %d-stage 3D U-Net, %dx%dx%d synthetic 1-ch patches, batch %d/GPU, %s activations" %
+                        (geom.name, TRAINER_DESC.get(geom.name, "nnUNetTrainerEWC"), geom.num_pool, geom.patch[0], geom.patch[1],
+                         geom.patch[2], geom.batch, precision),
             "global_batch": geom.batch * n_gpus, "patch": list(geom.patch), "parallelism": "dp%d" % n_gpus,
             "pool_op_kernel_sizes": [list(k) for k in geom.pool], "num_classes": geom.num_classes,
             "l2_policy": "inputs+activations (>3 GB per step) exceed the 126 MB L2; no explicit flush",
@@ -63,20 +80,83 @@ def workload_desc(geom, precision, n_gpus):
 # reference arm: the oracle port of the reference's PyTorch step on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step_fn(geom, batch):
+    """the oracle port of the reference's iteration for the workload's trainer (PyTorch CPU fp32, all host threads)"""
+    import copy
+    import numpy as np
     from b200unet import synth
     from oracle import cl_losses, step
     torch.set_num_threads(os.cpu_count() or 1)
-    net = step.build_network(geom.in_channels, geom.base_features, geom.num_classes, [list(k) for k in geom.pool],
-                             max_num_features=geom.max_features)
-    fisher, params = synth.make_ewc_state(list(net.named_parameters()))
     weights = cl_losses.ds_loss_weights(geom.num_pool)
-    opt = step.make_optimizer(net)
-    loss_fn = step.ewc_loss_fn(net, weights, {"A": fisher}, {"A": params}, 0.4)
     data, targets = synth.make_batch(geom, batch=batch)
+    pools = [list(k) for k in geom.pool]
+    if geom.name == "cfg4":
+        from oracle import vit_unet
+        torch.manual_seed(0)
+        net = vit_unet.Generic_ViT_UNet(geom.in_channels, geom.base_features, geom.num_classes, geom.num_pool,
+                                        [int(s) for s in geom.patch], pools)
+    else:
+        net = step.build_network(geom.in_channels, geom.base_features, geom.num_classes, pools, max_num_features=geom.max_features)
+    opt = step.make_optimizer(net)
+    if geom.name == "cfg3":       # LwF: one extra (no-grad) forward per old head + KL against the stored logits (lwf:298-370)
+        old_head = copy.deepcopy(net.seg_outputs.state_dict())
+        with torch.no_grad():
+            stored = net(data)[0]
+        base = step.base_loss_fn(weights)
 
-    def one():
-        return step.run_iteration(net, opt, data, targets, loss_fn)[0]
-    return one
+        def one():
+            cur = copy.deepcopy(net.seg_outputs.state_dict())
+            net.seg_outputs.load_state_dict(old_head)
+            with torch.no_grad():
+                pred = net(data)[0]
+            net.seg_outputs.load_state_dict(cur)
+            return step.run_iteration(net, opt, data, targets, lambda o, t: base(o, t) + cl_losses.lwf_distillation(pred, stored, 2.0))[0]
+        return one
+    if geom.name == "cfg4":       # PLOP: teacher forward, hooks on every conv of both nets, pseudo labels + local POD (plop:217-328)
+        teacher = copy.deepcopy(net)
+        acts, acts_o = {}, {}
+        for name, m in net.named_modules():
+            if 'conv.Conv' in str(type(m)):
+                m.register_forward_hook(lambda mod, i, o, name=name: acts.__setitem__(name, o.detach()))
+        for name, m in teacher.named_modules():
+            if 'conv.Conv' in str(type(m)):
+                m.register_forward_hook(lambda mod, i, o, name=name: acts_o.__setitem__(name, o.detach()))
+        thr = {i: torch.full((geom.num_classes,), 1e-3) for i in range(geom.num_pool)}
+
+        def loss_fn(out, tgt):
+            with torch.no_grad():
+                out_o = teacher(data)
+            a = {k: v for k, v in acts.items() if v.dim() == 5}
+            b = {k: v for k, v in acts_o.items() if v.dim() == 5}
+            return cl_losses.plop_loss(out, out_o, tgt, weights, thr, float(np.log(geom.num_classes)), a, b, 1e-2, 3)
+        return lambda: step.run_iteration(net, opt, data, targets, loss_fn)[0]
+    if geom.name == "cfg5":       # RW: two stored tasks, penalty every iteration, F / S update every 10 iterations (rw:231-265)
+        named = list(net.named_parameters())
+        fisher, params, scores = {}, {}, {}
+        for i, t in enumerate(("A", "B")):
+            fisher[t], params[t], scores[t] = synth.make_ewc_state(named, seed=7 + i, with_scores=True)
+        fisher["C"] = {n: torch.zeros_like(p) for n, p in named}
+        sc = {n: torch.zeros_like(p) for n, p in named}
+        state = {"count": 0, "prev": None}
+        loss_fn = step.rw_loss_fn(net, weights, fisher, params, scores, 0.4, strict_reference=False)
+
+        def one():
+            l = step.run_iteration(net, opt, data, targets, loss_fn)[0]
+            if state["count"] % 10 == 0:
+                prev = state["prev"]
+                for n, p in named:
+                    if p.grad is not None:
+                        fisher["C"][n], sc[n] = cl_losses.rw_update(p.detach(), p.grad.detach(), None if prev is None else prev[n],
+                                                                    fisher["C"][n], sc[n], 0.9)
+                state["prev"] = {n: p.detach().clone() for n, p in named}
+            state["count"] += 1
+            return l
+        return one
+    if geom.name == "cfg1":
+        loss_fn = step.base_loss_fn(weights)
+    else:
+        fisher, params = synth.make_ewc_state(list(net.named_parameters()))
+        loss_fn = step.ewc_loss_fn(net, weights, {"A": fisher}, {"A": params}, 0.4)
+    return lambda: step.run_iteration(net, opt, data, targets, loss_fn)[0]
 
 
 def time_cpu(geom, batch, steps, warmup, budget_s=None):
@@ -108,7 +188,7 @@ def run_reference(args, geom):
     total = sum(ts)
     val = geom.batch * len(ts) / total
     sample = "%d timed + %d warm-up steps of the full workload batch (B=%d), oracle port (PyTorch CPU fp32, eager)" % (len(ts), warmup, geom.batch)
-    line = {"impl": "reference", "metric": "3D patches/sec (EWC on)", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC.get(geom.name, METRIC["cfg2"]), "value": val, "unit": "patches/s", "n_gpus": args.gpus,
             "steps": len(ts), "warmup": warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_desc(geom, "fp32 (CPU)", 1),
@@ -217,7 +297,8 @@ def device_batch_generator(data, targets):
 
 def time_dominant_kernel(geom, precision, steps, warmup):
     """CUDA-event timing of the dominant kernel in isolation: forward 3x3x3 conv of the full-resolution
-    base->base layer (conv_blocks_context.0.blocks.1) at the workload's batch."""
+    base->base layer (conv_blocks_context.0.blocks.1) at the workload's batch, exactly as the training step launches it
+    (one kernel: convolution + bias + InstanceNorm partial sums in the epilogue)."""
     import ctypes as C
     from b200unet import _lib
     lib = _lib.load()
@@ -242,9 +323,9 @@ def time_dominant_kernel(geom, precision, steps, warmup):
         shadow = torch.empty(int(lib.b2_conv3d_shadow_bytes(C.byref(desc))), dtype=torch.uint8, device=dev)
         _lib.check(lib.b2_conv3d_make_shadow(C.byref(desc), w.data_ptr(), shadow.data_ptr(), st))
 
-        def call():
-            _lib.check(lib.b2_conv3d_fwd_shadow(C.byref(desc), x.data_ptr(), shadow.data_ptr(), bias.data_ptr(), z.data_ptr(),
-                                                scr.data_ptr(), st))
+        def call():    # the PRODUCT variant: InstanceNorm partial sums from the epilogue, as the training step launches it
+            _lib.check(lib.b2_conv3d_fwd_shadow_stats(C.byref(desc), x.data_ptr(), shadow.data_ptr(), bias.data_ptr(), z.data_ptr(),
+                                                      scr.data_ptr(), st))
     else:
         def call():
             _lib.check(lib.b2_conv3d_fwd(C.byref(desc), x.data_ptr(), w.data_ptr(), bias.data_ptr(), z.data_ptr(),
@@ -275,10 +356,61 @@ def dominant_traffic(geom):
             "algorithmic_bytes": d["algorithmic_bytes"], "source": d["source"]}
 
 
+def build_trainer(geom, precision, dev, ddp, cuda_graph):
+    """the trainer of the workload with its continual-learning state (synthetic)"""
+    from b200unet import synth
+    from b200unet import trainers as T
+    kw = dict(precision=precision, device=dev, ddp=ddp, seed=0, cuda_graph=cuda_graph)
+    if geom.name == "cfg3":
+        tr = T.nnUNetTrainerLWF(geom, task="task_prev", **kw)
+        tr.initialize()
+        tr.finish_task()
+        tr.start_task("task_new")
+        data, _ = synth.make_batch(geom, seed=99)
+        tr.store_target_logits([data])
+        return tr
+    if geom.name == "cfg4":
+        tr = T.nnUNetTrainerPLOP(geom, use_vit=True, **kw)
+        tr.initialize()
+        tr.start_new_task()
+        return tr
+    if geom.name == "cfg5":
+        tr = T.nnUNetTrainerRW(geom, strict_reference=False, fisher_update_after=10, **kw)
+        tr.initialize()
+        named = list(tr.network.named_parameters())
+        for i, t in enumerate(("task_A", "task_B")):
+            f, p, s_ = synth.make_ewc_state(named, seed=7 + i, with_scores=True)
+            tr.fisher[t] = {k: v.to(dev) for k, v in f.items()}
+            tr.params[t] = {k: v.to(dev) for k, v in p.items()}
+            tr.scores[t] = {k: v.to(dev) for k, v in s_.items()}
+        tr.start_task("task_C")
+        return tr
+    if geom.name == "cfg1":
+        tr = T.nnUNetTrainerSequential(geom, **kw)
+        tr.initialize()
+        return tr
+    tr = T.nnUNetTrainerEWC(geom, **kw)
+    tr.initialize()
+    fisher, params = synth.make_ewc_state(list(tr.network.named_parameters()), seed=7)
+    tr.fisher["task_prev"] = {k: v.to(dev) for k, v in fisher.items()}
+    tr.params["task_prev"] = {k: v.to(dev) for k, v in params.items()}
+    tr.loss.update_ewc_params(tr.fisher, tr.params)
+    tr.loss.update_network_params(tr.network.named_parameters())
+    return tr
+
+
+def in_step_kernel_us():
+    """duration of the dominant kernel INSIDE a training step, from the committed ncu launch list of this round"""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("in_step_us")
+    return None
+
+
 def run_ours(args, geom):
     import torch.distributed as dist
     from b200unet import _lib, synth
-    from b200unet.trainers import DataParallelGroup, nnUNetTrainerEWC
+    from b200unet.trainers import DataParallelGroup
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,14 +424,7 @@ def run_ours(args, geom):
         dist.init_process_group("nccl", device_id=dev)
         ddp = DataParallelGroup()
     precision = args.precision
-
-    trainer = nnUNetTrainerEWC(geom, precision=precision, device=dev, ddp=ddp, seed=0)
-    trainer.initialize()
-    fisher, params = synth.make_ewc_state(list(trainer.network.named_parameters()), seed=7)
-    trainer.fisher["task_prev"] = {k: v.to(dev) for k, v in fisher.items()}
-    trainer.params["task_prev"] = {k: v.to(dev) for k, v in params.items()}
-    trainer.loss.update_ewc_params(trainer.fisher, trainer.params)
-    trainer.loss.update_network_params(trainer.network.named_parameters())
+    trainer = build_trainer(geom, precision, dev, ddp, cuda_graph=not args.no_graph)
 
     data, targets = synth.make_batch(geom, seed=1234 + rank)     # rank-seeded patches
     h2d = data.numel() * 4 + sum(t.numel() * 4 for t in targets)
@@ -326,28 +451,35 @@ def run_ours(args, geom):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
 
+    # launches per step: counted on an eager (not yet captured) iteration; a captured step replays exactly these
+    trainer.run_iteration(gen_dev, detach=False)
+    l0 = _lib.launch_count()
+    trainer.run_iteration(gen_dev, detach=False)
+    launches_per_step = _lib.launch_count() - l0
     warm = max(args.warmup, 3)
     for _ in range(warm):
         trainer.run_iteration(gen_dev, detach=False)
     sampler = ClockSampler(local)
-    launches0 = _lib.launch_count()
     if rank == 0:
         sampler.start()
     ms_dev, _ = timed(gen_dev, args.steps, detach=False)
     clocks = sampler.stop() if rank == 0 else None
-    launches = _lib.launch_count() - launches0
-    # e2e: pinned host batches through the trainer's public iteration with its input pipelining switched on -- the H2D copy of
-    # batch i+1 runs on a copy stream while batch i computes; every timed step still issues one H2D copy of a full batch and
-    # reads its loss back to the host
-    trainer.prefetch_inputs = True
+    # e2e, default path: pinned HOST batches through trainer.run_iteration, every step copies its batch to the device (input
+    # patch on the compute stream, targets on a copy stream next to the forward pass) and reads its loss back to the host
     for _ in range(2):
         trainer.run_iteration(gen_host, detach=True)
     _, ms_e2e = timed(gen_host, args.steps, detach=True)
+    # e2e with the opt-in input pipelining (the H2D copy of batch i+1 overlaps step i; draws the generator one batch ahead)
+    trainer.prefetch_inputs = True
+    for _ in range(2):
+        trainer.run_iteration(gen_host, detach=True)
+    _, ms_e2e_pf = timed(gen_host, args.steps, detach=True)
     trainer.prefetch_inputs = False
 
     patches = geom.batch * world * args.steps
     value = patches / (ms_dev / 1e3)
     e2e = patches / (ms_e2e / 1e3)
+    e2e_pf = patches / (ms_e2e_pf / 1e3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -357,20 +489,33 @@ def run_ours(args, geom):
     kms, kflops = time_dominant_kernel(geom, precision, args.steps, warm)
     peak_tf = peaks["bf16_tflops"]
     achieved_tf = kflops / (kms * 1e-3) / 1e12
-    line = {"metric": "3D patches/sec (EWC on)", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+    step_tf = value / world * gflop_patch / 1e3
+    graphed = any(getattr(s_, "graph", None) is not None for s_ in trainer._steps.values())
+    line = {"metric": METRIC.get(geom.name, METRIC["cfg2"]), "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_desc(geom, precision, world),
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "api": "nnUNetTrainerEWC.run_iteration(generator of pinned host batches), prefetch_inputs=True (H2D of batch i+1 on a copy stream)"},
-            "gpu_launches": int(launches),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "trainer.run_iteration(generator of pinned host batches), default path (no look-ahead on the generator)",
+                    "with_prefetch_inputs": {"value": e2e_pf, "ms_per_step": ms_e2e_pf / args.steps,
+                                             "note": "opt-in: H2D of batch i+1 overlaps step i (draws the generator one batch ahead)"}},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "launches": {"per_step": int(launches_per_step), "cuda_graph": bool(graphed),
+                         "note": "kernels of libb2unet per step (counted on an eager iteration); with cuda_graph the timed steps "
+                                 "replay exactly these launches from two captured graphs (forward | loss+backward+optimiser)"},
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv3d 3x3x3 forward, %d->%d @ %dx%dx%d x B%d (conv_blocks_context.0.blocks.1)" %
+            "roofline": {"bound": "tensor", "kernel": "conv3d 3x3x3 forward + InstanceNorm partial sums (stats epilogue ON, the variant the "
+                                  "step runs), %d->%d @ %dx%dx%d x B%d (conv_blocks_context.0.blocks.1)" %
                                   (geom.base_features, geom.base_features, geom.patch[0], geom.patch[1], geom.patch[2], geom.batch),
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "kernel_ms": kms,
+                         "in_step_kernel_us": in_step_kernel_us(),
                          "traffic": dominant_traffic(geom),
-                         "step_frac_of_sustained_peak": value / world * gflop_patch / 1e3 / peaks.get("bf16_tflops_sustained", peak_tf)}}
+                         "step": {"achieved": step_tf, "unit": "TFLOP/s", "frac_of_burst": step_tf / peak_tf,
+                                  "frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", peak_tf),
+                                  "flops": "conv-stack fwd+bwd %.1f GFLOP/patch (teacher / ViT FLOPs not counted)" % gflop_patch},
+                         "step_frac_of_sustained_peak": step_tf / peaks.get("bf16_tflops_sustained", peak_tf)}}
     if world == 1 and not args.no_cpu_baseline:
         ts = time_cpu(geom, geom.batch, 1, 1)
         line["cpu_baseline"] = {"value": geom.batch / ts[0], "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
@@ -390,6 +535,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step instead of replaying the captured CUDA graphs")
     args = ap.parse_args()
     from b200unet.configs import CONFIGS
     geom = CONFIGS[args.workload]

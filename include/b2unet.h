@@ -91,6 +91,21 @@ int b2_unet_forward(b2_unet_plan* plan, const float* const* params, const float*
 int b2_unet_backward(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
                      float* const* grads, int32_t* has_grad_host, b2_stream_t stream);
 
+/* backward with gradient buckets (data-parallel training, SURVEY 8(e): the reference has no collective at all).  The
+ * plan differentiates the layers in descending parameter order, so the suffix [first_param, num_params) of the
+ * parameter list -- a contiguous tail of the caller's flat gradient arena -- is complete long before the first layers
+ * are.  Bucket k's two events (cudaEvent_t, caller-created) are recorded on the caller's stream and on the plan's
+ * weight-gradient stream when that suffix is complete; the caller lets its communication stream wait on both and
+ * all-reduces the bucket while the remaining layers are still running.  Buckets in descending first_param order. */
+typedef struct b2_grad_bucket {
+    int32_t first_param;
+    void*   event_main;   /* cudaEvent_t, nullable */
+    void*   event_side;   /* cudaEvent_t, nullable */
+} b2_grad_bucket;
+int b2_unet_backward_buckets(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
+                             float* const* grads, int32_t* has_grad_host, const b2_grad_bucket* buckets_host,
+                             int n_buckets, b2_stream_t stream);
+
 /* Partial passes for Generic_ViT_UNet (generic_ViT_UNet.py:217-287): the host runs the encoder stages, hands the first
  * skip to the ViT, writes the ViT result over the bottleneck activation (b2_unet_debug_view(2*num_pool+1, 1)) and
  * runs the decoder.  `parts` is a mask of B2_PART_*.  Forward: B2_PART_ENCODER converts the input and runs stages
@@ -108,6 +123,13 @@ int b2_unet_forward_parts(b2_unet_plan* plan, const float* const* params, const 
                           float* const* logits, int parts, b2_stream_t stream);
 int b2_unet_backward_parts(b2_unet_plan* plan, const float* const* params, const float* const* dlogits, void* workspace,
                            float* const* grads, int32_t* has_grad_host, int parts, b2_stream_t stream);
+
+/* LwF old-task heads (lwf:315-346, helpful_functions.py:226-259): logits of deep-supervision `level` for ANOTHER
+ * `seg_outputs[num_pool-1-level]` weight ([num_classes][C] fp32) on the decoder activation the last forward of this plan
+ * left in `workspace` -- the stored heads share the body with the running model, so one 1x1x1 launch per old head
+ * replaces one full network forward per old head. */
+int b2_unet_head_forward(b2_unet_plan* plan, void* workspace, int level, const float* weight, float* logits,
+                         b2_stream_t stream);
 
 /* Raw (pre-norm) output of conv module `conv_idx` kept by the last forward, as an NDHWC view into the workspace --
  * what the reference's forward hooks capture (plop:330-353: output.detach() of every conv.Conv* module).
@@ -187,6 +209,22 @@ size_t b2_sgd_scratch_bytes(int n_tensors, int64_t total_numel);
 int b2_sgd_clip_step(const b2_sgd_entry* table_host, int n_tensors, float lr, float momentum, float weight_decay,
                      int nesterov, float max_norm, int first_step, float* norm_out, void* scratch, b2_stream_t stream);
 
+/* Persistent device tables: the *_host entry points above rebuild and upload their tables on every call (host work and
+ * a pageable copy per step, not capturable in a CUDA graph).  A trainer builds each table once (b2_mt_blob_build into
+ * b2_mt_blob_bytes of HOST memory), copies it to the device and calls the *_dev variants: no host work per step.
+ * `part` = b2_mt_part_bytes(nblocks) of device scratch.  b2_sgd_clip_step_dev reads {lr, momentum, weight_decay,
+ * max_norm} from DEVICE memory so that a captured step follows the poly learning-rate schedule (MultiHead:294-301). */
+enum { B2_MT_PEN = 0, B2_MT_SGD = 1, B2_MT_RW = 2 };
+size_t b2_mt_blob_bytes(int kind, int n_tensors);
+int b2_mt_blob_build(int kind, const void* table_host, int n_tensors, void* blob_host, int32_t* nblocks_out);
+size_t b2_mt_part_bytes(int nblocks);
+int b2_quadpen_dev(const void* blob_dev, int n_tensors, int nblocks, float coef, float* loss_out, float* part,
+                   b2_stream_t stream);
+int b2_sgd_clip_step_dev(const void* blob_dev, int n_tensors, int nblocks, const float* hyper_dev, int nesterov,
+                         float* norm_out, float* part, b2_stream_t stream);
+int b2_rw_update_dev(const void* blob_dev, int n_tensors, int nblocks, float alpha, float eps, int have_prev,
+                     b2_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Distillation terms (value only or value+gradient), one sweep over student+teacher logits each.
  * b2_kd_lwf : deep_supervision.py:185-199 -- KL(softmax(t/T) || softmax(p/T)), 'batchmean' (sum / B), value only
@@ -234,6 +272,10 @@ size_t b2_conv3d_shadow_bytes(const b2_conv_desc* d);
 int b2_conv3d_make_shadow(const b2_conv_desc* d, const float* w_pt, void* shadow, b2_stream_t stream);
 int b2_conv3d_fwd_shadow(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
                          b2_stream_t stream);
+/* the variant the training step launches: one convolution kernel whose epilogue also writes the InstanceNorm partial
+ * sums into `scratch` (bench.py's roofline times this one) */
+int b2_conv3d_fwd_shadow_stats(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z,
+                               void* scratch, b2_stream_t stream);
 /* dx (nullable) = conv_transpose3d(dz, w); dw, dbias = parameter gradients (PyTorch layouts, overwritten) */
 int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx, int accumulate_dx,
                   float* dw, float* dbias, void* scratch, b2_stream_t stream);

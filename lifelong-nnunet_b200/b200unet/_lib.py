@@ -46,6 +46,13 @@ class SgdEntry(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("grad", C.c_void_p), ("momentum", C.c_void_p), ("numel", C.c_int64)]
 
 
+class GradBucket(C.Structure):
+    _fields_ = [("first_param", C.c_int32), ("event_main", C.c_void_p), ("event_side", C.c_void_p)]
+
+
+MT_PEN, MT_SGD, MT_RW = 0, 1, 2
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
                 ("cout", C.c_int32), ("stride", C.c_int32 * 3), ("in_pitch", C.c_int32), ("out_pitch", C.c_int32),
@@ -67,8 +74,10 @@ SIGNATURES = {
     "b2_unet_output_shape": (_I, [_VP, _I, C.POINTER(C.c_int32 * 3)]),
     "b2_unet_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "b2_unet_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b2_unet_backward_buckets": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(GradBucket), _I, _VP]),
     "b2_unet_forward_parts": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "b2_unet_backward_parts": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "b2_unet_head_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
     "b2_unet_num_convs": (_I, [_VP]),
     "b2_unet_conv_name": (_I, [_VP, _I, C.c_char_p]),
     "b2_unet_conv_output": (_I, [_VP, _VP, _I, C.POINTER(ActView)]),
@@ -82,6 +91,12 @@ SIGNATURES = {
     "b2_rw_update": (_I, [C.POINTER(RwEntry), _I, _F, _F, _I, _VP, _VP]),
     "b2_sgd_scratch_bytes": (_SZ, [_I, _I64]),
     "b2_sgd_clip_step": (_I, [C.POINTER(SgdEntry), _I, _F, _F, _F, _I, _F, _I, _VP, _VP, _VP]),
+    "b2_mt_blob_bytes": (_SZ, [_I, _I]),
+    "b2_mt_blob_build": (_I, [_I, _VP, _I, _VP, C.POINTER(C.c_int32)]),
+    "b2_mt_part_bytes": (_SZ, [_I]),
+    "b2_quadpen_dev": (_I, [_VP, _I, _I, _F, _VP, _VP, _VP]),
+    "b2_sgd_clip_step_dev": (_I, [_VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
+    "b2_rw_update_dev": (_I, [_VP, _I, _I, _F, _F, _I, _VP]),
     "b2_kd_scratch_bytes": (_SZ, [_I, _I, _I64]),
     "b2_kd_lwf": (_I, [_VP, _VP, _I, _I, _I64, _F, _VP, _VP, _VP]),
     "b2_kd_mib": (_I, [_VP, _VP, _I, _I, _I64, _F, _F, _VP, _VP, _VP, _VP]),
@@ -94,6 +109,7 @@ SIGNATURES = {
     "b2_conv3d_shadow_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "b2_conv3d_make_shadow": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP]),
     "b2_conv3d_fwd_shadow": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b2_conv3d_fwd_shadow_stats": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2_conv3d_bwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "b2_norm_scratch_bytes": (_SZ, [_I, _I64, _I]),
     "b2_norm_lrelu_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I64, _I, _I, _I, _I, _F, _VP]),

@@ -48,15 +48,17 @@ class _DSLossFunction(torch.autograd.Function):
         dls, parts, events = [], [], []
         need_grad = any(l.requires_grad for l in logits)
         cur = torch.cuda.current_stream(dev)
+        # every layout / dtype conversion is enqueued on the current stream BEFORE `start` is recorded: the side streams
+        # of the levels >= 1 wait on `start` only, so a conversion kernel issued later could race with their reads
+        logits = [None if (float(cfg['weights'][i]) == 0 and i > 0) else x.contiguous() for i, x in enumerate(logits)]
+        targets = [None if x is None else y.contiguous().float() for x, y in zip(logits, targets)]
         start = torch.cuda.Event()
         start.record(cur)
         for i, (x, y) in enumerate(zip(logits, targets)):
             w = float(cfg['weights'][i])
-            if w == 0 and i > 0:
+            if x is None:
                 dls.append(None)
                 continue
-            x = x.contiguous()
-            y = y.contiguous().float()
             B, Cc = int(x.shape[0]), int(x.shape[1])
             V = x[0, 0].numel()
             if y.numel() != B * V:

@@ -331,6 +331,24 @@ class Generic_UNet(nn.Module):
             return outs
         return outs[0]
 
+    def head_logits(self, weight, level=0):
+        """Logits of deep-supervision `level` for another ``seg_outputs[num_pool-1-level]`` weight on the decoder
+        activation the LAST forward left in the plan's workspace (LwF old-task heads, reference lwf:315-346: the stored
+        heads share the body with the running model)."""
+        plan = getattr(self, "_last_plan", None)
+        if plan is None:
+            raise RuntimeError("head_logits: run a forward first")
+        w = weight.detach()
+        if w.device != plan.workspace.device or w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.to(plan.workspace.device, torch.float32).contiguous()
+        if w.numel() != self.num_classes * self.seg_outputs[self.num_pool - 1 - level].weight.shape[1]:
+            raise ValueError("head weight has %d elements" % w.numel())
+        out = torch.empty(plan.out_shapes[level], dtype=torch.float32, device=w.device)
+        _lib.check(plan.lib.b2_unet_head_forward(plan.handle, C.c_void_p(plan.workspace.data_ptr()), int(level),
+                                                 C.c_void_p(w.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)))
+        return self.final_nonlin(out)
+
     def _fire_hooks(self, plan, outs):
         """Fire forward hooks of the conv modules with the raw conv outputs (reference plop:330-353) in execution
         order: encoder convs, then per decoder level tu.u, loc.u.0, loc.u.1, seg_outputs.u."""

@@ -29,30 +29,26 @@ class B2SGD(torch.optim.Optimizer):
             if not ps:
                 continue
             dev = ps[0].device
-            first = 0
             table = (_lib.SgdEntry * len(ps))()
             total = 0
             for i, p in enumerate(ps):
                 st = self.state[p]
                 if 'momentum_buffer' not in st:
+                    # torch.optim.SGD creates the buffer lazily PER PARAMETER as clone(d_p); a zero buffer run through
+                    # the warm update gives momentum * 0 + d_p = d_p, bit for bit, so parameters that first receive a
+                    # gradient in a later task (zero-weight head, ViT-bypassed bottleneck) need no special launch
                     st['momentum_buffer'] = torch.zeros_like(p)
-                    st['fresh'] = True
                 if not p.grad.is_contiguous():
                     p.grad = p.grad.contiguous()
                 table[i].theta, table[i].grad = p.data_ptr(), p.grad.data_ptr()
                 table[i].momentum, table[i].numel = st['momentum_buffer'].data_ptr(), p.numel()
                 total += p.numel()
-            fresh = [self.state[p].get('fresh', False) for p in ps]
-            if any(fresh) and not all(fresh):
-                raise RuntimeError("B2SGD: mixed fresh / warm momentum buffers in one group")
-            first = 1 if all(fresh) else 0
+            first = 0
             norm = torch.empty(1, dtype=torch.float32, device=dev)
             scr = torch.empty(int(lib.b2_sgd_scratch_bytes(len(ps), total)), dtype=torch.uint8, device=dev)
             _lib.check(lib.b2_sgd_clip_step(table, len(ps), float(group['lr']), float(group['momentum']),
                                             float(group['weight_decay']), int(group['nesterov']), float(max_norm),
                                             first, norm.data_ptr(), scr.data_ptr(), _stream(dev)))
-            for p in ps:
-                self.state[p]['fresh'] = False
             self.last_grad_norm = norm
 
     def step(self, closure=None):

@@ -21,13 +21,16 @@ gradient is added, so the regulariser is not multiplied by the world size.
 """
 import copy
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import deep_supervision as ds
+from .fused_step import FusedStep
 from .generic_UNet import Generic_UNet
 from .generic_ViT_UNet import Generic_ViT_UNet
+from .MultiHead_Module import MultiHead_Module
 from .optim import B2SGD, fisher_square, rw_update
 
 EPSILON = 1e-8  # reference rw/nnUNetTrainerRW.py module constant
@@ -76,8 +79,21 @@ class DataParallelGroup:
 class nnUNetTrainerMultiHead:
     def __init__(self, geometry, precision="bf16", batch_dice=False, device=None, ddp=None, initial_lr=1e-2,
                  weight_decay=3e-5, max_num_epochs=1000, seed=0, task="task_A", use_vit=False, vit_version='V1',
-                 vit_type='base'):
+                 vit_type='base', split="seg_outputs", transfer_heads=True, strict_reference=True, fused_step=True,
+                 cuda_graph=None):
         self.geometry = geometry
+        self.split, self.transfer_heads = split, transfer_heads       # run_training.py -s / --transfer_heads
+        # strict_reference: reproduce the reference's generator-exhaustion quirks Q1 / Q2; False = the
+        # documented math (every stored task is penalised on every iteration)
+        self.strict_reference = strict_reference
+        # fused_step: run training iterations as one enqueue program over the C ABI (fused_step.py) instead of through
+        # autograd; cuda_graph: capture that program after two warm-up iterations and replay it (env B2_CUDA_GRAPH=0/1)
+        self.fused_step = fused_step
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("B2_CUDA_GRAPH", "1") != "0"
+        self.cuda_graph = cuda_graph
+        self._steps, self._step_inputs = {}, None
+        self.mh_network = None
         self.use_vit, self.vit_version, self.vit_type = use_vit, vit_version, vit_type   # run_training.py --use_vit
         self.precision = precision
         self.batch_dice = batch_dice
@@ -110,6 +126,18 @@ class nnUNetTrainerMultiHead:
         self.network.precision = self.precision
         self.network.to(self.device)
         self.network.inference_apply_nonlin = lambda x: torch.softmax(x, 1)
+        # reference MultiHead:366-369: the body / head splitter around the network; the running model IS self.network
+        self.mh_network = MultiHead_Module(type(self.network), self.split, self.task, prev_trainer=self.network)
+        self.network = self.mh_network.model
+
+    def start_task(self, task):
+        """reference MultiHead.run_training :541-564: a new task gets a head (initialised from the first split, or from
+        the last trained head with transfer_heads) and the running model is assembled for it"""
+        if task not in self.mh_network.heads:
+            self.mh_network.add_new_task(task, use_init=not self.transfer_heads)
+        self.network = self.mh_network.assemble_model(task)
+        self.task = task
+        self._steps = {}
 
     # -- reference MultiHead:294-301 ---------------------------------------------------------------------------------
     def initialize_optimizer_and_scheduler(self):
@@ -169,7 +197,94 @@ class nnUNetTrainerMultiHead:
         self._sync_gradients()
 
     # -- reference MultiHead:598-656 (fp32 branch; bf16 needs no loss scaling) ----------------------------------------
+    # -- fused iteration (fused_step.py) ----------------------------------------------------------------------------------
+    def _use_fused(self, do_backprop, no_loss):
+        return (self.fused_step and do_backprop and not no_loss and not self.use_vit and
+                type(self.network) is Generic_UNet and self._fused_supported())
+
+    def _fused_supported(self):
+        return type(self.loss) is ds.MultipleOutputLoss2 and hasattr(self.loss.loss, 'cfg')
+
+    def _fused_spec(self):
+        """(hashable key, spec dict) of the iteration's loss composition; the key changes when a program must be rebuilt"""
+        return ("base",), dict(base='dcce', cfg=self.loss.loss.cfg(list(self.ds_loss_weights)))
+
+    def _fused_pre(self, step):
+        pass
+
+    def _fused_post(self, step):
+        pass
+
+    def _host_batch(self, data_generator):
+        data_dict = next(data_generator)
+        return maybe_to_torch(data_dict['data']), maybe_to_torch(data_dict['target'])
+
+    def _run_iteration_fused(self, data_generator, run_online_evaluation=False, detach=True):
+        """reference MultiHead:606-656 with the body (zero_grad ... optimizer.step) replaced by one FusedStep program"""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        pending = self._prefetched if (self.prefetch_inputs and self._prefetched is not None and
+                                       self._prefetched[0] is data_generator) else None
+        if pending is None:
+            data, target = self._host_batch(data_generator)
+        else:
+            data, target = pending[1], pending[2]
+        key, spec = self._fused_spec()
+        key = (tuple(data.shape), self.precision) + key
+        step = self._steps.get(key)
+        if step is None:
+            step = self._steps[key] = FusedStep(self, torch.empty(tuple(data.shape), dtype=torch.float32, device=dev),
+                                                [torch.empty(tuple(t.shape), device='meta') for t in target], spec)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        if pending is None:
+            # input patch on the compute stream (the forward needs it first); the deep-supervision targets follow on the copy
+            # stream while the forward runs and are awaited right before the loss kernels
+            step.data.copy_(data, non_blocking=True)
+            cs.wait_stream(cur)             # the previous iteration may still read step.targets
+            with torch.cuda.stream(cs):
+                for dst, src in zip(step.targets, target):
+                    dst.copy_(src, non_blocking=True)
+                tready = torch.cuda.Event()
+                tready.record(cs)
+        else:
+            cur.wait_event(pending[3])      # staged on the device by the previous iteration's prefetch
+            step.data.copy_(data)
+            data.record_stream(cur)
+            for dst, src in zip(step.targets, target):
+                dst.copy_(src)
+                src.record_stream(cur)
+            tready = None
+        self._fused_pre(step)
+        total = step.run(self.cuda_graph, tready)
+        self.network._last_plan = step.plan
+        if self.prefetch_inputs:            # opt-in: draw batch i+1 now and stage it on the device while batch i computes
+            try:
+                nd, nt = self._host_batch(data_generator)
+                with torch.cuda.stream(cs):
+                    nd = nd.to(dev, non_blocking=True)
+                    nt = [t.to(dev, non_blocking=True) for t in nt]
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                self._prefetched = (data_generator, nd, nt, ev)
+            except StopIteration:
+                self._prefetched = None
+        self._fused_post(step)
+        if run_online_evaluation:
+            self.run_online_evaluation(step.logits, step.targets)
+        self.update_after_iteration()
+        if not detach:
+            return total.clone()
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._loss_host.copy_(total, non_blocking=True)
+        cur.synchronize()
+        return self._loss_host.numpy().copy()
+
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
+        if self._use_fused(do_backprop, no_loss):
+            return self._run_iteration_fused(data_generator, run_online_evaluation, detach)
         data, target = self._next_batch(data_generator)
 
         self.optimizer.zero_grad()
@@ -222,14 +337,18 @@ class nnUNetTrainerMultiHead:
         cur.wait_event(ev)
         for t in ([data] if torch.is_tensor(data) else list(data)) + ([target] if torch.is_tensor(target) else list(target)):
             t.record_stream(cur)
-        self._prefetched = (data_generator,) + self._fetch(data_generator, self._copy_stream)
+        try:
+            self._prefetched = (data_generator,) + self._fetch(data_generator, self._copy_stream)
+        except StopIteration:        # finite generator: the batch in hand is the last one -- train on it
+            self._prefetched = None
         return data, target
 
     def update_after_iteration(self):
         """reference MultiHead_Module.update_after_iteration (MultiHead_Module.py:139-157) re-splits the model and
         deep-copies the head every iteration; here the active head's parameters ARE the running model's parameters
         (shared storage), so there is nothing to copy."""
-        return None
+        if self.mh_network is not None:
+            self.mh_network.update_after_iteration()
 
     # -- reference MultiHead:924-961 ------------------------------------------------------------------------------------
     def run_online_evaluation(self, output, target):
@@ -273,6 +392,27 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
         self.loss = ds.MultipleOutputLossEWC(self._base_loss(), self.ds_loss_weights, self.ewc_lambda, self.fisher,
                                              self.params, self.network.named_parameters())
 
+    def _net_params(self):
+        """Q1: the reference hands the loss a GENERATOR (ewc:247), which the first stored task exhausts"""
+        named = self.network.named_parameters()
+        return named if self.strict_reference else list(named)
+
+    def _fused_supported(self):
+        return type(self.loss) is ds.MultipleOutputLossEWC and hasattr(self.loss.loss, 'cfg')
+
+    def _penalty_names(self):
+        return [n for n, _ in self.network.named_parameters()
+                if ds._match(n, self.loss.match_case, self.loss.match, self.loss.match_true)]
+
+    def _fused_spec(self):
+        tasks = list(self.loss.tasks)
+        if self.strict_reference:
+            tasks = tasks[:1]
+        names = self._penalty_names()
+        pen = [(self.ewc_lambda / 2, self.fisher[t], self.params[t], None, names) for t in tasks] if names else []
+        key = ("ewc", tuple(tasks), tuple(id(self.fisher[t]) for t in tasks), len(names))
+        return key, dict(base='dcce', cfg=self.loss.loss.cfg(list(self.ds_loss_weights)), penalty=pen)
+
     def _forward_loss(self, data, target):
         # the data term goes through autograd; the penalty (value + analytic gradient) is added after backward, straight
         # into param.grad -- after the gradient all-reduce under data parallelism, because it is identical on every rank
@@ -288,18 +428,21 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
         self._last_penalty = self._penalty_after_backward()
 
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
+        if self._use_fused(do_backprop, no_loss):
+            return self._run_iteration_fused(data_generator, run_online_evaluation, detach)
         self._last_penalty = None
+        self.loss.update_network_params(self._net_params())
         loss = super().run_iteration(data_generator, do_backprop, run_online_evaluation, False, no_loss)
         if loss is not None:
             if not do_backprop:      # validation iterations: value of the regulariser without touching gradients
-                self.loss.update_network_params(self.network.named_parameters())
+                self.loss.update_network_params(self._net_params())
                 loss = self.loss._penalty(loss.detach(), self.ewc_lambda / 2)
             elif self._last_penalty is not None:
                 loss = loss.detach() + self._last_penalty
             if detach:
                 loss = loss.detach().cpu().numpy()
         # reference ewc:247 -- a fresh generator for the next iteration
-        self.loss.update_network_params(self.network.named_parameters())
+        self.loss.update_network_params(self._net_params())
         return loss
 
     def after_train(self, data_generator, num_batches=1):
@@ -324,7 +467,8 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
                 self.fisher[self.task][n] = torch.tensor([1], device=self.device)     # ewc:300-301
             self.params[self.task][n] = p.data.clone()
         self.loss.update_ewc_params(self.fisher, self.params)
-        self.loss.update_network_params(self.network.named_parameters())
+        self.loss.update_network_params(self._net_params())
+        self._steps = {}
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -341,13 +485,37 @@ class nnUNetTrainerRW(nnUNetTrainerMultiHead):
                                             self.params, self.scores, self.network.named_parameters())
 
     def start_task(self, task):
-        """reference rw:160-168"""
-        self.task = task
+        """reference rw:160-168 (+ the head bookkeeping of MultiHead.run_training :541-564)"""
+        super().start_task(task)
         self.params[task] = dict()
         self.fisher[task] = {n: torch.zeros_like(p, requires_grad=False) for n, p in self.network.named_parameters() if p.requires_grad}
         self.scores[task] = {n: torch.zeros_like(p, requires_grad=False) for n, p in self.network.named_parameters() if p.requires_grad}
         self.loss.update_rw_params(self.fisher, self.params, self.scores)
-        self.loss.update_network_params(self.network.named_parameters())
+        # Q2: the reference hands the loss a generator ONCE and never refreshes it: the penalty is evaluated on the first
+        # iteration after the stored tasks become non-empty and is silently zero afterwards (strict_reference); the
+        # documented math (deep_supervision.py:115-132) penalises every iteration (strict_reference=False)
+        self._rw_params_fresh = True
+        self.loss.update_network_params(self.network.named_parameters() if self.strict_reference
+                                        else list(self.network.named_parameters()))
+
+    def _fused_supported(self):
+        return type(self.loss) is ds.MultipleOutputLossRW and hasattr(self.loss.loss, 'cfg')
+
+    def _fused_spec(self):
+        tasks = list(self.loss.tasks)
+        if self.strict_reference:
+            tasks = tasks[:1] if getattr(self, "_rw_params_fresh", False) else []
+        names = [n for n, _ in self.network.named_parameters()
+                 if ds._match(n, self.loss.match_case, self.loss.match, self.loss.match_true)]
+        pen = [(self.rw_lambda, self.fisher[t], self.params[t], self.scores[t], names) for t in tasks] if names else []
+        key = ("rw", tuple(tasks), tuple(id(self.fisher[t]) for t in tasks), tuple(id(self.scores[t]) for t in tasks))
+        return key, dict(base='dcce', cfg=self.loss.loss.cfg(list(self.ds_loss_weights)), penalty=pen)
+
+    def _fused_post(self, step):
+        if self.strict_reference and getattr(self, "_rw_params_fresh", False) and self.loss.tasks:
+            self._rw_params_fresh = False
+            self.loss.update_network_params(iter(()))         # the generator is exhausted now (Q2)
+        self._update_f_s_values()
 
     def _forward_loss(self, data, target):
         output = self.network(data)
@@ -359,11 +527,24 @@ class nnUNetTrainerRW(nnUNetTrainerMultiHead):
         self._last_penalty = self.loss.penalty_into_grads(self.rw_lambda, self.loss.parameter_importance)
 
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False):
+        if self._use_fused(do_backprop, no_loss):
+            return self._run_iteration_fused(data_generator, run_online_evaluation, detach)
         self._last_penalty = None
         loss = super().run_iteration(data_generator, do_backprop, run_online_evaluation, False, no_loss)
-        if loss is not None and self._last_penalty is not None:
-            loss = loss.detach() + self._last_penalty
-        self._update_f_s_values()
+        if do_backprop and self.loss.tasks:
+            self._rw_params_fresh = False
+        if loss is not None:
+            if not do_backprop:      # validation iterations: the reference's forward always adds the penalty (deep_supervision.py:109-135)
+                loss = self.loss._penalty(loss.detach(), self.rw_lambda, self.loss.parameter_importance)
+            elif self._last_penalty is not None:
+                loss = loss.detach() + self._last_penalty
+        if do_backprop:
+            self._update_f_s_values()
+        else:
+            # rw:224 calls _update_f_s_values on validation iterations too, where its effect depends on the torch version
+            # (zero_grad leaves zeros under torch 1.9 -> F decays, None under torch >= 2 -> prev_param = {} and the next
+            # update raises KeyError); here validation iterations only advance the schedule counter
+            self.count += 1
         if detach and loss is not None:
             loss = loss.detach().cpu().numpy()
         return loss
@@ -424,6 +605,15 @@ class nnUNetTrainerMiB(nnUNetTrainerMultiHead, _TeacherMixin):
         self.loss = self.loss_base
         self.MiBLoss = ds.MultipleOutputLossMiB(self.alpha, self.lkd, self.ds_loss_weights)
 
+    def _fused_supported(self):
+        return self.network_old is None or type(self.network_old) is Generic_UNet
+
+    def _fused_spec(self):
+        cfg = self.loss_base.loss.cfg(list(self.ds_loss_weights))
+        if self.network_old is None:
+            return ("mib0",), dict(base='dcce', cfg=cfg)
+        return ("mib", id(self.network_old)), dict(base='ce255', cfg=cfg, teacher=self.network_old, mib=(self.alpha, self.lkd))
+
     def _forward_loss(self, data, target):
         output = self.network(data)
         if self.network_old is None:                       # first task: plain loss (mib:118-135)
@@ -467,6 +657,16 @@ class nnUNetTrainerPOD(nnUNetTrainerMultiHead, _TeacherMixin):
         return ({k: v for k, v in self.old_interm_results.items() if v.dim() == 5},
                 {k: v for k, v in self.interm_results.items() if v.dim() == 5})
 
+    def _fused_supported(self):
+        return self.network_old is None or type(self.network_old) is Generic_UNet
+
+    def _fused_spec(self):
+        cfg = self.loss_base.loss.cfg(list(self.ds_loss_weights))
+        if self.network_old is None:
+            return ("pod0",), dict(base='dcce', cfg=cfg)
+        return ("pod", id(self.network_old)), dict(base='dcce', cfg=cfg, teacher=self.network_old,
+                                                   pod=(self.pod_lambda, self.scales))
+
     def _forward_loss(self, data, target):
         output = self.network(data)
         if self.network_old is None:
@@ -495,6 +695,15 @@ class nnUNetTrainerPLOP(nnUNetTrainerPOD):
         self.max_entropy = torch.log(torch.tensor(C_).float()).item()
         self.thresholds = {i: torch.full((C_,), 1e-3, device=self.device) for i in range(self.geometry.num_pool)}
 
+    def _fused_spec(self):
+        cfg = self.loss_base.loss.cfg(list(self.ds_loss_weights))
+        if self.network_old is None:
+            return ("plop0",), dict(base='dcce', cfg=cfg)
+        thr = [self.thresholds[i].to(self.device).contiguous().float() for i in range(self.geometry.num_pool)]
+        return (("plop", id(self.network_old), float(self.max_entropy)),
+                dict(base='plop', cfg=cfg, teacher=self.network_old, pod=(self.pod_lambda, self.scales),
+                     plop=(thr, self.max_entropy)))
+
     def _forward_loss(self, data, target):
         output = self.network(data)
         if self.network_old is None:
@@ -510,10 +719,11 @@ class nnUNetTrainerLWF(nnUNetTrainerMultiHead):
     """LwF with the previous tasks' heads (reference lwf:298-370).  A head is the state of the split module
     (``seg_outputs`` by default, reference run_training.py:103-107); heads of finished tasks are frozen copies."""
 
-    def __init__(self, *a, lwf_temperature=2.0, split="seg_outputs", **kw):
+    def __init__(self, *a, lwf_temperature=2.0, **kw):
         super().__init__(*a, **kw)
-        self.lwf_temperature, self.split = lwf_temperature, split
-        self.heads = dict()          # task -> state_dict of the head sub-module
+        self.lwf_temperature = lwf_temperature
+        self.heads = dict()          # finished task -> state_dict snapshot of its head (the split module)
+        self.batch_idx = 0           # running index into the stored target logits (lwf:362)
         self.target_logits = dict()  # task -> list of stored full-res logits (lwf:247-251)
 
     def initialize_loss(self):
@@ -526,10 +736,47 @@ class nnUNetTrainerLWF(nnUNetTrainerMultiHead):
         return m
 
     def finish_task(self):
+        """end of a task: its head is frozen (MultiHead_Module keeps it under ``mh_network.heads[task]``; the snapshot below
+        is what the distillation reads)"""
         self.heads[self.task] = {k: v.detach().clone() for k, v in self._head_module().state_dict().items()}
+        self._steps = {}
+
+    def _fused_supported(self):
+        return (type(self.loss) is ds.MultipleOutputLossLWF and hasattr(self.loss.loss, 'cfg') and
+                (not self.heads or self._shared_body()))
+
+    def _fused_spec(self):
+        cfg = self.loss.loss.cfg(list(self.ds_loss_weights))
+        if not self.heads:
+            return ("lwf0",), dict(base='dcce', cfg=cfg)
+        P = self.geometry.num_pool
+        heads = [(t, self.heads[t]["%d.weight" % (P - 1)]) for t in self.heads]
+        return ("lwf", tuple(self.heads), tuple(id(self.heads[t]) for t in self.heads)), \
+            dict(base='dcce', cfg=cfg, lwf=(heads, self.lwf_temperature))
+
+    def _fused_pre(self, step):
+        if step.lwf is not None:
+            idx = self._cur_batch_idx
+            for h in step.lwf['heads']:
+                stored = self.target_logits[h['task']]
+                h['target'].copy_(stored[idx % len(stored)], non_blocking=True)
+
+    def _shared_body(self):
+        """the documented split (`-s seg_outputs`, run_training.py:103-107): a stored head is only the 1x1x1 output
+        convolutions, so every old head can be evaluated on the body activations of ONE forward"""
+        return self.split == "seg_outputs" and hasattr(self.network, "head_logits")
+
+    def _old_head_logits(self, task):
+        """full-resolution logits of stored head `task` on the activations of the last forward"""
+        P = self.geometry.num_pool
+        return self.network.head_logits(self.heads[task]["%d.weight" % (P - 1)], level=0)
 
     def _forward_with_head(self, data, task):
         """assemble_model(task) + eval forward + first output (lwf:315-346), without touching the training state"""
+        if self._shared_body():
+            with torch.no_grad():
+                self.network(data)
+            return self._old_head_logits(task)
         head = self._head_module()
         cur = {k: v.detach().clone() for k, v in head.state_dict().items()}
         head.load_state_dict(self.heads[task])
@@ -541,20 +788,41 @@ class nnUNetTrainerLWF(nnUNetTrainerMultiHead):
     def store_target_logits(self, data_batches):
         """reference helpful_functions.calculate_target_logits (:207-266): logits of every old head on the new task's
         batches, computed once before training"""
-        for task in self.heads:
-            self.target_logits[task] = [self._forward_with_head(to_cuda(maybe_to_torch(d), gpu_id=self.device.index), task)
-                                        for d in data_batches]
+        self.target_logits = {task: [] for task in self.heads}
+        for d in data_batches:
+            data = to_cuda(maybe_to_torch(d), gpu_id=self.device.index)
+            if self._shared_body():
+                with torch.no_grad():
+                    self.network(data)                   # one body forward per batch, every stored head on top of it
+                for task in self.heads:
+                    self.target_logits[task].append(self._old_head_logits(task))
+            else:
+                for task in self.heads:
+                    self.target_logits[task].append(self._forward_with_head(data, task))
+
+    def _forward_loss(self, data, target):
+        if not self.heads:
+            output = self.network(data)
+            return output, self.loss(output, target)
+        # the old heads' predictions of THIS batch (Q16: the intended "same batch"); with the documented split they are
+        # evaluated on the body activations the training forward just produced: same parameters, and eval == train for
+        # InstanceNorm without running stats / dropout p = 0
+        if self._shared_body():
+            output = self.network(data)
+            preds = [self._old_head_logits(task) for task in self.heads]
+        else:
+            preds = [self._forward_with_head(data, task) for task in self.heads]
+            output = self.network(data)
+        idx = self._cur_batch_idx
+        targets = [self.target_logits[task][idx % len(self.target_logits[task])] for task in self.heads]
+        self.loss.update_logits(preds, targets)
+        return output, self.loss(output, target)
 
     def run_iteration(self, data_generator, do_backprop=True, run_online_evaluation=False, detach=True, no_loss=False,
-                      batch_idx=0):
-        if self.heads:
-            # the reference intends "same batch" (Q16): peek the batch, run every old head on it, then train on it
-            data_dict = next(data_generator)
-            data = to_cuda(maybe_to_torch(data_dict['data']), gpu_id=self.device.index)
-            preds, targets = [], []
-            for task in self.heads:
-                preds.append(self._forward_with_head(data, task))
-                targets.append(self.target_logits[task][batch_idx % len(self.target_logits[task])])
-            self.loss.update_logits(preds, targets)
-            data_generator = iter([data_dict])
+                      batch_idx=None):
+        if batch_idx is None:
+            batch_idx = self.batch_idx
+            if do_backprop:
+                self.batch_idx += 1
+        self._cur_batch_idx = batch_idx
         return super().run_iteration(data_generator, do_backprop, run_online_evaluation, detach, no_loss)

@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(MT_THREADS) gradnorm_kernel(const int* __restr
 
 // norm = sqrt(sum); clip = min(1, max_norm/(norm+1e-6))  -> out[0] = norm, out[1] = clip
 __global__ void __launch_bounds__(256) clipcoef_kernel(const float* __restrict__ part, int n, float max_norm,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, const float* __restrict__ hyper) {
     pdl_grid_sync();
+    if (hyper) max_norm = hyper[3];
     __shared__ double red[32];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += (double)part[i];
@@ -198,8 +199,9 @@ __global__ void __launch_bounds__(256) clipcoef_kernel(const float* __restrict__
 __global__ void __launch_bounds__(MT_THREADS) sgd_kernel(const int* __restrict__ prefix, const long long* __restrict__ numel,
                                                          const b2_sgd_entry* __restrict__ ent, int n_tensors, float lr,
                                                          float momentum, float wd, int nesterov, int first_step,
-                                                         const float* __restrict__ clip) {
+                                                         const float* __restrict__ clip, const float* __restrict__ hyper) {
     pdl_grid_sync();
+    if (hyper) { lr = hyper[0]; momentum = hyper[1]; wd = hyper[2]; }   // device-resident schedule: a captured graph follows lr changes
     const MTLoc l = mt_locate(prefix, n_tensors, numel);
     const b2_sgd_entry e = ent[l.tensor];
     const float c = clip[1];
@@ -306,8 +308,72 @@ extern "C" int b2_sgd_clip_step(const b2_sgd_entry* table_host, int n_tensors, f
     const long long* numel = (const long long*)(dev + h.off_numel);
     const b2_sgd_entry* ent = (const b2_sgd_entry*)(dev + h.off_entries);
     B2_LAUNCH(gradnorm_kernel, h.nblocks, MT_THREADS, 0, st, prefix, numel, ent, n_tensors, part);
-    B2_LAUNCH(clipcoef_kernel, 1, 256, 0, st, part, h.nblocks, max_norm, clip);
-    B2_LAUNCH(sgd_kernel, h.nblocks, MT_THREADS, 0, st, prefix, numel, ent, n_tensors, lr, momentum, weight_decay, nesterov, first_step, clip);
+    B2_LAUNCH(clipcoef_kernel, 1, 256, 0, st, part, h.nblocks, max_norm, clip, (const float*)nullptr);
+    B2_LAUNCH(sgd_kernel, h.nblocks, MT_THREADS, 0, st, prefix, numel, ent, n_tensors, lr, momentum, weight_decay, nesterov, first_step, clip, (const float*)nullptr);
     if (norm_out) B2_CUDA(cudaMemcpyAsync(norm_out, clip, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return B2_OK;
+}
+
+// ---- persistent device tables ----------------------------------------------------------------------------------------
+// The *_host entry points above rebuild and upload their (tensor, chunk) tables on every call (a pageable host copy: it
+// serialises with the host and cannot be captured in a CUDA graph).  A trainer builds each table ONCE on the host
+// (b2_mt_blob_build), keeps it in device memory and runs the *_dev variants: no host work per step, graph-capturable.
+static size_t mt_entry_size(int kind) {
+    return kind == B2_MT_PEN ? sizeof(b2_pen_entry) : kind == B2_MT_SGD ? sizeof(b2_sgd_entry) : kind == B2_MT_RW ? sizeof(b2_rw_entry) : 0;
+}
+extern "C" size_t b2_mt_blob_bytes(int kind, int n_tensors) {
+    const size_t e = mt_entry_size(kind);
+    return e && n_tensors > 0 ? mt_table_bytes(n_tensors, e) : 0;
+}
+extern "C" int b2_mt_blob_build(int kind, const void* table_host, int n_tensors, void* blob_host, int32_t* nblocks_out) {
+    B2_CHECK_ARG(table_host && blob_host && nblocks_out && n_tensors > 0 && mt_entry_size(kind));
+    MTHost h;
+    if (kind == B2_MT_PEN) h = mt_build((const b2_pen_entry*)table_host, n_tensors);
+    else if (kind == B2_MT_SGD) h = mt_build((const b2_sgd_entry*)table_host, n_tensors);
+    else h = mt_build((const b2_rw_entry*)table_host, n_tensors);
+    memset(blob_host, 0, b2_mt_blob_bytes(kind, n_tensors));
+    memcpy(blob_host, h.blob.data(), h.blob.size());
+    *nblocks_out = h.nblocks;
+    return B2_OK;
+}
+static inline size_t blob_off_numel(int n) { return align_up((n + 1) * sizeof(int), 16); }
+static inline size_t blob_off_entries(int n) { return blob_off_numel(n) + align_up(n * sizeof(long long), 16); }
+
+extern "C" size_t b2_mt_part_bytes(int nblocks) { return align_up(((size_t)nblocks + 8) * sizeof(float)); }
+
+extern "C" int b2_quadpen_dev(const void* blob_dev, int n_tensors, int nblocks, float coef, float* loss_out, float* part,
+                              b2_stream_t stream) {
+    B2_CHECK_ARG(blob_dev && n_tensors > 0 && nblocks > 0 && loss_out && part);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* dev = (const char*)blob_dev;
+    B2_LAUNCH(quadpen_kernel, nblocks, MT_THREADS, 0, st, (const int*)dev, (const long long*)(dev + blob_off_numel(n_tensors)),
+              (const b2_pen_entry*)(dev + blob_off_entries(n_tensors)), n_tensors, coef, part);
+    B2_LAUNCH(ordered_sum_kernel, 1, 256, 0, st, (const float*)part, nblocks, coef, loss_out, 1);
+    return B2_OK;
+}
+
+extern "C" int b2_sgd_clip_step_dev(const void* blob_dev, int n_tensors, int nblocks, const float* hyper_dev, int nesterov,
+                                    float* norm_out, float* part, b2_stream_t stream) {
+    B2_CHECK_ARG(blob_dev && n_tensors > 0 && nblocks > 0 && hyper_dev && part);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* dev = (const char*)blob_dev;
+    const int* prefix = (const int*)dev;
+    const long long* numel = (const long long*)(dev + blob_off_numel(n_tensors));
+    const b2_sgd_entry* ent = (const b2_sgd_entry*)(dev + blob_off_entries(n_tensors));
+    float* clip = part + nblocks;
+    B2_LAUNCH(gradnorm_kernel, nblocks, MT_THREADS, 0, st, prefix, numel, ent, n_tensors, part);
+    B2_LAUNCH(clipcoef_kernel, 1, 256, 0, st, (const float*)part, nblocks, 0.f, clip, hyper_dev);
+    B2_LAUNCH(sgd_kernel, nblocks, MT_THREADS, 0, st, prefix, numel, ent, n_tensors, 0.f, 0.f, 0.f, nesterov, 0, (const float*)clip, hyper_dev);
+    if (norm_out) B2_CUDA(cudaMemcpyAsync(norm_out, clip, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return B2_OK;
+}
+
+extern "C" int b2_rw_update_dev(const void* blob_dev, int n_tensors, int nblocks, float alpha, float eps, int have_prev,
+                                b2_stream_t stream) {
+    B2_CHECK_ARG(blob_dev && n_tensors > 0 && nblocks > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* dev = (const char*)blob_dev;
+    B2_LAUNCH(rw_update_kernel, nblocks, MT_THREADS, 0, st, (const int*)dev, (const long long*)(dev + blob_off_numel(n_tensors)),
+              (const b2_rw_entry*)(dev + blob_off_entries(n_tensors)), n_tensors, alpha, eps, have_prev);
     return B2_OK;
 }

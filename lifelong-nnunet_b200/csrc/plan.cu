@@ -524,10 +524,12 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
 
 template <typename T>
 static int backward_t(b2_unet_plan* p, const float* const* prm, const float* const* dlogits, void* ws,
-                      float* const* grads, int32_t* has_grad, int parts, cudaStream_t st) {
+                      float* const* grads, int32_t* has_grad, int parts, cudaStream_t st,
+                      const b2_grad_bucket* buckets = nullptr, int n_buckets = 0) {
     const b2_unet_geometry& g = p->g;
     const int P_ = g.num_pool;
     int rc;
+    int next_bucket = 0;
     if (parts & B2_PART_DECODER)     // the decoder call opens a backward pass: every flag starts at 1
         for (size_t i = 0; i < p->params.size(); ++i) if (has_grad) has_grad[i] = 1;
     T* dzbuf[2] = {reinterpret_cast<T*>((char*)ws + p->off_grad) + p->dz_tmp.off,
@@ -537,6 +539,16 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
     const bool overlap = g_bwd_overlap && ensure_side_stream(p);
     cudaStream_t wst = overlap ? p->side : st;
     float* wscr = overlap ? SCR_WG(ws, p) : SCR(ws, p);
+    // gradient buckets (data-parallel overlap): layers finish in descending parameter order, so the arena region
+    // [first_param, end) of bucket k is complete once the layer owning `first_param` is enqueued -- record its events
+    auto bucket_done = [&](int lowest_param) -> int {
+        while (next_bucket < n_buckets && lowest_param <= buckets[next_bucket].first_param) {
+            if (buckets[next_bucket].event_main) B2_CUDA(cudaEventRecord((cudaEvent_t)buckets[next_bucket].event_main, st));
+            if (buckets[next_bucket].event_side) B2_CUDA(cudaEventRecord((cudaEvent_t)buckets[next_bucket].event_side, wst));
+            ++next_bucket;
+        }
+        return B2_OK;
+    };
     int layer_k = 0;
     bool wg_pending[2] = {false, false};
     bool skip_pending[8] = {false, false, false, false, false, false, false, false};
@@ -663,8 +675,11 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         }
         ConvBlock& l1 = p->convs[2 * (P_ + 1) + 2 * u + 1];
         ConvBlock& l0 = p->convs[2 * (P_ + 1) + 2 * u];
+        if ((rc = bucket_done(h.p_w))) return rc;
         if ((rc = conv_bwd(l1))) return rc;
+        if ((rc = bucket_done(l1.p_w))) return rc;
         if ((rc = conv_bwd(l0))) return rc;
+        if ((rc = bucket_done(l0.p_w))) return rc;
         Tconv& t = p->tconvs[u];
         bool tdg = false;
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -689,6 +704,7 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
         if (!(tdg && twg))
             if ((rc = tconv_bwd<T>(t.shape, P<T>(ws, p, t.in, false), P<T>(ws, p, t.dout, true), prm[t.p_w],
                                    tdg ? (T*)nullptr : P<T>(ws, p, t.din, true), twg ? (float*)nullptr : grads[t.p_w], SCR(ws, p), st))) return rc;
+        if ((rc = bucket_done(t.p_w))) return rc;
     }
     for (int d = P_; d >= 0; --d) {
         const bool on = d < P_ ? (parts & B2_PART_ENCODER) != 0 : (parts & B2_PART_BOTTLENECK) != 0;
@@ -703,11 +719,15 @@ static int backward_t(b2_unet_plan* p, const float* const* prm, const float* con
                         if (has_grad) has_grad[pi] = 0;
                     }
                 }
+            if ((rc = bucket_done(p->convs[2 * d].p_w))) return rc;
             continue;
         }
         if ((rc = conv_bwd(p->convs[2 * d + 1]))) return rc;
+        if ((rc = bucket_done(p->convs[2 * d + 1].p_w))) return rc;
         if ((rc = conv_bwd(p->convs[2 * d]))) return rc;
+        if ((rc = bucket_done(p->convs[2 * d].p_w))) return rc;
     }
+    if ((rc = bucket_done(0))) return rc;
     if (overlap) {   // join: every gradient is complete in the caller's stream order
         B2_CUDA(cudaEventRecord(p->ev_misc, wst));
         B2_CUDA(cudaStreamWaitEvent(st, p->ev_misc, 0));
@@ -813,6 +833,19 @@ extern "C" int b2_unet_backward(b2_unet_plan* plan, const float* const* params, 
     return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, B2_PART_ALL, st);
 }
 
+// backward with gradient buckets: events are recorded as soon as the arena suffix [first_param, end) is complete, so the
+// caller can all-reduce bucket k on a communication stream while the remaining layers are still being differentiated
+extern "C" int b2_unet_backward_buckets(b2_unet_plan* plan, const float* const* params, const float* const* dlogits,
+                                        void* workspace, float* const* grads, int32_t* has_grad_host,
+                                        const b2_grad_bucket* buckets_host, int n_buckets, b2_stream_t stream) {
+    B2_CHECK_ARG(plan && params && dlogits && workspace && grads && (n_buckets == 0 || buckets_host));
+    for (int i = 1; i < n_buckets; ++i) B2_CHECK_ARG(buckets_host[i].first_param < buckets_host[i - 1].first_param);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->g.act_dtype == B2_F32)
+        return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, B2_PART_ALL, st, buckets_host, n_buckets);
+    return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, B2_PART_ALL, st, buckets_host, n_buckets);
+}
+
 extern "C" int b2_unet_backward_parts(b2_unet_plan* plan, const float* const* params, const float* const* dlogits,
                                       void* workspace, float* const* grads, int32_t* has_grad_host, int parts,
                                       b2_stream_t stream) {
@@ -821,6 +854,24 @@ extern "C" int b2_unet_backward_parts(b2_unet_plan* plan, const float* const* pa
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->g.act_dtype == B2_F32) return backward_t<float>(plan, params, dlogits, workspace, grads, has_grad_host, parts, st);
     return backward_t<__nv_bfloat16>(plan, params, dlogits, workspace, grads, has_grad_host, parts, st);
+}
+
+// LwF (reference lwf:315-346): every stored task head differs from the running model only in the 1x1x1 `seg_outputs`
+// convolutions, so an old head's prediction is that head applied to the decoder activation the last forward left in the
+// workspace -- one 1x1x1 launch instead of one full network forward per head.
+extern "C" int b2_unet_head_forward(b2_unet_plan* plan, void* workspace, int level, const float* weight, float* logits,
+                                    b2_stream_t stream) {
+    B2_CHECK_ARG(plan && workspace && weight && logits && level >= 0 && level < plan->g.num_pool);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const Head& h : plan->heads) {
+        if (h.level != level) continue;
+        if (plan->g.act_dtype == B2_F32)
+            return seghead_fwd<float>(P<float>(workspace, plan, h.in, false), weight, logits, plan->g.batch, h.in.vox(), h.c,
+                                      plan->g.num_classes, h.in.pitch, st);
+        return seghead_fwd<__nv_bfloat16>(P<__nv_bfloat16>(workspace, plan, h.in, false), weight, logits, plan->g.batch, h.in.vox(),
+                                          h.c, plan->g.num_classes, h.in.pitch, st);
+    }
+    return fail(B2_EINVAL, "no head at level %lld%s", "", level);
 }
 
 extern "C" int b2_unet_num_convs(const b2_unet_plan* plan) { return plan ? (int)plan->conv_modules.size() : B2_EINVAL; }
@@ -918,17 +969,32 @@ extern "C" int b2_conv3d_make_shadow(const b2_conv_desc* d, const float* w_pt, v
     return weight_shadow_bf16(w_pt, d->cout, d->cin, (__nv_bfloat16*)shadow, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int b2_conv3d_fwd_shadow(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
-                                    b2_stream_t stream) {
-    B2_CHECK_ARG(d && x && shadow && z && d->dtype == B2_BF16);
+static int conv3d_fwd_shadow_impl(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
+                                  int epilogue_stats, cudaStream_t st) {
     ConvShape s = to_shape(d);
     if (!conv_tc_supported(s.cin, s.cout) || s.in_pitch % 8 != 0 || s.out_pitch % 8 != 0)
         return fail(B2_EUNSUPPORTED, "b2_conv3d_fwd_shadow: shape not covered by the tensor-core path%s", "");
     const int od = (s.d - 1) / s.stride[0] + 1, oh = (s.h - 1) / s.stride[1] + 1, ow = (s.w - 1) / s.stride[2] + 1;
     const size_t part_bytes = scratch ? b2_conv3d_scratch_bytes(d) - 2 * (size_t)27 * s.cin * s.cout * sizeof(float) - 256 : 0;
     float* part = scratch ? (float*)scratch + 2 * (size_t)27 * s.cin * s.cout : nullptr;
+    int stat_slots = 0;
     return conv_tc_launch((const __nv_bfloat16*)x, s.n, s.d, s.h, s.w, s.cin, s.in_pitch, (const __nv_bfloat16*)shadow, s.cout, bias,
-                          (__nv_bfloat16*)z, od, oh, ow, s.out_pitch, s.stride, 0, (cudaStream_t)stream, part, part_bytes);
+                          (__nv_bfloat16*)z, od, oh, ow, s.out_pitch, s.stride, 0, st, part, part_bytes,
+                          epilogue_stats && part ? &stat_slots : nullptr);
+}
+
+extern "C" int b2_conv3d_fwd_shadow(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z, void* scratch,
+                                    b2_stream_t stream) {
+    B2_CHECK_ARG(d && x && shadow && z && d->dtype == B2_BF16);
+    return conv3d_fwd_shadow_impl(d, x, shadow, bias, z, scratch, 0, (cudaStream_t)stream);
+}
+
+// the variant the training step runs: the same single launch, with the InstanceNorm partial sums (sum z, sum z^2 per
+// (n, c) and epilogue warp) produced by the convolution's epilogue into `scratch`
+extern "C" int b2_conv3d_fwd_shadow_stats(const b2_conv_desc* d, const void* x, const void* shadow, const float* bias, void* z,
+                                          void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(d && x && shadow && z && scratch && d->dtype == B2_BF16);
+    return conv3d_fwd_shadow_impl(d, x, shadow, bias, z, scratch, 1, (cudaStream_t)stream);
 }
 
 extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx,

@@ -65,3 +65,47 @@ def test_vit_unet_restatement_equals_reference_class():
     assert set(gold.files) == set(a)
     for k in gold.files:
         np.testing.assert_allclose(gold[k], a[k], rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("n_finished", [1, 2, 3])
+def test_rw_finish_task_restatement(n_finished):
+    """oracle.cl_losses.rw_finish_task == the reference's OWN lines rw/nnUNetTrainerRW.py:180-200, extracted from the
+    unmodified file and executed against a stand-in `self` (the trainer class itself needs nnunet's trainer stack)."""
+    import textwrap
+    import types
+    from oracle import cl_losses
+    src = open(os.path.join(REF, "nnunet_ext/training/network_training/rw/nnUNetTrainerRW.py")).read().splitlines()
+    lo = next(i for i, l in enumerate(src) if "Normalize the fisher values to be in range" in l)
+    hi = next(i for i, l in enumerate(src) if "Store the fisher and param values" in l and i > lo)
+    block = textwrap.dedent("\n".join(src[lo:hi]))
+    g = torch.Generator().manual_seed(3)
+    names = ["a.weight", "a.bias", "b.weight"]
+    shapes = [(4, 3, 3), (4,), (2, 5)]
+    tasks = ["A", "B", "C"][:n_finished]
+    cur = tasks[-1]
+    fisher = {t: {n: torch.rand(s, generator=g) for n, s in zip(names, shapes)} for t in tasks}
+    scores = {t: {n: 3 * torch.rand(s, generator=g) for n, s in zip(names, shapes)} for t in tasks}
+    me_f, me_s = cl_losses.rw_finish_task({k: v.clone() for k, v in fisher[cur].items()},
+                                          {k: v.clone() for k, v in scores[cur].items()}, n_finished)
+    self = types.SimpleNamespace(task=cur, fold=0, fisher=fisher, scores=scores,
+                                 already_trained_on={"0": {"finished_training_on": list(tasks)}})
+    exec(block, {"torch": torch, "EPSILON": 1e-8, "self": self})
+    for n in names:
+        assert torch.equal(self.fisher[cur][n], me_f[n]), n
+        assert torch.equal(self.scores[cur][n], me_s[n]), n
+
+
+def test_reference_own_multihead_test_passes_on_b200unet_multihead_module(tmp_path):
+    """the reference's test/network_architecture/test_MultiHead_Module.py, unmodified, with
+    ``nnunet_ext.network_architecture.MultiHead_Module`` resolved to b200unet's from-scratch mirror (nnunet_ext is a
+    namespace package: a directory earlier on sys.path that holds only that one module shadows the reference's)."""
+    import subprocess
+    d = tmp_path / "nnunet_ext" / "network_architecture"
+    d.mkdir(parents=True)
+    (d / "MultiHead_Module.py").write_text("from b200unet.MultiHead_Module import *  # noqa\n"
+                                           "from b200unet.MultiHead_Module import MultiHead_Module  # noqa\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), util.PKG, os.path.join(util.ROOT, "oracle", "shim"), REF]))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
+                        os.path.join(REF, "test", "network_architecture", "test_MultiHead_Module.py")],
+                       env=env, capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
