@@ -44,7 +44,14 @@ class PatchEmbed(nn.Module):
         if (gd * p, gh * p, gw * p) != (D, H, W):
             x = x[:, :, :gd * p, :gh * p, :gw * p]                         # Conv3d floor semantics
         tok = x.reshape(B, Cc, gd, p, gh, p, gw, p).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B, gd * gh * gw, Cc * p ** 3)
-        return F.linear(tok, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
+        out = F.linear(tok, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
+        if self.proj._forward_hooks:
+            # PLOP / POD hook every 'conv.Conv*' module (reference plop:330-353), the patch-embedding Conv3d included: hand
+            # the hooks what that module returns, (B, E, D/p, H/p, W/p)
+            conv_out = out.transpose(1, 2).reshape(B, -1, gd, gh, gw)
+            for hook in list(self.proj._forward_hooks.values()):
+                hook(self.proj, (x,), conv_out)
+        return out
 
 
 class Mlp(nn.Module):
