@@ -481,8 +481,7 @@ def run_ours(args, geom):
     e2e = patches / (ms_e2e / 1e3)
     e2e_pf = patches / (ms_e2e_pf / 1e3)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     peaks = load_peaks()
     gflop_patch = 3 * geom.fwd_flops_per_patch() / 1e9
@@ -521,9 +520,18 @@ def run_ours(args, geom):
         line["cpu_baseline"] = {"value": geom.batch / ts[0], "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "1 timed step (after 1 warm-up) of the full workload batch (B=%d), oracle port of the "
                                           "reference step (PyTorch CPU fp32 eager, %d threads)" % (geom.batch, os.cpu_count())}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """leave without tearing NCCL down: destroying a process group whose collectives were captured in CUDA graphs can
+    block at exit; every rank has produced its result by now, so synchronise and exit hard"""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

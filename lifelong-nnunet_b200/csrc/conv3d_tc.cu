@@ -334,9 +334,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // store + InstanceNorm partial sums of the fp32 values
                     float f[32], sq[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        f[e] = __uint_as_float(v[e]);
-                        if (bias) f[e] += bias[chan0 + c0 + e];
+                    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                    if (bias) {     // 16-byte loads (chan0 + c0 is a multiple of 32)
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + chan0 + c0);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 b = __ldg(b4 + e);
+                            f[4 * e] += b.x; f[4 * e + 1] += b.y; f[4 * e + 2] += b.z; f[4 * e + 3] += b.w;
+                        }
                     }
                     if (valid) {
 #pragma unroll
@@ -362,9 +367,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; j += 8) {
                         float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            f[e] = __uint_as_float(v[j + e]);
-                            if (bias) f[e] += bias[chan0 + c0 + j + e];
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+                        if (bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias + chan0 + c0 + j);
+                            const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                         }
                         if (accumulate) {
                             float o[8];

@@ -9,7 +9,12 @@
 // tcgen05.mma M = 128 (16 h x 8 w), K = 16, N = 3 * BN: the three kd taps of a (kh, kw) pair are ONE instruction that
 // updates the accumulators of the output slabs d-1, d, d+1 (consecutive slots of a 16-slot TMEM ring) -- see the comment
 // above conv_halo_kernel.  Warp roles: 0 slab producer, 1 MMA issuer, 2..5 epilogue (bias, bf16 store, InstanceNorm
-// partial sums), 6 weight producer.
+// partial sums), 6 weight producer, 7..10 a second epilogue set.  ncu (profiles/r02_ncu_halo32_source.txt) showed the round-1
+// kernel EPILOGUE-bound: the four epilogue warps were busy 85 % of the time (47 % of that in the per-slab 32 x 32
+// transpose-reductions of the InstanceNorm sums, 28 % in the TMEM load + 32 scalar bias loads) while the MMA warp waited
+// 45 % of its time.  Now (i) two epilogue sets drain alternate output slabs, (ii) for BN = 32 every thread keeps running
+// per-column sums of its own voxel row in registers and the cross-lane reduction happens ONCE per (CTA, sample), (iii) the
+// bias is loaded with 16-byte loads.
 #include <string.h>
 
 #include "kernels.h"
@@ -30,9 +35,10 @@ struct HaloParams {
     int merge;            // 1: the three kd taps of a (kh, kw) pair are ONE tcgen05.mma of N = 3*BN (see below)
     uint32_t idesc, idesc2, idesc3;   // instruction descriptors for N = BN, 2*BN, 3*BN
     uint32_t tmem_cols;
+    int dbg;              // probe switches (b2_set_option("halo_dbg")): 1 no global stores, 2 no MMA issue, 4 no TMA slab loads, 8 no TMEM loads, 16 empty epilogue, 32 arrive instead of commit, 64 no tempty wait
 };
 
-constexpr int HALO_THREADS = 224;  // warp 0: slab producer, 1: MMA, 2..5: epilogue, 6: weight producer
+constexpr int HALO_THREADS = 352;  // warp 0: slab producer, 1: MMA, 2..5: epilogue set 0, 6: weight producer, 7..10: epilogue set 1
 constexpr int HALO_MAX_SLOTS = 6;
 constexpr int HALO_MAX_ACC = 16;
 
@@ -67,7 +73,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < p.nslot; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], 1); }
         mbar_init(&wfull, 1);
-        for (int a = 0; a < p.nacc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+        for (int a = 0; a < p.nacc; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }   // one arrive per epilogue warp
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -98,6 +104,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 decode(item, n, h0, w0, d0, d1);
                 for (int s = d0 - 1; s <= d1; ++s) {
                     mbar_wait(&sempty[slot], ph ^ 1);
+                    if (p.dbg & 4) { mbar_arrive(&sfull[slot]); if (++slot == p.nslot) { slot = 0; ph ^= 1; } continue; }
                     mbar_expect_tx(&sfull[slot], SLAB_BYTES);
                     uint8_t* base = slabs + (size_t)slot * SLAB_BYTES;
 #pragma unroll
@@ -139,11 +146,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // output s+1 starts with this slab (kd = 0): its accumulator must have been drained
                     const bool v0 = (s + 1 >= d0) && (s + 1 < d1), v1 = (s >= d0) && (s < d1), v2 = (s - 1 >= d0) && (s - 1 < d1);
                     const uint32_t oc0 = ocb + (uint32_t)(s + 1 - d0), oc1 = oc0 - 1, oc2 = oc0 - 2;
-                    if (v0) mbar_wait(&tempty[oc0 & amask], ((oc0 >> p.nacc_log2) & 1) ^ 1);
+                    if (v0 && !(p.dbg & 64)) mbar_wait(&tempty[oc0 & amask], ((oc0 >> p.nacc_log2) & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_base = slab_lo0 + (uint32_t)slot * SLAB16;
-                        if (p.merge && v0 && v1 && v2 && (oc0 & amask) >= 2) {
+                        if (p.dbg & 2) {
+                        } else if (p.merge && v0 && v1 && v2 && (oc0 & amask) >= 2) {
                             const uint32_t d2 = tmem_base + (oc2 & amask) * (uint32_t)p.BN;
                             const uint32_t d0t = d2 + 2u * (uint32_t)p.BN;
 #pragma unroll
@@ -207,8 +215,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 }
                             }
                         }
-                        umma_commit(&sempty[slot]);                        // slab fully consumed
-                        if (v2) umma_commit(&tfull[oc2 & amask]);          // output s-1 complete (its kd = 2 taps were the last)
+                        if (p.dbg & 32) {      // probe: plain arrives instead of tcgen05.commit (only meaningful with the MMAs off)
+                            mbar_arrive(&sempty[slot]);
+                            if (v2) mbar_arrive(&tfull[oc2 & amask]);
+                        } else {
+                            umma_commit(&sempty[slot]);                        // slab fully consumed
+                            if (v2) umma_commit(&tfull[oc2 & amask]);          // output s-1 complete (its kd = 2 taps were the last)
+                        }
                     }
                     __syncwarp();
                     if (++slot == p.nslot) { slot = 0; sph ^= 1; }
@@ -217,16 +230,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
+        // ===================== epilogue (two sets of four warps; set e drains the output slabs with oc % 2 == e) ================
+        const int eset = warp >= 7 ? 1 : 0;
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int r = q * 32 + lane;
         const int w_ = r & 7, h_ = r >> 3;
         uint32_t oc = 0;   // running output counter: accumulator oc & amask, phase (oc >> nacc_log2) & 1
-        // InstanceNorm statistics of the produced tensor (fp32 accumulator values, before the bf16 rounding): lane = column
-        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+        // InstanceNorm statistics of the produced tensor (fp32 accumulator values, before the bf16 rounding)
+        const bool fast = es.part != nullptr && p.BN == 32;   // per-thread running sums, one reduction per (CTA, sample)
+        float s1[32], s2[32];                                 // fast: column sums of THIS thread's voxel row
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};   // generic: lane = column
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
         int n_cur = -1, n_done = 0;
-        const int st_slot = ((int)blockIdx.x / p.NS) * 4 + q;
+        const int st_slot = ((int)blockIdx.x / p.NS) * 8 + eset * 4 + q;
         auto st_write = [&](int nn, bool zero) {
+            if (fast) {
+                float a1 = 0.f, a2 = 0.f;
+                if (!zero) { a1 = transpose_reduce32(s1, lane); a2 = transpose_reduce32(s2, lane); }
+                *reinterpret_cast<float2*>(es.part + (((long long)nn * es.slots + st_slot) * es.C + cs * p.BN + lane) * 2) = make_float2(a1, a2);
+                return;
+            }
             for (int ch = 0; ch < p.BN / 32; ++ch) {
                 float a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -244,27 +268,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 n_done = n; n_cur = n;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) { st1[ch] = 0.f; st2[ch] = 0.f; }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
             }
             const int oh = h0 + h_, ow = w0 + w_;
             const bool valid = oh < p.H && ow < p.W;
             for (int od = d0; od < d1; ++od, ++oc) {
+                if ((int)(oc & 1u) != eset) continue;
                 const uint32_t acc = oc & amask;
                 __nv_bfloat16* row = dst + ((((long long)n * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + cs * p.BN;
                 mbar_wait(&tfull[acc], (oc >> p.nacc_log2) & 1);
                 tc_fence_after();
+                if (p.dbg & 16) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty[acc]); continue; }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < p.BN; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    tmem_ld_wait();
-                    float f[32];
+                    if (p.dbg & 8) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        f[e] = __uint_as_float(v[e]);
-                        if (bias) f[e] += bias[cs * p.BN + c0 + e];
+                        for (int e = 0; e < 32; ++e) v[e] = 0u;
+                    } else {
+                        tmem_ld32(taddr + c0, v);
                     }
-                    if (valid) {
+                    float f[32];
+                    if (bias) {     // (issued under the TMEM load's latency; 16-byte loads, L1-resident)
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + cs * p.BN + c0);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 b = __ldg(b4 + e);
+                            f[4 * e] = b.x; f[4 * e + 1] = b.y; f[4 * e + 2] = b.z; f[4 * e + 3] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) f[e] = 0.f;
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) f[e] += __uint_as_float(v[e]);
+                    if (valid && !((p.dbg & 1) && f[0] != 12345.f)) {
 #pragma unroll
                         for (int jj = 0; jj < 32; jj += 8) {
                             float o8[8];
@@ -279,7 +320,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             store8(row + c0 + jj, o8);
                         }
                     }
-                    if (es.part) {
+                    if (fast) {
+                        if (valid) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) { s1[e] += f[e]; s2[e] = fmaf(f[e], f[e], s2[e]); }
+                        }
+                    } else if (es.part) {
                         float sq[32];
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
@@ -293,8 +339,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (k == ch) { st1[k] += a1; st2[k] += a2; }
                     }
                 }
+                // one elected arrive per warp: 128 per-thread arrives on one mbarrier word are 128 serialised shared-memory
+                // atomics per slab, on the port the MMA operand reads saturate
                 tc_fence_before();
-                mbar_arrive(&tempty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
             }
         }
         if (es.part) {
@@ -313,6 +362,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int KC, int BN);
 
 int g_halo_merge = 1;
+int g_halo_dbg = 0;
 int g_epi_stats = 1;      // InstanceNorm statistics from the convolution epilogues (no second pass over z)
 int g_halo_nsplit = 1;   // allow splitting the output channels over CTA classes when the weights do not fit
 
@@ -381,6 +431,7 @@ int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, in
     B2_CHECK_ARG(src_pitch % 8 == 0 && dst_pitch % 8 == 0);
     p.dst_pitch = dst_pitch;
     p.w_pitch = w_pitch; p.w_row0 = w_row0;
+    p.dbg = g_halo_dbg;
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, src, N, D, H, W, K, src_pitch, K, 1, 1, 18, 8, 1, 1, 1);
     if (rc) return rc;
@@ -391,7 +442,7 @@ int conv_tc_halo_launch(const __nv_bfloat16* src, int N, int D, int H, int W, in
     EpiStats es{nullptr, 0, Nout, N};
     if (stat_slots) *stat_slots = 0;
     if (stat_part && stat_slots && g_epi_stats) {
-        es.slots = grid / p.NS * 4;
+        es.slots = grid / p.NS * 8;   // one slot per epilogue warp (two sets of four)
         if ((size_t)N * es.slots * Nout * 2 <= stat_part_floats) { es.part = stat_part; *stat_slots = es.slots; }
     }
     static bool a32 = false, a64 = false;

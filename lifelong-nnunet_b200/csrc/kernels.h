@@ -100,6 +100,7 @@ int first_layer_patches(const __nv_bfloat16* x, int N, int D, int H, int W, int 
 size_t first_layer_wgrad_part_floats(int N, int D, int H, int W, int cout);
 int first_layer_wgrad_tc(const __nv_bfloat16* P, const __nv_bfloat16* dz, int N, int D, int H, int W, int cin, int cout, int dz_pitch,
                          float* part, float* dw, float* dbias, cudaStream_t st);
+extern int g_halo_dbg;
 extern int g_use_halo, g_halo_merge, g_halo_nsplit, g_dgrad_one_launch, g_dgrad_mes, g_epi_stats;
 extern int g_wgrad_desc_mode, g_tc_wgrad, g_wgrad_dmerge, g_wgrad_direct, g_wgrad_halo;
 extern int g_use_tc;   // 1: tensor-core path for bf16 plans where supported (default), 0: SIMT only

@@ -753,6 +753,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "wgrad_direct")) { g_wgrad_direct = value; return B2_OK; }
     if (!strcmp(name, "wgrad_dmerge")) { g_wgrad_dmerge = value; return B2_OK; }
     if (!strcmp(name, "halo_merge")) { g_halo_merge = value; return B2_OK; }
+    if (!strcmp(name, "halo_dbg")) { g_halo_dbg = value; return B2_OK; }
     if (!strcmp(name, "halo_nsplit")) { g_halo_nsplit = value; return B2_OK; }
     if (!strcmp(name, "epi_stats")) { g_epi_stats = value; return B2_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value; return B2_OK; }
