@@ -97,7 +97,17 @@ class nnUNetTrainerMultiHead:
         self.use_vit, self.vit_version, self.vit_type = use_vit, vit_version, vit_type   # run_training.py --use_vit
         self.precision = precision
         self.batch_dice = batch_dice
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self.extension = getattr(type(self), "EXTENSION", "multihead")      # utilities/ext_map.py
+        self.fold = 0
+        self.already_trained_on = {"0": {"finished_training_on": [], "start_training_on": None, "fisher_at": None,
+                                         "params_at": None, "scores_at": None, "checkpoint_should_exist": False,
+                                         "tasks_at_time_of_checkpoint": [], "active_task_at_time_of_checkpoint": None}}
+        self._init_kwargs = dict(precision=precision, batch_dice=batch_dice, initial_lr=initial_lr, weight_decay=weight_decay,
+                                 max_num_epochs=max_num_epochs, seed=seed, task=task, use_vit=use_vit, vit_version=vit_version,
+                                 vit_type=vit_type, split=split, transfer_heads=transfer_heads, strict_reference=strict_reference)
         self.ddp = ddp
         self.initial_lr, self.weight_decay, self.max_num_epochs = initial_lr, weight_decay, max_num_epochs
         self.seed, self.task = seed, task
@@ -130,6 +140,25 @@ class nnUNetTrainerMultiHead:
         self.mh_network = MultiHead_Module(type(self.network), self.split, self.task, prev_trainer=self.network)
         self.network = self.mh_network.model
 
+    # -- checkpoints (reference MultiHead:1164-1313; formats in checkpoint.py) ------------------------------------------------
+    def init_args(self):
+        return dict(geometry=self.geometry, **self._init_kwargs)
+
+    def save_checkpoint(self, fname, save_optimizer=True):
+        from . import checkpoint
+        checkpoint.save_checkpoint(self, fname, save_optimizer)
+
+    def load_checkpoint(self, fname, train=True):
+        from . import checkpoint
+        return checkpoint.load_checkpoint(self, fname, train)
+
+    def finish_training_on(self, task=None):
+        """bookkeeping of MultiHead.run_training :575-590"""
+        t = self.task if task is None else task
+        ft = self.already_trained_on[str(self.fold)]["finished_training_on"]
+        if t not in ft:
+            ft.append(t)
+
     def start_task(self, task):
         """reference MultiHead.run_training :541-564: a new task gets a head (initialised from the first split, or from
         the last trained head with transfer_heads) and the running model is assembled for it"""
@@ -137,6 +166,7 @@ class nnUNetTrainerMultiHead:
             self.mh_network.add_new_task(task, use_init=not self.transfer_heads)
         self.network = self.mh_network.assemble_model(task)
         self.task = task
+        self.already_trained_on[str(self.fold)]["start_training_on"] = task
         self._steps = {}
 
     # -- reference MultiHead:294-301 ---------------------------------------------------------------------------------
@@ -378,10 +408,21 @@ class nnUNetTrainerMultiHead:
 
 class nnUNetTrainerSequential(nnUNetTrainerMultiHead):
     """Plain sequential fine-tuning baseline (BASELINE.json config 1): the MultiHead iteration as is."""
+    EXTENSION = "sequential"
 
 
 # ------------------------------------------------------------------------------------------------------------------------
 class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
+    EXTENSION = "ewc"
+
+    def save_importance(self, path):
+        from . import checkpoint
+        checkpoint.save_importance(self, path)
+
+    def load_importance(self, path):
+        from . import checkpoint
+        checkpoint.load_importance(self, path)
+
     def __init__(self, *a, ewc_lambda=0.4, **kw):
         super().__init__(*a, **kw)
         self.ewc_lambda = ewc_lambda
@@ -471,8 +512,130 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
         self._steps = {}
 
 
+class _MaskedEWC(nnUNetTrainerEWC):
+    """EWC restricted to name-matched parameters (reference ewc_vit / ewc_ln / ewc_unet: `EWCLoss(..., True, MATCH,
+    MATCH_TRUE)`), SURVEY 8(f) rank 3.  After every iteration the reference hands the loss a LIST of the selected
+    parameters (ewc_vit:68-69), so -- unlike plain EWC (Q1) -- every stored task is penalised; `after_train` drops the
+    Fisher / parameter entries outside the mask (ewc_vit:79-88)."""
+    MATCH, MATCH_TRUE = ['ViT'], True
+
+    def initialize_loss(self):
+        self.loss = ds.MultipleOutputLossEWC(self._base_loss(), self.ds_loss_weights, self.ewc_lambda, self.fisher, self.params,
+                                             self._net_params(), True, list(self.MATCH), self.MATCH_TRUE)
+
+    def _selected(self, name):
+        return ds._match(name, True, self.MATCH, self.MATCH_TRUE)
+
+    def _net_params(self):
+        return [(n, p) for n, p in self.network.named_parameters() if self._selected(n)]
+
+    def _fused_spec(self):
+        key, spec = super()._fused_spec()
+        names = self._penalty_names()
+        tasks = list(self.loss.tasks)            # a list is handed over: no generator exhaustion
+        spec['penalty'] = [(self.loss.ewc_lambda / 2, self.fisher[t], self.params[t], None, names) for t in tasks] if names else []
+        return ("ewc-masked", tuple(tasks), tuple(id(self.fisher[t]) for t in tasks), len(names), float(self.loss.ewc_lambda)), spec
+
+    def _penalty_after_backward(self):
+        return self.loss.penalty_into_grads(self.loss.ewc_lambda / 2)
+
+    def after_train(self, data_generator, num_batches=1):
+        super().after_train(data_generator, num_batches)
+        for d in (self.fisher, self.params):
+            for task in list(d.keys()):
+                for key in list(d[task].keys()):
+                    if not self._selected(key):
+                        del d[task][key]
+        self.loss.update_ewc_params(self.fisher, self.params)
+        self.loss.update_network_params(self._net_params())
+
+
+class nnUNetTrainerEWCViT(_MaskedEWC):
+    """reference ewc_vit/nnUNetTrainerEWCViT.py:33-88 -- EWC on the ViT parameters only"""
+    MATCH, MATCH_TRUE = ['ViT'], True
+
+
+class nnUNetTrainerEWCLN(_MaskedEWC):
+    """reference ewc_ln/nnUNetTrainerEWCLN.py:33-98 -- EWC on the ViT's LayerNorm parameters only"""
+    MATCH, MATCH_TRUE = ['ViT', 'norm'], True
+
+
+class nnUNetTrainerEWCUNet(_MaskedEWC):
+    """reference ewc_unet/nnUNetTrainerEWCUNet.py:33-90 -- EWC on everything except the ViT"""
+    MATCH, MATCH_TRUE = ['ViT'], False
+
+
+class _FreezeAfterFirstTask(nnUNetTrainerMultiHead):
+    """reference frozen_vit / frozen_unet / frozen_nonln `run_training` (:28-62): when the SECOND task starts, the selected
+    parameters are frozen for good (running model, body and first head share the Parameter objects here)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.frozen = False
+
+    def _freeze(self, name):
+        raise NotImplementedError
+
+    def start_task(self, task):
+        if not self.frozen and len(self.mh_network.heads) == 1 and task not in self.mh_network.heads:
+            for mod in (self.network, self.mh_network.body, self.mh_network.heads[list(self.mh_network.heads.keys())[0]]):
+                for name, param in mod.named_parameters():
+                    if self._freeze(name):
+                        param.requires_grad = False
+            self.frozen = True
+        super().start_task(task)
+
+
+class nnUNetTrainerFrozenViT(_FreezeAfterFirstTask):
+    def _freeze(self, name):
+        return 'ViT' in name                                    # frozen_vit:36-39
+
+
+class nnUNetTrainerFrozenUNet(_FreezeAfterFirstTask):
+    def _freeze(self, name):
+        return 'ViT' not in name                                # frozen_unet:36-40
+
+
+class nnUNetTrainerFrozenNonLN(_FreezeAfterFirstTask):
+    def _freeze(self, name):
+        return 'norm' not in name or 'ViT' not in name          # frozen_nonln:36-43: everything but the ViT's LayerNorms
+
+
+class nnUNetTrainerFrozEWC(nnUNetTrainerEWCViT):
+    """reference froz_ewc/nnUNetTrainerFrozEWC.py:81-161: the ViT is frozen on every second task and EWC-regularised on the
+    others; `adaptive` scales the EWC weight by e^(-1/3) while the ViT is frozen (:107,:117)."""
+
+    def __init__(self, *a, adaptive=False, **kw):
+        super().__init__(*a, **kw)
+        self.adaptive = adaptive
+
+    def freeze_ViT(self, freeze):
+        for mod in (self.network, self.mh_network.body, self.mh_network.heads[list(self.mh_network.heads.keys())[0]]):
+            for name, param in mod.named_parameters():
+                if 'ViT' in name:
+                    param.requires_grad = not freeze
+
+    def start_task(self, task):
+        n_heads, known = len(self.mh_network.heads), task in self.mh_network.heads
+        freeze = (not known) if n_heads % 2 == 1 else known     # froz_ewc:92-130
+        self.freeze_ViT(freeze)
+        if self.adaptive:
+            self.loss.ewc_lambda = self.ewc_lambda * math.exp(-1 / 3) if freeze else self.ewc_lambda
+        super().start_task(task)
+
+
 # ------------------------------------------------------------------------------------------------------------------------
 class nnUNetTrainerRW(nnUNetTrainerMultiHead):
+    EXTENSION = "rw"
+
+    def save_importance(self, path):
+        from . import checkpoint
+        checkpoint.save_importance(self, path)
+
+    def load_importance(self, path):
+        from . import checkpoint
+        checkpoint.load_importance(self, path)
+
     def __init__(self, *a, rw_lambda=0.4, rw_alpha=0.9, fisher_update_after=10, **kw):
         super().__init__(*a, **kw)
         self.rw_lambda, self.alpha, self.fisher_update_after = rw_lambda, rw_alpha, fisher_update_after

@@ -78,40 +78,45 @@ __global__ void __launch_bounds__(256) norm_fwd_kernel(const T* __restrict__ z, 
 }
 
 // sums[n][c] = {S1, S2} from the per-slab partials; dgamma[c] = sum_n S2; dbeta[c] = sum_n S1.
-// One WARP per channel (8 channels per block): lanes stride the slabs with independent loads in flight, double
-// accumulation, fixed xor-shuffle tree => bit-reproducible.  (The first version gave a channel 8 serial lanes inside a
-// single block per 32 channels: 17 us of pure load latency per layer.)
+// One BLOCK (8 warps) per channel: threads stride the slabs with independent loads in flight, double accumulation, fixed
+// xor-shuffle tree per warp and a fixed-order sum over the warps => bit-reproducible.  (Round 1: one warp per channel, four
+// blocks per launch at c = 32: 13 us of serialised L2 round trips per layer.)
 __global__ void __launch_bounds__(256) norm_bwd_finalize_kernel(const float* __restrict__ part, int n, int slabs, int c,
                                                                 float* __restrict__ sums, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta) {
     pdl_grid_sync();
-    const int cc = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (cc >= c) return;
+    __shared__ double sh1[8], sh2[8];
+    const int cc = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double g = 0.0, b = 0.0;
     for (int nn = 0; nn < n; ++nn) {
         double s1 = 0.0, s2 = 0.0;
         const float* p = part + ((long long)nn * slabs * c + cc) * 2;
-        // batches of 8 independent loads (a plain `s += load` loop compiles to one exposed L2 round trip per element)
-        for (int t0 = lane; t0 < slabs; t0 += 256) {
-            float2 v[8];
+        for (int t0 = threadIdx.x; t0 < slabs; t0 += 1024) {
+            float2 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = t0 + 32 * u;
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + 256 * u;
                 v[u] = t < slabs ? *reinterpret_cast<const float2*>(p + (long long)t * c * 2) : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
+            for (int u = 0; u < 4; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
         }
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-        if (lane == 0) {
-            sums[((long long)nn * c + cc) * 2] = (float)s1;
-            sums[((long long)nn * c + cc) * 2 + 1] = (float)s2;
+        __syncthreads();
+        if (lane == 0) { sh1[warp] = s1; sh2[warp] = s2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { a1 += sh1[w]; a2 += sh2[w]; }
+            sums[((long long)nn * c + cc) * 2] = (float)a1;
+            sums[((long long)nn * c + cc) * 2 + 1] = (float)a2;
+            b += a1;
+            g += a2;
         }
-        b += s1;
-        g += s2;
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         if (dgamma) dgamma[cc] = (float)g;
         if (dbeta) dbeta[cc] = (float)b;
     }
@@ -492,7 +497,7 @@ static int norm_bwd_launch(const T* z, const T* y, const T* dy, const float* sta
     dim3 grid(slabs, n);
     B2_LAUNCH((norm_bwd_reduce_kernel<T, VW, RC, ROWS>), grid, 256, sh, st, z, y, dy, stats, gamma, beta, slabs, vox, c, z_pitch, y_pitch,
               dy_pitch, slope, part);
-    B2_LAUNCH(norm_bwd_finalize_kernel, cdiv(c, 8), 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
+    B2_LAUNCH(norm_bwd_finalize_kernel, c, 256, 0, st, part, n, slabs, c, sums, dgamma, dbeta);
     const dim3 g2 = apply_grid(n, vox, c / VW);
     const float inv_v = (float)(1.0 / (double)vox);
     B2_LAUNCH((norm_bwd_apply_kernel<T, VW, RC, ROWS>), g2, 256, 0, st, z, y, dy, stats, gamma, beta, sums, dz, n, vox, c, z_pitch, y_pitch,

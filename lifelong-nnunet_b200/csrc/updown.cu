@@ -6,6 +6,8 @@
 // nnunet's Generic_UNet (Appendix A); forward order restated at reference generic_ViT_UNet.py:261-286.  The transposed
 // convolution writes straight into the channel slice [0,Cout) of the concat buffer (pitch 2*Cout), which removes
 // torch.cat (generic_ViT_UNet.py:263).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -318,6 +320,48 @@ __global__ void __launch_bounds__(256) seghead_dgrad_kernel(const float* __restr
     }
 }
 
+// dy = w^T dlogits for c % 16 == 0: one thread per (voxel, 16-channel block).  lane = voxel => the NCDHW dlogits are read
+// with coalesced 128-byte loads (one per class), the 16 x ncls weights sit in registers, no 64-bit division anywhere
+// (grid.y = sample, grid.z = channel block).  Round 1's kernel was instruction-bound: four threads per voxel, each with
+// two 64-bit div / mod per element (71 us for the full-resolution head against a 25 us HBM floor).
+template <typename T, int NCLS>
+__global__ void __launch_bounds__(256, 3) seghead_dgrad32_kernel(const float* __restrict__ w, const float* __restrict__ dl,
+                                                              T* __restrict__ dy, int accumulate, int vox, int c, int dy_pitch) {
+    pdl_grid_sync();
+    const int nn = blockIdx.y, cb = blockIdx.z;
+    float wr[NCLS][16];
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wr[k][j] = __ldg(w + k * c + cb * 16 + j);
+    const float* dln = dl + (long long)nn * NCLS * vox;
+    T* dyn = dy + (long long)nn * vox * dy_pitch + cb * 16;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < vox; v += gridDim.x * 256) {
+        float d[NCLS];
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) d[k] = dln[(long long)k * vox + v];
+        T* p = dyn + (long long)v * dy_pitch;
+#pragma unroll
+        for (int j0 = 0; j0 < 16; j0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k) a = fmaf(d[k], wr[k][j0 + j], a);
+                acc[j] = a;
+            }
+            if (accumulate) {
+                float o[8];
+                load8(p + j0, o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += o[j];
+            }
+            store8(p + j0, acc);
+        }
+    }
+}
+
 // dw[k][c] partial per (slab, sample): thread = (channel group of VW, row lane); VW-wide vector loads of y.
 // grid = (slabs, n): a slab never straddles two samples, so the loop carries no 64-bit division.
 template <typename T, int VW>
@@ -476,7 +520,14 @@ int seghead_bwd(const T* y, const float* w, const float* dlogits, T* dy, int acc
         long long grid = (total + 255) / 256;
         long long cap = (long long)num_sms() * 16;
         if (grid > cap) grid = cap;
-        if (v8) B2_LAUNCH((seghead_dgrad_kernel<T, 8>), (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
+        if (v8 && c % 16 == 0 && ncls >= 2 && ncls <= 4 && vox < (1LL << 31) && !std::is_same<T, float>::value) {
+            long long gx = (vox + 255) / 256, capx = (long long)num_sms() * 12 / (n * (c / 16)) + 1;
+            if (gx > capx) gx = capx;
+            dim3 g3((unsigned)gx, n, c / 16);
+            if (ncls == 2) B2_LAUNCH((seghead_dgrad32_kernel<T, 2>), g3, 256, 0, st, w, dlogits, dy, accumulate, (int)vox, c, dy_pitch);
+            else if (ncls == 3) B2_LAUNCH((seghead_dgrad32_kernel<T, 3>), g3, 256, 0, st, w, dlogits, dy, accumulate, (int)vox, c, dy_pitch);
+            else B2_LAUNCH((seghead_dgrad32_kernel<T, 4>), g3, 256, 0, st, w, dlogits, dy, accumulate, (int)vox, c, dy_pitch);
+        } else if (v8) B2_LAUNCH((seghead_dgrad_kernel<T, 8>), (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
         else B2_LAUNCH((seghead_dgrad_kernel<T, 1>), (int)grid, 256, (size_t)ncls * c * sizeof(float), st, w, dlogits, dy, accumulate, n, vox, c, ncls, dy_pitch);
     }
     if (dw) {
