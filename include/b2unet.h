@@ -148,6 +148,42 @@ int b2_unet_conv_output(const b2_unet_plan* plan, void* workspace, int conv_idx,
 int b2_unet_debug_view(const b2_unet_plan* plan, void* workspace, int block_idx, int which, b2_act_view* out);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Vision Transformer of Generic_ViT_UNet V1 (network_architecture/vision_transformer.py:218-458; hybrid forward
+ * generic_ViT_UNet.py:217-287): 3D patch embedding (Conv3d k = s = patch, :43-50,70-78) of the first skip, class token +
+ * position embedding (:423-428), `depth` pre-norm blocks (LayerNorm, qkv, softmax attention, proj, LayerNorm, fc1-GELU-fc2,
+ * :186-198), final LayerNorm, class token -> Linear(embed -> out_features) (:436-458); the result IS the bottleneck
+ * activation of the U-Net (`x.reshape(size)`, generic_ViT_UNet.py:253).  bf16 operands, fp32 accumulation / residual stream.
+ * params / grads: device pointers in named_parameters() order of the reference module: cls_token, pos_embed_0,
+ * blocks.layer.i.{norm1.weight, norm1.bias, attn.qkv.weight, attn.qkv.bias, attn.proj.weight, attn.proj.bias, norm2.weight,
+ * norm2.bias, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias} (i < depth), norm.weight, norm.bias,
+ * patch_embeds.0.proj.weight, patch_embeds.0.proj.bias, heads.0.weight, heads.0.bias  (b2_vit_num_params entries).
+ * forward: skip0 = NDHWC bf16 view of the ViT input (a plan activation, b2_unet_debug_view(1, 1)); the output goes to
+ * `out_view` (NDHWC view of the bottleneck activation, debug view (2*num_pool+1, 1)) and / or `out_dense` ([B][F] fp32).
+ * backward: d(output) from `dout_view` (debug view (2*num_pool+1, 2)) or `dout_dense`; parameter gradients OVERWRITTEN;
+ * the input gradient is ADDED into `dskip0` (debug view (1, 2)) when given.  Fixed-order reductions: bit-reproducible.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct b2_vit_desc {
+    int32_t batch, in_channels, D, H, W;     /* ViT input: first skip of the U-Net */
+    int32_t patch;                            /* cubic patch edge (generic_ViT_UNet.py:148) */
+    int32_t embed, heads, depth, mlp_ratio;   /* 768 / 12 / 12 / 4 for 'base' (generic_ViT_UNet.py:64-66) */
+    int32_t out_features;                     /* == out_c * out_d * out_h * out_w */
+    int32_t out_c, out_d, out_h, out_w;       /* bottleneck activation */
+    float   ln_eps;                           /* 1e-6 */
+} b2_vit_desc;
+typedef struct b2_vit_plan b2_vit_plan;
+int b2_vit_plan_create(const b2_vit_desc* desc, b2_vit_plan** out);
+void b2_vit_plan_destroy(b2_vit_plan* plan);
+size_t b2_vit_workspace_bytes(const b2_vit_plan* plan);
+int b2_vit_num_params(const b2_vit_plan* plan);
+/* byte offset inside the workspace of the patch-embedding output [B * tokens][embed] bf16 (what a forward hook on the
+ * patch-embedding Conv3d observes, plop:330-353) */
+size_t b2_vit_tokens_offset(const b2_vit_plan* plan);
+int b2_vit_forward(b2_vit_plan* plan, const float* const* params, const b2_act_view* skip0, void* workspace,
+                   const b2_act_view* out_view, float* out_dense, int keep_for_backward, b2_stream_t stream);
+int b2_vit_backward(b2_vit_plan* plan, const float* const* params, const b2_act_view* dout_view, const float* dout_dense,
+                    void* workspace, const b2_act_view* dskip0, float* const* grads, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Deep-supervision Dice+CE loss, value and gradient in one sweep.  Replaces nnunet MultipleOutputLoss2(DC_and_CE_loss
  * ({'batch_dice':..,'smooth':1e-5,'do_bg':False},{})) built at MultiHead:1385-1386.
  * logits: (B,C,V) fp32; target: (B,1,V) fp32 class ids; weight = ds weight of this level; dlogits (nullable) gets

@@ -46,6 +46,13 @@ class SgdEntry(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("grad", C.c_void_p), ("momentum", C.c_void_p), ("numel", C.c_int64)]
 
 
+class VitDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("in_channels", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("patch", C.c_int32), ("embed", C.c_int32), ("heads", C.c_int32), ("depth", C.c_int32), ("mlp_ratio", C.c_int32),
+                ("out_features", C.c_int32), ("out_c", C.c_int32), ("out_d", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+                ("ln_eps", C.c_float)]
+
+
 class GradBucket(C.Structure):
     _fields_ = [("first_param", C.c_int32), ("event_main", C.c_void_p), ("event_side", C.c_void_p)]
 
@@ -82,6 +89,13 @@ SIGNATURES = {
     "b2_unet_conv_name": (_I, [_VP, _I, C.c_char_p]),
     "b2_unet_conv_output": (_I, [_VP, _VP, _I, C.POINTER(ActView)]),
     "b2_unet_debug_view": (_I, [_VP, _VP, _I, _I, C.POINTER(ActView)]),
+    "b2_vit_plan_create": (_I, [C.POINTER(VitDesc), C.POINTER(_VP)]),
+    "b2_vit_plan_destroy": (None, [_VP]),
+    "b2_vit_workspace_bytes": (_SZ, [_VP]),
+    "b2_vit_num_params": (_I, [_VP]),
+    "b2_vit_tokens_offset": (_SZ, [_VP]),
+    "b2_vit_forward": (_I, [_VP, _VP, C.POINTER(ActView), _VP, C.POINTER(ActView), _VP, _I, _VP]),
+    "b2_vit_backward": (_I, [_VP, _VP, C.POINTER(ActView), _VP, _VP, C.POINTER(ActView), _VP, _VP]),
     "b2_dsloss_scratch_bytes": (_SZ, [_I, _I, _I64]),
     "b2_dsloss_fwd_bwd": (_I, [_VP, _VP, _I, _I, _I64, _F, _I, _F, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "b2_quadpen_scratch_bytes": (_SZ, [_I, _I64]),

@@ -192,8 +192,14 @@ class Generic_ViT_UNet(Generic_UNet):
                 skip0, token = _EncoderFunction.forward(_NullCtx(), self, plan, x, with_bott, *params)
         if store_vit_input:
             self.ViT_in = skip0.clone()
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.precision != "fp32"):
-            vit_out = self.ViT(skip0)
+        if self.precision != "fp32" and self.ViT.native_supported(skip0):
+            # bf16 mode: the whole ViT runs in the hand-written kernels of csrc/vit.cu; its input gradient is added straight
+            # into the plan's gradient buffer of the first skip (so the encoder backward needs no extra add)
+            bott = _view(plan, 2 * P + 1, 1)
+            vit_out = self.ViT.forward_native(skip0, _view(plan, 1, 2) if grad else None, tuple(int(v) for v in bott.shape[1:]))
+        else:
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.precision != "fp32"):
+                vit_out = self.ViT(skip0)
         if grad:
             outs = _DecoderFunction.apply(self, plan, vit_out, token, *params)
         else:

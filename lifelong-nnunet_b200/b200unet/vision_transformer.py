@@ -2,19 +2,26 @@
 nnunet_ext/network_architecture/vision_transformer.py:218-458) for the ``Generic_ViT_UNet`` V1 build: one 3D patch
 embedding, one head, no LSA / SPT / task-specific LayerNorms (those variants raise).
 
-Scope note: the ViT is ~17 % of cfg4's FLOPs and is plain library GEMM
-work; it runs on the GPU through ATen (cuBLAS GEMMs, fused SDPA attention), NOT through hand-written kernels.  The
-roofline claims of this repository cover the convolutional stack only.  The tensors handed over by the CUDA plan are
-consumed in place: the first skip arrives as a channels-last strided view of the plan's workspace and is patchified by
-one gather copy (the k = s = patch Conv3d of vision_transformer.py:50 is a GEMM over non-overlapping patches).
+Two execution paths:
+* bf16 mode (production): the whole ViT -- patch embedding, 12 blocks, final norm, head, forward AND backward -- runs in
+  hand-written kernels behind the C ABI (csrc/vit.cu, b2_vit_forward / b2_vit_backward): every Linear on the tcgen05
+  gather-GEMM, a shared-memory attention kernel with recomputation in backward, LayerNorm / GELU / reductions as fused
+  HBM-bound kernels.  No ATen / cuBLAS kernel is launched.  The first skip is consumed in place as a channels-last view of
+  the U-Net plan's workspace and the input gradient is added straight into the plan's gradient buffer.
+* fp32 parity mode (and `store_attn_weights`): the same arithmetic through ATen in fp32 (library GEMMs), the reference
+  the native path is tested against at the 1e-3 level of the oracle.
 
 state_dict keys / named_parameters() order are the reference's (cls_token, pos_embed_0, blocks.layer.N.{norm1,
 attn.{qkv,proj},norm2,mlp.{fc1,fc2}}, norm, patch_embeds.0.proj, heads.0) so checkpoints and name-keyed Fisher
 dictionaries (`'ViT'` / `'norm'` substring filters, ewc_ln/nnUNetTrainerEWCLN.py:49-50) keep working.
 """
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from . import _lib
 
 VIT_TYPES = {'base': {'embed_size': 768, 'head': 12, 'layers': 12},
              'large': {'embed_size': 1024, 'head': 16, 'layers': 24},
@@ -148,6 +155,50 @@ class VisionTransformer(nn.Module):
         nn.init.trunc_normal_(self.heads[0].weight, std=.02)
         nn.init.zeros_(self.heads[0].bias)
 
+    # -- native path (csrc/vit.cu) ------------------------------------------------------------------------------------------
+    def _native_params(self):
+        """parameters in named_parameters() order of the reference module (what b2_vit_forward expects)"""
+        ps = [self.cls_token, self.pos_embed_0]
+        for blk in self.blocks.layer:
+            ps += [blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias, blk.attn.proj.weight, blk.attn.proj.bias,
+                   blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
+        pe = self.patch_embeds[0]
+        ps += [self.norm.weight, self.norm.bias, pe.proj.weight, pe.proj.bias, self.heads[0].weight, self.heads[0].bias]
+        return ps
+
+    def native_supported(self, x):
+        blk = self.blocks.layer[0]
+        return (x.is_cuda and x.dtype == torch.bfloat16 and not self.store_attn_weights and self.embed_dim == blk.attn.num_heads * 64
+                and self.embed_dim <= 1024 and x.shape[0] <= 4 and x.shape[1] % 8 == 0 and x.stride(1) == 1)
+
+    def _native_plan(self, x, out_shape):
+        key = (tuple(x.shape), x.device, tuple(out_shape))
+        plans = self.__dict__.setdefault('_vplans', {})
+        if key not in plans:
+            lib = _lib.load()
+            d = _lib.VitDesc()
+            d.batch, d.in_channels, d.D, d.H, d.W = (int(v) for v in x.shape)
+            d.patch = self.patch_embeds[0].patch
+            d.embed, d.heads, d.depth, d.mlp_ratio = self.embed_dim, self.blocks.layer[0].attn.num_heads, self.block_depth, 4
+            d.out_features = self.num_classes
+            d.out_c, d.out_d, d.out_h, d.out_w = (int(v) for v in out_shape)
+            d.ln_eps = float(self.norm.eps)
+            h = C.c_void_p()
+            _lib.check(lib.b2_vit_plan_create(C.byref(d), C.byref(h)))
+            ws = torch.empty(int(lib.b2_vit_workspace_bytes(h)), dtype=torch.uint8, device=x.device)
+            plans[key] = (h, ws)
+        return plans[key]
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop('_vplans', None)          # C handles / workspaces are never copied (teachers are deep copies of the network)
+        return d
+
+    def forward_native(self, x, dskip, out_shape):
+        """x: channels-last bf16 view (B, C, D, H, W) of the first skip; dskip: the matching gradient view of the U-Net plan
+        (the input gradient is ADDED into it by the backward kernels); returns the dense [B, F] fp32 head output"""
+        return _ViTNativeFunction.apply(self, x, dskip, tuple(out_shape), *self._native_params())
+
     def register_new_task(self, task_name):
         raise NotImplementedError("task-specific LayerNorms (vision_transformer.py:380-416) are not built yet")
 
@@ -163,3 +214,60 @@ class VisionTransformer(nn.Module):
         x, ws = self.blocks(x)
         self.attn_weights = ws if self.store_attn_weights else None
         return self.heads[idx](self.pre_logits(self.norm(x)[:, 0]))
+
+
+def _view_of(t):
+    from .deep_supervision import _act_view
+    v, keep = _act_view(t)
+    if keep.data_ptr() != t.data_ptr():
+        raise RuntimeError("ViT native path needs channels-last bf16 views of the plan's workspace")
+    return v
+
+
+class _ViTNativeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vit, x, dskip, out_shape, *params):
+        lib = _lib.load()
+        h, ws = vit._native_plan(x, out_shape)
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
+                raise RuntimeError("ViT parameters must be contiguous fp32 tensors on the input's device")
+        need = any(ctx.needs_input_grad)      # (grad mode is off inside Function.forward: is_grad_enabled() would say False)
+        pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        out = torch.empty((x.shape[0], vit.num_classes), dtype=torch.float32, device=x.device)
+        vx = _view_of(x.detach())
+        _lib.check(lib.b2_vit_forward(h, pp, C.byref(vx), C.c_void_p(ws.data_ptr()), None, C.c_void_p(out.data_ptr()), 1 if need else 0,
+                                      C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        pe = vit.patch_embeds[0]
+        if pe.proj._forward_hooks:      # PLOP / POD hook every conv module (reference plop:330-353): the patch-embedding output
+            gd, gh, gw = (int(x.shape[2 + i]) // pe.patch for i in range(3))
+            n_tok = x.shape[0] * gd * gh * gw
+            off = int(lib.b2_vit_tokens_offset(h))
+            tok = ws[off:off + n_tok * vit.embed_dim * 2].view(torch.bfloat16)
+            conv_out = tok.view(x.shape[0], gd, gh, gw, vit.embed_dim).permute(0, 4, 1, 2, 3)
+            for hook in list(pe.proj._forward_hooks.values()):
+                hook(pe.proj, (x,), conv_out)
+        ctx.vit, ctx.h, ctx.ws, ctx.params, ctx.dskip, ctx.x = vit, h, ws, params, dskip, x
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        params = ctx.params
+        dev = dout.device
+        dout = dout.contiguous().float()
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        grads, o = [], 0
+        for p in params:
+            grads.append(flat[o:o + p.numel()].view(p.shape))
+            o += p.numel()
+        pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        gp = (C.c_void_p * len(params))(*[g.data_ptr() for g in grads])
+        vd = _view_of(ctx.dskip) if ctx.dskip is not None else None
+        _lib.check(lib.b2_vit_backward(ctx.h, pp, None, C.c_void_p(dout.data_ptr()), C.c_void_p(ctx.ws.data_ptr()),
+                                       None if vd is None else C.byref(vd), gp,
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        ctx.vit._last_flat_grad = flat
+        return (None, None, None, None) + tuple(g if p.requires_grad else None for g, p in zip(grads, params))

@@ -60,6 +60,7 @@ struct TcConvParams {
     int oo_d, oo_h, oo_w;
     int q_scatter, q_channels, qk_h, qk_w;   // transposed-conv forward: GEMM column -> (q = col / q_channels, channel = col % q_channels)
     int ntaps;
+    int out_f32;                 // 1: the produced tensor is fp32 (plain GEMM use: weight gradients of the ViT linears)
     int stages;
     int num_tiles;               // output tiles x ksplit
     int nprod;                   // active TMA producer warps (<= stages, so that a producer can never lap the ring)
@@ -362,6 +363,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         if (k == ch) { st1[k] += a1; st2[k] += a2; }
+                } else if (valid && p.out_f32) {
+                    float* rowf = reinterpret_cast<float*>(dst) + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + chan0 + c0 + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                        *reinterpret_cast<float4*>(rowf + j) = o;
+                    }
                 } else if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
@@ -435,6 +444,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(TcConvParams p, cons
             const float* pp = partial + (((size_t)ks * otiles + otile) * 128 + r) * p.BN + cg * 8;
             const float4 a = *reinterpret_cast<const float4*>(pp), b = *reinterpret_cast<const float4*>(pp + 4);
             f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+        }
+        if (p.out_f32) {
+            float* rowf = reinterpret_cast<float*>(dst) + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0 + cg * 8;
+            *reinterpret_cast<float4*>(rowf) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(rowf + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            continue;
         }
         __nv_bfloat16* row = dst + ((((long long)on * p.D + od) * p.H + oh) * p.W + ow) * p.dst_pitch + chan0 + cg * 8;
         if (accumulate) {
@@ -696,6 +711,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     p.os_d = g.os[0]; p.os_h = g.os[1]; p.os_w = g.os[2];
     p.oo_d = g.oo[0]; p.oo_h = g.oo[1]; p.oo_w = g.oo[2];
     p.q_scatter = g.q_scatter; p.q_channels = g.q_scatter ? g.q_channels : 1; p.qk_h = g.qk[1]; p.qk_w = g.qk[2];
+    p.out_f32 = g.out_f32;
     p.fd_qch = make_fastdiv(p.q_channels); p.fd_qkw = make_fastdiv(p.qk_w); p.fd_qkh = make_fastdiv(p.qk_h);
     p.fd_nblk = make_fastdiv(nblk); p.fd_ntw = make_fastdiv(p.nt_w); p.fd_nth = make_fastdiv(p.nt_h); p.fd_ntd = make_fastdiv(p.nt_d);
     p.ntaps = g.ntaps;
@@ -767,7 +783,7 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     EpiStats es{nullptr, 0, g.Nout, g.N};
     if (g.stat_slots) *g.stat_slots = 0;
     // (few K iterations per tile = epilogue-bound kernel: a separate streaming pass over z is cheaper there)
-    if (g.stat_part && g.stat_slots && g_epi_stats && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256 &&
+    if (g.stat_part && g.stat_slots && g_epi_stats && !g.out_f32 && p.TN == 1 && nblk == 1 && ksplit == 1 && !g.q_scatter && g.nclass <= 1 && BN <= 256 &&
         !g.accumulate && kiters_total >= 8) {
         es.slots = grid * 4 * TC_EPI_SETS;
         if ((size_t)g.N * es.slots * g.Nout * 2 <= g.stat_part_floats) { es.part = g.stat_part; *g.stat_slots = es.slots; }
@@ -811,6 +827,23 @@ size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout) {
     int nblk = cdiv(Nout, 256);
     if (tiles * nblk * 2 > num_sms()) return 0;
     return (size_t)num_sms() * 2 * 128 * 256;   // ksplit * otiles <= num_sms, BN <= 256 (x2 slack for ragged boxes)
+}
+
+// Plain GEMM on the gather kernel (one tap, unit lattice):  out[m][n] = sum_k A[m][k] * W[n][k] (+ bias[n]),  A: [M][K] bf16 with
+// row pitch lda, W: [N][K] bf16 dense, out: bf16 or fp32 with row pitch ldo.  M is tiled in boxes of 128 consecutive rows
+// (rows past M are zero-filled by TMA and never stored), so the row block is described as an (M/64 x 8 x 8) lattice when M is
+// a multiple of 64 and as a (1 x 1 x M) row otherwise.  K % 32 == 0, N % 32 == 0, lda % 8 == 0, ldo % 8 == 0.
+// `scratch` (optional) enables split-K for launches with few output tiles (fp32 partials + ordered reduce: bit-reproducible).
+int gemm_tn_bf16(const __nv_bfloat16* A, int M, int K, int lda, const __nv_bfloat16* W, int N, const float* bias, void* out, int ldo,
+                 int out_f32, float* scratch, size_t scratch_bytes, cudaStream_t st) {
+    B2_CHECK_ARG(A && W && out && M >= 1 && K % 32 == 0 && N % 32 == 0 && lda % 8 == 0 && ldo % 8 == 0 && lda >= K);
+    TcGather g;
+    const int D = M % 64 == 0 ? M / 64 : 1, H = M % 64 == 0 ? 8 : 1, Wd = M % 64 == 0 ? 8 : M;
+    fill_common(g, A, 1, D, H, Wd, K, lda, W, N, bias, (__nv_bfloat16*)out, D, H, Wd, ldo, 0);
+    g.w_rows = N; g.ntaps = 1; g.out_f32 = out_f32;
+    g.tap_off[0][0] = g.tap_off[0][1] = g.tap_off[0][2] = 0; g.tap_w[0] = 0;
+    g.splitk_scratch = scratch; g.splitk_scratch_bytes = scratch_bytes;
+    return conv_tc_gather(g, st);
 }
 
 // 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)

@@ -66,8 +66,11 @@ struct TcGather {
     int mes, mes_nst, mes_blk_rows, mes_nb[12], mes_blk0[13], mes_wrow[27], mes_cls[27], mes_first[27];
     // optional InstanceNorm partials from the epilogue: part[N][*stat_slots][Nout][2] (see EpiStats in tc_common.cuh)
     float* stat_part; size_t stat_part_floats; int* stat_slots;
+    int out_f32;                                                    // produced tensor is fp32 (GEMM use)
 };
 int conv_tc_gather(const TcGather& g, cudaStream_t st);
+int gemm_tn_bf16(const __nv_bfloat16* A, int M, int K, int lda, const __nv_bfloat16* W, int N, const float* bias, void* out, int ldo,
+                 int out_f32, float* scratch, size_t scratch_bytes, cudaStream_t st);
 int conv_tc_dgrad_strided(const __nv_bfloat16* dz, int N, int Do, int Ho, int Wo, int Cout, int dz_pitch, const __nv_bfloat16* wd,
                           int Cin, __nv_bfloat16* dx, int Di, int Hi, int Wi, int dx_pitch, const int stride[3], int accumulate,
                           cudaStream_t st);
