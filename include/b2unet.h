@@ -287,6 +287,18 @@ int b2_online_eval(const float* logits, const float* target, int B, int C, int64
                    void* scratch /* >= b2_kd_scratch_bytes */, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Sliding-window inference aggregation (validation / evaluation sweep; reference inference/predict.py:117-401 and
+ * evaluation/evaluator.py drive nnunet's SegmentationNetwork.predict_3D).  One fused launch per predicted patch:
+ * agg[c][z0+z][y0+y][x0+x] += scale * gauss[z][y][x] * softmax_c(logits[:, mirror(z, y, x)]);  wsum[..] += gauss (once per
+ * patch position: add_weight).  flip_mask bit 0 / 1 / 2: the network saw the patch mirrored along d / h / w (test-time
+ * mirroring).  b2_sliding_finalize: agg /= wsum in place (class probabilities), seg = argmax (nullable).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b2_sliding_accumulate(const float* logits, int C, int pd, int ph, int pw, const float* gauss, float* agg, float* wsum,
+                          int D, int H, int W, int z0, int y0, int x0, int flip_mask, float scale, int add_weight,
+                          b2_stream_t stream);
+int b2_sliding_finalize(float* agg, const float* wsum, int C, int64_t V, int32_t* seg, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Building blocks, exported so tests can check every kernel against the oracle in isolation.
  * Weight layouts: `w_pt` = PyTorch Conv3d weight [Cout][Cin][3][3][3]; the plan keeps per-step shadows
  * w_f = [27][Cin][Cout] and w_b = [27][Cout][Cin] (activation dtype for tensor-core paths, fp32 otherwise).

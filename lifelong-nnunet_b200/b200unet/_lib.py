@@ -118,6 +118,8 @@ SIGNATURES = {
     "b2_pod_scratch_bytes": (_SZ, [C.POINTER(ActView), _I]),
     "b2_pod_local": (_I, [C.POINTER(ActView), C.POINTER(ActView), _I, _VP, _VP, _VP]),
     "b2_online_eval": (_I, [_VP, _VP, _I, _I, _I64, _VP, _VP, _VP]),
+    "b2_sliding_accumulate": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _I, _VP]),
+    "b2_sliding_finalize": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
     "b2_conv3d_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "b2_conv3d_fwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
     "b2_conv3d_shadow_bytes": (_SZ, [C.POINTER(ConvDesc)]),

@@ -275,17 +275,20 @@ __global__ void scalar_finalize_kernel(const float* __restrict__ part, int n, do
 __global__ void __launch_bounds__(256) plop_mask_kernel(const float* __restrict__ x_old, const float* __restrict__ target,
                                                         int C, int D, int H, int W, const float* __restrict__ thr,
                                                         float max_entropy, int8_t* __restrict__ code,
-                                                        float* __restrict__ numden /*[B][W][2]*/) {
+                                                        float* __restrict__ numden /*[Z][B][W][2]*/) {
     pdl_grid_sync();
-    // one block per (b, w-chunk of 32 columns): threads x = w lane, y = row lanes; ordered reduce over (d,h)
+    // one block per (b, w-chunk of 32 columns, row chunk z): threads x = w lane, y = row lanes; ordered reduce over (d,h).
+    // (Round 1 had no row chunks: 12 blocks for a 48x192x192 level, 575 us per launch.)
     __shared__ float sh[8][32][2];
     const int b = blockIdx.y;
     const int w = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
     const long long V = (long long)D * H * W;
     const float factor = 1.f / logf((float)C + 1e-8f);
     float num = 0.f, den = 0.f;
+    const int rows_per = (D * H + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int r_begin = (int)blockIdx.z * rows_per, r_end = r_begin + rows_per < D * H ? r_begin + rows_per : D * H;
     if (w < W) {
-        for (int r = lane; r < D * H; r += 8) {
+        for (int r = r_begin + lane; r < r_end; r += 8) {
             const long long v = (long long)r * W + w;
             float xs[MAXC];
             float m = -INFINITY;
@@ -319,8 +322,9 @@ __global__ void __launch_bounds__(256) plop_mask_kernel(const float* __restrict_
     if (lane == 0 && w < W) {
         float a = 0.f, d = 0.f;
         for (int l = 0; l < 8; ++l) { a += sh[l][threadIdx.x][0]; d += sh[l][threadIdx.x][1]; }
-        numden[((long long)b * W + w) * 2] = a;
-        numden[((long long)b * W + w) * 2 + 1] = d;
+        float* nd = numden + (long long)blockIdx.z * gridDim.y * W * 2;
+        nd[((long long)b * W + w) * 2] = a;
+        nd[((long long)b * W + w) * 2 + 1] = d;
     }
 }
 
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(256) plop_ce_reduce_kernel(const float* __rest
 }
 
 // finalize: value = weight * mean_{b,w}(num/den) * (ce_p/cnt_p + ce_n/cnt_n); coef = {fbar/cnt_p, fbar/cnt_n} * weight
-__global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ numden, int B,
+__global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ numden, int nz, int B,
                                      int W, float weight, float* __restrict__ coef, float* __restrict__ loss_out) {
     pdl_grid_sync();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -369,7 +373,11 @@ __global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts,
     for (int i = 0; i < nparts; ++i)
         for (int k = 0; k < 4; ++k) s[k] += part[(long long)i * 4 + k];
     double f = 0.0;
-    for (int i = 0; i < B * W; ++i) f += (double)(numden[i * 2] / numden[i * 2 + 1]);  // fp32 division like torch
+    for (int i = 0; i < B * W; ++i) {
+        float num = 0.f, den = 0.f;     // counts: exact in fp32 in any order
+        for (int z = 0; z < nz; ++z) { num += numden[((long long)z * B * W + i) * 2]; den += numden[((long long)z * B * W + i) * 2 + 1]; }
+        f += (double)(num / den);  // fp32 division like torch
+    }
     f /= (double)(B * W);
     const double lp = s[0] / s[1], ln = s[2] / s[3];
     loss_out[0] += (float)(weight * f * (lp + ln));
@@ -484,7 +492,7 @@ extern "C" size_t b2_kd_scratch_bytes(int B, int C, int64_t V) {
     (void)C;
     size_t slabs = loss_slabs(B, V);
     // plop needs: code (B*V bytes) + numden + partials + coef
-    return align_up((size_t)B * V + 256) + align_up(((size_t)B * slabs * 4 + (size_t)B * 4096 * 2 + 16) * sizeof(float));
+    return align_up((size_t)B * V + 256) + align_up(((size_t)B * slabs * 4 + (size_t)32 * B * 4096 * 2 + 16) * sizeof(float));
 }
 
 extern "C" int b2_kd_lwf(const float* pred, const float* teacher, int B, int C, int64_t V, float temperature,
@@ -523,13 +531,17 @@ extern "C" int b2_plop_pseudo(const float* x, const float* x_old, const float* t
     int8_t* code = (int8_t*)scratch;
     float* f = (float*)((char*)scratch + align_up((size_t)B * V + 256));
     float* numden = f;
-    float* part = numden + (size_t)B * W * 2;
+    int nz = (4 * num_sms()) / (cdiv(W, 32) * B);      // row chunks: fill the GPU
+    if (nz > 32) nz = 32;
+    if (nz > cdiv(D * H, 8)) nz = cdiv(D * H, 8);
+    if (nz < 1) nz = 1;
+    float* part = numden + (size_t)nz * B * W * 2;
     float* coef = part + (size_t)B * slabs * 4;
-    dim3 g1(cdiv(W, 32), B);
+    dim3 g1(cdiv(W, 32), B, nz);
     B2_LAUNCH(plop_mask_kernel, g1, 256, 0, st, x_old, target, C, D, H, W, thresholds, max_entropy, code, numden);
     dim3 g2(slabs, B);
     B2_LAUNCH(plop_ce_reduce_kernel, g2, 256, 0, st, x, target, code, C, V, slabs, part);
-    B2_LAUNCH(plop_finalize_kernel, 1, 32, 0, st, part, B * slabs, numden, B, W, weight, coef, loss_out);
+    B2_LAUNCH(plop_finalize_kernel, 1, 32, 0, st, part, B * slabs, numden, nz, B, W, weight, coef, loss_out);
     if (dlogits) {
         long long total = (long long)B * V;
         long long g = (total + 255) / 256, cap = (long long)num_sms() * 16;

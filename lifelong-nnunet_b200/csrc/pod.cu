@@ -16,13 +16,16 @@
 namespace b2 {
 
 constexpr int MAXS = 6;
+constexpr int POD_MAXZ = 16;
 struct PodGeom {
     int B, D, H, W, C, pitch_a, pitch_b;
     int nscale;
     int e[MAXS], n[MAXS];
 };
 
-// block = (32 channels) x (8 lanes); grid = (B*D, ceil(C/32)); out[(bd*C + c)*2 + {0,1}] = {sqrt row, sqrt col}
+// block = (32 channels) x (8 lanes); grid = (B*D, ceil(C/32), Z): block z owns the rows / columns y, x = lane + 8 (z + Z k);
+// out[((bd*C + c)*Z + z)*2 + {0,1}] = partial {sum of squared row means, sum of squared column means}; pod_sqrt_kernel adds the
+// Z partials in order and takes the roots.  (Round 1 had no z split: 96 blocks for a 48x192x192 layer, 0.3-0.8 ms per layer.)
 template <typename T>
 __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict__ a, const T* __restrict__ b,
                                                   float* __restrict__ out) {
@@ -38,7 +41,7 @@ __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict
             const int e = g.e[s], n = g.n[s];
             const float inv = 1.f / (float)e;
             // rows: y in [0, n*e), segments k along x
-            for (int y = lane; y < n * e; y += 8)
+            for (int y = lane + 8 * (int)blockIdx.z; y < n * e; y += 8 * (int)gridDim.z)
                 for (int k = 0; k < n; ++k) {
                     float sum = 0.f;
                     for (int x = k * e; x < (k + 1) * e; ++x) {
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict
                     srow += m * m;
                 }
             // cols: x in [0, n*e), segments k along y
-            for (int x = lane; x < n * e; x += 8)
+            for (int x = lane + 8 * (int)blockIdx.z; x < n * e; x += 8 * (int)gridDim.z)
                 for (int k = 0; k < n; ++k) {
                     float sum = 0.f;
                     for (int y = k * e; y < (k + 1) * e; ++y) {
@@ -67,9 +70,21 @@ __global__ void __launch_bounds__(256) pod_kernel(PodGeom g, const T* __restrict
     if (lane == 0 && c < g.C) {
         float r = 0.f, q = 0.f;
         for (int l = 0; l < 8; ++l) { r += sh[l][threadIdx.x][0]; q += sh[l][threadIdx.x][1]; }
-        out[((long long)bd * g.C + c) * 2] = sqrtf(r);
-        out[((long long)bd * g.C + c) * 2 + 1] = sqrtf(q);
+        out[(((long long)bd * g.C + c) * gridDim.z + blockIdx.z) * 2] = r;
+        out[(((long long)bd * g.C + c) * gridDim.z + blockIdx.z) * 2 + 1] = q;
     }
+}
+
+// roots[i*2 + {0,1}] = sqrt(sum_z part[(i*Z + z)*2 + {0,1}])
+__global__ void __launch_bounds__(256) pod_sqrt_kernel(const float* __restrict__ part, long long n, int Z, float* __restrict__ roots) {
+    pdl_grid_sync();
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n * 2) return;
+    const long long e = i >> 1;
+    const int k = (int)(i & 1);
+    float s = 0.f;
+    for (int z = 0; z < Z; ++z) s += part[(e * Z + z) * 2 + k];
+    roots[i] = sqrtf(s);
 }
 
 __global__ void __launch_bounds__(256) pod_finalize_kernel(const float* __restrict__ part, long long n, double scale,
@@ -89,7 +104,7 @@ using namespace b2;
 extern "C" size_t b2_pod_scratch_bytes(const b2_act_view* a, int scales) {
     (void)scales;
     if (!a) return 0;
-    return align_up((size_t)a->n * a->d * a->c * 2 * sizeof(float) + 256);
+    return align_up((size_t)a->n * a->d * a->c * 2 * (POD_MAXZ + 1) * sizeof(float) + 256);
 }
 
 extern "C" int b2_pod_local(const b2_act_view* a, const b2_act_view* a_old, int scales, float* value_out, void* scratch,
@@ -111,11 +126,17 @@ extern "C" int b2_pod_local(const b2_act_view* a, const b2_act_view* a_old, int 
         tiles += (long long)n * n;
     }
     if (tiles == 0) return fail(B2_EINVAL, "local_POD produced no tile (reference would fail on zip(None))%s", "");
-    float* part = (float*)scratch;
-    dim3 grid(a->n * a->d, cdiv(a->c, 32));
+    const long long n = (long long)a->n * a->d * a->c * 2;
+    int Z = (4 * num_sms()) / (a->n * a->d * cdiv(a->c, 32));
+    if (Z > POD_MAXZ) Z = POD_MAXZ;
+    if (Z > cdiv(a->w, 8)) Z = cdiv(a->w, 8);
+    if (Z < 1) Z = 1;
+    float* roots = (float*)scratch;
+    float* part = roots + n;
+    dim3 grid(a->n * a->d, cdiv(a->c, 32), Z);
     if (a->dtype == B2_F32) B2_LAUNCH(pod_kernel<float>, grid, 256, 0, st, g, (const float*)a->ptr, (const float*)a_old->ptr, part);
     else B2_LAUNCH(pod_kernel<__nv_bfloat16>, grid, 256, 0, st, g, (const __nv_bfloat16*)a->ptr, (const __nv_bfloat16*)a_old->ptr, part);
-    const long long n = (long long)a->n * a->d * a->c * 2;
-    B2_LAUNCH(pod_finalize_kernel, 1, 256, 0, st, part, n, 1.0 / (double)n, value_out);
+    B2_LAUNCH(pod_sqrt_kernel, cdiv(n, 256), 256, 0, st, (const float*)part, n / 2, Z, roots);
+    B2_LAUNCH(pod_finalize_kernel, 1, 256, 0, st, (const float*)roots, n, 1.0 / (double)n, value_out);
     return B2_OK;
 }

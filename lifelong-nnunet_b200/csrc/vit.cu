@@ -320,46 +320,43 @@ __global__ void __launch_bounds__(256) assemble_tokens_bwd_kernel(const float* _
 // ---------------------------------------------------------------------------------------------------------------
 // attention (head dim 64), qkv: [B*T][3E] bf16 with column = which * E + h * 64 + d
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int AT_QB = 32;        // rows (queries or keys) per block
-constexpr int AT_THREADS = 256;  // 8 warps, 4 rows each
+constexpr int AT_THREADS = 256;  // 8 warps
+constexpr int AT_LD = 66;        // padded row (64 dims + 2): rows 132 B apart => a fixed dim over 32 consecutive rows hits 32 banks,
+                                 // and a fixed row over consecutive dims is contiguous: ONE copy serves both access patterns
 
-// transposed load of one 64-column slice of `src` rows [0, T) into shared [64][Tp] bf16
-__device__ __forceinline__ void load_transposed(const __nv_bfloat16* __restrict__ src, long long ld, int T, int Tp, __nv_bfloat16* dstT) {
+// copy the 64-column slice `src[j][0..64)` (row pitch ld) of rows [0, T) into shared [Tp][AT_LD]; rows >= T are zero
+__device__ __forceinline__ void load_rows(const __nv_bfloat16* __restrict__ src, long long ld, int T, int Tp, __nv_bfloat16* dst) {
     for (int i = threadIdx.x; i < Tp * 8; i += AT_THREADS) {
         const int j = i >> 3, d8 = (i & 7) * 8;
-        float v[8];
-        if (j < T) load8(src + (long long)j * ld + d8, v);
-        else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dstT[(d8 + e) * Tp + j] = __float2bfloat16_rn(v[e]);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j < T) v = *reinterpret_cast<const uint4*>(src + (long long)j * ld + d8);
+        uint32_t* o = reinterpret_cast<uint32_t*>(dst + j * AT_LD + d8);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
     }
 }
 
 // out[b*T + i][h*64 + d] = sum_j softmax_j(scale q_i.k_j) v_j[d];  lse[(b*H + h)*T + i] = log sum_j exp(scale q_i.k_j)
+// grid = (B*H, row blocks): a block stages K and V of its head once and its 8 warps walk the block's queries
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                              float* __restrict__ lse, int B, int H, int T, int Tp, float scale) {
+                                                              float* __restrict__ lse, int B, int H, int T, int Tp, int rows_per_block,
+                                                              float scale) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int E = H * 64;
-    __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [64][Tp]
-    __nv_bfloat16* Vs = Kt + 64 * Tp;                                            // [T][64]
-    float* ps = reinterpret_cast<float*>(Vs + (size_t)Tp * 64);                  // [8][Tp]
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [Tp][AT_LD]
+    __nv_bfloat16* Vs = Ks + (size_t)Tp * AT_LD;                                 // [Tp][AT_LD]
+    float* ps = reinterpret_cast<float*>(Vs + (size_t)Tp * AT_LD);               // [8][Tp]
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const long long ld = 3LL * E;
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
-    load_transposed(base + E, ld, T, Tp, Kt);
-    for (int i = threadIdx.x; i < T * 8; i += AT_THREADS) {
-        const int j = i >> 3, d8 = (i & 7) * 8;
-        *reinterpret_cast<uint4*>(Vs + j * 64 + d8) = *reinterpret_cast<const uint4*>(base + 2 * E + (long long)j * ld + d8);
-    }
+    load_rows(base + E, ld, T, Tp, Ks);
+    load_rows(base + 2 * E, ld, T, Tp, Vs);
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* pw = ps + (size_t)w * Tp;
     const int nk = Tp / 32;
-    for (int qi = blockIdx.y * AT_QB + w; qi < T && qi < (blockIdx.y + 1) * AT_QB; qi += 8) {
+    const int q_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
+    for (int qi = blockIdx.y * rows_per_block + w; qi < q_end; qi += 8) {
         const __nv_bfloat16* qr = base + (long long)qi * ld;
         const float q0 = __bfloat162float(qr[lane]) * scale, q1 = __bfloat162float(qr[lane + 32]) * scale;
         float acc[16];
@@ -367,10 +364,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __nv_bfloat1
         for (int k = 0; k < 16; ++k) acc[k] = 0.f;
         for (int d = 0; d < 64; ++d) {
             const float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
-            const __nv_bfloat16* kr = Kt + d * Tp + lane;
+            const __nv_bfloat16* kr = Ks + lane * AT_LD + d;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                if (k < nk) acc[k] = fmaf(qd, __bfloat162float(kr[32 * k]), acc[k]);
+                if (k < nk) acc[k] = fmaf(qd, __bfloat162float(kr[32 * k * AT_LD]), acc[k]);
         }
         float m = -INFINITY;
 #pragma unroll
@@ -393,9 +390,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __nv_bfloat1
             if (k < nk) pw[lane + 32 * k] = acc[k] * inv;
         __syncwarp();
         float o0 = 0.f, o1 = 0.f;
+#pragma unroll 4
         for (int j = 0; j < T; ++j) {
             const float pj = pw[j];
-            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + j * 64 + 2 * lane));
+            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + j * AT_LD + 2 * lane));
             o0 = fmaf(pj, vv.x, o0);
             o1 = fmaf(pj, vv.y, o1);
         }
@@ -409,28 +407,24 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ O,
                                                                 const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                                                                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ Drow, int B, int H,
-                                                                int T, int Tp, float scale) {
+                                                                int T, int Tp, int rows_per_block, float scale) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int E = H * 64;
-    __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(smraw);   // [64][Tp]
-    __nv_bfloat16* Vt = Kt + 64 * Tp;                              // [64][Tp]
-    __nv_bfloat16* Ks = Vt + 64 * Tp;                              // [T][64]
-    float* ps = reinterpret_cast<float*>(Ks + (size_t)Tp * 64);    // [8][Tp]
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);   // [Tp][AT_LD]
+    __nv_bfloat16* Vs = Ks + (size_t)Tp * AT_LD;                   // [Tp][AT_LD]
+    float* ps = reinterpret_cast<float*>(Vs + (size_t)Tp * AT_LD); // [8][Tp]
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const long long ld = 3LL * E;
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
-    load_transposed(base + E, ld, T, Tp, Kt);
-    load_transposed(base + 2 * E, ld, T, Tp, Vt);
-    for (int i = threadIdx.x; i < T * 8; i += AT_THREADS) {
-        const int j = i >> 3, d8 = (i & 7) * 8;
-        *reinterpret_cast<uint4*>(Ks + j * 64 + d8) = *reinterpret_cast<const uint4*>(base + E + (long long)j * ld + d8);
-    }
+    load_rows(base + E, ld, T, Tp, Ks);
+    load_rows(base + 2 * E, ld, T, Tp, Vs);
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* pw = ps + (size_t)w * Tp;
     const int nk = Tp / 32;
-    for (int qi = blockIdx.y * AT_QB + w; qi < T && qi < (blockIdx.y + 1) * AT_QB; qi += 8) {
+    const int q_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
+    for (int qi = blockIdx.y * rows_per_block + w; qi < q_end; qi += 8) {
         const __nv_bfloat16* qr = base + (long long)qi * ld;
         const long long orow = ((long long)b * T + qi) * E + h * 64;
         const float q0 = __bfloat162float(qr[lane]) * scale, q1 = __bfloat162float(qr[lane + 32]) * scale;
@@ -444,13 +438,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const __nv_bfloa
         for (int d = 0; d < 64; ++d) {
             const float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
             const float gd = __shfl_sync(0xffffffffu, d < 32 ? g0 : g1, d & 31);
-            const __nv_bfloat16* kr = Kt + d * Tp + lane;
-            const __nv_bfloat16* vr = Vt + d * Tp + lane;
+            const __nv_bfloat16* kr = Ks + lane * AT_LD + d;
+            const __nv_bfloat16* vr = Vs + lane * AT_LD + d;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 if (k < nk) {
-                    s[k] = fmaf(qd, __bfloat162float(kr[32 * k]), s[k]);
-                    dp[k] = fmaf(gd, __bfloat162float(vr[32 * k]), dp[k]);
+                    s[k] = fmaf(qd, __bfloat162float(kr[32 * k * AT_LD]), s[k]);
+                    dp[k] = fmaf(gd, __bfloat162float(vr[32 * k * AT_LD]), dp[k]);
                 }
         }
 #pragma unroll
@@ -461,9 +455,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const __nv_bfloa
             }
         __syncwarp();
         float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
         for (int j = 0; j < T; ++j) {
             const float dsj = pw[j];
-            const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + j * 64 + 2 * lane));
+            const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + j * AT_LD + 2 * lane));
             a0 = fmaf(dsj, kk.x, a0);
             a1 = fmaf(dsj, kk.y, a1);
         }
@@ -473,23 +468,24 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const __nv_bfloa
     }
 }
 
-// dK, dV:  dv_j = sum_i p_ij dO_i;  dk_j = scale sum_i dS_ij q_i      (block = 32 keys, loops over all queries)
+// dK, dV:  dv_j = sum_i p_ij dO_i;  dk_j = scale sum_i dS_ij q_i      (a block stages Q and dO of its head and walks its keys)
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
                                                                  const float* __restrict__ lse, const float* __restrict__ Drow,
-                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, int Tp, float scale) {
+                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, int Tp,
+                                                                 int rows_per_block, float scale) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int E = H * 64;
-    __nv_bfloat16* Qt = reinterpret_cast<__nv_bfloat16*>(smraw);   // [64][Tp]
-    __nv_bfloat16* Gt = Qt + 64 * Tp;                              // dO^T [64][Tp]
-    float* ps = reinterpret_cast<float*>(Gt + 64 * Tp);            // [8][2][Tp]: p_ij and dS_ij over i
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);   // [Tp][AT_LD]
+    __nv_bfloat16* Gs = Qs + (size_t)Tp * AT_LD;                   // dO [Tp][AT_LD]
+    float* ps = reinterpret_cast<float*>(Gs + (size_t)Tp * AT_LD); // [8][2][Tp]: p_ij and dS_ij over i
     float* Ls = ps + (size_t)16 * Tp;                              // [Tp] lse, [Tp] D
     const int bh = blockIdx.x, b = bh / H, h = bh % H;
     const long long ld = 3LL * E;
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
     const __nv_bfloat16* gbase = dO + (long long)b * T * E + h * 64;
-    load_transposed(base, ld, T, Tp, Qt);
-    load_transposed(gbase, E, T, Tp, Gt);
+    load_rows(base, ld, T, Tp, Qs);
+    load_rows(gbase, E, T, Tp, Gs);
     for (int i = threadIdx.x; i < Tp; i += AT_THREADS) {
         Ls[i] = i < T ? lse[(long long)bh * T + i] : 0.f;
         Ls[Tp + i] = i < T ? Drow[(long long)bh * T + i] : 0.f;
@@ -499,7 +495,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const __nv_bflo
     float* pp = ps + (size_t)w * 2 * Tp;
     float* pd = pp + Tp;
     const int nk = Tp / 32;
-    for (int kj = blockIdx.y * AT_QB + w; kj < T && kj < (blockIdx.y + 1) * AT_QB; kj += 8) {
+    const int k_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
+    for (int kj = blockIdx.y * rows_per_block + w; kj < k_end; kj += 8) {
         const __nv_bfloat16* kr = base + E + (long long)kj * ld;
         const __nv_bfloat16* vr = base + 2 * E + (long long)kj * ld;
         const float k0 = __bfloat162float(kr[lane]) * scale, k1 = __bfloat162float(kr[lane + 32]) * scale;
@@ -510,13 +507,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const __nv_bflo
         for (int d = 0; d < 64; ++d) {
             const float kd = __shfl_sync(0xffffffffu, d < 32 ? k0 : k1, d & 31);
             const float vd = __shfl_sync(0xffffffffu, d < 32 ? v0 : v1, d & 31);
-            const __nv_bfloat16* qr = Qt + d * Tp + lane;
-            const __nv_bfloat16* gr = Gt + d * Tp + lane;
+            const __nv_bfloat16* qr = Qs + lane * AT_LD + d;
+            const __nv_bfloat16* gr = Gs + lane * AT_LD + d;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 if (k < nk) {
-                    s[k] = fmaf(kd, __bfloat162float(qr[32 * k]), s[k]);
-                    dp[k] = fmaf(vd, __bfloat162float(gr[32 * k]), dp[k]);
+                    s[k] = fmaf(kd, __bfloat162float(qr[32 * k * AT_LD]), s[k]);
+                    dp[k] = fmaf(vd, __bfloat162float(gr[32 * k * AT_LD]), dp[k]);
                 }
         }
 #pragma unroll
@@ -529,10 +526,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const __nv_bflo
             }
         __syncwarp();
         float dv0 = 0.f, dv1 = 0.f, dk0 = 0.f, dk1 = 0.f;
+#pragma unroll 4
         for (int i = 0; i < T; ++i) {
             const float p = pp[i], dsi = pd[i];
-            const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + (long long)i * E + 2 * lane));
-            const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (long long)i * ld + 2 * lane));
+            const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Gs + i * AT_LD + 2 * lane));
+            const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Qs + i * AT_LD + 2 * lane));
             dv0 = fmaf(p, gg.x, dv0); dv1 = fmaf(p, gg.y, dv1);
             dk0 = fmaf(dsi, qq.x, dk0); dk1 = fmaf(dsi, qq.y, dk1);
         }
@@ -824,7 +822,12 @@ extern "C" int b2_vit_forward(b2_vit_plan* p, const float* const* params, const 
     if (Mp > M) B2_CUDA(cudaMemsetAsync(X + (size_t)M * E, 0, (size_t)(Mp - M) * E * 4, st));
     B2_LAUNCH(assemble_tokens_kernel, (int)grid_for((long long)M * E, 1), 256, 0, st, (const __nv_bfloat16*)tok, P_.cls(), P_.pos(), X, d.batch, p->np, E);
     __nv_bfloat16* tmp = at<__nv_bfloat16>(ws, p->s_tmp);
-    const size_t at_smem = (size_t)64 * p->Tp * 2 + (size_t)p->Tp * 64 * 2 + (size_t)8 * p->Tp * 4;
+    const size_t at_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)8 * p->Tp * 4;
+    // row blocks per (batch, head): enough blocks to fill the GPU, few enough that staging K / V is amortised
+    int at_blocks = cdiv(num_sms(), d.batch * H);
+    if (at_blocks > cdiv(T, 32)) at_blocks = cdiv(T, 32);
+    const int at_rows = cdiv(cdiv(T, at_blocks), 8) * 8;
+    at_blocks = cdiv(T, at_rows);
     static bool at_attr = false;
     if (!at_attr) { B2_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); at_attr = true; }
     for (int l = 0; l < d.depth; ++l) {
@@ -846,8 +849,8 @@ extern "C" int b2_vit_forward(b2_vit_plan* p, const float* const* params, const 
             B2_CUDA(cudaMemsetAsync(Xn2 + (size_t)M * E, 0, (size_t)(Mp - M) * E * 2, st));
         }
         if ((rc = gemm_tn_bf16(Xn, Mp, E, E, (__nv_bfloat16*)(wb + p->w_qkv), 3 * E, P_.blk(l, 3), qkv, 3 * E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
-        B2_LAUNCH(attn_fwd_kernel, dim3(d.batch * H, cdiv(T, AT_QB)), AT_THREADS, at_smem, st, (const __nv_bfloat16*)qkv, O, (float*)(bb + p->b_lse),
-                  d.batch, H, T, p->Tp, 0.125f);
+        B2_LAUNCH(attn_fwd_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, at_smem, st, (const __nv_bfloat16*)qkv, O, (float*)(bb + p->b_lse),
+                  d.batch, H, T, p->Tp, at_rows, 0.125f);
         if ((rc = gemm_tn_bf16(O, Mp, E, E, (__nv_bfloat16*)(wb + p->w_proj), E, P_.blk(l, 5), tmp, E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
         B2_LAUNCH(add_bf16_kernel, (int)grid_for((long long)M * E, 4), 256, 0, st, X, (const __nv_bfloat16*)tmp, (long long)M * E);
         B2_CUDA(cudaMemcpyAsync(Xmid, X, (size_t)Mp * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -913,8 +916,12 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
     // transposed operands: columns [M, Mp) must be zero (they are contraction padding)
     B2_CUDA(cudaMemsetAsync(tA, 0, (size_t)4 * E * Mp * 2, st));
     B2_CUDA(cudaMemsetAsync(tB, 0, (size_t)4 * E * Mp * 2, st));
-    const size_t q_smem = (size_t)3 * 64 * p->Tp * 2 + (size_t)8 * p->Tp * 4;
-    const size_t kv_smem = (size_t)2 * 64 * p->Tp * 2 + (size_t)16 * p->Tp * 4 + (size_t)2 * p->Tp * 4;
+    const size_t q_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)8 * p->Tp * 4;
+    const size_t kv_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)16 * p->Tp * 4 + (size_t)2 * p->Tp * 4;
+    int at_blocks = cdiv(num_sms(), d.batch * H);
+    if (at_blocks > cdiv(T, 32)) at_blocks = cdiv(T, 32);
+    const int at_rows = cdiv(cdiv(T, at_blocks), 8) * 8;
+    at_blocks = cdiv(T, at_rows);
     static bool at_attr = false;
     if (!at_attr) {
         B2_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -951,10 +958,11 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
         if ((rc = linear_bwd(tmp, E, (const __nv_bfloat16*)(bb + p->b_O), E, (const __nv_bfloat16*)(wb + p->w_projT), tmp2, GB(l, 4), GB(l, 5)))) return rc;
         __nv_bfloat16* dqkv = tmp;     // [Mp][3E]
         B2_CUDA(cudaMemsetAsync(dqkv + (size_t)M * 3 * E, 0, (size_t)(Mp - M) * 3 * E * 2, st));
-        B2_LAUNCH(attn_bwd_q_kernel, dim3(d.batch * H, cdiv(T, AT_QB)), AT_THREADS, q_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
-                  (const __nv_bfloat16*)(bb + p->b_O), (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), dqkv, Drow, d.batch, H, T, p->Tp, 0.125f);
-        B2_LAUNCH(attn_bwd_kv_kernel, dim3(d.batch * H, cdiv(T, AT_QB)), AT_THREADS, kv_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
-                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, p->Tp, 0.125f);
+        B2_LAUNCH(attn_bwd_q_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, q_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
+                  (const __nv_bfloat16*)(bb + p->b_O), (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), dqkv, Drow, d.batch, H, T, p->Tp,
+                  at_rows, 0.125f);
+        B2_LAUNCH(attn_bwd_kv_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, kv_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
+                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, p->Tp, at_rows, 0.125f);
         if ((rc = linear_bwd(dqkv, 3 * E, (const __nv_bfloat16*)(bb + p->b_Xn), E, (const __nv_bfloat16*)(wb + p->w_qkvT), tmp2, GB(l, 2), GB(l, 3)))) return rc;
         if ((rc = ln_bwd<__nv_bfloat16>(tmp2, E, (const float*)(bb + p->b_Xin), E, (const float*)(bb + p->b_st1), P_.blk(l, 0), dX, E, 1, M, E, part,
                                         GB(l, 0), GB(l, 1), st))) return rc;

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_losses.py tests/test_gpu_trainers.py -m gpu -q -x --timeout 500 --timeout-method=thread > gpurun_out/v4_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/v4_pytest.log; tail -4 gpurun_out/v4_pytest.log
+timeout 900 python -m pytest tests/test_gpu_baseline_configs.py -m gpu -q --timeout 500 --timeout-method=thread -k "cfg4 or plop or pod" > gpurun_out/v4_pytest2.log 2>&1
+echo "pytest exit $?" >> gpurun_out/v4_pytest2.log; tail -4 gpurun_out/v4_pytest2.log
+timeout 400 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v4_bench_cfg4.json 2> gpurun_out/v4_bench_cfg4.err
+python - <<'P'
+import json
+try:
+    d=json.loads(open('gpurun_out/v4_bench_cfg4.json').read().strip().splitlines()[-1]); print('cfg4', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'])
+except Exception as e: print('cfg4 ERR', e); print(open('gpurun_out/v4_bench_cfg4.err').read()[-1500:])
+P
