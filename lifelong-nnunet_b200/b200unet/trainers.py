@@ -406,6 +406,83 @@ class nnUNetTrainerMultiHead:
         return [float(2 * i / (2 * i + j + k + 1e-8)) for i, j, k in zip(tp, fp, fn)]
 
 
+    # -- reference MultiHead:678-901 (validation sweep) and :963-1049 ---------------------------------------------------
+    def _perform_validation(self, val_generators, nr_batches, use_head=None, call_for_eval=False):
+        """Per-subject validation on every task (reference MultiHead:678-901 minus its plans / dataset / file plumbing):
+        `val_generators` maps task -> generator of {'data', 'target', 'keys'} batches.  For each task the matching head is
+        assembled (`use_head` when the task has none, :779-783), `nr_batches` batches run without backprop with the
+        per-subject tp / fp / fn evaluation (`eval_batch = False`, :703), then Dice / IoU per subject and mask are stored in
+        `self.validation_results['epoch_N'][task]` (:963-1049).  Returns that dictionary."""
+        self.eval_batch = False
+        active = self.task
+        if not hasattr(self, "validation_results"):
+            self.validation_results = {}
+        self.network.eval()
+        try:
+            for task, gen in val_generators.items():
+                head = task if (self.mh_network is None or task in self.mh_network.heads) else use_head
+                assert head is not None, ("The task to perform validation/evaluation on is not in the head and no head_name "
+                                          "that should be used instead (use_head) is provided.")
+                if self.mh_network is not None and head != self.mh_network.active_task:
+                    self.network = self.mh_network.assemble_model(head)
+                self.task = task
+                self.subject_names_raw = []
+                with torch.no_grad():
+                    for _ in range(nr_batches):
+                        batch = next(gen)
+                        self.subject_names_raw.append(list(batch['keys']))
+                        self.run_iteration(iter([batch]), False, True, no_loss=call_for_eval)
+                self.finish_online_evaluation_extended(task)
+        finally:
+            if self.mh_network is not None and self.mh_network.active_task != active and active in self.mh_network.heads:
+                self.network = self.mh_network.assemble_model(active)
+            self.task = active
+            self.network.train()
+            self.eval_batch = True
+        return self.validation_results
+
+    def finish_online_evaluation_extended(self, task, unique_subject_names=None):
+        """reference MultiHead:963-1049: sum tp / fp / fn over all patches of a subject, then per subject and foreground
+        mask IoU = tp / (tp + fp + fn) and Dice = 2 tp / (2 tp + fp + fn) (no smoothing: an absent, unpredicted mask is NaN)"""
+        names = np.array(self.subject_names_raw).flatten()
+        tp = np.concatenate(self.online_eval_tp, 0).reshape(len(names), -1)
+        fp = np.concatenate(self.online_eval_fp, 0).reshape(len(names), -1)
+        fn = np.concatenate(self.online_eval_fn, 0).reshape(len(names), -1)
+        subjects = list(np.unique(names)) if unique_subject_names is None else list(unique_subject_names)
+        store = {}
+        for subject in subjects:
+            idx = np.where(names == subject)
+            i, j, k = tp[idx].sum(0), fp[idx].sum(0), fn[idx].sum(0)
+            if np.isnan(i).any():
+                continue
+            with np.errstate(invalid='ignore', divide='ignore'):
+                iou, dc = i / (i + j + k), 2 * i / (2 * i + j + k)
+            store[str(subject)] = {'mask_' + str(c + 1): {'IoU': np.float64(iou[c]), 'Dice': np.float64(dc[c])}
+                                   for c in range(len(iou))}
+        if not hasattr(self, "validation_results"):
+            self.validation_results = {}
+        self.validation_results.setdefault('epoch_' + str(self.epoch), {})[task] = store
+        self.online_eval_tp, self.online_eval_fp, self.online_eval_fn = [], [], []
+        self.subject_names_raw = []
+        return store
+
+    def predict_preprocessed_data_return_seg_and_softmax(self, data, do_mirroring=True, mirror_axes=(0, 1, 2),
+                                                         use_sliding_window=True, step_size=0.5, use_gaussian=True, **_):
+        """nnunet nnUNetTrainer.predict_preprocessed_data_return_seg_and_softmax -> SegmentationNetwork.predict_3D
+        (what the reference's inference/predict.py:117-401 and evaluation sweep call): tiled sliding-window prediction of
+        one preprocessed case, on the CUDA path (b200unet/inference.py).  Returns numpy (segmentation, class probabilities)."""
+        from . import inference
+        assert use_sliding_window, "only the tiled (sliding-window) prediction is implemented"
+        training = self.network.training
+        self.network.eval()
+        try:
+            seg, probs = inference.predict_3D(self.network, data, self.geometry.patch, do_mirroring, tuple(mirror_axes),
+                                              step_size, use_gaussian)
+        finally:
+            self.network.train(training)
+        return seg.cpu().numpy(), probs.cpu().numpy()
+
+
 class nnUNetTrainerSequential(nnUNetTrainerMultiHead):
     """Plain sequential fine-tuning baseline (BASELINE.json config 1): the MultiHead iteration as is."""
     EXTENSION = "sequential"

@@ -136,3 +136,34 @@ def test_loads_a_checkpoint_laid_out_by_the_reference_multihead_module(tmp_path)
         assert torch.equal(p, rsd[n]), n
     assert torch.equal(tr.mh_network.heads["A"].seg_outputs[0].weight, ref.heads["A"].seg_outputs[0].weight)
     assert set(tr.mh_network.state_dict().keys()) == set(ref.state_dict().keys())
+
+
+def test_sliding_window_steps_and_gaussian_known_answers():
+    """nnunet _compute_steps_for_sliding_window: patch 128 on 200 voxels at step 0.5 -> ceil(72/64)+1 = 3 equidistant origins"""
+    from b200unet import inference
+    from oracle import sliding_window
+    assert inference.compute_steps_for_sliding_window((128,), (200,), 0.5) == [[0, 36, 72]]
+    assert inference.compute_steps_for_sliding_window((16, 32, 32), (16, 32, 33), 0.5) == [[0], [0], [0, 1]]
+    assert inference.compute_steps_for_sliding_window((16, 32, 32), (20, 45, 50), 0.5) == sliding_window.compute_steps((16, 32, 32), (20, 45, 50), 0.5)
+    g = inference.get_gaussian((8, 16, 16))
+    assert g.dtype.name == "float32" and float(g.max()) == 1.0 and float(g.min()) > 0 and g[4, 8, 8] == 1.0
+    assert torch.equal(torch.from_numpy(g), sliding_window.gaussian_map((8, 16, 16)))
+
+
+def test_finish_online_evaluation_extended_per_subject_dice_iou():
+    """reference MultiHead:963-1049: counts summed per subject name; IoU = tp/(tp+fp+fn), Dice = 2tp/(2tp+fp+fn)"""
+    import numpy as np
+    from b200unet.trainers import nnUNetTrainerSequential
+    tr = _mk(nnUNetTrainerSequential, task="A")
+    tr.subject_names_raw = [["a", "b"], ["b", "a"]]
+    tr.online_eval_tp = [np.array([[4., 1.], [2., 0.]]), np.array([[1., 1.], [3., 2.]])]
+    tr.online_eval_fp = [np.array([[1., 0.], [1., 0.]]), np.array([[0., 1.], [0., 1.]])]
+    tr.online_eval_fn = [np.array([[0., 2.], [1., 0.]]), np.array([[2., 0.], [1., 1.]])]
+    tr.epoch = 3
+    store = tr.finish_online_evaluation_extended("A")
+    assert tr.validation_results["epoch_3"]["A"] is store and sorted(store) == ["a", "b"]
+    # subject a: tp (7, 3) fp (1, 1) fn (1, 3);  subject b: tp (3, 1) fp (1, 1) fn (3, 0)
+    assert math.isclose(store["a"]["mask_1"]["Dice"], 14 / 16) and math.isclose(store["a"]["mask_1"]["IoU"], 7 / 9)
+    assert math.isclose(store["a"]["mask_2"]["Dice"], 6 / 10) and math.isclose(store["b"]["mask_2"]["IoU"], 1 / 2)
+    assert math.isclose(store["b"]["mask_1"]["Dice"], 6 / 10)
+    assert tr.online_eval_tp == [] and tr.subject_names_raw == []
