@@ -142,9 +142,9 @@ class Generic_ViT_UNet(Generic_UNet):
                                       "You provided '{}'".format(vit_type)
         self.version = vit_version.title()
         assert self.version in ['V1', 'V2', 'V3', 'V4'], 'Please provide a correct version (V1, V2, V3 or V4), not {}.'.format(vit_version)
-        if self.version != 'V1' or split_gpu or ViT_task_specific_ln or do_LSA or do_SPT:
+        if self.version != 'V1' or split_gpu or do_LSA or do_SPT:
             raise NotImplementedError("b200unet.Generic_ViT_UNet: only vit_version='V1' on one device without "
-                                      "task-specific LayerNorms / LSA / SPT is implemented (no eager fallback)")
+                                      "LSA / SPT is implemented (no eager fallback)")
         self.split_gpu, self.use_skip = False, 0
         self.ViT_types = VIT_TYPES
         # sizes the reference obtains from a dry run (generic_ViT_UNet.py:85-131) follow from the pooling geometry
@@ -165,7 +165,7 @@ class Generic_ViT_UNet(Generic_UNet):
         vit = VisionTransformer(ViT_2d=False, img_size=self.img_size, patch_size=self.patch_size,
                                 img_depth=[self.img_size[0]], in_chans=self.in_chans, num_classes=self.num_classesViT,
                                 embed_dim=cfg['embed_size'], depth=cfg['layers'], num_heads=cfg['head'], mlp_ratio=4,
-                                qkv_bias=True)
+                                qkv_bias=True, task_specific_ln=ViT_task_specific_ln, task_name=first_task_name)
         # registration order of generic_ViT_UNet.py:193-211
         parts = {n: getattr(self, n) for n in ('conv_blocks_localization', 'conv_blocks_context', 'td', 'tu', 'seg_outputs')}
         for n in parts:

@@ -80,7 +80,7 @@ class nnUNetTrainerMultiHead:
     def __init__(self, geometry, precision="bf16", batch_dice=False, device=None, ddp=None, initial_lr=1e-2,
                  weight_decay=3e-5, max_num_epochs=1000, seed=0, task="task_A", use_vit=False, vit_version='V1',
                  vit_type='base', split="seg_outputs", transfer_heads=True, strict_reference=True, fused_step=True,
-                 cuda_graph=None):
+                 cuda_graph=None, ViT_task_specific_ln=False):
         self.geometry = geometry
         self.split, self.transfer_heads = split, transfer_heads       # run_training.py -s / --transfer_heads
         # strict_reference: reproduce the reference's generator-exhaustion quirks Q1 / Q2; False = the
@@ -95,6 +95,7 @@ class nnUNetTrainerMultiHead:
         self._steps, self._step_inputs = {}, None
         self.mh_network = None
         self.use_vit, self.vit_version, self.vit_type = use_vit, vit_version, vit_type   # run_training.py --use_vit
+        self.ViT_task_specific_ln = bool(ViT_task_specific_ln)                           # run_training.py --task_specific_ln
         self.precision = precision
         self.batch_dice = batch_dice
         if device is None:
@@ -107,7 +108,8 @@ class nnUNetTrainerMultiHead:
                                          "tasks_at_time_of_checkpoint": [], "active_task_at_time_of_checkpoint": None}}
         self._init_kwargs = dict(precision=precision, batch_dice=batch_dice, initial_lr=initial_lr, weight_decay=weight_decay,
                                  max_num_epochs=max_num_epochs, seed=seed, task=task, use_vit=use_vit, vit_version=vit_version,
-                                 vit_type=vit_type, split=split, transfer_heads=transfer_heads, strict_reference=strict_reference)
+                                 vit_type=vit_type, split=split, transfer_heads=transfer_heads, strict_reference=strict_reference,
+                                 ViT_task_specific_ln=ViT_task_specific_ln)
         self.ddp = ddp
         self.initial_lr, self.weight_decay, self.max_num_epochs = initial_lr, weight_decay, max_num_epochs
         self.seed, self.task = seed, task
@@ -130,7 +132,10 @@ class nnUNetTrainerMultiHead:
         if self.use_vit:     # MultiHead:357 -> nnViTUNetTrainer.initialize_network (:117-125)
             self.network = Generic_ViT_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool,
                                             [int(s) for s in g.patch], vit_version=self.vit_version,
-                                            vit_type=self.vit_type, **kw)
+                                            vit_type=self.vit_type, ViT_task_specific_ln=self.ViT_task_specific_ln,
+                                            first_task_name=self.task, **kw)
+            if self.ViT_task_specific_ln:    # nnViTUNetTrainer.py:128-129
+                self.network.ViT.use_task(self.task)
         else:
             self.network = Generic_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool, **kw)
         self.network.precision = self.precision
@@ -164,10 +169,21 @@ class nnUNetTrainerMultiHead:
         the last trained head with transfer_heads) and the running model is assembled for it"""
         if task not in self.mh_network.heads:
             self.mh_network.add_new_task(task, use_init=not self.transfer_heads)
+        new_lns = False
+        if self.use_vit and self.ViT_task_specific_ln:      # MultiHead:554-561
+            if task not in self.network.ViT.norm:
+                self.network.ViT.register_new_task(task)
+                new_lns = True
+            self.network.ViT.use_task(task)
         self.network = self.mh_network.assemble_model(task)
         self.task = task
         self.already_trained_on[str(self.fold)]["start_training_on"] = task
         self._steps = {}
+        if new_lns and self.optimizer is not None:          # the new LayerNorms are trainable parameters of this task
+            known = {id(p) for g in self.optimizer.param_groups for p in g['params']}
+            fresh = [p for p in self.network.parameters() if id(p) not in known]
+            if fresh:
+                self.optimizer.param_groups[0]['params'].extend(fresh)
 
     # -- reference MultiHead:294-301 ---------------------------------------------------------------------------------
     def initialize_optimizer_and_scheduler(self):

@@ -1,6 +1,7 @@
 """``VisionTransformer`` -- host-side mirror of the reference's 3D ViT (reference
 nnunet_ext/network_architecture/vision_transformer.py:218-458) for the ``Generic_ViT_UNet`` V1 build: one 3D patch
-embedding, one head, no LSA / SPT / task-specific LayerNorms (those variants raise).
+embedding, one head, optionally task-specific LayerNorms (:380-416); LSA / SPT raise (SPT cannot run on 3D inputs in the
+reference either: its Rearrange pattern is 4-D).
 
 Two execution paths:
 * bf16 mode (production): the whole ViT -- patch embedding, 12 blocks, final norm, head, forward AND backward -- runs in
@@ -31,16 +32,17 @@ VIT_TYPES = {'base': {'embed_size': 768, 'head': 12, 'layers': 12},
 class PatchEmbed(nn.Module):
     """vision_transformer.py:16-79, 3D branch: cubic patches of edge `patch`, flattened in (d, h, w) raster order."""
 
-    def __init__(self, img_size, patch, in_chans, embed_dim):
+    def __init__(self, img_size, patch, in_chans, embed_dim, task_specific_ln=False, task_name=None):
         super().__init__()
         d, h, w = (int(s) for s in img_size)
         self.img_size, self.patch_size = (d, h, w), (d, patch, patch)     # attribute quirk of :43-44 kept
         self.patch = int(patch)
         self.grid_size = (d // patch, h // patch, w // patch)
         self.num_patches = (w // patch) * (h // patch) * (d // patch)     # :47
-        self.flatten, self.embed2D, self.task_specific_ln = True, False, False
+        self.flatten, self.embed2D, self.task_specific_ln = True, False, bool(task_specific_ln)
         self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch, stride=patch)   # parameter container
-        self.norm = nn.Identity()
+        # Generic_ViT_UNet passes norm_layer=None: Identity, or a ModuleDict of Identities per task (:55-57)
+        self.norm = nn.ModuleDict({task_name: nn.Identity()}) if self.task_specific_ln else nn.Identity()
 
     def forward(self, x, task_name=None):
         B, Cc, D, H, W = x.shape
@@ -98,25 +100,42 @@ class Attention(nn.Module):
 
 
 class Block(nn.Module):
-    def __init__(self, dim, num_heads, eps):
+    """vision_transformer.py:153-198: with task-specific LNs, norm1 / norm2 are ModuleDicts keyed by task name and
+    `use_task_name` (set through VisionTransformer.use_task) selects the pair used by forward"""
+
+    def __init__(self, dim, num_heads, eps, task_specific_ln=False, task_name=None):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim, eps=eps)
+        self.task_specific_ln = bool(task_specific_ln)
+        if self.task_specific_ln:
+            self.use_task_name = None
+            assert task_name is not None and isinstance(task_name, str), \
+                "When using task specific LNs, than please provide a task_name during initialization.."
+        mk = lambda: nn.ModuleDict({task_name: nn.LayerNorm(dim, eps=eps)}) if self.task_specific_ln else nn.LayerNorm(dim, eps=eps)
+        self.norm1 = mk()
         self.attn = Attention(dim, num_heads)
         self.drop_path = nn.Identity()
-        self.norm2 = nn.LayerNorm(dim, eps=eps)
+        self.norm2 = mk()
         self.mlp = Mlp(dim, 4 * dim)
-        self.task_specific_ln = False
+
+    def norms(self):
+        """the (norm1, norm2) LayerNorm pair the next forward uses"""
+        if not self.task_specific_ln:
+            return self.norm1, self.norm2
+        assert self.use_task_name is not None and isinstance(self.use_task_name, str), \
+            "When using task specific LNs, than please set a task_name for the forward call using ViT.use_task(..).."
+        return self.norm1[self.use_task_name], self.norm2[self.use_task_name]
 
     def forward(self, x):
-        a, w = self.attn(self.norm1(x))
+        n1, n2 = self.norms()
+        a, w = self.attn(n1(x))
         x = x + a
-        return x + self.mlp(self.norm2(x)), w
+        return x + self.mlp(n2(x)), w
 
 
 class Encoder(nn.Module):
-    def __init__(self, depth, dim, num_heads, eps):
+    def __init__(self, depth, dim, num_heads, eps, task_specific_ln=False, task_name=None):
         super().__init__()
-        self.layer = nn.ModuleList([Block(dim, num_heads, eps) for _ in range(depth)])
+        self.layer = nn.ModuleList([Block(dim, num_heads, eps, task_specific_ln, task_name) for _ in range(depth)])
 
     def forward(self, x):
         ws = []
@@ -131,10 +150,14 @@ class VisionTransformer(nn.Module):
                  num_heads=12, mlp_ratio=4, qkv_bias=True, task_specific_ln=False, task_name=None, is_LSA=False,
                  is_SPT=False, **ignored):
         super().__init__()
-        if ViT_2d or task_specific_ln or is_LSA or is_SPT or mlp_ratio != 4 or not qkv_bias:
-            raise NotImplementedError("b200unet.VisionTransformer: only the 3D V1 build without LSA / SPT / task-specific "
-                                      "LayerNorms is implemented")
-        self.LSA, self.SPT, self.task_specific_ln = False, False, False
+        if task_specific_ln:
+            assert not is_SPT and not is_LSA, "Currently, we do not provide the combination for task specific LNs and either LSA, SPT or both.."
+            assert task_name is not None and isinstance(task_name, str), \
+                "When using task specific LNs, than please provide a task_name during initialization.."
+        if ViT_2d or is_LSA or is_SPT or mlp_ratio != 4 or not qkv_bias:
+            raise NotImplementedError("b200unet.VisionTransformer: only the 3D build without LSA / SPT is implemented")
+        self.LSA, self.SPT, self.task_specific_ln = False, False, bool(task_specific_ln)
+        self.task_name_use = None
         self.block_depth, self.embed_dim, self.num_features = depth, embed_dim, embed_dim
         self.num_tokens, self.num_classes = 1, int(num_classes)
         self.attn_weights = None
@@ -142,11 +165,13 @@ class VisionTransformer(nn.Module):
         eps = 1e-6
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         pe = PatchEmbed((img_depth[0], img_size[1], img_size[2]) if len(img_size) == 3 else (img_depth[0],) + tuple(img_size),
-                        patch_size[0], in_chans, embed_dim)
+                        patch_size[0], in_chans, embed_dim, self.task_specific_ln, task_name)
         self.pos_embed_0 = nn.Parameter(torch.zeros(1, pe.num_patches + 1, embed_dim))
         self.pos_drop = nn.Identity()
-        self.blocks = Encoder(depth, embed_dim, num_heads, eps)
-        self.norm = nn.LayerNorm(embed_dim, eps=eps)
+        self.blocks = Encoder(depth, embed_dim, num_heads, eps, self.task_specific_ln, task_name)
+        self._ln_eps = eps
+        self.norm = nn.ModuleDict({task_name: nn.LayerNorm(embed_dim, eps=eps)}) if self.task_specific_ln \
+            else nn.LayerNorm(embed_dim, eps=eps)
         self.pre_logits = nn.Identity()
         self.patch_embeds = nn.ModuleList([pe])
         self.heads = nn.ModuleList([nn.Linear(embed_dim, self.num_classes)])
@@ -160,11 +185,22 @@ class VisionTransformer(nn.Module):
         """parameters in named_parameters() order of the reference module (what b2_vit_forward expects)"""
         ps = [self.cls_token, self.pos_embed_0]
         for blk in self.blocks.layer:
-            ps += [blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias, blk.attn.proj.weight, blk.attn.proj.bias,
-                   blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
+            n1, n2 = blk.norms()          # task-specific LNs: the active task's pair (the kernels see plain LayerNorms)
+            ps += [n1.weight, n1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias, blk.attn.proj.weight, blk.attn.proj.bias,
+                   n2.weight, n2.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
         pe = self.patch_embeds[0]
-        ps += [self.norm.weight, self.norm.bias, pe.proj.weight, pe.proj.bias, self.heads[0].weight, self.heads[0].bias]
+        norm = self._final_norm(None)
+        ps += [norm.weight, norm.bias, pe.proj.weight, pe.proj.bias, self.heads[0].weight, self.heads[0].bias]
         return ps
+
+    def _final_norm(self, task_name):
+        if not self.task_specific_ln:
+            return self.norm
+        if task_name is None:
+            assert self.task_name_use is not None, ("Either set the task_name during forward or using the use_task function "
+                                                    "when training with task specific LNs..")
+            task_name = self.task_name_use
+        return self.norm[task_name]
 
     def native_supported(self, x):
         blk = self.blocks.layer[0]
@@ -182,7 +218,7 @@ class VisionTransformer(nn.Module):
             d.embed, d.heads, d.depth, d.mlp_ratio = self.embed_dim, self.blocks.layer[0].attn.num_heads, self.block_depth, 4
             d.out_features = self.num_classes
             d.out_c, d.out_d, d.out_h, d.out_w = (int(v) for v in out_shape)
-            d.ln_eps = float(self.norm.eps)
+            d.ln_eps = float(self._ln_eps)
             h = C.c_void_p()
             _lib.check(lib.b2_vit_plan_create(C.byref(d), C.byref(h)))
             ws = torch.empty(int(lib.b2_vit_workspace_bytes(h)), dtype=torch.uint8, device=x.device)
@@ -200,20 +236,35 @@ class VisionTransformer(nn.Module):
         return _ViTNativeFunction.apply(self, x, dskip, tuple(out_shape), *self._native_params())
 
     def register_new_task(self, task_name):
-        raise NotImplementedError("task-specific LayerNorms (vision_transformer.py:380-416) are not built yet")
+        """vision_transformer.py:380-401: a fresh LayerNorm set (final norm, every block's norm1 / norm2, Identity for the
+        patch embedding) under `task_name`; selecting it is use_task's job"""
+        assert not (self.SPT or self.LSA), "When using SPT or LSA, task specific LNs are not allowed, so you can not call this function.."
+        assert self.task_specific_ln, "register_new_task needs a ViT built with task_specific_ln=True"
+        ref = next(iter(self.norm.values())).weight
+        mk = lambda: nn.LayerNorm(self.embed_dim, eps=self._ln_eps).to(device=ref.device, dtype=ref.dtype)
+        self.norm[task_name] = mk()
+        for pe in self.patch_embeds:
+            pe.norm[task_name] = nn.Identity()
+        for blk in self.blocks.layer:
+            blk.norm1[task_name], blk.norm2[task_name] = mk(), mk()
 
     def use_task(self, task_name):
-        raise NotImplementedError("task-specific LayerNorms (vision_transformer.py:380-416) are not built yet")
+        """vision_transformer.py:403-416"""
+        assert not (self.SPT or self.LSA), "When using SPT or LSA, task specific LNs are not allowed, so you can not call this function.."
+        self.task_name_use = task_name
+        for blk in self.blocks.layer:
+            blk.use_task_name = task_name
 
     def forward(self, x, idx=0, task_name=None):   # :418-458
         for blk in self.blocks.layer:
             blk.attn.store_weights = self.store_attn_weights
+        norm = self._final_norm(task_name)
         x = self.patch_embeds[idx](x, task_name)
         cls = self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype)
         x = torch.cat((cls, x), dim=1) + getattr(self, 'pos_embed_' + str(idx)).to(x.dtype)
         x, ws = self.blocks(x)
         self.attn_weights = ws if self.store_attn_weights else None
-        return self.heads[idx](self.pre_logits(self.norm(x)[:, 0]))
+        return self.heads[idx](self.pre_logits(norm(x)[:, 0]))
 
 
 def _view_of(t):

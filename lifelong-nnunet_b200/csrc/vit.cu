@@ -7,8 +7,8 @@
 //     split-K with an ordered fp32 reduction when a launch has few output tiles).  Backward: dX = dY W uses the transposed
 //     bf16 weight shadow, dW = dY^T X uses transposed bf16 activation copies and writes fp32 straight into the gradient.
 //   * LayerNorm, GELU, residual adds, token assembly, bias gradients: HBM-bound elementwise / two-stage reductions.
-//   * attention over T = 433 tokens x 64 dims per head: 0.6 GFLOP per pass -- a shared-memory SIMT kernel per (batch, head,
-//     query block), softmax in fp32, backward by recomputation from the saved log-sum-exp (no T x T tensor in HBM).
+//   * attention over T = 433 tokens x 64 dims per head: 1.2 GFLOP per pass -- flash-style warp-MMA kernels per (batch, head,
+//     64-row block), online softmax in fp32, backward by recomputation from the saved log-sum-exp (no T x T tensor in HBM).
 //   * head Linear(E -> prod(bottleneck)) acts on the B class tokens only: a streaming GEMV over the fp32 weight (212 MB at
 //     cfg4), written straight into the plan's NDHWC bottleneck activation; backward = outer product + ordered GEMV.
 // All reductions are fixed-order (bit-reproducible).  The residual stream is kept in fp32.
@@ -319,226 +319,370 @@ __global__ void __launch_bounds__(256) assemble_tokens_bwd_kernel(const float* _
 
 // ---------------------------------------------------------------------------------------------------------------
 // attention (head dim 64), qkv: [B*T][3E] bf16 with column = which * E + h * 64 + d
+//
+// Flash-style warp-MMA kernels (mma.sync.m16n8k16 bf16 -> fp32; 1.2 GFLOP per pass at cfg4 is far too small for a tcgen05
+// pipeline to pay for its set-up): a CTA of 4 warps owns 64 rows (queries, or keys in the dK / dV kernel), a warp 16 of them.
+// The other side streams through shared memory in blocks of 64 rows, double-buffered with cp.async; row pitch 144 B makes
+// every ldmatrix phase conflict-free.  Forward: online softmax in fp32 (exp2 with the scale folded in), P rounded to bf16
+// for the P V product, log-sum-exp saved.  Backward: recomputation from the saved log-sum-exp; dQ in one kernel (per query
+// block, over all keys) and dK / dV in another (per key block, over all queries), so that no gradient needs an atomic:
+// every output element is produced by ONE thread in a fixed order (bit-reproducible).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int AT_THREADS = 256;  // 8 warps
-constexpr int AT_LD = 66;        // padded row (64 dims + 2): rows 132 B apart => a fixed dim over 32 consecutive rows hits 32 banks,
-                                 // and a fixed row over consecutive dims is contiguous: ONE copy serves both access patterns
+constexpr int FA_THREADS = 128;  // 4 warps x 16 rows
+constexpr int FA_ROWS = 64;
+constexpr int FA_LD = 72;        // bf16 elements per shared-memory row (64 dims + 8 pad = 144 B)
+constexpr int FA_TILE = FA_ROWS * FA_LD;
+constexpr float LOG2E = 1.4426950408889634f;
 
-// copy the 64-column slice `src[j][0..64)` (row pitch ld) of rows [0, T) into shared [Tp][AT_LD]; rows >= T are zero
-__device__ __forceinline__ void load_rows(const __nv_bfloat16* __restrict__ src, long long ld, int T, int Tp, __nv_bfloat16* dst) {
-    for (int i = threadIdx.x; i < Tp * 8; i += AT_THREADS) {
-        const int j = i >> 3, d8 = (i & 7) * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (j < T) v = *reinterpret_cast<const uint4*>(src + (long long)j * ld + d8);
-        uint32_t* o = reinterpret_cast<uint32_t*>(dst + j * AT_LD + d8);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// stage rows [r0, r0 + 64) of a 64-column slice (row pitch ld elements) into a shared tile; rows >= T repeat row T - 1 (finite
+// values; the consumers mask them)
+__device__ __forceinline__ void fa_stage(const __nv_bfloat16* __restrict__ src, long long ld, int r0, int T, __nv_bfloat16* tile) {
+    for (int i = threadIdx.x; i < FA_ROWS * 8; i += FA_THREADS) {
+        const int r = i >> 3, c8 = (i & 7) * 8;
+        const int gr = min(r0 + r, T - 1);
+        cp_async16(tile + r * FA_LD + c8, src + (long long)gr * ld + c8);
+    }
+}
+// A fragments (16 rows x 64 dims) of a warp's rows [w16, w16 + 16) of a tile
+__device__ __forceinline__ void fa_load_a(uint32_t (&a)[4][4], const __nv_bfloat16* tile, int w16, int lane) {
+    const __nv_bfloat16* p = tile + (w16 + (lane & 7) + ((lane >> 3) & 1) * 8) * FA_LD + (lane >> 4) * 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldsm4(a[kk], p + kk * 16);
+}
+// acc[16 x 64] = A (16 x 64 dims) . tile^T   (tile: 64 rows x 64 dims; acc column = tile row)
+__device__ __forceinline__ void fa_mma_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], const __nv_bfloat16* tile, int lane) {
+    const __nv_bfloat16* p = tile + ((lane & 7) + (lane >> 4) * 8) * FA_LD + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int nb2 = 0; nb2 < 4; ++nb2)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t b[4];
+            ldsm4(b, p + nb2 * 16 * FA_LD + kk * 16);
+            mma_bf16(acc[2 * nb2], a[kk], b[0], b[1]);
+            mma_bf16(acc[2 * nb2 + 1], a[kk], b[2], b[3]);
+        }
+}
+// acc[16 x 64 dims] += P (16 x 64 rows of the tile, A fragments) . tile   (tile: 64 rows x 64 dims)
+__device__ __forceinline__ void fa_mma_nn(float (&acc)[8][4], const uint32_t (&pa)[4][4], const __nv_bfloat16* tile, int lane) {
+    const __nv_bfloat16* p = tile + ((lane & 7) + ((lane >> 3) & 1) * 8) * FA_LD + (lane >> 4) * 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int nb2 = 0; nb2 < 4; ++nb2) {
+            uint32_t b[4];
+            ldsm4t(b, p + kk * 16 * FA_LD + nb2 * 16);
+            mma_bf16(acc[2 * nb2], pa[kk], b[0], b[1]);
+            mma_bf16(acc[2 * nb2 + 1], pa[kk], b[2], b[3]);
+        }
+}
+// accumulator tile (16 x 64, fp32) -> A fragments (bf16)
+__device__ __forceinline__ void fa_acc_to_a(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        pa[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    }
+}
+// write a warp's 16 x 64 accumulator (times `mul`) as bf16 rows (row pitch ld) for rows < T
+__device__ __forceinline__ void fa_store(const float (&acc)[8][4], float mul0, float mul1, __nv_bfloat16* __restrict__ dst, long long ld,
+                                         int row0, int T, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        if (row0 + g < T)
+            *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g) * ld + nb * 8 + 2 * t) = pack_bf16(acc[nb][0] * mul0, acc[nb][1] * mul0);
+        if (row0 + g + 8 < T)
+            *reinterpret_cast<uint32_t*>(dst + (long long)(row0 + g + 8) * ld + nb * 8 + 2 * t) = pack_bf16(acc[nb][2] * mul1, acc[nb][3] * mul1);
     }
 }
 
 // out[b*T + i][h*64 + d] = sum_j softmax_j(scale q_i.k_j) v_j[d];  lse[(b*H + h)*T + i] = log sum_j exp(scale q_i.k_j)
-// grid = (B*H, row blocks): a block stages K and V of its head once and its 8 warps walk the block's queries
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                              float* __restrict__ lse, int B, int H, int T, int Tp, int rows_per_block,
-                                                              float scale) {
+__global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                              float* __restrict__ lse, int B, int H, int T, float scale) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
-    const int E = H * 64;
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [Tp][AT_LD]
-    __nv_bfloat16* Vs = Ks + (size_t)Tp * AT_LD;                                 // [Tp][AT_LD]
-    float* ps = reinterpret_cast<float*>(Vs + (size_t)Tp * AT_LD);               // [8][Tp]
-    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
+    __nv_bfloat16* Ks = Qs + FA_TILE;                                // [2][64][FA_LD]
+    __nv_bfloat16* Vs = Ks + 2 * FA_TILE;                            // [2][64][FA_LD]
+    const int E = H * 64, bh = blockIdx.x, b = bh / H, h = bh % H;
     const long long ld = 3LL * E;
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
-    load_rows(base + E, ld, T, Tp, Ks);
-    load_rows(base + 2 * E, ld, T, Tp, Vs);
-    __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* pw = ps + (size_t)w * Tp;
-    const int nk = Tp / 32;
-    const int q_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
-    for (int qi = blockIdx.y * rows_per_block + w; qi < q_end; qi += 8) {
-        const __nv_bfloat16* qr = base + (long long)qi * ld;
-        const float q0 = __bfloat162float(qr[lane]) * scale, q1 = __bfloat162float(qr[lane + 32]) * scale;
-        float acc[16];
+    const int q0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    fa_stage(base, ld, q0, T, Qs);
+    fa_stage(base + E, ld, 0, T, Ks);
+    fa_stage(base + 2 * E, ld, 0, T, Vs);
+    cp_async_commit();
+    uint32_t aq[4][4];
+    float o[8][4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-        for (int d = 0; d < 64; ++d) {
-            const float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
-            const __nv_bfloat16* kr = Ks + lane * AT_LD + d;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nk) acc[k] = fmaf(qd, __bfloat162float(kr[32 * k * AT_LD]), acc[k]);
+    for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const float sl2 = scale * LOG2E;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int cur = jb & 1;
+        if (jb + 1 < nblk) {
+            fa_stage(base + E, ld, (jb + 1) * FA_ROWS, T, Ks + (cur ^ 1) * FA_TILE);
+            fa_stage(base + 2 * E, ld, (jb + 1) * FA_ROWS, T, Vs + (cur ^ 1) * FA_TILE);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        float m = -INFINITY;
+        __syncthreads();
+        if (jb == 0) fa_load_a(aq, Qs, warp * 16, lane);
+        float s[8][4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk && lane + 32 * k < T) m = fmaxf(m, acc[k]);
+        for (int nb = 0; nb < 8; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        fa_mma_nt(s, aq, Ks + cur * FA_TILE, lane);
+        float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk) {
-                const float e = lane + 32 * k < T ? expf(acc[k] - m) : 0.f;
-                acc[k] = e;
-                s += e;
-            }
-        s = warp_sum(s);
-        const float inv = 1.f / s;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk) pw[lane + 32 * k] = acc[k] * inv;
-        __syncwarp();
-        float o0 = 0.f, o1 = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < T; ++j) {
-            const float pj = pw[j];
-            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + j * AT_LD + 2 * lane));
-            o0 = fmaf(pj, vv.x, o0);
-            o1 = fmaf(pj, vv.y, o1);
+        for (int nb = 0; nb < 8; ++nb) {
+            const int j = jb * FA_ROWS + nb * 8 + 2 * t;
+            if (j >= T) s[nb][0] = s[nb][2] = -INFINITY;
+            if (j + 1 >= T) s[nb][1] = s[nb][3] = -INFINITY;
+            bm0 = fmaxf(bm0, fmaxf(s[nb][0], s[nb][1]));
+            bm1 = fmaxf(bm1, fmaxf(s[nb][2], s[nb][3]));
         }
-        *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * T + qi) * E + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0, o1);
-        if (lane == 0) lse[(long long)bh * T + qi] = m + logf(s);
-        __syncwarp();
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);       // finite: every key block holds at least one valid key
+        const float al0 = exp2f((m0 - n0) * sl2), al1 = exp2f((m1 - n1) * sl2);
+        m0 = n0; m1 = n1;
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = exp2f((s[nb][0] - n0) * sl2); s[nb][1] = exp2f((s[nb][1] - n0) * sl2);
+            s[nb][2] = exp2f((s[nb][2] - n1) * sl2); s[nb][3] = exp2f((s[nb][3] - n1) * sl2);
+            r0 += s[nb][0] + s[nb][1];
+            r1 += s[nb][2] + s[nb][3];
+            o[nb][0] *= al0; o[nb][1] *= al0; o[nb][2] *= al1; o[nb][3] *= al1;
+        }
+        l0 = l0 * al0 + r0;
+        l1 = l1 * al1 + r1;
+        uint32_t pa[4][4];
+        fa_acc_to_a(pa, s);
+        fa_mma_nn(o, pa, Vs + cur * FA_TILE, lane);
+        __syncthreads();
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const int row0 = q0 + warp * 16;
+    fa_store(o, 1.f / l0, 1.f / l1, out + (long long)b * T * E + h * 64, E, row0, T, lane);
+    if (t == 0) {
+        if (row0 + g < T) lse[(long long)bh * T + row0 + g] = m0 * scale + logf(l0);
+        if (row0 + g + 8 < T) lse[(long long)bh * T + row0 + g + 8] = m1 * scale + logf(l1);
     }
 }
 
 // dQ (and the row terms D_i = dO_i . O_i):  dS_ij = p_ij (dO_i . v_j - D_i);  dq_i = scale sum_j dS_ij k_j
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ O,
+__global__ void __launch_bounds__(FA_THREADS) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ O,
                                                                 const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                                                                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ Drow, int B, int H,
-                                                                int T, int Tp, int rows_per_block, float scale) {
+                                                                int T, float scale) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
-    const int E = H * 64;
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);   // [Tp][AT_LD]
-    __nv_bfloat16* Vs = Ks + (size_t)Tp * AT_LD;                   // [Tp][AT_LD]
-    float* ps = reinterpret_cast<float*>(Vs + (size_t)Tp * AT_LD); // [8][Tp]
-    const int bh = blockIdx.x, b = bh / H, h = bh % H;
-    const long long ld = 3LL * E;
-    const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
-    load_rows(base + E, ld, T, Tp, Ks);
-    load_rows(base + 2 * E, ld, T, Tp, Vs);
-    __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* pw = ps + (size_t)w * Tp;
-    const int nk = Tp / 32;
-    const int q_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
-    for (int qi = blockIdx.y * rows_per_block + w; qi < q_end; qi += 8) {
-        const __nv_bfloat16* qr = base + (long long)qi * ld;
-        const long long orow = ((long long)b * T + qi) * E + h * 64;
-        const float q0 = __bfloat162float(qr[lane]) * scale, q1 = __bfloat162float(qr[lane + 32]) * scale;
-        const float g0 = __bfloat162float(dO[orow + lane]), g1 = __bfloat162float(dO[orow + lane + 32]);
-        float dsum = g0 * __bfloat162float(O[orow + lane]) + g1 * __bfloat162float(O[orow + lane + 32]);
-        dsum = warp_sum(dsum);
-        const float L = lse[(long long)bh * T + qi];
-        float s[16], dp[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) { s[k] = 0.f; dp[k] = 0.f; }
-        for (int d = 0; d < 64; ++d) {
-            const float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
-            const float gd = __shfl_sync(0xffffffffu, d < 32 ? g0 : g1, d & 31);
-            const __nv_bfloat16* kr = Ks + lane * AT_LD + d;
-            const __nv_bfloat16* vr = Vs + lane * AT_LD + d;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nk) {
-                    s[k] = fmaf(qd, __bfloat162float(kr[32 * k * AT_LD]), s[k]);
-                    dp[k] = fmaf(gd, __bfloat162float(vr[32 * k * AT_LD]), dp[k]);
-                }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk) {
-                const float p = lane + 32 * k < T ? expf(s[k] - L) : 0.f;
-                pw[lane + 32 * k] = p * (dp[k] - dsum);
-            }
-        __syncwarp();
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < T; ++j) {
-            const float dsj = pw[j];
-            const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + j * AT_LD + 2 * lane));
-            a0 = fmaf(dsj, kk.x, a0);
-            a1 = fmaf(dsj, kk.y, a1);
-        }
-        *reinterpret_cast<__nv_bfloat162*>(dqkv + ((long long)b * T + qi) * ld + h * 64 + 2 * lane) = __floats2bfloat162_rn(a0 * scale, a1 * scale);
-        if (lane == 0) Drow[(long long)bh * T + qi] = dsum;
-        __syncwarp();
-    }
-}
-
-// dK, dV:  dv_j = sum_i p_ij dO_i;  dk_j = scale sum_i dS_ij q_i      (a block stages Q and dO of its head and walks its keys)
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
-                                                                 const float* __restrict__ lse, const float* __restrict__ Drow,
-                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, int Tp,
-                                                                 int rows_per_block, float scale) {
-    pdl_grid_sync();
-    extern __shared__ __align__(16) uint8_t smraw[];
-    const int E = H * 64;
-    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);   // [Tp][AT_LD]
-    __nv_bfloat16* Gs = Qs + (size_t)Tp * AT_LD;                   // dO [Tp][AT_LD]
-    float* ps = reinterpret_cast<float*>(Gs + (size_t)Tp * AT_LD); // [8][2][Tp]: p_ij and dS_ij over i
-    float* Ls = ps + (size_t)16 * Tp;                              // [Tp] lse, [Tp] D
-    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
+    __nv_bfloat16* Gs = Qs + FA_TILE;                                // dO [64][FA_LD]
+    __nv_bfloat16* Ks = Gs + FA_TILE;                                // [2][64][FA_LD]
+    __nv_bfloat16* Vs = Ks + 2 * FA_TILE;                            // [2][64][FA_LD]
+    float* Ds = reinterpret_cast<float*>(Vs + 2 * FA_TILE);          // [64]
+    const int E = H * 64, bh = blockIdx.x, b = bh / H, h = bh % H;
     const long long ld = 3LL * E;
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
     const __nv_bfloat16* gbase = dO + (long long)b * T * E + h * 64;
-    load_rows(base, ld, T, Tp, Qs);
-    load_rows(gbase, E, T, Tp, Gs);
-    for (int i = threadIdx.x; i < Tp; i += AT_THREADS) {
-        Ls[i] = i < T ? lse[(long long)bh * T + i] : 0.f;
-        Ls[Tp + i] = i < T ? Drow[(long long)bh * T + i] : 0.f;
-    }
-    __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* pp = ps + (size_t)w * 2 * Tp;
-    float* pd = pp + Tp;
-    const int nk = Tp / 32;
-    const int k_end = (blockIdx.y + 1) * rows_per_block < T ? (blockIdx.y + 1) * rows_per_block : T;
-    for (int kj = blockIdx.y * rows_per_block + w; kj < k_end; kj += 8) {
-        const __nv_bfloat16* kr = base + E + (long long)kj * ld;
-        const __nv_bfloat16* vr = base + 2 * E + (long long)kj * ld;
-        const float k0 = __bfloat162float(kr[lane]) * scale, k1 = __bfloat162float(kr[lane + 32]) * scale;
-        const float v0 = __bfloat162float(vr[lane]), v1 = __bfloat162float(vr[lane + 32]);
-        float s[16], dp[16];
+    const __nv_bfloat16* obase = O + (long long)b * T * E + h * 64;
+    const int q0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    fa_stage(base, ld, q0, T, Qs);
+    fa_stage(gbase, E, q0, T, Gs);
+    fa_stage(base + E, ld, 0, T, Ks);
+    fa_stage(base + 2 * E, ld, 0, T, Vs);
+    cp_async_commit();
+    {   // D_i = dO_i . O_i: two threads per row, 32 dims each, fixed order
+        const int r = threadIdx.x >> 1, half = threadIdx.x & 1, gr = min(q0 + r, T - 1);
+        float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { s[k] = 0.f; dp[k] = 0.f; }
-        for (int d = 0; d < 64; ++d) {
-            const float kd = __shfl_sync(0xffffffffu, d < 32 ? k0 : k1, d & 31);
-            const float vd = __shfl_sync(0xffffffffu, d < 32 ? v0 : v1, d & 31);
-            const __nv_bfloat16* qr = Qs + lane * AT_LD + d;
-            const __nv_bfloat16* gr = Gs + lane * AT_LD + d;
+        for (int c = 0; c < 4; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(gbase + (long long)gr * E + half * 32 + c * 8);
+            const uint4 o4 = *reinterpret_cast<const uint4*>(obase + (long long)gr * E + half * 32 + c * 8);
+            const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* op = reinterpret_cast<const __nv_bfloat162*>(&o4);
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nk) {
-                    s[k] = fmaf(kd, __bfloat162float(qr[32 * k * AT_LD]), s[k]);
-                    dp[k] = fmaf(vd, __bfloat162float(gr[32 * k * AT_LD]), dp[k]);
-                }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk) {
-                const int i = lane + 32 * k;
-                const float p = i < T ? expf(s[k] - Ls[i]) : 0.f;
-                pp[i] = p;
-                pd[i] = p * (dp[k] - Ls[Tp + i]);
+            for (int e = 0; e < 4; ++e) {
+                const float2 x = __bfloat1622float2(ap[e]), y = __bfloat1622float2(op[e]);
+                acc = fmaf(x.x, y.x, acc);
+                acc = fmaf(x.y, y.y, acc);
             }
-        __syncwarp();
-        float dv0 = 0.f, dv1 = 0.f, dk0 = 0.f, dk1 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < T; ++i) {
-            const float p = pp[i], dsi = pd[i];
-            const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Gs + i * AT_LD + 2 * lane));
-            const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Qs + i * AT_LD + 2 * lane));
-            dv0 = fmaf(p, gg.x, dv0); dv1 = fmaf(p, gg.y, dv1);
-            dk0 = fmaf(dsi, qq.x, dk0); dk1 = fmaf(dsi, qq.y, dk1);
         }
-        __nv_bfloat16* orow = dqkv + ((long long)b * T + kj) * ld + h * 64 + 2 * lane;
-        *reinterpret_cast<__nv_bfloat162*>(orow + E) = __floats2bfloat162_rn(dk0 * scale, dk1 * scale);
-        *reinterpret_cast<__nv_bfloat162*>(orow + 2 * E) = __floats2bfloat162_rn(dv0, dv1);
-        __syncwarp();
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) {
+            Ds[r] = acc;
+            if (q0 + r < T) Drow[(long long)bh * T + q0 + r] = acc;
+        }
     }
+    const int row0 = q0 + warp * 16;
+    const float L0 = lse[(long long)bh * T + min(row0 + g, T - 1)] * LOG2E, L1 = lse[(long long)bh * T + min(row0 + g + 8, T - 1)] * LOG2E;
+    uint32_t aq[4][4], ag[4][4];
+    float dq[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) dq[nb][0] = dq[nb][1] = dq[nb][2] = dq[nb][3] = 0.f;
+    const float sl2 = scale * LOG2E;
+    float D0 = 0.f, D1 = 0.f;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int cur = jb & 1;
+        if (jb + 1 < nblk) {
+            fa_stage(base + E, ld, (jb + 1) * FA_ROWS, T, Ks + (cur ^ 1) * FA_TILE);
+            fa_stage(base + 2 * E, ld, (jb + 1) * FA_ROWS, T, Vs + (cur ^ 1) * FA_TILE);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (jb == 0) {
+            fa_load_a(aq, Qs, warp * 16, lane);
+            fa_load_a(ag, Gs, warp * 16, lane);
+            D0 = Ds[warp * 16 + g];
+            D1 = Ds[warp * 16 + g + 8];
+        }
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+            dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+        }
+        fa_mma_nt(s, aq, Ks + cur * FA_TILE, lane);
+        fa_mma_nt(dp, ag, Vs + cur * FA_TILE, lane);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int j = jb * FA_ROWS + nb * 8 + 2 * t;
+            const bool v0 = j < T, v1 = j + 1 < T;
+            s[nb][0] = v0 ? exp2f(s[nb][0] * sl2 - L0) * (dp[nb][0] - D0) : 0.f;
+            s[nb][1] = v1 ? exp2f(s[nb][1] * sl2 - L0) * (dp[nb][1] - D0) : 0.f;
+            s[nb][2] = v0 ? exp2f(s[nb][2] * sl2 - L1) * (dp[nb][2] - D1) : 0.f;
+            s[nb][3] = v1 ? exp2f(s[nb][3] * sl2 - L1) * (dp[nb][3] - D1) : 0.f;
+        }
+        uint32_t pa[4][4];
+        fa_acc_to_a(pa, s);
+        fa_mma_nn(dq, pa, Ks + cur * FA_TILE, lane);
+        __syncthreads();
+    }
+    fa_store(dq, scale, scale, dqkv + (long long)b * T * ld + h * 64, ld, row0, T, lane);
+}
+
+// dK, dV:  dv_j = sum_i p_ij dO_i;  dk_j = scale sum_i dS_ij q_i      (a CTA owns 64 keys and streams the queries / dO)
+__global__ void __launch_bounds__(FA_THREADS) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
+                                                                 const float* __restrict__ lse, const float* __restrict__ Drow,
+                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, float scale) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) uint8_t smraw[];
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
+    __nv_bfloat16* Vs = Ks + FA_TILE;                                // [64][FA_LD]
+    __nv_bfloat16* Qs = Vs + FA_TILE;                                // [2][64][FA_LD]
+    __nv_bfloat16* Gs = Qs + 2 * FA_TILE;                            // dO [2][64][FA_LD]
+    float* Ls = reinterpret_cast<float*>(Gs + 2 * FA_TILE);          // [2][64] lse * log2(e)
+    float* Ds = Ls + 2 * FA_ROWS;                                    // [2][64]
+    const int E = H * 64, bh = blockIdx.x, b = bh / H, h = bh % H;
+    const long long ld = 3LL * E;
+    const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
+    const __nv_bfloat16* gbase = dO + (long long)b * T * E + h * 64;
+    const int k0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3;
+    auto stage_rows = [&](int ib, int buf) {
+        fa_stage(base, ld, ib * FA_ROWS, T, Qs + buf * FA_TILE);
+        fa_stage(gbase, E, ib * FA_ROWS, T, Gs + buf * FA_TILE);
+        if (threadIdx.x < FA_ROWS) {
+            const int i = min(ib * FA_ROWS + (int)threadIdx.x, T - 1);
+            Ls[buf * FA_ROWS + threadIdx.x] = lse[(long long)bh * T + i] * LOG2E;
+            Ds[buf * FA_ROWS + threadIdx.x] = Drow[(long long)bh * T + i];
+        }
+    };
+    fa_stage(base + E, ld, k0, T, Ks);
+    fa_stage(base + 2 * E, ld, k0, T, Vs);
+    stage_rows(0, 0);
+    cp_async_commit();
+    uint32_t ak[4][4], av[4][4];
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        dk[nb][0] = dk[nb][1] = dk[nb][2] = dk[nb][3] = 0.f;
+        dv[nb][0] = dv[nb][1] = dv[nb][2] = dv[nb][3] = 0.f;
+    }
+    const float sl2 = scale * LOG2E;
+    for (int ib = 0; ib < nblk; ++ib) {
+        const int cur = ib & 1;
+        if (ib + 1 < nblk) {
+            stage_rows(ib + 1, cur ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (ib == 0) {
+            fa_load_a(ak, Ks, warp * 16, lane);
+            fa_load_a(av, Vs, warp * 16, lane);
+        }
+        // transposed scores: rows = my keys, columns = the block's queries
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+            dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+        }
+        fa_mma_nt(s, ak, Qs + cur * FA_TILE, lane);
+        fa_mma_nt(dp, av, Gs + cur * FA_TILE, lane);
+        const float* Lc = Ls + cur * FA_ROWS;
+        const float* Dc = Ds + cur * FA_ROWS;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int c = nb * 8 + 2 * t, i = ib * FA_ROWS + c;
+            const bool v0 = i < T, v1 = i + 1 < T;
+            const float La = Lc[c], Lb = Lc[c + 1], Da = Dc[c], Db = Dc[c + 1];
+            const float p0 = v0 ? exp2f(s[nb][0] * sl2 - La) : 0.f, p1 = v1 ? exp2f(s[nb][1] * sl2 - Lb) : 0.f;
+            const float p2 = v0 ? exp2f(s[nb][2] * sl2 - La) : 0.f, p3 = v1 ? exp2f(s[nb][3] * sl2 - Lb) : 0.f;
+            s[nb][0] = p0; s[nb][1] = p1; s[nb][2] = p2; s[nb][3] = p3;
+            dp[nb][0] = p0 * (dp[nb][0] - Da); dp[nb][1] = p1 * (dp[nb][1] - Db);
+            dp[nb][2] = p2 * (dp[nb][2] - Da); dp[nb][3] = p3 * (dp[nb][3] - Db);
+        }
+        uint32_t pa[4][4];
+        fa_acc_to_a(pa, s);
+        fa_mma_nn(dv, pa, Gs + cur * FA_TILE, lane);
+        fa_acc_to_a(pa, dp);
+        fa_mma_nn(dk, pa, Qs + cur * FA_TILE, lane);
+        __syncthreads();
+    }
+    const int row0 = k0 + warp * 16;
+    __nv_bfloat16* ob = dqkv + (long long)b * T * ld + h * 64;
+    fa_store(dk, scale, scale, ob + E, ld, row0, T, lane);
+    fa_store(dv, 1.f, 1.f, ob + 2 * E, ld, row0, T, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -681,7 +825,7 @@ extern "C" int b2_vit_plan_create(const b2_vit_desc* desc, b2_vit_plan** out) {
     p->Mt = d.batch * p->np; p->Mtp = (p->Mt + 127) / 128 * 128;
     p->Kp = d.in_channels * d.patch * d.patch * d.patch;
     p->Tp = (p->T + 31) / 32 * 32;
-    if (p->Tp > 512 || p->Kp % 32 != 0) { delete p; return fail(B2_EUNSUPPORTED, "ViT: more than 512 tokens or patch volume not a multiple of 32%s", ""); }
+    if (p->Kp % 32 != 0) { delete p; return fail(B2_EUNSUPPORTED, "ViT: patch volume not a multiple of 32%s", ""); }
     const size_t E = p->E, Mp = p->Mp, M4 = 4 * E;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
@@ -822,14 +966,8 @@ extern "C" int b2_vit_forward(b2_vit_plan* p, const float* const* params, const 
     if (Mp > M) B2_CUDA(cudaMemsetAsync(X + (size_t)M * E, 0, (size_t)(Mp - M) * E * 4, st));
     B2_LAUNCH(assemble_tokens_kernel, (int)grid_for((long long)M * E, 1), 256, 0, st, (const __nv_bfloat16*)tok, P_.cls(), P_.pos(), X, d.batch, p->np, E);
     __nv_bfloat16* tmp = at<__nv_bfloat16>(ws, p->s_tmp);
-    const size_t at_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)8 * p->Tp * 4;
-    // row blocks per (batch, head): enough blocks to fill the GPU, few enough that staging K / V is amortised
-    int at_blocks = cdiv(num_sms(), d.batch * H);
-    if (at_blocks > cdiv(T, 32)) at_blocks = cdiv(T, 32);
-    const int at_rows = cdiv(cdiv(T, at_blocks), 8) * 8;
-    at_blocks = cdiv(T, at_rows);
-    static bool at_attr = false;
-    if (!at_attr) { B2_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); at_attr = true; }
+    const size_t at_smem = (size_t)5 * FA_TILE * 2;
+    const int at_blocks = cdiv(T, FA_ROWS);
     for (int l = 0; l < d.depth; ++l) {
         char* bb = (char*)ws + p->off_blocks + (size_t)l * p->blk_bytes;
         char* wb = (char*)ws + p->off_w + (size_t)l * p->w_blk_bytes;
@@ -849,8 +987,8 @@ extern "C" int b2_vit_forward(b2_vit_plan* p, const float* const* params, const 
             B2_CUDA(cudaMemsetAsync(Xn2 + (size_t)M * E, 0, (size_t)(Mp - M) * E * 2, st));
         }
         if ((rc = gemm_tn_bf16(Xn, Mp, E, E, (__nv_bfloat16*)(wb + p->w_qkv), 3 * E, P_.blk(l, 3), qkv, 3 * E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
-        B2_LAUNCH(attn_fwd_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, at_smem, st, (const __nv_bfloat16*)qkv, O, (float*)(bb + p->b_lse),
-                  d.batch, H, T, p->Tp, at_rows, 0.125f);
+        B2_LAUNCH(attn_fwd_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, at_smem, st, (const __nv_bfloat16*)qkv, O, (float*)(bb + p->b_lse),
+                  d.batch, H, T, 0.125f);
         if ((rc = gemm_tn_bf16(O, Mp, E, E, (__nv_bfloat16*)(wb + p->w_proj), E, P_.blk(l, 5), tmp, E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
         B2_LAUNCH(add_bf16_kernel, (int)grid_for((long long)M * E, 4), 256, 0, st, X, (const __nv_bfloat16*)tmp, (long long)M * E);
         B2_CUDA(cudaMemcpyAsync(Xmid, X, (size_t)Mp * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -916,16 +1054,13 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
     // transposed operands: columns [M, Mp) must be zero (they are contraction padding)
     B2_CUDA(cudaMemsetAsync(tA, 0, (size_t)4 * E * Mp * 2, st));
     B2_CUDA(cudaMemsetAsync(tB, 0, (size_t)4 * E * Mp * 2, st));
-    const size_t q_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)8 * p->Tp * 4;
-    const size_t kv_smem = (size_t)2 * p->Tp * AT_LD * 2 + (size_t)16 * p->Tp * 4 + (size_t)2 * p->Tp * 4;
-    int at_blocks = cdiv(num_sms(), d.batch * H);
-    if (at_blocks > cdiv(T, 32)) at_blocks = cdiv(T, 32);
-    const int at_rows = cdiv(cdiv(T, at_blocks), 8) * 8;
-    at_blocks = cdiv(T, at_rows);
+    const size_t q_smem = (size_t)6 * FA_TILE * 2 + FA_ROWS * 4;
+    const size_t kv_smem = (size_t)6 * FA_TILE * 2 + 4 * FA_ROWS * 4;
+    const int at_blocks = cdiv(T, FA_ROWS);
     static bool at_attr = false;
     if (!at_attr) {
-        B2_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        B2_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem));
+        B2_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv_smem));
         at_attr = true;
     }
     // dy = bf16(dX) (pad rows are zero because dX's are)
@@ -958,11 +1093,11 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
         if ((rc = linear_bwd(tmp, E, (const __nv_bfloat16*)(bb + p->b_O), E, (const __nv_bfloat16*)(wb + p->w_projT), tmp2, GB(l, 4), GB(l, 5)))) return rc;
         __nv_bfloat16* dqkv = tmp;     // [Mp][3E]
         B2_CUDA(cudaMemsetAsync(dqkv + (size_t)M * 3 * E, 0, (size_t)(Mp - M) * 3 * E * 2, st));
-        B2_LAUNCH(attn_bwd_q_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, q_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
-                  (const __nv_bfloat16*)(bb + p->b_O), (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), dqkv, Drow, d.batch, H, T, p->Tp,
-                  at_rows, 0.125f);
-        B2_LAUNCH(attn_bwd_kv_kernel, dim3(d.batch * H, at_blocks), AT_THREADS, kv_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
-                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, p->Tp, at_rows, 0.125f);
+        B2_LAUNCH(attn_bwd_q_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, q_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
+                  (const __nv_bfloat16*)(bb + p->b_O), (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), dqkv, Drow, d.batch, H, T,
+                  0.125f);
+        B2_LAUNCH(attn_bwd_kv_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, kv_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
+                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, 0.125f);
         if ((rc = linear_bwd(dqkv, 3 * E, (const __nv_bfloat16*)(bb + p->b_Xn), E, (const __nv_bfloat16*)(wb + p->w_qkvT), tmp2, GB(l, 2), GB(l, 3)))) return rc;
         if ((rc = ln_bwd<__nv_bfloat16>(tmp2, E, (const float*)(bb + p->b_Xin), E, (const float*)(bb + p->b_st1), P_.blk(l, 0), dX, E, 1, M, E, part,
                                         GB(l, 0), GB(l, 1), st))) return rc;

@@ -21,6 +21,7 @@ CASES = [
     (2, 8, (16, 32, 32), 16, 128, 2, 2, (16, 2, 4, 4)),        # 4 + 1 tokens (the tiny ViT-U-Net geometry)
     (2, 32, (16, 64, 64), 8, 128, 2, 2, (8, 4, 4, 4)),         # 128 + 1 tokens: several key chunks per warp in attention
     (1, 16, (8, 24, 40), 8, 64, 1, 1, (4, 1, 3, 5)),           # ragged volume (floor semantics of the k = s Conv3d), batch 1
+    (2, 32, (24, 96, 96), 8, 128, 2, 1, (8, 3, 4, 4)),         # 432 + 1 tokens (the cfg4 token count): 7 key blocks, ragged last block
 ]
 
 

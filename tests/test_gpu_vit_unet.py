@@ -131,3 +131,36 @@ def test_trainer_step_with_vit():
     od = dict(onet.named_parameters())
     for n, p in tr.network.named_parameters():
         assert rel_err(p, od[n]) < 2e-2 if "conv.bias" in n else rel_err(p, od[n]) < 5e-3, n
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trainer_with_task_specific_layernorms(precision):
+    """ViT task-specific LayerNorms (vision_transformer.py:380-416, MultiHead:554-561) on the CUDA path: a second task
+    registers a fresh LN set, trains only that set (the first task's LNs receive no gradient and stay bit-identical), and
+    switching back selects the first set again.  The loss of the first iteration on task B equals the loss the same weights
+    give with task A's (identical, freshly initialised) LNs: fresh LNs are (1, 0) like A's untouched ones."""
+    from b200unet import synth
+    from b200unet.configs import CONFIGS
+    from b200unet.trainers import nnUNetTrainerMultiHead
+    geom = CONFIGS["tiny32"] if precision == "bf16" else CONFIGS["tiny"]
+    tr = nnUNetTrainerMultiHead(geom, precision=precision, use_vit=True, ViT_task_specific_ln=True, task="A", cuda_graph=False)
+    tr.initialize()
+    vit = tr.network.ViT
+    assert vit.task_name_use == "A" and list(vit.norm.keys()) == ["A"]
+    batch = lambda s: iter([dict(zip(("data", "target"), synth.make_batch(geom, seed=s)))])
+    la0 = float(tr.run_iteration(batch(1), do_backprop=False))
+    tr.start_task("B")
+    assert list(vit.norm.keys()) == ["A", "B"] and vit.task_name_use == "B"
+    lb0 = float(tr.run_iteration(batch(1), do_backprop=False))
+    assert abs(la0 - lb0) <= 1e-6 * abs(la0)
+    a_before = {n: p.detach().clone() for n, p in vit.named_parameters() if ".A." in n}
+    b_before = {n: p.detach().clone() for n, p in vit.named_parameters() if ".B." in n}
+    for s in range(3):
+        tr.run_iteration(batch(2 + s))
+    torch.cuda.synchronize()
+    cur = dict(vit.named_parameters())
+    assert all(torch.equal(cur[n], v) for n, v in a_before.items())
+    assert sum(int(not torch.equal(cur[n], v)) for n, v in b_before.items()) > len(b_before) // 2
+    tr.start_task("A")
+    assert vit.task_name_use == "A" and vit.blocks.layer[0].use_task_name == "A"
+    assert np.isfinite(float(tr.run_iteration(batch(9), do_backprop=False)))

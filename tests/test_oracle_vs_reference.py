@@ -109,3 +109,37 @@ def test_reference_own_multihead_test_passes_on_b200unet_multihead_module(tmp_pa
                         os.path.join(REF, "test", "network_architecture", "test_MultiHead_Module.py")],
                        env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_task_specific_ln_vit_equals_reference_class():
+    """b200unet.VisionTransformer with task-specific LayerNorms == the reference's class (vision_transformer.py, unmodified,
+    on the timm shim): state_dict keys / parameter order after register_new_task, identical outputs per selected task"""
+    for p in (os.path.join(util.ROOT, "oracle", "shim"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from nnunet_ext.network_architecture.vision_transformer import PatchEmbed as RefPE, VisionTransformer as RefViT
+    from b200unet.vision_transformer import VisionTransformer
+    kw = dict(ViT_2d=False, img_size=[16, 32, 32], patch_size=(16, 16), img_depth=[16], in_chans=8, num_classes=96,
+              embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, qkv_bias=True, task_specific_ln=True, task_name='A')
+    torch.manual_seed(0)
+    ref = RefViT(representation_size=None, distilled=False, drop_rate=0, attn_drop_rate=0, drop_path_rate=0, embed_layer=RefPE,
+                 norm_layer=None, act_layer=None, weight_init='', **kw)
+    mine = VisionTransformer(**kw)
+    for v in (ref, mine):
+        v.register_new_task('B')
+    assert [(n, tuple(q.shape)) for n, q in ref.named_parameters()] == [(n, tuple(q.shape)) for n, q in mine.named_parameters()]
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, q in ref.named_parameters():
+            if 'norm' in n or 'pos_embed' in n:
+                q.copy_(1 + 0.2 * torch.randn(q.shape, generator=g))
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn((2, 8, 16, 32, 32), generator=g)
+    for task in ('A', 'B'):
+        ref.use_task(task)
+        mine.use_task(task)
+        np.testing.assert_allclose(mine(x).detach().numpy(), ref(x).detach().numpy(), rtol=1e-5, atol=1e-6)
+    a = mine(x, task_name='A')
+    mine.use_task('B')
+    assert not torch.allclose(a, mine(x))

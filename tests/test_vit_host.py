@@ -44,7 +44,7 @@ def test_commdiv():
 
 
 @pytest.mark.parametrize("kw", [dict(vit_version='V2'), dict(vit_version='V4'), dict(do_LSA=True), dict(do_SPT=True),
-                                dict(ViT_task_specific_ln=True, first_task_name='a'), dict(split_gpu=True)])
+                                dict(split_gpu=True)])
 def test_unsupported_variants_raise(kw):
     with pytest.raises(NotImplementedError):
         _product(**kw)
@@ -53,3 +53,33 @@ def test_unsupported_variants_raise(kw):
 def test_cpu_forward_refuses():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _product()(torch.zeros(2, 1, 16, 32, 32))
+
+
+def test_task_specific_layernorms_register_and_select():
+    """vision_transformer.py:380-416: LNs live in ModuleDicts keyed by task; register_new_task adds a fresh set, use_task
+    selects the set the forward (and the native kernel parameter table) uses"""
+    net = _product(ViT_task_specific_ln=True, first_task_name='A')
+    vit = net.ViT
+    keys = list(vit.state_dict().keys())
+    assert 'blocks.layer.0.norm1.A.weight' in keys and 'norm.A.bias' in keys and 'blocks.layer.11.norm2.A.weight' in keys
+    with pytest.raises(AssertionError):
+        vit._native_params()                 # no task selected yet (Block.forward asserts the same, :190)
+    vit.use_task('A')
+    n0 = len(list(vit.parameters()))
+    vit.register_new_task('B')
+    assert len(list(vit.parameters())) == n0 + 2 * (2 * 12 + 1)
+    assert isinstance(vit.patch_embeds[0].norm['B'], torch.nn.Identity)
+    with torch.no_grad():
+        vit.blocks.layer[3].norm1['B'].weight.fill_(2.0)
+    pa = vit._native_params()
+    vit.use_task('B')
+    pb = vit._native_params()
+    assert len(pa) == len(pb) == 2 + 12 * 12 + 6
+    i = 2 + 3 * 12
+    assert pa[i] is vit.blocks.layer[3].norm1['A'].weight and pb[i] is vit.blocks.layer[3].norm1['B'].weight
+    assert pb[-6] is vit.norm['B'].weight and pa[2 + 12 * 12] is vit.norm['A'].weight
+    x = torch.randn(2, 8, 16, 32, 32)
+    ya, yb = vit(x, task_name=None), None
+    vit.use_task('A')
+    yb = vit(x)
+    assert not torch.allclose(ya, yb)        # the B set (norm1 weight 2) was used for ya
