@@ -299,6 +299,65 @@ int b2_sliding_accumulate(const float* logits, int C, int pd, int ph, int pw, co
 int b2_sliding_finalize(float* agg, const float* wsum, int C, int64_t V, int32_t* seg, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * GPU-side patch pipeline.  Replaces nnunet's DataLoader3D + batchgenerators'
+ * get_moreDA_augmentation (reference call sites training/network_training/multihead/nnUNetTrainerMultiHead.py:505-511 and
+ * :904-922; both packages un-vendored) with the preprocessed cases resident in HBM.  The HOST draws the random parameters
+ * (lifelong-nnunet_b200/b200unet/augment.py) and passes one small record per sample / per (sample, channel); the kernels
+ * apply them.  Every `*_host` table is read during the call (kernel arguments), so the caller may reuse it at once.
+ * Limits: B <= B2_AUG_MAX_SAMPLES, B * C <= B2_AUG_MAX_BC, <= B2_AUG_MAX_SCALES deep-supervision targets.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define B2_AUG_MAX_SAMPLES 32
+#define B2_AUG_MAX_BC 64
+#define B2_AUG_MAX_SCALES 6
+#define B2_AUG_MAX_RADIUS 4
+typedef struct {
+    const float* volume;     /* device: preprocessed case [C + 1][D][H][W] fp32, LAST channel = segmentation (nnunet .npy layout) */
+    int32_t dhw[3];
+    int32_t lb[3];           /* crop origin inside the case; may reach outside: data padded with 0, segmentation with -1 */
+} b2_aug_case;
+/* DataLoader3D.generate_train_batch: data [B][C][g], seg [B][1][g] = crops of extent gdhw */
+int b2_aug_crop(const b2_aug_case* cases_host, int B, int C, const int32_t gdhw[3], float* data, float* seg, b2_stream_t stream);
+
+typedef struct {
+    float m[9];              /* source offset (d, h, w) = m (row-major 3x3) . (output voxel - (patch - 1) / 2) */
+    float ctr[3];            /* source centre in the crop: extent / 2 - 0.5 (batchgenerators augment_spatial, random_crop=False) */
+    int32_t lb[3];           /* modified == 0: plain centre crop at this origin (no interpolation) */
+    int32_t modified;
+} b2_aug_spatial_params;
+/* SpatialTransform (rotation + scaling): data = cubic B-spline interpolation (scipy map_coordinates order 3, mode constant 0;
+ * `crop_data` is overwritten by its B-spline coefficients for the modified samples), segmentation = per-label linear
+ * interpolation thresholded at 0.5 (batchgenerators interpolate_img, is_seg, order 1, cval -1). */
+int b2_aug_spatial(const b2_aug_spatial_params* tf_host, int B, int C, const int32_t gdhw[3], const int32_t pdhw[3], float* crop_data,
+                   const float* crop_seg, float* data_out, float* seg_out, b2_stream_t stream);
+
+/* per (sample, channel) statistics {mean, std (ddof 0), min, max} of data [BC][V] -> stats_out [BC][4] */
+size_t b2_aug_stats_scratch_bytes(int BC, int64_t V);
+int b2_aug_stats(const float* data, int BC, int64_t V, float* stats_out, void* scratch, b2_stream_t stream);
+
+enum { B2_AUG_NONE = 0, B2_AUG_NOISE = 1, B2_AUG_MUL = 2, B2_AUG_CONTRAST = 3, B2_AUG_GAMMA_A = 4, B2_AUG_GAMMA_B = 5 };
+typedef struct {
+    int32_t op;              /* NOISE: x += p0 * N(0,1) (counter-based generator keyed by seed and element index);  MUL: x *= p0;
+                              * CONTRAST: clip((x - mean) * p0 + mean, min, max) with stats_a;
+                              * GAMMA_A: ((x - min) / (range + 1e-7)) ^ p0 * (range + 1e-7) + min with stats_a, on -x when p1 != 0;
+                              * GAMMA_B (retain_stats): (x - mean_b) / (std_b + 1e-8) * std_a + mean_a, on -x when p1 != 0 */
+    float p[3];
+} b2_aug_op;
+int b2_aug_pointwise(const b2_aug_op* ops_host, int BC, int64_t V, float* data, const float* stats_a, const float* stats_b,
+                     uint64_t seed, b2_stream_t stream);
+
+typedef struct {
+    int32_t radius;          /* 0: channel left untouched */
+    float w[B2_AUG_MAX_RADIUS + 1];   /* w[|t|], normalised (scipy gaussian_filter, truncate 4, reflect boundaries) */
+} b2_aug_blur_taps;
+int b2_aug_blur(const b2_aug_blur_taps* kernels_host, int BC, const int32_t pdhw[3], float* data, float* tmp, b2_stream_t stream);
+
+/* MirrorTransform (flips bit 0 / 1 / 2 = axis d / h / w) + RemoveLabelTransform(-1, 0) + DownsampleSegForDSTransform2 (order 0:
+ * target voxel q reads stride * q + stride / 2): data_out [B][C][p], targets_host[k] [B][1][p / stride_k] */
+int b2_aug_finalize(const int32_t* flips_host, int B, int C, const int32_t pdhw[3], const float* data, const float* seg,
+                    float* data_out, float* const* targets_host, const int32_t* strides_host /* [n_scales][3] */, int n_scales,
+                    b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Building blocks, exported so tests can check every kernel against the oracle in isolation.
  * Weight layouts: `w_pt` = PyTorch Conv3d weight [Cout][Cin][3][3][3]; the plan keeps per-step shadows
  * w_f = [27][Cin][Cout] and w_b = [27][Cout][Cin] (activation dtype for tensor-core paths, fp32 otherwise).

@@ -66,6 +66,26 @@ class ConvDesc(C.Structure):
                 ("dtype", C.c_int32)]
 
 
+class AugCase(C.Structure):
+    _fields_ = [("volume", C.c_void_p), ("dhw", C.c_int32 * 3), ("lb", C.c_int32 * 3)]
+
+
+class AugSpatial(C.Structure):
+    _fields_ = [("m", C.c_float * 9), ("ctr", C.c_float * 3), ("lb", C.c_int32 * 3), ("modified", C.c_int32)]
+
+
+class AugOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("p", C.c_float * 3)]
+
+
+class AugBlur(C.Structure):
+    _fields_ = [("radius", C.c_int32), ("w", C.c_float * 5)]
+
+
+AUG_NONE, AUG_NOISE, AUG_MUL, AUG_CONTRAST, AUG_GAMMA_A, AUG_GAMMA_B = range(6)
+AUG_MAX_SAMPLES, AUG_MAX_BC, AUG_MAX_SCALES, AUG_MAX_RADIUS = 32, 64, 6, 4
+
+
 # name -> (restype, argtypes); mirrors include/b2unet.h one to one (tests/test_abi.py checks the export list)
 _VP, _I, _F, _I64, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
@@ -120,6 +140,13 @@ SIGNATURES = {
     "b2_online_eval": (_I, [_VP, _VP, _I, _I, _I64, _VP, _VP, _VP]),
     "b2_sliding_accumulate": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _I, _VP]),
     "b2_sliding_finalize": (_I, [_VP, _VP, _I, _I64, _VP, _VP]),
+    "b2_aug_crop": (_I, [C.POINTER(AugCase), _I, _I, C.POINTER(C.c_int32 * 3), _VP, _VP, _VP]),
+    "b2_aug_spatial": (_I, [C.POINTER(AugSpatial), _I, _I, C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _VP, _VP, _VP, _VP, _VP]),
+    "b2_aug_stats_scratch_bytes": (_SZ, [_I, _I64]),
+    "b2_aug_stats": (_I, [_VP, _I, _I64, _VP, _VP, _VP]),
+    "b2_aug_pointwise": (_I, [C.POINTER(AugOp), _I, _I64, _VP, _VP, _VP, C.c_uint64, _VP]),
+    "b2_aug_blur": (_I, [C.POINTER(AugBlur), _I, C.POINTER(C.c_int32 * 3), _VP, _VP, _VP]),
+    "b2_aug_finalize": (_I, [C.POINTER(C.c_int32), _I, _I, C.POINTER(C.c_int32 * 3), _VP, _VP, _VP, C.POINTER(_VP), C.POINTER(C.c_int32), _I, _VP]),
     "b2_conv3d_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "b2_conv3d_fwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),
     "b2_conv3d_shadow_bytes": (_SZ, [C.POINTER(ConvDesc)]),
