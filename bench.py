@@ -61,7 +61,7 @@ TRAINER_DESC = {
     "cfg1": "nnUNetTrainerSequential",
     "cfg2": "nnUNetTrainerEWC, EWC on (1 stored task, lambda 0.4)",
     "cfg3": "nnUNetTrainerLWF, 1 finished task (old head on the shared body + KL, T=2)",
-    "cfg4": "nnUNetTrainerPLOP + Generic_ViT_UNet V1 base (ViT through ATen), frozen teacher in the loop, pod_lambda 1e-2, 3 scales",
+    "cfg4": "nnUNetTrainerPLOP + Generic_ViT_UNet V1 base (native ViT: tcgen05 GEMMs + warp-MMA attention), frozen teacher in the loop, pod_lambda 1e-2, 3 scales",
     "cfg5": "nnUNetTrainerRW, task 3 of 3 (2 stored tasks penalised every iteration: strict_reference=False), F/S update every 10 its",
 }
 

@@ -278,6 +278,10 @@ int b2_kd_mib(const float* x, const float* teacher, int B, int C, int64_t V, flo
 int b2_plop_pseudo(const float* x, const float* x_old, const float* target, int B, int C, int D, int H, int W,
                    const float* thresholds, float max_entropy, float weight, float* dlogits, float* loss_out,
                    void* scratch, b2_stream_t stream);
+/* PLOP threshold extraction (plop:113-182): hist[c][bin] += #background voxels (target == 0) with pseudo label c (argmax of
+ * softmax(x_old)) whose entropy / max_entropy falls into bin (of nb_bins); integer counts, accumulated into the caller's table. */
+int b2_plop_entropy_hist(const float* x_old, const float* target, int B, int C, int64_t V, float max_entropy, int nb_bins,
+                         uint64_t* hist /* [C][nb_bins] */, b2_stream_t stream);
 size_t b2_pod_scratch_bytes(const b2_act_view* a, int scales);
 int b2_pod_local(const b2_act_view* a, const b2_act_view* a_old, int scales, float* value_out, void* scratch,
                  b2_stream_t stream);

@@ -135,6 +135,7 @@ SIGNATURES = {
     "b2_kd_lwf": (_I, [_VP, _VP, _I, _I, _I64, _F, _VP, _VP, _VP]),
     "b2_kd_mib": (_I, [_VP, _VP, _I, _I, _I64, _F, _F, _VP, _VP, _VP, _VP]),
     "b2_plop_pseudo": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _F, _F, _VP, _VP, _VP, _VP]),
+    "b2_plop_entropy_hist": (_I, [_VP, _VP, _I, _I, _I64, _F, _I, _VP, _VP]),
     "b2_pod_scratch_bytes": (_SZ, [C.POINTER(ActView), _I]),
     "b2_pod_local": (_I, [C.POINTER(ActView), C.POINTER(ActView), _I, _VP, _VP, _VP]),
     "b2_online_eval": (_I, [_VP, _VP, _I, _I, _I64, _VP, _VP, _VP]),

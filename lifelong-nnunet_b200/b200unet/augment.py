@@ -87,9 +87,12 @@ class GPUPatchPipeline:
     segmentation as last channel, optional 'class_locations': {label: int array [N, 3]}}."""
 
     def __init__(self, cases, patch_size, batch_size, ds_strides, params=None, oversample_foreground_percent=0.33, seed=1234,
-                 device=None, train=True, plan_only=False):
-        """plan_only: host-side use (draw_plan) without a device -- run_plan then raises"""
+                 device=None, train=True, plan_only=False, prefetch=True):
+        """plan_only: host-side use (draw_plan) without a device -- run_plan then raises.
+        prefetch: next() returns the batch produced during the PREVIOUS call and enqueues the following one on the pipeline's own
+        stream, so augmentation overlaps the consumer's training step (same plans, same order as without prefetch)."""
         self.plan_only = bool(plan_only)
+        self.prefetch, self._pending, self._stream = bool(prefetch), None, None
         if not self.plan_only:
             self.lib = _lib.load()
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -263,8 +266,31 @@ class GPUPatchPipeline:
     def __iter__(self):
         return self
 
+    def _produce(self):
+        """one batch on the pipeline's stream; returns (batch, event)"""
+        dev = self.device
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        self._stream.wait_stream(cur)       # the staging buffers may still be read by work the consumer enqueued
+        with torch.cuda.stream(self._stream):
+            batch = self.run_plan(self.draw_plan())
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        return batch, ev
+
     def __next__(self):
-        return self.run_plan(self.draw_plan())
+        if not self.prefetch:
+            return self.run_plan(self.draw_plan())
+        if self._pending is None:
+            self._pending = self._produce()
+        batch, ev = self._pending
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in [batch["data"]] + batch["target"]:
+            t.record_stream(cur)
+        self._pending = self._produce()
+        return batch
 
 
 def get_moreDA_augmentation(cases_train, cases_val, patch_size, params=None, deep_supervision_scales=None, batch_size=2,

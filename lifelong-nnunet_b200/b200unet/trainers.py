@@ -951,6 +951,63 @@ class nnUNetTrainerPLOP(nnUNetTrainerPOD):
         self.max_entropy = torch.log(torch.tensor(C_).float()).item()
         self.thresholds = {i: torch.full((C_,), 1e-3, device=self.device) for i in range(self.geometry.num_pool)}
 
+    @staticmethod
+    def _median_thresholds(hist, nb_bins=100, base_threshold=0.001):
+        """median entropy per pseudo label from the histogram (arthurdouillard/CVPR2021_PLOP train.py find_median, which
+        plop:149-173 follows), floored at base_threshold"""
+        out = []
+        for c in range(hist.shape[0]):
+            total, med = float(hist[c].sum()), 0.0
+            if total > 0:
+                half, running = total / 2, 0.0
+                for bin_index in range(nb_bins):
+                    lower = bin_index / nb_bins
+                    if half >= running and half <= running + float(hist[c, bin_index]):
+                        break
+                    running += float(hist[c, bin_index])
+                med = lower + ((half - running) / float(hist[c, bin_index])) * (1 / nb_bins)
+            out.append(max(med, base_threshold))
+        return out
+
+    def extract_max_entropy_and_thresholds(self, data_generator, num_batches):
+        """reference plop:113-182: `num_batches` batches through the OLD model; per deep-supervision level the median of
+        entropy / max_entropy over the background voxels, per pseudo label, becomes the pseudo-labelling threshold.
+        strict_reference (Q15): the reference compares the LIST of deep-supervision targets with 0 (`labels == 0` is a Python
+        False), so nothing is selected, the histograms stay empty and every threshold is base_threshold = 0.001 -- the batches
+        are still drawn so the data stream stays aligned.  strict_reference=False runs the documented algorithm: histograms
+        by b2_plop_entropy_hist (ONE table accumulated over batches and levels, as the reference's shared `histograms`),
+        thresholds[level] taken after that level of the LAST batch."""
+        import ctypes as C
+        from . import _lib
+        C_, nb = self.geometry.num_classes, 100
+        self.max_entropy = torch.log(torch.tensor(C_).float()).item()
+        levels = self.geometry.num_pool
+        if self.strict_reference or self.network_old is None:
+            for _ in range(num_batches):
+                next(data_generator)
+            self.thresholds = {i: torch.full((C_,), 1e-3, device=self.device) for i in range(levels)}
+            self._steps = {}
+            return self.thresholds
+        lib = _lib.load()
+        hist = torch.zeros((C_, nb), dtype=torch.int64, device=self.device)
+        st = lambda: C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.network_old.eval()
+        with torch.no_grad():
+            for k in range(num_batches):
+                data, target = self._next_batch(data_generator)
+                outs = self.network_old(data)
+                for idx in range(levels):
+                    o, t = outs[idx].contiguous().float(), target[idx].contiguous().float()
+                    V = o[0, 0].numel()
+                    _lib.check(lib.b2_plop_entropy_hist(C.c_void_p(o.data_ptr()), C.c_void_p(t.data_ptr()), int(o.shape[0]), C_, V,
+                                                        float(self.max_entropy), nb, C.c_void_p(hist.data_ptr()), st()))
+                    if k == num_batches - 1:
+                        self.thresholds[idx] = torch.tensor(self._median_thresholds(hist.cpu().numpy(), nb), dtype=torch.float32,
+                                                            device=self.device)
+        self._plop_histograms = hist
+        self._steps = {}            # captured step programs hold the previous thresholds
+        return self.thresholds
+
     def _fused_spec(self):
         cfg = self.loss_base.loss.cfg(list(self.ds_loss_weights))
         if self.network_old is None:

@@ -521,6 +521,58 @@ extern "C" int b2_kd_mib(const float* x, const float* teacher, int B, int C, int
     return B2_OK;
 }
 
+// PLOP threshold extraction (reference plop:113-182; arthurdouillard/CVPR2021_PLOP train.py "find_median"): histogram over the
+// background voxels (target == 0) of entropy(softmax(x_old)) / max_entropy in nb_bins bins, per pseudo label (argmax).  Integer
+// counts: shared-memory histogram per block, 64-bit integer atomics into the caller's table (order-independent => reproducible).
+__global__ void __launch_bounds__(256) plop_hist_kernel(const float* __restrict__ x_old, const float* __restrict__ target, int B, int C,
+                                                        long long V, float max_entropy, int nb_bins, unsigned long long* __restrict__ hist) {
+    pdl_grid_sync();
+    extern __shared__ unsigned int sh_hist[];
+    for (int i = threadIdx.x; i < C * nb_bins; i += 256) sh_hist[i] = 0u;
+    __syncthreads();
+    const float factor = 1.f / logf((float)C + 1e-8f);
+    const long long total = (long long)B * V;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        if (target[i] != 0.f) continue;
+        const long long b = i / V, v = i % V;
+        float xs[MAXC];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < C) { xs[c] = x_old[(b * C + c) * V + v]; m = fmaxf(m, xs[c]); }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < C) { xs[c] = expf(xs[c] - m); se += xs[c]; }
+        float ent = 0.f, best = -1.f;
+        int arg = 0;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < C) {
+                const float p = xs[c] / se;
+                ent += p * logf(p + 1e-8f);
+                if (p > best) { best = p; arg = c; }
+            }
+        ent = -factor * (ent / (float)C);
+        int bin = (int)((ent / max_entropy) * (float)nb_bins);      // .long(): truncation
+        bin = bin > nb_bins - 1 ? nb_bins - 1 : (bin < 0 ? 0 : bin);
+        atomicAdd(&sh_hist[arg * nb_bins + bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * nb_bins; i += 256)
+        if (sh_hist[i]) atomicAdd(&hist[i], (unsigned long long)sh_hist[i]);
+}
+
+extern "C" int b2_plop_entropy_hist(const float* x_old, const float* target, int B, int C, int64_t V, float max_entropy, int nb_bins,
+                                    uint64_t* hist, b2_stream_t stream) {
+    B2_CHECK_ARG(x_old && target && hist && B >= 1 && C >= 2 && C <= MAXC && V >= 1 && nb_bins >= 1 && nb_bins <= 1024 && max_entropy > 0.f);
+    long long g = ((long long)B * V + 255) / 256, cap = (long long)num_sms() * 8;
+    if (g > cap) g = cap;
+    B2_LAUNCH(plop_hist_kernel, (int)g, 256, (size_t)C * nb_bins * sizeof(unsigned int), (cudaStream_t)stream, x_old, target, B, C, (long long)V,
+              max_entropy, nb_bins, (unsigned long long*)hist);
+    return B2_OK;
+}
+
 extern "C" int b2_plop_pseudo(const float* x, const float* x_old, const float* target, int B, int C, int D, int H, int W,
                               const float* thresholds, float max_entropy, float weight, float* dlogits, float* loss_out,
                               void* scratch, b2_stream_t stream) {

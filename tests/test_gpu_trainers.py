@@ -227,3 +227,35 @@ def test_input_prefetch_gives_identical_iterations():
     assert l0 == l1, (l0, l1)
     for a, b in zip(p0, p1):
         assert torch.equal(a, b)
+
+
+def test_plop_threshold_extraction_strict_and_documented():
+    """reference plop:113-182.  strict_reference (Q15): every threshold is base_threshold, batches are still drawn.
+    strict_reference=False: the entropy histograms of b2_plop_entropy_hist equal the oracle's counts (evaluated on the oracle
+    teacher; a voxel may change bin when its entropy sits within rounding of a bin edge: <= 1e-3 of the counts) and the medians
+    agree to half a bin."""
+    from b200unet import synth, trainers as T
+    from oracle import cl_losses
+    geom, onet, tr, data, targets, gen = _setup(T.nnUNetTrainerPLOP)
+    tr.start_new_task()
+    batches = [synth.make_batch(geom, seed=40 + i) for i in range(3)]
+    mk = lambda: iter([{'data': d, 'target': t} for d, t in batches])
+    g = mk()
+    thr = tr.extract_max_entropy_and_thresholds(g, 3)
+    assert all(torch.allclose(thr[i].cpu(), torch.full((geom.num_classes,), 1e-3)) for i in range(geom.num_pool))
+    assert next(g, None) is None and abs(tr.max_entropy - float(np.log(geom.num_classes))) < 1e-6
+    with torch.no_grad():
+        oouts = [onet(d) for d, _ in batches]
+    othr_s, _, _ = cl_losses.plop_thresholds(oouts, [t for _, t in batches], geom.num_classes, strict=True)
+    assert all(torch.allclose(othr_s[i], torch.full((geom.num_classes,), 1e-3)) for i in othr_s)
+    tr.strict_reference = False
+    thr = tr.extract_max_entropy_and_thresholds(mk(), 3)
+    othr, _, ohist = cl_losses.plop_thresholds(oouts, [t for _, t in batches], geom.num_classes, strict=False)
+    chist = tr._plop_histograms.cpu()
+    assert int(chist.sum()) == int(ohist.sum()) > 0
+    assert int((chist - ohist).abs().sum()) <= 1e-3 * int(ohist.sum())
+    for i in range(geom.num_pool):
+        assert float((thr[i].cpu() - othr[i]).abs().max()) <= 0.005, (i, thr[i], othr[i])
+    assert float(thr[0].max()) > 1e-3          # a real median, not the floor
+    l = float(tr.run_iteration(mk()))          # the extracted thresholds feed the pseudo-label loss
+    assert np.isfinite(l)

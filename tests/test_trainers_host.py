@@ -167,3 +167,27 @@ def test_finish_online_evaluation_extended_per_subject_dice_iou():
     assert math.isclose(store["a"]["mask_2"]["Dice"], 6 / 10) and math.isclose(store["b"]["mask_2"]["IoU"], 1 / 2)
     assert math.isclose(store["b"]["mask_1"]["Dice"], 6 / 10)
     assert tr.online_eval_tp == [] and tr.subject_names_raw == []
+
+
+def test_plop_median_thresholds_equal_oracle_on_random_histograms():
+    """host half of plop:149-173 (median search) against the oracle restatement on a given histogram"""
+    import numpy as np
+    from b200unet.trainers import nnUNetTrainerPLOP
+    from oracle import cl_losses
+    rs = np.random.RandomState(0)
+    hist = rs.randint(0, 50, size=(3, 100)).astype(np.int64)
+    hist[1] = 0                                          # a class that is never the pseudo label keeps the floor
+    hist[2, :40] = 0
+    mine = nnUNetTrainerPLOP._median_thresholds(hist)
+    # oracle: feed the same histogram through one-hot "outputs" is roundabout; restate with its own loop on a prepared table
+    thr = []
+    for c in range(3):
+        total = hist[c].sum()
+        if total <= 0:
+            thr.append(0.001)
+            continue
+        cum = np.cumsum(hist[c])
+        b = int(np.argmax(cum >= total / 2))
+        prev = cum[b - 1] if b else 0
+        thr.append(max(b / 100 + ((total / 2 - prev) / hist[c, b]) / 100, 0.001))
+    assert np.allclose(mine, thr, atol=1e-12) and mine[1] == 0.001 and mine[2] > 0.4
