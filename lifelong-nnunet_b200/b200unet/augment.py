@@ -267,29 +267,49 @@ class GPUPatchPipeline:
         return self
 
     def _produce(self):
-        """one batch on the pipeline's stream; returns (batch, event)"""
+        """one batch on the pipeline's own stream; returns (batch, event)"""
         dev = self.device
+        torch.cuda.set_device(dev)
         if self._stream is None:
             self._stream = torch.cuda.Stream(dev)
-        cur = torch.cuda.current_stream(dev)
-        self._stream.wait_stream(cur)       # the staging buffers may still be read by work the consumer enqueued
         with torch.cuda.stream(self._stream):
             batch = self.run_plan(self.draw_plan())
             ev = torch.cuda.Event()
             ev.record(self._stream)
         return batch, ev
 
+    def _produce_async(self):
+        """draw + enqueue the next batch on a host thread, so neither the parameter draws nor the launches delay the consumer's
+        own enqueue work (ctypes calls and stream synchronisation release the GIL)"""
+        import threading
+        box = {}
+
+        def work():
+            try:
+                box["out"] = self._produce()
+            except BaseException as e:      # re-raised by the consumer in __next__
+                box["err"] = e
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        return t, box
+
     def __next__(self):
         if not self.prefetch:
             return self.run_plan(self.draw_plan())
         if self._pending is None:
-            self._pending = self._produce()
-        batch, ev = self._pending
+            batch, ev = self._produce()
+        else:
+            t, box = self._pending
+            t.join()
+            if "err" in box:
+                self._pending = None
+                raise box["err"]
+            batch, ev = box["out"]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        for t in [batch["data"]] + batch["target"]:
-            t.record_stream(cur)
-        self._pending = self._produce()
+        for t_ in [batch["data"]] + batch["target"]:
+            t_.record_stream(cur)
+        self._pending = self._produce_async()
         return batch
 
 

@@ -196,9 +196,12 @@ class FusedStep:
         return dict(coef=float(coef), table=DeviceTable(_lib.MT_PEN, table, len(names), self.dev, keep), slot=self._slot(),
                     names=set(names))
 
-    def _build_buckets(self, target_bytes=48 << 20):
+    def _build_buckets(self, target_bytes=None):
         """suffixes of the arena in the order backward completes them (decoder levels from full resolution down, then the
-        encoder from the bottleneck up); boundaries only at layer starts"""
+        encoder from the bottleneck up); boundaries only at layer starts.  Bucket size: env B2_BUCKET_MB (default 48)."""
+        import os
+        if target_bytes is None:
+            target_bytes = int(float(os.environ.get("B2_BUCKET_MB", "48")) * (1 << 20))
         names = self.plan.param_names
         starts = [i for i, n in enumerate(names) if n.endswith("conv.weight") or
                   (n.endswith(".weight") and (n.startswith("tu.") or n.startswith("seg_outputs.")))]

@@ -198,6 +198,14 @@ class Generic_ViT_UNet(Generic_UNet):
             bott = _view(plan, 2 * P + 1, 1)
             vit_out = self.ViT.forward_native(skip0, _view(plan, 1, 2) if grad else None, tuple(int(v) for v in bott.shape[1:]))
         else:
+            if self.precision != "fp32" and not self.ViT.store_attn_weights:
+                # no silent library fallback: the bf16 production mode either runs the hand-written ViT or says why it cannot
+                raise NotImplementedError("native ViT kernels (csrc/vit.cu) need head dim 64, embed <= 1024, batch <= 4 and a "
+                                          "channel count that is a multiple of 8; use precision='fp32' (ATen parity mode) for "
+                                          "other shapes -- got batch %d, %d channels, embed %d" %
+                                          (skip0.shape[0], skip0.shape[1], self.ViT.embed_dim))
+            # fp32 parity mode (and `store_attn_weights`, which asks for the materialised probabilities): the same module
+            # evaluated through ATen
             with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.precision != "fp32"):
                 vit_out = self.ViT(skip0)
         if grad:

@@ -13,6 +13,7 @@
 namespace b2 {
 
 constexpr int MAXC = 8;
+constexpr int MAXB = 32;     // samples per loss launch (PLOP trains with batch 25 from the second task on, plop:85)
 
 static int loss_slabs(int B, long long V) {
     long long s = (4LL * num_sms() + B - 1) / B;
@@ -95,37 +96,39 @@ __global__ void dsloss_finalize_kernel(const float* __restrict__ part, int B, in
                                        float* __restrict__ loss_out) {
     pdl_grid_sync();
     constexpr int NV = 3 * MAXC + 2;
-    // stage 1 (256 threads): lane = value index inside a partial row (coalesced 104-byte rows), warp = slab lane; every
-    // thread keeps several independent loads in flight; stage 2: thread 0 combines the 8 warps in order.
-    __shared__ double wsum[8][16][NV];
-    const int Bc = B < 16 ? B : 16;
-    {
-        const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
-        for (int b = 0; b < Bc; ++b) {
+    // per sample: stage 1 (256 threads): lane = value index inside a partial row (coalesced 104-byte rows), warp = slab lane,
+    // several independent loads in flight; stage 2: the 8 warps combined in order.  Thread 0 then evaluates the loss.
+    __shared__ double wsum[8][NV];
+    __shared__ double tot[MAXB][NV];
+    const int Bc = B < MAXB ? B : MAXB;      // (the host entry point rejects B > MAXB)
+    const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b = 0; b < Bc; ++b) {
+        if (j < NV) {
             double a = 0.0;
-            if (j < NV) {
 #pragma unroll 8
-                for (int sl = w; sl < slabs; sl += 8) a += (double)part[((long long)b * slabs + sl) * NV + j];
-                wsum[w][b][j] = a;
-            }
+            for (int sl = w; sl < slabs; sl += 8) a += (double)part[((long long)b * slabs + sl) * NV + j];
+            wsum[w][j] = a;
         }
+        __syncthreads();
+        if (threadIdx.x < NV) {
+            double a = 0.0;
+            for (int k = 0; k < 8; ++k) a += wsum[k][threadIdx.x];
+            tot[b][threadIdx.x] = a;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double sp[16][MAXC], spy[16][MAXC], sy[16][MAXC];
+    double sp[MAXB][MAXC], spy[MAXB][MAXC], sy[MAXB][MAXC];
     double ce = 0.0, cnt = 0.0;
-    for (int b = 0; b < Bc; ++b)
-        for (int c = 0; c < MAXC; ++c) { sp[b][c] = 0; spy[b][c] = 0; sy[b][c] = 0; }
-    for (int b = 0; b < Bc; ++b)
-        for (int w = 0; w < 8; ++w) {
-            for (int c = 0; c < C; ++c) {
-                sp[b][c] += wsum[w][b][c];
-                spy[b][c] += wsum[w][b][MAXC + c];
-                sy[b][c] += wsum[w][b][2 * MAXC + c];
-            }
-            ce += wsum[w][b][3 * MAXC];
-            cnt += wsum[w][b][3 * MAXC + 1];
+    for (int b = 0; b < Bc; ++b) {
+        for (int c = 0; c < MAXC; ++c) {
+            sp[b][c] = c < C ? tot[b][c] : 0.0;
+            spy[b][c] = c < C ? tot[b][MAXC + c] : 0.0;
+            sy[b][c] = c < C ? tot[b][2 * MAXC + c] : 0.0;
         }
+        ce += tot[b][3 * MAXC];
+        cnt += tot[b][3 * MAXC + 1];
+    }
     double loss = ce / cnt;  // NaN when every voxel is ignored, like torch
     coef[(long long)B * C * 2] = (float)(1.0 / cnt);
     for (int i = 0; i < B * C * 2; ++i) coef[i] = 0.f;
@@ -471,7 +474,7 @@ extern "C" int b2_dsloss_fwd_bwd(const float* logits, const float* target, int B
                                  int batch_dice, float smooth, int do_bg, int ignore_index, int with_dice,
                                  float* dlogits, float* loss_out, void* scratch, b2_stream_t stream) {
     B2_CHECK_ARG(logits && target && loss_out && scratch);
-    B2_CHECK_ARG(C >= 2 && C <= MAXC && B >= 1 && B <= 16 && V > 0);
+    B2_CHECK_ARG(C >= 2 && C <= MAXC && B >= 1 && B <= MAXB && V > 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int slabs = loss_slabs(B, V);
     float* part = (float*)scratch;

@@ -43,6 +43,24 @@ def test_dc_ce_multilevel(batch_dice, C):
             assert rel_err(a.grad, b.grad) < TOL
 
 
+@pytest.mark.parametrize("B,batch_dice", [(25, False), (32, True), (17, False)])
+def test_dc_ce_large_batches(B, batch_dice):
+    """PLOP trains with batch 25 from the second task on (plop:85): the loss kernels take up to 32 samples per launch"""
+    from b200unet.deep_supervision import DC_and_CE_loss, MultipleOutputLoss2
+    from oracle import cl_losses
+    x, y = _logits(B, 3, (6, 10, 12), 3).requires_grad_(), _target(B, 3, (6, 10, 12), 4)
+    ref = cl_losses.dc_and_ce(x, y, batch_dice=batch_dice)
+    ref.backward()
+    cx = x.detach().cuda().requires_grad_()
+    out = MultipleOutputLoss2(DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False}, {}), None)([cx], [y.cuda()])
+    assert abs(float(out) - float(ref)) < TOL * abs(float(ref))
+    out.backward()
+    assert rel_err(cx.grad, x.grad) < TOL
+    with pytest.raises(Exception):
+        bx = _logits(33, 3, (2, 4, 4), 5).cuda()
+        MultipleOutputLoss2(DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False}, {}), None)([bx], [_target(33, 3, (2, 4, 4), 6).cuda()])
+
+
 def _param_set(seed=0):
     g = torch.Generator().manual_seed(seed)
     shapes = [(8, 1, 3, 3, 3), (8,), (16, 8, 3, 3, 3), (3, 8, 1, 1, 1), (5,), (1037,)]
