@@ -390,6 +390,21 @@ int b2_conv3d_fwd_shadow_stats(const b2_conv_desc* d, const void* x, const void*
 /* dx (nullable) = conv_transpose3d(dz, w); dw, dbias = parameter gradients (PyTorch layouts, overwritten) */
 int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx, int accumulate_dx,
                   float* dw, float* dbias, void* scratch, b2_stream_t stream);
+/* kernel == stride transposed convolution (nn.ConvTranspose3d(k = s, bias=False), the `tu` modules) as a standalone op on NDHWC
+ * buffers: what Generic_ViT_UNet V2 / V3 apply outside the decoder to fuse the bottleneck / the skips into the ViT input
+ * (reference generic_ViT_UNet.py:299-338).  w_pt: PyTorch layout [Cin][Cout][kd][kh][kw].  scratch >= b2_tconv3d_scratch_bytes. */
+typedef struct b2_tconv_desc {
+    int32_t n, d, h, w;       /* input spatial */
+    int32_t cin, cout;
+    int32_t k[3];             /* kernel == stride, 1 or 2 per axis */
+    int32_t in_pitch, out_pitch;
+    int32_t dtype;
+} b2_tconv_desc;
+size_t b2_tconv3d_scratch_bytes(const b2_tconv_desc* d);
+int b2_tconv3d_fwd(const b2_tconv_desc* d, const void* x, const float* w_pt, void* y, void* scratch, b2_stream_t stream);
+/* dx (nullable, overwritten) = strided conv of dy with w; dw (nullable, overwritten) = weight gradient, fp32 PyTorch layout */
+int b2_tconv3d_bwd(const b2_tconv_desc* d, const void* x, const void* dy, const float* w_pt, void* dx, float* dw, void* scratch,
+                   b2_stream_t stream);
 /* y = lrelu(gamma * (z - mean) * rstd + beta) */
 int b2_norm_lrelu_fwd(const void* z, const float* stats, const float* gamma, const float* beta, void* y, int n,
                       int64_t vox, int c, int z_pitch, int y_pitch, int dtype, float slope, b2_stream_t stream);

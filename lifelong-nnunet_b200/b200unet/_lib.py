@@ -86,6 +86,11 @@ AUG_NONE, AUG_NOISE, AUG_MUL, AUG_CONTRAST, AUG_GAMMA_A, AUG_GAMMA_B = range(6)
 AUG_MAX_SAMPLES, AUG_MAX_BC, AUG_MAX_SCALES, AUG_MAX_RADIUS = 32, 64, 6, 4
 
 
+class TconvDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+                ("k", C.c_int32 * 3), ("in_pitch", C.c_int32), ("out_pitch", C.c_int32), ("dtype", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/b2unet.h one to one (tests/test_abi.py checks the export list)
 _VP, _I, _F, _I64, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 SIGNATURES = {
@@ -155,6 +160,9 @@ SIGNATURES = {
     "b2_conv3d_fwd_shadow": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2_conv3d_fwd_shadow_stats": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2_conv3d_bwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "b2_tconv3d_scratch_bytes": (_SZ, [C.POINTER(TconvDesc)]),
+    "b2_tconv3d_fwd": (_I, [C.POINTER(TconvDesc), _VP, _VP, _VP, _VP, _VP]),
+    "b2_tconv3d_bwd": (_I, [C.POINTER(TconvDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2_norm_scratch_bytes": (_SZ, [_I, _I64, _I]),
     "b2_norm_lrelu_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I64, _I, _I, _I, _I, _F, _VP]),
     "b2_norm_lrelu_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I64, _I, _I, _I, _I, _I, _I, _F, _VP, _VP]),

@@ -230,10 +230,12 @@ class VisionTransformer(nn.Module):
         d.pop('_vplans', None)          # C handles / workspaces are never copied (teachers are deep copies of the network)
         return d
 
-    def forward_native(self, x, dskip, out_shape):
-        """x: channels-last bf16 view (B, C, D, H, W) of the first skip; dskip: the matching gradient view of the U-Net plan
-        (the input gradient is ADDED into it by the backward kernels); returns the dense [B, F] fp32 head output"""
-        return _ViTNativeFunction.apply(self, x, dskip, tuple(out_shape), *self._native_params())
+    def forward_native(self, x, dskip, out_shape, return_input_grad=False):
+        """x: channels-last bf16 tensor (B, C, D, H, W), e.g. the first skip as a view of the U-Net plan; dskip: the matching
+        gradient view of the plan (the input gradient is ADDED into it by the backward kernels) or None; return_input_grad:
+        hand the input gradient to autograd instead (V2 / V3, where the ViT input is computed by further ops); returns the
+        dense [B, F] fp32 head output"""
+        return _ViTNativeFunction.apply(self, x, dskip, tuple(out_shape), bool(return_input_grad), *self._native_params())
 
     def register_new_task(self, task_name):
         """vision_transformer.py:380-401: a fresh LayerNorm set (final norm, every block's norm1 / norm2, Identity for the
@@ -277,7 +279,7 @@ def _view_of(t):
 
 class _ViTNativeFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vit, x, dskip, out_shape, *params):
+    def forward(ctx, vit, x, dskip, out_shape, return_dx, *params):
         lib = _lib.load()
         h, ws = vit._native_plan(x, out_shape)
         for p in params:
@@ -298,7 +300,7 @@ class _ViTNativeFunction(torch.autograd.Function):
             conv_out = tok.view(x.shape[0], gd, gh, gw, vit.embed_dim).permute(0, 4, 1, 2, 3)
             for hook in list(pe.proj._forward_hooks.values()):
                 hook(pe.proj, (x,), conv_out)
-        ctx.vit, ctx.h, ctx.ws, ctx.params, ctx.dskip, ctx.x = vit, h, ws, params, dskip, x
+        ctx.vit, ctx.h, ctx.ws, ctx.params, ctx.dskip, ctx.x, ctx.return_dx = vit, h, ws, params, dskip, x, return_dx
         ctx.set_materialize_grads(False)
         return out
 
@@ -316,9 +318,14 @@ class _ViTNativeFunction(torch.autograd.Function):
             o += p.numel()
         pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
         gp = (C.c_void_p * len(params))(*[g.data_ptr() for g in grads])
-        vd = _view_of(ctx.dskip) if ctx.dskip is not None else None
+        dx = None
+        if ctx.return_dx:          # the kernels ADD the input gradient into the buffer they are given
+            dx = torch.empty(tuple(ctx.x.shape), dtype=ctx.x.dtype, device=dev, memory_format=torch.channels_last_3d).zero_()
+            vd = _view_of(dx)
+        else:
+            vd = _view_of(ctx.dskip) if ctx.dskip is not None else None
         _lib.check(lib.b2_vit_backward(ctx.h, pp, None, C.c_void_p(dout.data_ptr()), C.c_void_p(ctx.ws.data_ptr()),
                                        None if vd is None else C.byref(vd), gp,
                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         ctx.vit._last_flat_grad = flat
-        return (None, None, None, None) + tuple(g if p.requires_grad else None for g, p in zip(grads, params))
+        return (None, dx, None, None, None) + tuple(g if p.requires_grad else None for g, p in zip(grads, params))

@@ -998,6 +998,50 @@ extern "C" int b2_conv3d_fwd_shadow_stats(const b2_conv_desc* d, const void* x, 
     return conv3d_fwd_shadow_impl(d, x, shadow, bias, z, scratch, 1, (cudaStream_t)stream);
 }
 
+static TconvShape to_tshape(const b2_tconv_desc* d) {
+    TconvShape s;
+    s.n = d->n; s.d = d->d; s.h = d->h; s.w = d->w; s.cin = d->cin; s.cout = d->cout;
+    for (int a = 0; a < 3; ++a) s.k[a] = d->k[a];
+    s.in_pitch = d->in_pitch; s.out_pitch = d->out_pitch;
+    return s;
+}
+static bool tconv_desc_ok(const b2_tconv_desc* d) {
+    if (!d || d->n < 1 || d->d < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1 || d->in_pitch < d->cin || d->out_pitch < d->cout)
+        return false;
+    for (int a = 0; a < 3; ++a)
+        if (d->k[a] != 1 && d->k[a] != 2) return false;
+    return d->dtype == B2_F32 || d->dtype == B2_BF16;
+}
+
+extern "C" size_t b2_tconv3d_scratch_bytes(const b2_tconv_desc* d) {
+    if (!tconv_desc_ok(d)) return 0;
+    const TconvShape s = to_tshape(d);
+    const size_t k8 = (size_t)s.k[0] * s.k[1] * s.k[2];
+    return align_up(k8 * s.cin * s.cout * sizeof(float)) + align_up(tconv_bwd_scratch_floats(s) * sizeof(float)) + 256;
+}
+
+extern "C" int b2_tconv3d_fwd(const b2_tconv_desc* d, const void* x, const float* w_pt, void* y, void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(tconv_desc_ok(d) && x && w_pt && y && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TconvShape s = to_tshape(d);
+    float* wq = (float*)scratch;
+    int rc = tconv_shadow(w_pt, s.cin, s.cout, s.k[0] * s.k[1] * s.k[2], wq, st);
+    if (rc) return rc;
+    if (d->dtype == B2_F32) return tconv_fwd_q<float>(s, (const float*)x, wq, (float*)y, st);
+    return tconv_fwd_q<__nv_bfloat16>(s, (const __nv_bfloat16*)x, wq, (__nv_bfloat16*)y, st);
+}
+
+extern "C" int b2_tconv3d_bwd(const b2_tconv_desc* d, const void* x, const void* dy, const float* w_pt, void* dx, float* dw, void* scratch,
+                              b2_stream_t stream) {
+    B2_CHECK_ARG(tconv_desc_ok(d) && x && dy && w_pt && scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const TconvShape s = to_tshape(d);
+    const size_t k8 = (size_t)s.k[0] * s.k[1] * s.k[2];
+    float* part = (float*)((char*)scratch + align_up(k8 * s.cin * s.cout * sizeof(float)));
+    if (d->dtype == B2_F32) return tconv_bwd<float>(s, (const float*)x, (const float*)dy, w_pt, (float*)dx, dw, part, st);
+    return tconv_bwd<__nv_bfloat16>(s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, w_pt, (__nv_bfloat16*)dx, dw, part, st);
+}
+
 extern "C" int b2_conv3d_bwd(const b2_conv_desc* d, const void* x, const void* dz, const float* w_pt, void* dx,
                              int accumulate_dx, float* dw, float* dbias, void* scratch, b2_stream_t stream) {
     B2_CHECK_ARG(d && x && dz && w_pt && scratch);

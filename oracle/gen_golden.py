@@ -156,7 +156,7 @@ def vit_values(net):
     return res
 
 
-def reference_vit_unet():
+def reference_vit_unet(vit_version='V1'):
     """The reference's own class, built as nnViTUNetTrainer.py:117-125 does, on the tiny geometry."""
     from torch import nn
     from nnunet.network_architecture.initialization import InitWeights_He
@@ -165,7 +165,7 @@ def reference_vit_unet():
     net = Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], 2, 2, nn.Conv3d, nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True},
                            nn.Dropout3d, {'p': 0, 'inplace': True}, nn.LeakyReLU, {'negative_slope': 1e-2, 'inplace': True},
                            True, False, lambda x: x, InitWeights_He(1e-2), [[2, 2, 2], [2, 2, 2]], [[3, 3, 3]] * 3,
-                           False, True, True, vit_version='V1', vit_type='base')
+                           False, True, True, vit_version=vit_version, vit_type='base')
     return vit_unet.fill_parameters(net, VIT_SEED)
 
 

@@ -127,10 +127,11 @@ class VisionTransformer(nn.Module):
 
 
 class Generic_ViT_UNet(Generic_UNet):
-    """V1: the ViT reads the first skip; its class-token head output, reshaped, replaces the bottleneck activation."""
+    """V1: the ViT reads the first skip; its class-token head output, reshaped, replaces the bottleneck activation.
+    V2 (:299-313): the ViT reads first skip + bottleneck up-sampled through all `tu`; V3 (:316-338): plus every skip up-sampled."""
 
     def __init__(self, input_channels, base_num_features, num_classes, num_pool, patch_size, pool_op_kernel_sizes,
-                 conv_kernel_sizes=None, vit_type='base', max_num_features=None):
+                 conv_kernel_sizes=None, vit_type='base', max_num_features=None, vit_version='V1'):
         if conv_kernel_sizes is None:
             conv_kernel_sizes = [[3, 3, 3]] * (num_pool + 1)
         super().__init__(input_channels, base_num_features, num_classes, num_pool, 2, 2, nn.Conv3d, nn.InstanceNorm3d,
@@ -158,15 +159,32 @@ class Generic_ViT_UNet(Generic_UNet):
         table = dict(parts)
         for n in ('conv_blocks_localization', 'conv_blocks_context', 'ViT', 'td', 'tu', 'seg_outputs'):
             setattr(self, n, vit if n == 'ViT' else table[n])
-        self.version = 'V1'
+        self.version = vit_version.title()
+        assert self.version in ('V1', 'V2', 'V3')
+
+    def vit_input(self, skips, last_context):   # :290-338
+        if self.version == 'V1':
+            return skips[0]
+        t = last_context
+        for u in range(len(self.tu)):
+            t = self.tu[u](t)
+        if self.version == 'V2':
+            return skips[0] + t
+        vit_in = torch.zeros(skips[0].size()) + t
+        for idx, skip in enumerate(reversed(skips)):
+            t = skip
+            for u in range(idx + 1, len(self.tu)):
+                t = self.tu[u](t)
+            vit_in = vit_in + t
+        return vit_in
 
     def forward(self, x):   # :217-287
         skips, seg = [], []
         for d in range(len(self.conv_blocks_context) - 1):
             x = self.conv_blocks_context[d](x)
             skips.append(x)
-        x = self.conv_blocks_context[-1](x)          # computed, only its size is used
-        x = self.ViT(skips[0]).reshape(x.size())
+        x = self.conv_blocks_context[-1](x)          # V1: computed, only its size is used
+        x = self.ViT(self.vit_input(skips, x)).reshape(x.size())
         for u in range(len(self.tu)):
             x = self.conv_blocks_localization[u](torch.cat((self.tu[u](x), skips[-(u + 1)]), dim=1))
             seg.append(self.final_nonlin(self.seg_outputs[u](x)))

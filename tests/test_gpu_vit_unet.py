@@ -164,3 +164,56 @@ def test_trainer_with_task_specific_layernorms(precision):
     tr.start_task("A")
     assert vit.task_name_use == "A" and vit.blocks.layer[0].use_task_name == "A"
     assert np.isfinite(float(tr.run_iteration(batch(9), do_backprop=False)))
+
+
+def _pair_v(version, precision):
+    from b200unet.generic_ViT_UNet import Generic_ViT_UNet
+    from oracle import gen_golden, vit_unet
+    onet = vit_unet.fill_parameters(vit_unet.Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], [[2, 2, 2], [2, 2, 2]], vit_version=version),
+                                    gen_golden.VIT_SEED)
+    cnet = Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], pool_op_kernel_sizes=[[2, 2, 2], [2, 2, 2]], conv_kernel_sizes=[[3, 3, 3]] * 3,
+                            vit_version=version)
+    cnet.load_state_dict(onet.state_dict())
+    cnet.precision = precision
+    return onet, cnet.cuda(), gen_golden.vit_case()
+
+
+@pytest.mark.parametrize("version", ["V2", "V3"])
+def test_v2_v3_forward_backward_match_oracle(version):
+    """Generic_ViT_UNet V2 / V3 (generic_ViT_UNet.py:290-338; oracle pinned to the reference class in
+    tests/test_oracle_vs_reference.py): the ViT input is fused from the first skip and the bottleneck (V3: and every skip)
+    up-sampled through the `tu` chain -- b2_tconv3d_fwd / _bwd outside the plan.  fp32: logits 1e-3; gradients of the parameters
+    the new data flow touches (tu weights used twice, live bottleneck convolutions, ViT) 5e-3 / cosine."""
+    onet, cnet, (x, up) = _pair_v(version, "fp32")
+    oo = onet(x)
+    (sum((o * u).sum() for o, u in zip(oo, up)) / 1000.0).backward()
+    co = cnet(x.cuda())
+    for a, b in zip(co, oo):
+        assert a.shape == b.shape and rel_err(a, b) < TOL, (version, rel_err(a, b))
+    (sum((o * u.cuda()).sum() for o, u in zip(co, up)) / 1000.0).backward()
+    od, cd = dict(onet.named_parameters()), dict(cnet.named_parameters())
+    cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double().cpu(), b.flatten().double(), dim=0))
+    for n in ("tu.0.weight", "tu.1.weight", "conv_blocks_context.2.0.blocks.0.conv.weight", "conv_blocks_context.2.1.blocks.0.conv.weight",
+              "ViT.patch_embeds.0.proj.weight", "ViT.heads.0.weight", "ViT.blocks.layer.5.mlp.fc1.weight",
+              "conv_blocks_context.0.blocks.0.conv.weight", "conv_blocks_context.1.blocks.1.conv.weight", "seg_outputs.1.weight"):
+        assert cd[n].grad is not None and od[n].grad is not None, n
+        assert cos(cd[n].grad, od[n].grad) > 0.999 and rel_err(cd[n].grad, od[n].grad) < 5e-2, (n, rel_err(cd[n].grad, od[n].grad))
+    assert rel_err(cd["tu.0.weight"].grad, od["tu.0.weight"].grad) < 5e-3
+    assert rel_err(cd["conv_blocks_context.2.1.blocks.0.conv.weight"].grad, od["conv_blocks_context.2.1.blocks.0.conv.weight"].grad) < 5e-3
+
+
+@pytest.mark.parametrize("version", ["V2", "V3"])
+def test_v2_v3_bf16_native_vit(version):
+    """production precision: native ViT kernels on the fused input, input gradient handed back to autograd for the tu chain"""
+    onet, cnet, (x, up) = _pair_v(version, "bf16")
+    oo = onet(x)
+    (sum((o * u).sum() for o, u in zip(oo, up)) / 1000.0).backward()
+    co = cnet(x.cuda())
+    (sum((o * u.cuda()).sum() for o, u in zip(co, up)) / 1000.0).backward()
+    cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten().double().cpu(), b.flatten().double(), dim=0))
+    for a, b in zip(co, oo):
+        assert cos(a, b) > 0.99
+    od, cd = dict(onet.named_parameters()), dict(cnet.named_parameters())
+    for n in ("tu.0.weight", "tu.1.weight", "conv_blocks_context.2.1.blocks.0.conv.weight", "ViT.heads.0.weight",
+              "ViT.patch_embeds.0.proj.weight", "conv_blocks_context.0.blocks.0.conv.weight"):
+        assert cd[n].grad is not None and cos(cd[n].grad, od[n].grad) > 0.9, (n, cos(cd[n].grad, od[n].grad))

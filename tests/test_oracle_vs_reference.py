@@ -143,3 +143,23 @@ def test_task_specific_ln_vit_equals_reference_class():
     a = mine(x, task_name='A')
     mine.use_task('B')
     assert not torch.allclose(a, mine(x))
+
+
+@pytest.mark.parametrize("version", ["V2", "V3"])
+def test_vit_unet_v2_v3_restatement_equals_reference_class(version):
+    """oracle/vit_unet.py V2 / V3 (ViT input fused from the first skip, the up-sampled bottleneck and -- V3 -- every up-sampled
+    skip) == the reference's class (generic_ViT_UNet.py:290-338): identical logits and gradient norms, and here the bottleneck
+    convolutions DO receive gradients."""
+    for p in (os.path.join(util.ROOT, "oracle", "shim"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from oracle import gen_golden, vit_unet
+    ref = gen_golden.reference_vit_unet(version)
+    mine = vit_unet.Generic_ViT_UNet(1, 8, 3, 2, [16, 32, 32], [[2, 2, 2], [2, 2, 2]], vit_version=version)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict())
+    a, b = gen_golden.vit_values(ref), gen_golden.vit_values(mine)
+    assert set(a) == set(b)
+    for k in a:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-7, err_msg=k)
+    assert a["gnorm/conv_blocks_context.2.0.blocks.0.conv.weight"] > 0
