@@ -169,6 +169,11 @@ typedef struct b2_vit_desc {
     int32_t out_features;                     /* == out_c * out_d * out_h * out_w */
     int32_t out_c, out_d, out_h, out_w;       /* bottleneck activation */
     float   ln_eps;                           /* 1e-6 */
+    int32_t lsa;                              /* Locality Self-Attention (vision_transformer.py:90-135): qkv without bias (null
+                                               * entries in the parameter table), diagonal of the scores masked, one learnable
+                                               * temperature vector [heads] per block appended after the tail parameters */
+    int32_t lsa_mask;                         /* number of leading tokens whose self-score is masked: the reference sizes its mask
+                                               * from the 2-D patch count, (H / p) (W / p) + 1 (vision_transformer.py:289-294) */
 } b2_vit_desc;
 typedef struct b2_vit_plan b2_vit_plan;
 int b2_vit_plan_create(const b2_vit_desc* desc, b2_vit_plan** out);

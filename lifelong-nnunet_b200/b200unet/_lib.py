@@ -50,7 +50,7 @@ class VitDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("in_channels", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("patch", C.c_int32), ("embed", C.c_int32), ("heads", C.c_int32), ("depth", C.c_int32), ("mlp_ratio", C.c_int32),
                 ("out_features", C.c_int32), ("out_c", C.c_int32), ("out_d", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
-                ("ln_eps", C.c_float)]
+                ("ln_eps", C.c_float), ("lsa", C.c_int32), ("lsa_mask", C.c_int32)]
 
 
 class GradBucket(C.Structure):

@@ -256,9 +256,9 @@ class Generic_ViT_UNet(Generic_UNet):
                                       "You provided '{}'".format(vit_type)
         self.version = vit_version.title()
         assert self.version in ['V1', 'V2', 'V3', 'V4'], 'Please provide a correct version (V1, V2, V3 or V4), not {}.'.format(vit_version)
-        if self.version == 'V4' or split_gpu or do_LSA or do_SPT:
-            raise NotImplementedError("b200unet.Generic_ViT_UNet: vit_version V1 / V2 / V3 on one device without "
-                                      "LSA / SPT are implemented (no eager fallback)")
+        if self.version == 'V4' or split_gpu or do_SPT:
+            raise NotImplementedError("b200unet.Generic_ViT_UNet: vit_version V1 / V2 / V3 on one device (optionally with LSA or "
+                                      "task-specific LayerNorms) are implemented; V4, SPT and split_gpu are not (no eager fallback)")
         self.prepare = {'V1': '_get_ViT_inputV1', 'V2': '_get_ViT_inputV2', 'V3': '_get_ViT_inputV3'}
         self.split_gpu, self.use_skip = False, 0
         self.ViT_types = VIT_TYPES
@@ -280,7 +280,7 @@ class Generic_ViT_UNet(Generic_UNet):
         vit = VisionTransformer(ViT_2d=False, img_size=self.img_size, patch_size=self.patch_size,
                                 img_depth=[self.img_size[0]], in_chans=self.in_chans, num_classes=self.num_classesViT,
                                 embed_dim=cfg['embed_size'], depth=cfg['layers'], num_heads=cfg['head'], mlp_ratio=4,
-                                qkv_bias=True, task_specific_ln=ViT_task_specific_ln, task_name=first_task_name)
+                                qkv_bias=True, task_specific_ln=ViT_task_specific_ln, task_name=first_task_name, is_LSA=do_LSA)
         # registration order of generic_ViT_UNet.py:193-211
         parts = {n: getattr(self, n) for n in ('conv_blocks_localization', 'conv_blocks_context', 'td', 'tu', 'seg_outputs')}
         for n in parts:

@@ -80,7 +80,7 @@ class nnUNetTrainerMultiHead:
     def __init__(self, geometry, precision="bf16", batch_dice=False, device=None, ddp=None, initial_lr=1e-2,
                  weight_decay=3e-5, max_num_epochs=1000, seed=0, task="task_A", use_vit=False, vit_version='V1',
                  vit_type='base', split="seg_outputs", transfer_heads=True, strict_reference=True, fused_step=True,
-                 cuda_graph=None, ViT_task_specific_ln=False):
+                 cuda_graph=None, ViT_task_specific_ln=False, do_LSA=False):
         self.geometry = geometry
         self.split, self.transfer_heads = split, transfer_heads       # run_training.py -s / --transfer_heads
         # strict_reference: reproduce the reference's generator-exhaustion quirks Q1 / Q2; False = the
@@ -96,6 +96,7 @@ class nnUNetTrainerMultiHead:
         self.mh_network = None
         self.use_vit, self.vit_version, self.vit_type = use_vit, vit_version, vit_type   # run_training.py --use_vit
         self.ViT_task_specific_ln = bool(ViT_task_specific_ln)                           # run_training.py --task_specific_ln
+        self.do_LSA = bool(do_LSA)                                                       # run_training.py --do_LSA
         self.precision = precision
         self.batch_dice = batch_dice
         if device is None:
@@ -109,7 +110,7 @@ class nnUNetTrainerMultiHead:
         self._init_kwargs = dict(precision=precision, batch_dice=batch_dice, initial_lr=initial_lr, weight_decay=weight_decay,
                                  max_num_epochs=max_num_epochs, seed=seed, task=task, use_vit=use_vit, vit_version=vit_version,
                                  vit_type=vit_type, split=split, transfer_heads=transfer_heads, strict_reference=strict_reference,
-                                 ViT_task_specific_ln=ViT_task_specific_ln)
+                                 ViT_task_specific_ln=ViT_task_specific_ln, do_LSA=do_LSA)
         self.ddp = ddp
         self.initial_lr, self.weight_decay, self.max_num_epochs = initial_lr, weight_decay, max_num_epochs
         self.seed, self.task = seed, task
@@ -133,7 +134,7 @@ class nnUNetTrainerMultiHead:
             self.network = Generic_ViT_UNet(g.in_channels, g.base_features, g.num_classes, g.num_pool,
                                             [int(s) for s in g.patch], vit_version=self.vit_version,
                                             vit_type=self.vit_type, ViT_task_specific_ln=self.ViT_task_specific_ln,
-                                            first_task_name=self.task, **kw)
+                                            first_task_name=self.task, do_LSA=self.do_LSA, **kw)
             if self.ViT_task_specific_ln:    # nnViTUNetTrainer.py:128-129
                 self.network.ViT.use_task(self.task)
         else:

@@ -75,21 +75,40 @@ class Mlp(nn.Module):
 
 
 class Attention(nn.Module):
-    """vision_transformer.py:136-150 (non-LSA branch).  The probabilities are only materialised when the owner asked
-    for them (``VisionTransformer.store_attn_weights``); otherwise the fused SDPA kernel is used."""
+    """vision_transformer.py:81-151.  Plain branch (:136-150): qkv with bias, fixed scale head_dim^-0.5, `proj`.  LSA branch
+    (Locality Self-Attention, :90-135): qkv WITHOUT bias (xavier-normal), a learnable temperature per head (`scale`), the diagonal
+    of the score matrix masked out (-987654321 before the softmax), output through `to_out`; timm's `proj` stays registered but
+    unused, as in the reference.  The probabilities are only materialised when the owner asked for them
+    (``VisionTransformer.store_attn_weights``) or for LSA in the ATen path; otherwise the fused SDPA kernel is used."""
 
-    def __init__(self, dim, num_heads):
+    def __init__(self, dim, num_heads, is_LSA=False, num_patches=16):
         super().__init__()
         self.num_heads = num_heads
-        self.scale = (dim // num_heads) ** -0.5
-        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.LSA = bool(is_LSA)
+        self.qkv = nn.Linear(dim, dim * 3, bias=not self.LSA)
         self.proj = nn.Linear(dim, dim)
-        self.LSA = False
         self.store_weights = False
+        if self.LSA:
+            self.num_patches, self.heads, self.dim, self.inner_dim = num_patches, num_heads, dim, (dim // num_heads) * num_heads
+            nn.init.xavier_normal_(self.qkv.weight)
+            self.to_out = nn.Sequential(nn.Linear(self.inner_dim, dim), nn.Dropout(0.))
+            self.scale = nn.Parameter((dim // num_heads) ** -0.5 * torch.ones(num_heads))
+            self.mask = torch.nonzero(torch.eye(num_patches + 1, num_patches + 1) == 1, as_tuple=False)
+        else:
+            self.scale = (dim // num_heads) ** -0.5
 
     def forward(self, x):
         B, N, Cc = x.shape
         q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, Cc // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        if self.LSA:
+            dots = (q @ k.transpose(-2, -1)) * self.scale.to(q.dtype).view(1, -1, 1, 1)
+            # quirk: the reference sizes the mask from the 2-D patch count (vision_transformer.py:289-294), so in 3-D only the
+            # first num_patches + 1 tokens mask their own score
+            m = torch.zeros(N, dtype=torch.bool, device=x.device)
+            m[:self.num_patches + 1] = True
+            dots = dots.masked_fill(torch.diag(m), -987654321)
+            w = dots.softmax(dim=-1)
+            return self.to_out((w @ v).transpose(1, 2).reshape(B, N, Cc)), w
         if self.store_weights:
             w = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1)
             o = w @ v
@@ -103,7 +122,7 @@ class Block(nn.Module):
     """vision_transformer.py:153-198: with task-specific LNs, norm1 / norm2 are ModuleDicts keyed by task name and
     `use_task_name` (set through VisionTransformer.use_task) selects the pair used by forward"""
 
-    def __init__(self, dim, num_heads, eps, task_specific_ln=False, task_name=None):
+    def __init__(self, dim, num_heads, eps, task_specific_ln=False, task_name=None, is_LSA=False, num_patches=16):
         super().__init__()
         self.task_specific_ln = bool(task_specific_ln)
         if self.task_specific_ln:
@@ -112,7 +131,7 @@ class Block(nn.Module):
                 "When using task specific LNs, than please provide a task_name during initialization.."
         mk = lambda: nn.ModuleDict({task_name: nn.LayerNorm(dim, eps=eps)}) if self.task_specific_ln else nn.LayerNorm(dim, eps=eps)
         self.norm1 = mk()
-        self.attn = Attention(dim, num_heads)
+        self.attn = Attention(dim, num_heads, is_LSA, num_patches)
         self.drop_path = nn.Identity()
         self.norm2 = mk()
         self.mlp = Mlp(dim, 4 * dim)
@@ -133,9 +152,9 @@ class Block(nn.Module):
 
 
 class Encoder(nn.Module):
-    def __init__(self, depth, dim, num_heads, eps, task_specific_ln=False, task_name=None):
+    def __init__(self, depth, dim, num_heads, eps, task_specific_ln=False, task_name=None, is_LSA=False, num_patches=16):
         super().__init__()
-        self.layer = nn.ModuleList([Block(dim, num_heads, eps, task_specific_ln, task_name) for _ in range(depth)])
+        self.layer = nn.ModuleList([Block(dim, num_heads, eps, task_specific_ln, task_name, is_LSA, num_patches) for _ in range(depth)])
 
     def forward(self, x):
         ws = []
@@ -154,9 +173,10 @@ class VisionTransformer(nn.Module):
             assert not is_SPT and not is_LSA, "Currently, we do not provide the combination for task specific LNs and either LSA, SPT or both.."
             assert task_name is not None and isinstance(task_name, str), \
                 "When using task specific LNs, than please provide a task_name during initialization.."
-        if ViT_2d or is_LSA or is_SPT or mlp_ratio != 4 or not qkv_bias:
-            raise NotImplementedError("b200unet.VisionTransformer: only the 3D build without LSA / SPT is implemented")
-        self.LSA, self.SPT, self.task_specific_ln = False, False, bool(task_specific_ln)
+        if ViT_2d or is_SPT or mlp_ratio != 4 or not qkv_bias:
+            raise NotImplementedError("b200unet.VisionTransformer: only the 3D build without SPT is implemented (SPT is 2-D only "
+                                      "in the reference: its Rearrange pattern takes 4-D inputs)")
+        self.LSA, self.SPT, self.task_specific_ln = bool(is_LSA), False, bool(task_specific_ln)
         self.task_name_use = None
         self.block_depth, self.embed_dim, self.num_features = depth, embed_dim, embed_dim
         self.num_tokens, self.num_classes = 1, int(num_classes)
@@ -168,7 +188,10 @@ class VisionTransformer(nn.Module):
                         patch_size[0], in_chans, embed_dim, self.task_specific_ln, task_name)
         self.pos_embed_0 = nn.Parameter(torch.zeros(1, pe.num_patches + 1, embed_dim))
         self.pos_drop = nn.Identity()
-        self.blocks = Encoder(depth, embed_dim, num_heads, eps, self.task_specific_ln, task_name)
+        # (the reference rebuilds the blocks WITHOUT LSA when task-specific LNs are on, :303-306 -- the combination is asserted away)
+        # LSA's mask size comes from the 2-D timm patch embedding that exists at that point of the reference's constructor (:289)
+        n2d = (pe.img_size[1] // pe.patch) * (pe.img_size[2] // pe.patch)
+        self.blocks = Encoder(depth, embed_dim, num_heads, eps, self.task_specific_ln, task_name, self.LSA, n2d)
         self._ln_eps = eps
         self.norm = nn.ModuleDict({task_name: nn.LayerNorm(embed_dim, eps=eps)}) if self.task_specific_ln \
             else nn.LayerNorm(embed_dim, eps=eps)
@@ -186,11 +209,15 @@ class VisionTransformer(nn.Module):
         ps = [self.cls_token, self.pos_embed_0]
         for blk in self.blocks.layer:
             n1, n2 = blk.norms()          # task-specific LNs: the active task's pair (the kernels see plain LayerNorms)
-            ps += [n1.weight, n1.bias, blk.attn.qkv.weight, blk.attn.qkv.bias, blk.attn.proj.weight, blk.attn.proj.bias,
+            a = blk.attn
+            out = a.to_out[0] if a.LSA else a.proj      # LSA: no qkv bias (None -> null pointer), output through `to_out`
+            ps += [n1.weight, n1.bias, a.qkv.weight, a.qkv.bias, out.weight, out.bias,
                    n2.weight, n2.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias]
         pe = self.patch_embeds[0]
         norm = self._final_norm(None)
         ps += [norm.weight, norm.bias, pe.proj.weight, pe.proj.bias, self.heads[0].weight, self.heads[0].bias]
+        if self.LSA:                      # one learnable temperature vector [heads] per block, after the tail
+            ps += [blk.attn.scale for blk in self.blocks.layer]
         return ps
 
     def _final_norm(self, task_name):
@@ -219,6 +246,8 @@ class VisionTransformer(nn.Module):
             d.out_features = self.num_classes
             d.out_c, d.out_d, d.out_h, d.out_w = (int(v) for v in out_shape)
             d.ln_eps = float(self._ln_eps)
+            d.lsa = int(self.LSA)
+            d.lsa_mask = int(self.blocks.layer[0].attn.num_patches + 1) if self.LSA else 0
             h = C.c_void_p()
             _lib.check(lib.b2_vit_plan_create(C.byref(d), C.byref(h)))
             ws = torch.empty(int(lib.b2_vit_workspace_bytes(h)), dtype=torch.uint8, device=x.device)
@@ -283,10 +312,10 @@ class _ViTNativeFunction(torch.autograd.Function):
         lib = _lib.load()
         h, ws = vit._native_plan(x, out_shape)
         for p in params:
-            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
+            if p is not None and (p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device):
                 raise RuntimeError("ViT parameters must be contiguous fp32 tensors on the input's device")
         need = any(ctx.needs_input_grad)      # (grad mode is off inside Function.forward: is_grad_enabled() would say False)
-        pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        pp = (C.c_void_p * len(params))(*[None if p is None else p.data_ptr() for p in params])
         out = torch.empty((x.shape[0], vit.num_classes), dtype=torch.float32, device=x.device)
         vx = _view_of(x.detach())
         _lib.check(lib.b2_vit_forward(h, pp, C.byref(vx), C.c_void_p(ws.data_ptr()), None, C.c_void_p(out.data_ptr()), 1 if need else 0,
@@ -310,14 +339,17 @@ class _ViTNativeFunction(torch.autograd.Function):
         params = ctx.params
         dev = dout.device
         dout = dout.contiguous().float()
-        total = sum(p.numel() for p in params)
+        total = sum(p.numel() for p in params if p is not None)
         flat = torch.empty(total, dtype=torch.float32, device=dev)
         grads, o = [], 0
         for p in params:
+            if p is None:
+                grads.append(None)
+                continue
             grads.append(flat[o:o + p.numel()].view(p.shape))
             o += p.numel()
-        pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        gp = (C.c_void_p * len(params))(*[g.data_ptr() for g in grads])
+        pp = (C.c_void_p * len(params))(*[None if p is None else p.data_ptr() for p in params])
+        gp = (C.c_void_p * len(params))(*[None if g is None else g.data_ptr() for g in grads])
         dx = None
         if ctx.return_dx:          # the kernels ADD the input gradient into the buffer they are given
             dx = torch.empty(tuple(ctx.x.shape), dtype=ctx.x.dtype, device=dev, memory_format=torch.channels_last_3d).zero_()
@@ -328,4 +360,4 @@ class _ViTNativeFunction(torch.autograd.Function):
                                        None if vd is None else C.byref(vd), gp,
                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         ctx.vit._last_flat_grad = flat
-        return (None, dx, None, None, None) + tuple(g if p.requires_grad else None for g, p in zip(grads, params))
+        return (None, dx, None, None, None) + tuple(g if (p is not None and p.requires_grad) else None for g, p in zip(grads, params))

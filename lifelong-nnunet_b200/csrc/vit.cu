@@ -423,8 +423,11 @@ __device__ __forceinline__ void fa_store(const float (&acc)[8][4], float mul0, f
 }
 
 // out[b*T + i][h*64 + d] = sum_j softmax_j(scale q_i.k_j) v_j[d];  lse[(b*H + h)*T + i] = log sum_j exp(scale q_i.k_j)
+// LSA (vision_transformer.py:90-135): `scale_h` (nullable) = learnable temperature per head replacing `scale`; `diag`: the score of
+// token i with itself is masked out before the softmax for i < diag (the reference builds its mask from the 2-D patch count)
 __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                              float* __restrict__ lse, int B, int H, int T, float scale) {
+                                                              float* __restrict__ lse, int B, int H, int T, float scale,
+                                                              const float* __restrict__ scale_h, int diag) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
@@ -435,6 +438,8 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat1
     const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
     const int q0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    if (scale_h) scale = scale_h[h];
+    const int qi0 = q0 + warp * 16 + g, qi1 = qi0 + 8;      // this thread's two query rows
     fa_stage(base, ld, q0, T, Qs);
     fa_stage(base + E, ld, 0, T, Ks);
     fa_stage(base + 2 * E, ld, 0, T, Vs);
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat1
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    const float sl2 = scale * LOG2E;
+    const float sl2 = LOG2E;          // the scores are scaled right after the MMA (a learnable LSA temperature may be negative)
     for (int jb = 0; jb < nblk; ++jb) {
         const int cur = jb & 1;
         if (jb + 1 < nblk) {
@@ -464,15 +469,26 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat1
         float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] *= scale; s[nb][1] *= scale; s[nb][2] *= scale; s[nb][3] *= scale;
             const int j = jb * FA_ROWS + nb * 8 + 2 * t;
             if (j >= T) s[nb][0] = s[nb][2] = -INFINITY;
             if (j + 1 >= T) s[nb][1] = s[nb][3] = -INFINITY;
+            if (diag) {      // only the first `diag` tokens mask themselves (see b2_vit_desc.lsa_mask)
+                if (j == qi0 && j < diag) s[nb][0] = -INFINITY;
+                if (j + 1 == qi0 && j + 1 < diag) s[nb][1] = -INFINITY;
+                if (j == qi1 && j < diag) s[nb][2] = -INFINITY;
+                if (j + 1 == qi1 && j + 1 < diag) s[nb][3] = -INFINITY;
+            }
             bm0 = fmaxf(bm0, fmaxf(s[nb][0], s[nb][1]));
             bm1 = fmaxf(bm1, fmaxf(s[nb][2], s[nb][3]));
         }
         bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
         bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-        const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);       // finite: every key block holds at least one valid key
+        // every key block holds at least one valid key; with the diagonal mask a block whose only valid key is the row's own
+        // token (T % 64 == 1) is empty for that row: keep the running maximum finite so exp2(-inf - -inf) never appears
+        float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+        if (n0 == -INFINITY) n0 = 0.f;
+        if (n1 == -INFINITY) n1 = 0.f;
         const float al0 = exp2f((m0 - n0) * sl2), al1 = exp2f((m1 - n1) * sl2);
         m0 = n0; m1 = n1;
         float r0 = 0.f, r1 = 0.f;
@@ -496,8 +512,8 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat1
     const int row0 = q0 + warp * 16;
     fa_store(o, 1.f / l0, 1.f / l1, out + (long long)b * T * E + h * 64, E, row0, T, lane);
     if (t == 0) {
-        if (row0 + g < T) lse[(long long)bh * T + row0 + g] = m0 * scale + logf(l0);
-        if (row0 + g + 8 < T) lse[(long long)bh * T + row0 + g + 8] = m1 * scale + logf(l1);
+        if (row0 + g < T) lse[(long long)bh * T + row0 + g] = m0 + logf(l0);
+        if (row0 + g + 8 < T) lse[(long long)bh * T + row0 + g + 8] = m1 + logf(l1);
     }
 }
 
@@ -505,7 +521,8 @@ __global__ void __launch_bounds__(FA_THREADS) attn_fwd_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(FA_THREADS) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ O,
                                                                 const __nv_bfloat16* __restrict__ dO, const float* __restrict__ lse,
                                                                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ Drow, int B, int H,
-                                                                int T, float scale) {
+                                                                int T, float scale, const float* __restrict__ scale_h, int diag,
+                                                                float* __restrict__ dscale_part /* [B*H][gridDim.y], nullable */) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
@@ -520,6 +537,9 @@ __global__ void __launch_bounds__(FA_THREADS) attn_bwd_q_kernel(const __nv_bfloa
     const __nv_bfloat16* obase = O + (long long)b * T * E + h * 64;
     const int q0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    if (scale_h) scale = scale_h[h];
+    const int qi0 = q0 + warp * 16 + g, qi1 = qi0 + 8;
+    float dsc = 0.f;                                                  // sum of dS_ij (q_i . k_j) over this thread's entries
     fa_stage(base, ld, q0, T, Qs);
     fa_stage(gbase, E, q0, T, Gs);
     fa_stage(base + E, ld, 0, T, Ks);
@@ -584,10 +604,17 @@ __global__ void __launch_bounds__(FA_THREADS) attn_bwd_q_kernel(const __nv_bfloa
         for (int nb = 0; nb < 8; ++nb) {
             const int j = jb * FA_ROWS + nb * 8 + 2 * t;
             const bool v0 = j < T, v1 = j + 1 < T;
-            s[nb][0] = v0 ? exp2f(s[nb][0] * sl2 - L0) * (dp[nb][0] - D0) : 0.f;
-            s[nb][1] = v1 ? exp2f(s[nb][1] * sl2 - L0) * (dp[nb][1] - D0) : 0.f;
-            s[nb][2] = v0 ? exp2f(s[nb][2] * sl2 - L1) * (dp[nb][2] - D1) : 0.f;
-            s[nb][3] = v1 ? exp2f(s[nb][3] * sl2 - L1) * (dp[nb][3] - D1) : 0.f;
+            const bool a0 = v0 && !(j < diag && j == qi0), a1 = v1 && !(j + 1 < diag && j + 1 == qi0);
+            const bool a2 = v0 && !(j < diag && j == qi1), a3 = v1 && !(j + 1 < diag && j + 1 == qi1);
+            const float r0 = s[nb][0], r1 = s[nb][1], r2 = s[nb][2], r3 = s[nb][3];       // raw q . k
+            s[nb][0] = a0 ? exp2f(r0 * sl2 - L0) * (dp[nb][0] - D0) : 0.f;
+            s[nb][1] = a1 ? exp2f(r1 * sl2 - L0) * (dp[nb][1] - D0) : 0.f;
+            s[nb][2] = a2 ? exp2f(r2 * sl2 - L1) * (dp[nb][2] - D1) : 0.f;
+            s[nb][3] = a3 ? exp2f(r3 * sl2 - L1) * (dp[nb][3] - D1) : 0.f;
+            if (dscale_part) {      // rows >= T are clamped copies of row T - 1: they must not count
+                if (qi0 < T) dsc += s[nb][0] * r0 + s[nb][1] * r1;
+                if (qi1 < T) dsc += s[nb][2] * r2 + s[nb][3] * r3;
+            }
         }
         uint32_t pa[4][4];
         fa_acc_to_a(pa, s);
@@ -595,12 +622,31 @@ __global__ void __launch_bounds__(FA_THREADS) attn_bwd_q_kernel(const __nv_bfloa
         __syncthreads();
     }
     fa_store(dq, scale, scale, dqkv + (long long)b * T * ld + h * 64, ld, row0, T, lane);
+    if (dscale_part) {              // fixed-order CTA reduction: lanes by shuffle tree, the four warps in order
+        dsc = warp_sum(dsc);
+        __syncthreads();
+        if (lane == 0) Ds[warp] = dsc;
+        __syncthreads();
+        if (threadIdx.x == 0) dscale_part[(long long)bh * gridDim.y + blockIdx.y] = (Ds[0] + Ds[1]) + (Ds[2] + Ds[3]);
+    }
+}
+
+// dscale[h] = sum over batch and query blocks of the per-CTA partials (fixed order)
+__global__ void __launch_bounds__(32) attn_dscale_final_kernel(const float* __restrict__ part, int B, int H, int nblk, float* __restrict__ dscale) {
+    pdl_grid_sync();
+    const int h = blockIdx.x * 32 + threadIdx.x;
+    if (h >= H) return;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < nblk; ++k) s += part[((long long)b * H + h) * nblk + k];
+    dscale[h] = s;
 }
 
 // dK, dV:  dv_j = sum_i p_ij dO_i;  dk_j = scale sum_i dS_ij q_i      (a CTA owns 64 keys and streams the queries / dO)
 __global__ void __launch_bounds__(FA_THREADS) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dO,
                                                                  const float* __restrict__ lse, const float* __restrict__ Drow,
-                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, float scale) {
+                                                                 __nv_bfloat16* __restrict__ dqkv, int B, int H, int T, float scale,
+                                                                 const float* __restrict__ scale_h, int diag) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smraw);     // [64][FA_LD]
@@ -615,6 +661,8 @@ __global__ void __launch_bounds__(FA_THREADS) attn_bwd_kv_kernel(const __nv_bflo
     const __nv_bfloat16* gbase = dO + (long long)b * T * E + h * 64;
     const int k0 = blockIdx.y * FA_ROWS, nblk = (T + FA_ROWS - 1) / FA_ROWS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3;
+    if (scale_h) scale = scale_h[h];
+    const int kj0 = k0 + warp * 16 + (lane >> 2), kj1 = kj0 + 8;     // this thread's two key rows
     auto stage_rows = [&](int ib, int buf) {
         fa_stage(base, ld, ib * FA_ROWS, T, Qs + buf * FA_TILE);
         fa_stage(gbase, E, ib * FA_ROWS, T, Gs + buf * FA_TILE);
@@ -666,8 +714,10 @@ __global__ void __launch_bounds__(FA_THREADS) attn_bwd_kv_kernel(const __nv_bflo
             const int c = nb * 8 + 2 * t, i = ib * FA_ROWS + c;
             const bool v0 = i < T, v1 = i + 1 < T;
             const float La = Lc[c], Lb = Lc[c + 1], Da = Dc[c], Db = Dc[c + 1];
-            const float p0 = v0 ? exp2f(s[nb][0] * sl2 - La) : 0.f, p1 = v1 ? exp2f(s[nb][1] * sl2 - Lb) : 0.f;
-            const float p2 = v0 ? exp2f(s[nb][2] * sl2 - La) : 0.f, p3 = v1 ? exp2f(s[nb][3] * sl2 - Lb) : 0.f;
+            const bool a0 = v0 && !(i < diag && i == kj0), a1 = v1 && !(i + 1 < diag && i + 1 == kj0);
+            const bool a2 = v0 && !(i < diag && i == kj1), a3 = v1 && !(i + 1 < diag && i + 1 == kj1);
+            const float p0 = a0 ? exp2f(s[nb][0] * sl2 - La) : 0.f, p1 = a1 ? exp2f(s[nb][1] * sl2 - Lb) : 0.f;
+            const float p2 = a2 ? exp2f(s[nb][2] * sl2 - La) : 0.f, p3 = a3 ? exp2f(s[nb][3] * sl2 - Lb) : 0.f;
             s[nb][0] = p0; s[nb][1] = p1; s[nb][2] = p2; s[nb][3] = p3;
             dp[nb][0] = p0 * (dp[nb][0] - Da); dp[nb][1] = p1 * (dp[nb][1] - Db);
             dp[nb][2] = p2 * (dp[nb][2] - Da); dp[nb][3] = p3 * (dp[nb][3] - Db);
@@ -872,13 +922,15 @@ extern "C" int b2_vit_plan_create(const b2_vit_desc* desc, b2_vit_plan** out) {
 extern "C" void b2_vit_plan_destroy(b2_vit_plan* p) { delete p; }
 extern "C" size_t b2_vit_workspace_bytes(const b2_vit_plan* p) { return p ? p->total : 0; }
 extern "C" size_t b2_vit_tokens_offset(const b2_vit_plan* p) { return p ? p->off_tok : 0; }
-extern "C" int b2_vit_num_params(const b2_vit_plan* p) { return p ? 2 + 12 * p->d.depth + 6 : B2_EINVAL; }
+// LSA: one temperature vector [heads] per block appended after the 6 tail parameters; the qkv bias entries are null
+extern "C" int b2_vit_num_params(const b2_vit_plan* p) { return p ? 2 + 12 * p->d.depth + 6 + (p->d.lsa ? p->d.depth : 0) : B2_EINVAL; }
 
 namespace {
 struct VP {   // parameter pointers in named_parameters() order
     const float* const* p; int depth;
     const float* cls() const { return p[0]; }
     const float* pos() const { return p[1]; }
+    const float* lsa_scale(int l) const { return p[2 + 12 * depth + 6 + l]; }
     const float* blk(int l, int i) const { return p[2 + 12 * l + i]; }   // 0 n1w 1 n1b 2 qkvw 3 qkvb 4 projw 5 projb 6 n2w 7 n2b 8 fc1w 9 fc1b 10 fc2w 11 fc2b
     const float* normw() const { return p[2 + 12 * depth]; }
     const float* normb() const { return p[3 + 12 * depth]; }
@@ -988,7 +1040,7 @@ extern "C" int b2_vit_forward(b2_vit_plan* p, const float* const* params, const 
         }
         if ((rc = gemm_tn_bf16(Xn, Mp, E, E, (__nv_bfloat16*)(wb + p->w_qkv), 3 * E, P_.blk(l, 3), qkv, 3 * E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
         B2_LAUNCH(attn_fwd_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, at_smem, st, (const __nv_bfloat16*)qkv, O, (float*)(bb + p->b_lse),
-                  d.batch, H, T, 0.125f);
+                  d.batch, H, T, 0.125f, d.lsa ? P_.lsa_scale(l) : (const float*)nullptr, d.lsa ? d.lsa_mask : 0);
         if ((rc = gemm_tn_bf16(O, Mp, E, E, (__nv_bfloat16*)(wb + p->w_proj), E, P_.blk(l, 5), tmp, E, 0, gscr, p->gemm_scr_bytes, st))) return rc;
         B2_LAUNCH(add_bf16_kernel, (int)grid_for((long long)M * E, 4), 256, 0, st, X, (const __nv_bfloat16*)tmp, (long long)M * E);
         B2_CUDA(cudaMemcpyAsync(Xmid, X, (size_t)Mp * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -1076,7 +1128,7 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
         if ((r = transpose(dOut, M, N, N, tA, Mp, st))) return r;
         if ((r = transpose(In, M, K, K, tB, Mp, st))) return r;
         if ((r = gemm_tn_bf16(tA, N, Mp, Mp, tB, K, nullptr, dW, K, 1, gscr, p->gemm_scr_bytes, st))) return r;
-        return colsum<__nv_bfloat16>(dOut, M, N, N, part, db, st);
+        return db ? colsum<__nv_bfloat16>(dOut, M, N, N, part, db, st) : B2_OK;     // (LSA: qkv has no bias)
     };
     for (int l = dep - 1; l >= 0; --l) {
         char* bb = (char*)ws + p->off_blocks + (size_t)l * p->blk_bytes;
@@ -1093,11 +1145,16 @@ extern "C" int b2_vit_backward(b2_vit_plan* p, const float* const* params, const
         if ((rc = linear_bwd(tmp, E, (const __nv_bfloat16*)(bb + p->b_O), E, (const __nv_bfloat16*)(wb + p->w_projT), tmp2, GB(l, 4), GB(l, 5)))) return rc;
         __nv_bfloat16* dqkv = tmp;     // [Mp][3E]
         B2_CUDA(cudaMemsetAsync(dqkv + (size_t)M * 3 * E, 0, (size_t)(Mp - M) * 3 * E * 2, st));
+        const float* sc_h = d.lsa ? P_.lsa_scale(l) : (const float*)nullptr;
+        float* dsc_part = d.lsa ? part : (float*)nullptr;        // [B*H][at_blocks] (the colsum partials are consumed by now)
         B2_LAUNCH(attn_bwd_q_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, q_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
                   (const __nv_bfloat16*)(bb + p->b_O), (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), dqkv, Drow, d.batch, H, T,
-                  0.125f);
+                  0.125f, sc_h, d.lsa ? d.lsa_mask : 0, dsc_part);
+        if (d.lsa)
+            B2_LAUNCH(attn_dscale_final_kernel, cdiv(H, 32), 32, 0, st, (const float*)dsc_part, d.batch, H, at_blocks, G(2 + 12 * dep + 6 + l));
         B2_LAUNCH(attn_bwd_kv_kernel, dim3(d.batch * H, at_blocks), FA_THREADS, kv_smem, st, (const __nv_bfloat16*)(bb + p->b_qkv),
-                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, 0.125f);
+                  (const __nv_bfloat16*)tmp2, (const float*)(bb + p->b_lse), (const float*)Drow, dqkv, d.batch, H, T, 0.125f, sc_h,
+                  d.lsa ? d.lsa_mask : 0);
         if ((rc = linear_bwd(dqkv, 3 * E, (const __nv_bfloat16*)(bb + p->b_Xn), E, (const __nv_bfloat16*)(wb + p->w_qkvT), tmp2, GB(l, 2), GB(l, 3)))) return rc;
         if ((rc = ln_bwd<__nv_bfloat16>(tmp2, E, (const float*)(bb + p->b_Xin), E, (const float*)(bb + p->b_st1), P_.blk(l, 0), dX, E, 1, M, E, part,
                                         GB(l, 0), GB(l, 1), st))) return rc;

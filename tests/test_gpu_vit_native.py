@@ -25,17 +25,21 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("lsa", [False, True])
 @pytest.mark.parametrize("case", CASES)
-def test_native_vit_forward_backward_vs_aten_fp32(case):
+def test_native_vit_forward_backward_vs_aten_fp32(case, lsa):
+    """lsa: Locality Self-Attention (learnable per-head temperature -- also its gradient --, masked diagonal, bias-free qkv)"""
     from b200unet.vision_transformer import VisionTransformer
     B, Cc, (D, H, W), patch, E, heads, depth, oshape = case
     F_ = oshape[0] * oshape[1] * oshape[2] * oshape[3]
     torch.manual_seed(0)
     vit = VisionTransformer(ViT_2d=False, img_size=[D, H, W], patch_size=(patch, patch), img_depth=[D], in_chans=Cc, num_classes=F_,
-                            embed_dim=E, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True).cuda()
+                            embed_dim=E, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True, is_LSA=lsa).cuda()
     with torch.no_grad():      # non-trivial values everywhere (the reference leaves pos_embed / biases at zero)
         for n, p in vit.named_parameters():
-            if p.dim() == 1 or 'pos_embed' in n or 'cls' in n:
+            if n.endswith('attn.scale'):
+                p.mul_(1.0 + 0.3 * torch.randn_like(p))
+            elif p.dim() == 1 or 'pos_embed' in n or 'cls' in n:
                 p.copy_(0.1 * torch.randn_like(p) + (1.0 if 'norm' in n and n.endswith('weight') else 0.0))
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn((B, Cc, D, H, W), generator=g, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last_3d)
@@ -44,7 +48,7 @@ def test_native_vit_forward_backward_vs_aten_fp32(case):
     xr = x.float().requires_grad_()
     out_ref = vit(xr)
     (out_ref * u).sum().backward()
-    ref_grads = {n: p.grad.clone() for n, p in vit.named_parameters()}
+    ref_grads = {n: p.grad.clone() for n, p in vit.named_parameters() if p.grad is not None}
     dx_ref = xr.grad.clone()
     vit.zero_grad(set_to_none=True)
     # native
@@ -56,6 +60,9 @@ def test_native_vit_forward_backward_vs_aten_fp32(case):
     torch.cuda.synchronize()
     bad = []
     for n, p in vit.named_parameters():
+        if lsa and '.attn.proj.' in n:          # timm's proj stays registered but unused under LSA (no gradient in either path)
+            assert p.grad is None and n not in ref_grads
+            continue
         assert p.grad is not None, n
         c = _cos(p.grad, ref_grads[n])
         ratio = float(p.grad.double().norm() / (ref_grads[n].double().norm() + 1e-30))

@@ -163,3 +163,39 @@ def test_vit_unet_v2_v3_restatement_equals_reference_class(version):
     for k in a:
         np.testing.assert_allclose(a[k], b[k], rtol=1e-6, atol=1e-7, err_msg=k)
     assert a["gnorm/conv_blocks_context.2.0.blocks.0.conv.weight"] > 0
+
+
+def test_lsa_vit_equals_reference_class():
+    """b200unet.VisionTransformer with Locality Self-Attention == the reference's class (vision_transformer.py:81-151): parameter
+    names / order (attn.scale first, bias-free qkv, unused timm proj, to_out), state_dict keys, outputs and gradients"""
+    for p in (os.path.join(util.ROOT, "oracle", "shim"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from nnunet_ext.network_architecture.vision_transformer import PatchEmbed as RefPE, VisionTransformer as RefViT
+    from b200unet.vision_transformer import VisionTransformer
+    kw = dict(ViT_2d=False, img_size=[16, 32, 32], patch_size=(8, 8), img_depth=[16], in_chans=8, num_classes=96,
+              embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, qkv_bias=True, is_LSA=True)
+    torch.manual_seed(0)
+    ref = RefViT(representation_size=None, distilled=False, drop_rate=0, attn_drop_rate=0, drop_path_rate=0, embed_layer=RefPE,
+                 norm_layer=None, act_layer=None, weight_init='', **kw)
+    mine = VisionTransformer(**kw)
+    assert [(n, tuple(q.shape)) for n, q in ref.named_parameters()] == [(n, tuple(q.shape)) for n, q in mine.named_parameters()]
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, q in ref.named_parameters():
+            if 'scale' in n or 'pos_embed' in n or 'norm' in n:
+                q.add_(0.2 * torch.randn(q.shape, generator=g))
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn((2, 8, 16, 32, 32), generator=g)
+    u = torch.randn((2, 96), generator=g)
+    (ref(x) * u).sum().backward()
+    (mine(x) * u).sum().backward()
+    np.testing.assert_allclose(mine(x).detach().numpy(), ref(x).detach().numpy(), rtol=1e-5, atol=1e-5)
+    rg = dict(ref.named_parameters())
+    for n, q in mine.named_parameters():
+        if rg[n].grad is None:
+            assert q.grad is None, n            # timm's proj is registered but unused under LSA
+        else:
+            np.testing.assert_allclose(q.grad.numpy(), rg[n].grad.numpy(), rtol=1e-4, atol=2e-5, err_msg=n)
+    assert rg["blocks.layer.0.attn.scale"].grad is not None and rg["blocks.layer.0.attn.proj.weight"].grad is None

@@ -43,7 +43,7 @@ def test_commdiv():
     assert max(x for x in commDiv(20, 30) if x <= 16) == 10
 
 
-@pytest.mark.parametrize("kw", [dict(vit_version='V4'), dict(do_LSA=True), dict(do_SPT=True),
+@pytest.mark.parametrize("kw", [dict(vit_version='V4'), dict(do_SPT=True),
                                 dict(split_gpu=True)])
 def test_unsupported_variants_raise(kw):
     with pytest.raises(NotImplementedError):
