@@ -368,18 +368,34 @@ __global__ void __launch_bounds__(256) plop_ce_reduce_kernel(const float* __rest
 }
 
 // finalize: value = weight * mean_{b,w}(num/den) * (ce_p/cnt_p + ce_n/cnt_n); coef = {fbar/cnt_p, fbar/cnt_n} * weight
-__global__ void plop_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ numden, int nz, int B,
-                                     int W, float weight, float* __restrict__ coef, float* __restrict__ loss_out) {
+__global__ void __launch_bounds__(256) plop_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ numden,
+                                                            int nz, int B, int W, float weight, float* __restrict__ coef,
+                                                            float* __restrict__ loss_out) {
     pdl_grid_sync();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double s[4] = {0, 0, 0, 0};
-    for (int i = 0; i < nparts; ++i)
+    // one block: strided partial sums per thread, shuffle tree per warp, the 8 warps combined in order (fixed order throughout;
+    // the single-thread version of round 1 spent 195 us per launch on dependent loads)
+    __shared__ double sh[8][5];
+    double s[4] = {0, 0, 0, 0}, f = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256)
         for (int k = 0; k < 4; ++k) s[k] += part[(long long)i * 4 + k];
-    double f = 0.0;
-    for (int i = 0; i < B * W; ++i) {
+    for (int i = threadIdx.x; i < B * W; i += 256) {
         float num = 0.f, den = 0.f;     // counts: exact in fp32 in any order
         for (int z = 0; z < nz; ++z) { num += numden[((long long)z * B * W + i) * 2]; den += numden[((long long)z * B * W + i) * 2 + 1]; }
         f += (double)(num / den);  // fp32 division like torch
+    }
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+    f = warp_sum(f);
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 4; ++k) sh[threadIdx.x >> 5][k] = s[k];
+        sh[threadIdx.x >> 5][4] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int k = 0; k < 4; ++k) s[k] = 0.0;
+    f = 0.0;
+    for (int w = 0; w < 8; ++w) {
+        for (int k = 0; k < 4; ++k) s[k] += sh[w][k];
+        f += sh[w][4];
     }
     f /= (double)(B * W);
     const double lp = s[0] / s[1], ln = s[2] / s[3];
@@ -596,7 +612,7 @@ extern "C" int b2_plop_pseudo(const float* x, const float* x_old, const float* t
     B2_LAUNCH(plop_mask_kernel, g1, 256, 0, st, x_old, target, C, D, H, W, thresholds, max_entropy, code, numden);
     dim3 g2(slabs, B);
     B2_LAUNCH(plop_ce_reduce_kernel, g2, 256, 0, st, x, target, code, C, V, slabs, part);
-    B2_LAUNCH(plop_finalize_kernel, 1, 32, 0, st, part, B * slabs, numden, nz, B, W, weight, coef, loss_out);
+    B2_LAUNCH(plop_finalize_kernel, 1, 256, 0, st, part, B * slabs, numden, nz, B, W, weight, coef, loss_out);
     if (dlogits) {
         long long total = (long long)B * V;
         long long g = (total + 255) / 256, cap = (long long)num_sms() * 16;
