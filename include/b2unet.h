@@ -323,6 +323,8 @@ typedef struct {
     const float* volume;     /* device: preprocessed case [C + 1][D][H][W] fp32, LAST channel = segmentation (nnunet .npy layout) */
     int32_t dhw[3];
     int32_t lb[3];           /* crop origin inside the case; may reach outside: data padded with 0, segmentation with -1 */
+    int32_t win_lo[3], win_hi[3];   /* only crop voxels inside this window are written (all of it: 0 .. gdhw; a sample without a
+                              * spatial transform only needs its centre window) */
 } b2_aug_case;
 /* DataLoader3D.generate_train_batch: data [B][C][g], seg [B][1][g] = crops of extent gdhw */
 int b2_aug_crop(const b2_aug_case* cases_host, int B, int C, const int32_t gdhw[3], float* data, float* seg, b2_stream_t stream);

@@ -67,7 +67,8 @@ class ConvDesc(C.Structure):
 
 
 class AugCase(C.Structure):
-    _fields_ = [("volume", C.c_void_p), ("dhw", C.c_int32 * 3), ("lb", C.c_int32 * 3)]
+    _fields_ = [("volume", C.c_void_p), ("dhw", C.c_int32 * 3), ("lb", C.c_int32 * 3), ("win_lo", C.c_int32 * 3),
+                ("win_hi", C.c_int32 * 3)]
 
 
 class AugSpatial(C.Structure):

@@ -87,12 +87,15 @@ class GPUPatchPipeline:
     segmentation as last channel, optional 'class_locations': {label: int array [N, 3]}}."""
 
     def __init__(self, cases, patch_size, batch_size, ds_strides, params=None, oversample_foreground_percent=0.33, seed=1234,
-                 device=None, train=True, plan_only=False, prefetch=True):
+                 device=None, train=True, plan_only=False, prefetch=True, prefetch_delay=1e-3):
         """plan_only: host-side use (draw_plan) without a device -- run_plan then raises.
         prefetch: next() returns the batch produced during the PREVIOUS call and enqueues the following one on the pipeline's own
         stream, so augmentation overlaps the consumer's training step (same plans, same order as without prefetch)."""
         self.plan_only = bool(plan_only)
         self.prefetch, self._pending, self._stream = bool(prefetch), None, None
+        # the producer thread starts its (GIL-holding) parameter draws this long after next() returned, so the consumer's own
+        # enqueue work for the step -- a few hundred microseconds of Python -- is not stretched by GIL hand-overs
+        self.prefetch_delay = float(prefetch_delay)
         if not self.plan_only:
             self.lib = _lib.load()
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -200,6 +203,12 @@ class GPUPatchPipeline:
             cases[j].volume = self.vols[ci].data_ptr()
             cases[j].dhw = (C.c_int32 * 3)(*self.shapes[ci])
             cases[j].lb = (C.c_int32 * 3)(*plan["lb"][j])
+            sp = plan["spatial"][j]
+            if sp["angles"] is None and sp["scale"] is None:      # only the centre window is ever read
+                lo = [(g - q) // 2 for g, q in zip(self.gen_patch, self.patch)]
+                cases[j].win_lo, cases[j].win_hi = (C.c_int32 * 3)(*lo), (C.c_int32 * 3)(*[l + q for l, q in zip(lo, self.patch)])
+            else:
+                cases[j].win_lo, cases[j].win_hi = (C.c_int32 * 3)(0, 0, 0), (C.c_int32 * 3)(*self.gen_patch)
         _lib.check(lib.b2_aug_crop(cases, B, Cc, C.byref(g3), ptr(self._crop_data), ptr(self._crop_seg), st))
         tf = (_lib.AugSpatial * B)()
         for j, sp in enumerate(plan["spatial"]):
@@ -286,6 +295,9 @@ class GPUPatchPipeline:
 
         def work():
             try:
+                if self.prefetch_delay > 0:
+                    import time
+                    time.sleep(self.prefetch_delay)
                 box["out"] = self._produce()
             except BaseException as e:      # re-raised by the consumer in __next__
                 box["err"] = e

@@ -32,22 +32,27 @@ struct AugFinal {
     int32_t n_scales;
 };
 
-// data[b][c][z][y][x] / seg[b][0][z][y][x] = case volume at lb + (z, y, x), constants outside
-__global__ void __launch_bounds__(256) aug_crop_kernel(AugCrops cr, int B, int C, int gd, int gh, int gw, float* __restrict__ data,
+// data[b][c][z][y][x] / seg[b][0][z][y][x] = case volume at lb + (z, y, x), constants outside; only the window [win_lo, win_hi) of
+// the crop is written (a sample without a spatial transform only ever reads the centre window).
+// grid = (plane chunks, gd, B * (C + 1)): one integer division per element (a flat index costs five, which made this kernel
+// instruction-bound at 185 us per batch).
+__global__ void __launch_bounds__(256) aug_crop_kernel(AugCrops cr, int C, int gd, int gh, int gw, float* __restrict__ data,
                                                        float* __restrict__ seg) {
     pdl_grid_sync();
-    const long long gv = (long long)gd * gh * gw, total = (long long)B * (C + 1) * gv;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int x = (int)(i % gw), y = (int)((i / gw) % gh), z = (int)((i / ((long long)gw * gh)) % gd);
-        const int c = (int)((i / gv) % (C + 1)), b = (int)(i / (gv * (C + 1)));
-        const b2_aug_case& k = cr.c[b];
-        const int sz = k.lb[0] + z, sy = k.lb[1] + y, sx = k.lb[2] + x;
-        const bool in = sz >= 0 && sz < k.dhw[0] && sy >= 0 && sy < k.dhw[1] && sx >= 0 && sx < k.dhw[2];
-        float v = c == C ? -1.f : 0.f;
-        if (in) v = k.volume[(((long long)c * k.dhw[0] + sz) * k.dhw[1] + sy) * k.dhw[2] + sx];
-        if (c == C) seg[(long long)b * gv + ((long long)z * gh + y) * gw + x] = v;
-        else data[((long long)b * C + c) * gv + ((long long)z * gh + y) * gw + x] = v;
-    }
+    const int z = blockIdx.y, bc = blockIdx.z, b = bc / (C + 1), c = bc - b * (C + 1);
+    const b2_aug_case& k = cr.c[b];
+    if (z < k.win_lo[0] || z >= k.win_hi[0]) return;
+    const int pidx = blockIdx.x * 256 + threadIdx.x;
+    if (pidx >= gh * gw) return;
+    const int y = pidx / gw, x = pidx - y * gw;
+    if (y < k.win_lo[1] || y >= k.win_hi[1] || x < k.win_lo[2] || x >= k.win_hi[2]) return;
+    const int sz = k.lb[0] + z, sy = k.lb[1] + y, sx = k.lb[2] + x;
+    const bool in = sz >= 0 && sz < k.dhw[0] && sy >= 0 && sy < k.dhw[1] && sx >= 0 && sx < k.dhw[2];
+    float v = c == C ? -1.f : 0.f;
+    if (in) v = k.volume[(((long long)c * k.dhw[0] + sz) * k.dhw[1] + sy) * k.dhw[2] + sx];
+    const long long gv = (long long)gd * gh * gw, o = ((long long)z * gh + y) * gw + x;
+    if (c == C) seg[(long long)b * gv + o] = v;
+    else data[((long long)b * C + c) * gv + o] = v;
 }
 
 // scipy ni_splines.c, order 3 (one pole z = sqrt(3) - 2), mirror boundary: gain, exact causal initialisation over the whole line,
@@ -319,26 +324,30 @@ __global__ void __launch_bounds__(256) aug_blur_kernel(AugBlurs bl, int pd, int 
     }
 }
 
-// mirror + label clean-up + deep-supervision targets
+// mirror + label clean-up + deep-supervision targets.  blockIdx.y selects the output: 0 = network input (one thread per voxel),
+// 1 + k = deep-supervision target k (one thread per TARGET voxel q, which reads source voxel stride * q + stride / 2 -- the order-0
+// resize rule -- so no thread ever tests divisibility).
 __global__ void __launch_bounds__(256) aug_finalize_kernel(AugFinal f, int B, int C, int pd, int ph, int pw, const float* __restrict__ data,
                                                            const float* __restrict__ seg, float* __restrict__ data_out) {
     pdl_grid_sync();
-    const long long pv = (long long)pd * ph * pw, total = (long long)B * pv;
+    const long long pv = (long long)pd * ph * pw;
+    const int which = blockIdx.y;
+    int kz = 1, ky = 1, kx = 1;
+    if (which > 0) { kz = f.stride[which - 1][0]; ky = f.stride[which - 1][1]; kx = f.stride[which - 1][2]; }
+    const int td = pd / kz, th = ph / ky, tw = pw / kx;
+    const long long tv = (long long)td * th * tw, total = (long long)B * tv;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int x = (int)(i % pw), y = (int)((i / pw) % ph), z = (int)((i / ((long long)pw * ph)) % pd), b = (int)(i / pv);
+        const int qx = (int)(i % tw), qy = (int)((i / tw) % th), qz = (int)((i / ((long long)tw * th)) % td), b = (int)(i / tv);
+        const int z = qz * kz + kz / 2, y = qy * ky + ky / 2, x = qx * kx + kx / 2;
         const int fl = f.flips[b];
         const int sz = (fl & 1) ? pd - 1 - z : z, sy = (fl & 2) ? ph - 1 - y : y, sx = (fl & 4) ? pw - 1 - x : x;
-        const long long src = ((long long)sz * ph + sy) * pw + sx, o = ((long long)z * ph + y) * pw + x;
-        for (int c = 0; c < C; ++c) data_out[((long long)b * C + c) * pv + o] = data[((long long)b * C + c) * pv + src];
-        float lab = seg[(long long)b * pv + src];
-        if (lab == -1.f) lab = 0.f;
-        for (int k = 0; k < f.n_scales; ++k) {
-            // resize order 0: output voxel q reads input floor((q + 0.5) * stride) = stride * q + stride / 2
-            const int kz = f.stride[k][0], ky = f.stride[k][1], kx = f.stride[k][2];
-            if ((z - kz / 2) % kz || (y - ky / 2) % ky || (x - kx / 2) % kx || z < kz / 2 || y < ky / 2 || x < kx / 2) continue;
-            const int qz = (z - kz / 2) / kz, qy = (y - ky / 2) / ky, qx = (x - kx / 2) / kx;
-            const int td = pd / kz, th = ph / ky, tw = pw / kx;
-            if (qz < td && qy < th && qx < tw) f.targets[k][(((long long)b * td + qz) * th + qy) * tw + qx] = lab;
+        const long long src = ((long long)sz * ph + sy) * pw + sx;
+        if (which == 0) {
+            for (int c = 0; c < C; ++c) data_out[((long long)b * C + c) * pv + i - (long long)b * tv] = data[((long long)b * C + c) * pv + src];
+        } else {
+            float lab = seg[(long long)b * pv + src];
+            if (lab == -1.f) lab = 0.f;
+            f.targets[which - 1][i] = lab;
         }
     }
 }
@@ -359,8 +368,11 @@ extern "C" int b2_aug_crop(const b2_aug_case* cases_host, int B, int C, const in
         B2_CHECK_ARG(cases_host[b].volume != nullptr);
         cr.c[b] = cases_host[b];
     }
-    const long long total = (long long)B * (C + 1) * gdhw[0] * gdhw[1] * gdhw[2];
-    B2_LAUNCH(aug_crop_kernel, grid1d(total, 256), 256, 0, stream, cr, B, C, gdhw[0], gdhw[1], gdhw[2], data, seg);
+    for (int b = 0; b < B; ++b)
+        for (int a = 0; a < 3; ++a) B2_CHECK_ARG(cases_host[b].win_lo[a] >= 0 && cases_host[b].win_hi[a] <= gdhw[a]);
+    B2_CHECK_ARG(gdhw[0] <= 65535 && B * (C + 1) <= 65535);
+    B2_LAUNCH(aug_crop_kernel, dim3(cdiv((long long)gdhw[1] * gdhw[2], 256), gdhw[0], B * (C + 1)), 256, 0, stream, cr, C, gdhw[0], gdhw[1],
+              gdhw[2], data, seg);
     return B2_OK;
 }
 
@@ -454,6 +466,8 @@ extern "C" int b2_aug_finalize(const int32_t* flips_host, int B, int C, const in
         }
     }
     const long long total = (long long)B * pdhw[0] * pdhw[1] * pdhw[2];
-    B2_LAUNCH(aug_finalize_kernel, grid1d(total, 256), 256, 0, stream, f, B, C, pdhw[0], pdhw[1], pdhw[2], data, seg, data_out);
+    int gx = grid1d(total, 256);
+    if (gx > 2048) gx = 2048;
+    B2_LAUNCH(aug_finalize_kernel, dim3(gx, 1 + n_scales), 256, 0, stream, f, B, C, pdhw[0], pdhw[1], pdhw[2], data, seg, data_out);
     return B2_OK;
 }

@@ -33,7 +33,7 @@ def test_ctypes_stub_of_the_doc_binds_the_built_library():
     ns2 = {"C": ns["C"], "lib": ns["lib"]}
     exec(head, ns2)
     assert [f[0] for f in ns2["AugCase"]._fields_] == [f[0] for f in _lib.AugCase._fields_]
-    assert ns["C"].sizeof(ns2["AugCase"]) == ns["C"].sizeof(_lib.AugCase) == 32
+    assert ns["C"].sizeof(ns2["AugCase"]) == ns["C"].sizeof(_lib.AugCase) == 56
     assert len(ns["lib"].b2_aug_crop.argtypes) == len(_lib.SIGNATURES["b2_aug_crop"][1])
 
 
