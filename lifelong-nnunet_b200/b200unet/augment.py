@@ -87,14 +87,14 @@ class GPUPatchPipeline:
     segmentation as last channel, optional 'class_locations': {label: int array [N, 3]}}."""
 
     def __init__(self, cases, patch_size, batch_size, ds_strides, params=None, oversample_foreground_percent=0.33, seed=1234,
-                 device=None, train=True, plan_only=False, prefetch=True, prefetch_delay=1e-3):
+                 device=None, train=True, plan_only=False, prefetch=True, prefetch_delay=0.0):
         """plan_only: host-side use (draw_plan) without a device -- run_plan then raises.
         prefetch: next() returns the batch produced during the PREVIOUS call and enqueues the following one on the pipeline's own
         stream, so augmentation overlaps the consumer's training step (same plans, same order as without prefetch)."""
         self.plan_only = bool(plan_only)
         self.prefetch, self._pending, self._stream = bool(prefetch), None, None
-        # the producer thread starts its (GIL-holding) parameter draws this long after next() returned, so the consumer's own
-        # enqueue work for the step -- a few hundred microseconds of Python -- is not stretched by GIL hand-overs
+        # optional: the producer thread starts its (GIL-holding) parameter draws this long after next() returned (measured: no
+        # gain at cfg2 -- the cost of feeding a training step from the pipeline is the GPU time of its kernels, not host contention)
         self.prefetch_delay = float(prefetch_delay)
         if not self.plan_only:
             self.lib = _lib.load()

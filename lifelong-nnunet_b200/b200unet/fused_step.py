@@ -417,9 +417,11 @@ class FusedStep:
             if targets_ready is not None:
                 cur.wait_event(targets_ready)
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
+            # thread-local capture mode: other host threads (e.g. the GPU patch pipeline's producer thread, which allocates and
+            # launches on its own stream) may keep issuing CUDA calls while this thread captures
+            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
                 self.enqueue_forward()
-            with torch.cuda.graph(gb, pool=ga.pool()):
+            with torch.cuda.graph(gb, pool=ga.pool(), capture_error_mode="thread_local"):
                 self.enqueue_rest()
             self.graph = (ga, gb)
             ga.replay()
