@@ -362,6 +362,12 @@ typedef struct {
 } b2_aug_blur_taps;
 int b2_aug_blur(const b2_aug_blur_taps* kernels_host, int BC, const int32_t pdhw[3], float* data, float* tmp, b2_stream_t stream);
 
+/* SimulateLowResolutionTransform on ONE (sample, channel) volume [pd][ph][pw], in place: nearest-neighbour resize down to tdhw, cubic
+ * B-spline resize back (both skimage.transform.resize(mode='edge', anti_aliasing=False) == scipy.ndimage.zoom(grid_mode=True,
+ * mode='nearest')), result clipped to the value range of the down-sampled volume (skimage clip=True). */
+size_t b2_aug_lowres_scratch_bytes(const int32_t pdhw[3]);
+int b2_aug_lowres(float* vol, const int32_t pdhw[3], const int32_t tdhw[3], void* scratch, b2_stream_t stream);
+
 /* MirrorTransform (flips bit 0 / 1 / 2 = axis d / h / w) + RemoveLabelTransform(-1, 0) + DownsampleSegForDSTransform2 (order 0:
  * target voxel q reads stride * q + stride / 2): data_out [B][C][p], targets_host[k] [B][1][p / stride_k] */
 int b2_aug_finalize(const int32_t* flips_host, int B, int C, const int32_t pdhw[3], const float* data, const float* seg,

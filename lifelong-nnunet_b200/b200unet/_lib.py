@@ -153,6 +153,8 @@ SIGNATURES = {
     "b2_aug_stats": (_I, [_VP, _I, _I64, _VP, _VP, _VP]),
     "b2_aug_pointwise": (_I, [C.POINTER(AugOp), _I, _I64, _VP, _VP, _VP, C.c_uint64, _VP]),
     "b2_aug_blur": (_I, [C.POINTER(AugBlur), _I, C.POINTER(C.c_int32 * 3), _VP, _VP, _VP]),
+    "b2_aug_lowres_scratch_bytes": (_SZ, [C.POINTER(C.c_int32 * 3)]),
+    "b2_aug_lowres": (_I, [_VP, C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), _VP, _VP]),
     "b2_aug_finalize": (_I, [C.POINTER(C.c_int32), _I, _I, C.POINTER(C.c_int32 * 3), _VP, _VP, _VP, C.POINTER(_VP), C.POINTER(C.c_int32), _I, _VP]),
     "b2_conv3d_scratch_bytes": (_SZ, [C.POINTER(ConvDesc)]),
     "b2_conv3d_fwd": (_I, [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP]),

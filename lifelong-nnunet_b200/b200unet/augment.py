@@ -8,13 +8,13 @@ batch is a handful of kernel launches behind the C ABI (csrc/augment.cu, ``b2_au
 
   crop with foreground oversampling (DataLoader3D) -> SpatialTransform (rotation +-30 deg / scaling 0.7-1.4, p 0.2 each;
   data order 3, segmentation order 1 per label) -> GaussianNoise (p 0.1) -> GaussianBlur (p 0.2, per channel 0.5) ->
-  BrightnessMultiplicative (p 0.15) -> ContrastAugmentation (p 0.15) -> Gamma on the inverted image (p 0.1) -> Gamma (p 0.3),
-  both with retain_stats -> Mirror -> RemoveLabel(-1, 0) -> deep-supervision targets (order 0) -> {'data', 'target', 'keys'}
+  BrightnessMultiplicative (p 0.15) -> ContrastAugmentation (p 0.15) -> SimulateLowResolution (p 0.25, per channel 0.5: nearest
+  down to 50-100 %, cubic up) -> Gamma on the inverted image (p 0.1) -> Gamma (p 0.3), both with retain_stats -> Mirror -> RemoveLabel(-1, 0) -> deep-supervision targets (order 0) -> {'data', 'target', 'keys'}
 
 The HOST draws every random number (`draw_plan`, numpy RandomState, order documented there) into a small plain-dict "plan";
 `run_plan` turns a plan into kernel launches.  tests/ hands the same plan to the CPU restatement (oracle/augment.py, which calls
-scipy.ndimage like batchgenerators does) and compares.  Not implemented: elastic deformation (off in nnU-Net's 3D default),
-SimulateLowResolutionTransform (skimage resize pair), the cascade / mask transforms.
+scipy.ndimage like batchgenerators does) and compares.  Not implemented: elastic deformation (off in nnU-Net's 3D default), the
+cascade / mask transforms.
 """
 import ctypes as C
 import math
@@ -33,6 +33,7 @@ DEFAULT_3D_PARAMS = {           # nnunet default_3D_augmentation_params as set u
     "p_blur": 0.2, "blur_sigma": (0.5, 1.0), "p_blur_per_channel": 0.5,
     "p_brightness": 0.15, "brightness_range": (0.75, 1.25),
     "p_contrast": 0.15, "contrast_range": (0.75, 1.25),
+    "p_lowres": 0.25, "lowres_zoom": (0.5, 1.0), "p_lowres_per_channel": 0.5,
     "p_gamma_inverted": 0.1, "p_gamma": 0.3, "gamma_range": (0.7, 1.5),
     "do_mirror": True, "mirror_axes": (0, 1, 2),
 }
@@ -133,6 +134,8 @@ class GPUPatchPipeline:
         V = pp[0] * pp[1] * pp[2]
         self._stats_a, self._stats_b = torch.empty((B * Cc, 4), **f32), torch.empty((B * Cc, 4), **f32)
         self._scr = torch.empty(int(self.lib.b2_aug_stats_scratch_bytes(B * Cc, V)), dtype=torch.uint8, device=self.device)
+        self._lowres_scr = torch.empty(int(self.lib.b2_aug_lowres_scratch_bytes(C.byref((C.c_int32 * 3)(*pp)))), dtype=torch.uint8,
+                                       device=self.device)
         self.launches_last = 0
 
     # -- host: every random number of one batch, in this order -------------------------------------------------------------
@@ -140,7 +143,8 @@ class GPUPatchPipeline:
         rs, p, B, Cc = self.rs, self.params, self.batch_size, self.C
         gen, patch = np.array(self.gen_patch), np.array(self.patch)
         plan = {"cases": [int(i) for i in rs.choice(len(self.keys), B, True)], "lb": [], "spatial": [], "noise": [], "blur": [],
-                "brightness": [], "contrast": [], "gamma_inv": [], "gamma": [], "flips": [], "seed": int(rs.randint(0, 2 ** 31 - 1))}
+                "brightness": [], "contrast": [], "lowres": [], "gamma_inv": [], "gamma": [], "flips": [],
+                "seed": int(rs.randint(0, 2 ** 31 - 1))}
         for j, ci in enumerate(plan["cases"]):
             # DataLoader3D.generate_train_batch: the last round(B * oversample) samples are forced to contain foreground
             force_fg = not (j < round(B * (1 - self.oversample)))
@@ -176,6 +180,8 @@ class GPUPatchPipeline:
                                       if on and rs.uniform() < p["p_brightness"] else [None] * Cc)
             plan["contrast"].append([_two_sided(rs, p["contrast_range"]) for _ in range(Cc)]
                                     if on and rs.uniform() < p["p_contrast"] else [None] * Cc)
+            plan["lowres"].append([float(rs.uniform(*p["lowres_zoom"])) if rs.uniform() < p["p_lowres_per_channel"] else None
+                                   for _ in range(Cc)] if on and rs.uniform() < p["p_lowres"] else [None] * Cc)
             plan["gamma_inv"].append([_two_sided(rs, p["gamma_range"]) for _ in range(Cc)]
                                      if on and rs.uniform() < p["p_gamma_inverted"] else [None] * Cc)
             plan["gamma"].append([_two_sided(rs, p["gamma_range"]) for _ in range(Cc)]
@@ -260,6 +266,13 @@ class GPUPatchPipeline:
             _lib.check(lib.b2_aug_blur(taps, B * Cc, C.byref(p3), ptr(self._data), ptr(self._tmp), st))
         pointwise(_lib.AUG_MUL, plan["brightness"])
         pointwise(_lib.AUG_CONTRAST, plan["contrast"], stats=True)
+        for j in range(B):                       # SimulateLowResolutionTransform: one (sample, channel) volume per call
+            for c in range(Cc):
+                zoom = plan.get("lowres", [[None] * Cc] * B)[j][c]
+                if zoom is None:
+                    continue
+                t3 = (C.c_int32 * 3)(*[max(2, int(np.round(q * zoom))) for q in self.patch])
+                _lib.check(lib.b2_aug_lowres(ptr(self._data[j, c]), C.byref(p3), C.byref(t3), ptr(self._lowres_scr), st))
         pointwise(_lib.AUG_GAMMA_A, plan["gamma_inv"], p1=1.0, stats=True)
         pointwise(_lib.AUG_GAMMA_A, plan["gamma"], p1=0.0, stats=True)
         data = torch.empty_like(self._data)

@@ -324,6 +324,71 @@ __global__ void __launch_bounds__(256) aug_blur_kernel(AugBlurs bl, int pd, int 
     }
 }
 
+// ---- SimulateLowResolutionTransform (batchgenerators augment_linear_downsampling_scipy: skimage resize order 0 down, order 3 up,
+// mode 'edge' == scipy.ndimage.zoom(grid_mode=True, mode='nearest')), one (sample, channel) volume per call -----------------------
+constexpr int LR_PAD = 12;      // scipy pre-pads by 12 samples ('nearest') before the spline prefilter
+__device__ __forceinline__ unsigned int lr_encode(float f) {     // order-preserving map float -> uint (min / max by integer atomics)
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float lr_decode(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// padded[i][j][k] = vol[nearest source of clamp(i - 12, 0, t - 1) ...]: output voxel q reads input floor((q + 0.5) * p / t)
+__global__ void __launch_bounds__(256) aug_lowres_down_kernel(const float* __restrict__ vol, int pd, int ph, int pw, int td, int th, int tw,
+                                                              float* __restrict__ padded, unsigned int* __restrict__ minmax) {
+    pdl_grid_sync();
+    const int Ph = th + 2 * LR_PAD, Pw = tw + 2 * LR_PAD;
+    const int i = blockIdx.y, pidx = blockIdx.x * 256 + threadIdx.x;
+    float v = 0.f;
+    const bool on = pidx < Ph * Pw;
+    if (on) {
+        const int j = pidx / Pw, k = pidx - j * Pw;
+        const int qz = min(max(i - LR_PAD, 0), td - 1), qy = min(max(j - LR_PAD, 0), th - 1), qx = min(max(k - LR_PAD, 0), tw - 1);
+        const int sz = min((int)floor((qz + 0.5) * ((double)pd / td)), pd - 1), sy = min((int)floor((qy + 0.5) * ((double)ph / th)), ph - 1),
+                  sx = min((int)floor((qx + 0.5) * ((double)pw / tw)), pw - 1);
+        v = vol[((long long)sz * ph + sy) * pw + sx];
+        padded[((long long)i * Ph + j) * Pw + k] = v;
+    }
+    float mn = on ? v : INFINITY, mx = on ? v : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {       // min / max are order-independent: integer atomics stay reproducible
+        atomicMin(&minmax[0], lr_encode(mn));
+        atomicMax(&minmax[1], lr_encode(mx));
+    }
+}
+
+// out[z][y][x] = clip(cubic B-spline of the prefiltered padded volume at (o + 0.5) * t / p - 0.5 + 12, min, max)
+__global__ void __launch_bounds__(256) aug_lowres_up_kernel(const float* __restrict__ coef, int td, int th, int tw, int pd, int ph, int pw,
+                                                            const unsigned int* __restrict__ minmax, float* __restrict__ out) {
+    pdl_grid_sync();
+    const int Ph = th + 2 * LR_PAD, Pw = tw + 2 * LR_PAD;
+    const int z = blockIdx.y, pidx = blockIdx.x * 256 + threadIdx.x;
+    if (pidx >= ph * pw) return;
+    const int y = pidx / pw, x = pidx - y * pw;
+    const double cz = (z + 0.5) * ((double)td / pd) - 0.5 + LR_PAD, cy = (y + 0.5) * ((double)th / ph) - 0.5 + LR_PAD,
+                 cx = (x + 0.5) * ((double)tw / pw) - 0.5 + LR_PAD;
+    const int iz = (int)floor(cz), iy = (int)floor(cy), ix = (int)floor(cx);
+    float wz[4], wy[4], wx[4];
+    bspline3((float)(cz - iz), wz); bspline3((float)(cy - iy), wy); bspline3((float)(cx - ix), wx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float az = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float* row = coef + ((long long)(iz - 1 + a) * Ph + (iy - 1 + b)) * Pw + ix - 1;
+            az += wy[b] * (wx[0] * row[0] + wx[1] * row[1] + wx[2] * row[2] + wx[3] * row[3]);
+        }
+        acc += wz[a] * az;
+    }
+    const float lo = lr_decode(minmax[0]), hi = lr_decode(minmax[1]);
+    out[((long long)z * ph + y) * pw + x] = fminf(fmaxf(acc, lo), hi);
+}
+
 // mirror + label clean-up + deep-supervision targets.  blockIdx.y selects the output: 0 = network input (one thread per voxel),
 // 1 + k = deep-supervision target k (one thread per TARGET voxel q, which reads source voxel stride * q + stride / 2 -- the order-0
 // resize rule -- so no thread ever tests divisibility).
@@ -469,5 +534,32 @@ extern "C" int b2_aug_finalize(const int32_t* flips_host, int B, int C, const in
     int gx = grid1d(total, 256);
     if (gx > 2048) gx = 2048;
     B2_LAUNCH(aug_finalize_kernel, dim3(gx, 1 + n_scales), 256, 0, stream, f, B, C, pdhw[0], pdhw[1], pdhw[2], data, seg, data_out);
+    return B2_OK;
+}
+
+extern "C" size_t b2_aug_lowres_scratch_bytes(const int32_t pdhw[3]) {
+    return ((size_t)(pdhw[0] + 2 * LR_PAD) * (pdhw[1] + 2 * LR_PAD) * (pdhw[2] + 2 * LR_PAD)) * sizeof(float) + 256;
+}
+
+extern "C" int b2_aug_lowres(float* vol, const int32_t pdhw[3], const int32_t tdhw[3], void* scratch, b2_stream_t stream) {
+    B2_CHECK_ARG(vol && scratch);
+    for (int a = 0; a < 3; ++a) B2_CHECK_ARG(tdhw[a] >= 2 && tdhw[a] <= pdhw[a] && pdhw[a] <= 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* minmax = (unsigned int*)scratch;
+    float* padded = (float*)((char*)scratch + 256);
+    const int Pd = tdhw[0] + 2 * LR_PAD, Ph = tdhw[1] + 2 * LR_PAD, Pw = tdhw[2] + 2 * LR_PAD;
+    B2_CUDA(cudaMemsetAsync(minmax, 0xFF, 4, st));
+    B2_CUDA(cudaMemsetAsync(minmax + 1, 0x00, 4, st));
+    B2_LAUNCH(aug_lowres_down_kernel, dim3(cdiv((long long)Ph * Pw, 256), Pd), 256, 0, st, (const float*)vol, pdhw[0], pdhw[1], pdhw[2], tdhw[0],
+              tdhw[1], tdhw[2], padded, minmax);
+    AugSpatials sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.s[0].modified = 1;
+    for (int axis = 0; axis < 3; ++axis) {
+        const long long lines = (long long)Pd * Ph * Pw / (axis == 0 ? Pd : axis == 1 ? Ph : Pw);
+        B2_LAUNCH(aug_prefilter_kernel, grid1d(lines, 128), 128, 0, st, sp, 1, 1, Pd, Ph, Pw, axis, padded);
+    }
+    B2_LAUNCH(aug_lowres_up_kernel, dim3(cdiv((long long)pdhw[1] * pdhw[2], 256), pdhw[0]), 256, 0, st, (const float*)padded, tdhw[0], tdhw[1],
+              tdhw[2], pdhw[0], pdhw[1], pdhw[2], (const unsigned int*)minmax, vol);
     return B2_OK;
 }

@@ -75,6 +75,17 @@ def normal_field(seed, start, count):
     return (np.sqrt(-2.0 * np.log(u1.astype(np.float64))) * np.cos(2.0 * np.pi * u2.astype(np.float64))).astype(np.float32)
 
 
+def simulate_low_resolution(x, zoom):
+    """batchgenerators augment_linear_downsampling_scipy (per channel): skimage resize(order 0) down to round(shape * zoom) and
+    resize(order 3) back, mode 'edge', anti_aliasing off, clip to the input range -- skimage's n-d resize IS
+    scipy.ndimage.zoom(grid_mode=True, mode='nearest')"""
+    shp = np.array(x.shape)
+    target = np.maximum(np.round(shp * zoom).astype(int), 2)
+    down = ndi.zoom(x.astype(float), target / shp, order=0, mode="nearest", grid_mode=True)
+    up = ndi.zoom(down, shp / target, order=3, mode="nearest", grid_mode=True)
+    return np.clip(up, down.min(), down.max()).astype(np.float32)
+
+
 def gamma(x, g, invert):
     """batchgenerators augment_gamma, per channel, retain_stats=True"""
     if invert:
@@ -114,6 +125,8 @@ def apply_plan(cases, plan, patch, gen_patch, ds_strides):
             if plan["contrast"][j][c] is not None:      # augment_contrast, preserve_range=True
                 mn, lo, hi = x.mean(), x.min(), x.max()
                 x = np.clip((x - mn) * plan["contrast"][j][c] + mn, lo, hi)
+            if plan.get("lowres") and plan["lowres"][j][c] is not None:
+                x = simulate_low_resolution(x, plan["lowres"][j][c])
             if plan["gamma_inv"][j][c] is not None:
                 x = gamma(x, plan["gamma_inv"][j][c], True)
             if plan["gamma"][j][c] is not None:

@@ -82,7 +82,8 @@ def test_oracle_noise_generator_is_standard_normal_and_counter_based():
 def test_oracle_identity_plan_is_a_centre_crop_and_ds_targets_pick_odd_voxels():
     cases = _cases()
     plan = {"cases": [0], "lb": [[2, 3, 4]], "spatial": [{"angles": None, "scale": None}], "noise": [None], "blur": [[None, None]],
-            "brightness": [[None, None]], "contrast": [[None, None]], "gamma_inv": [[None, None]], "gamma": [[None, None]],
+            "brightness": [[None, None]], "contrast": [[None, None]], "lowres": [[None, None]], "gamma_inv": [[None, None]],
+            "gamma": [[None, None]],
             "flips": [0], "seed": 1}
     d, t, _ = oaug.apply_plan([c["data"] for c in cases], plan, (16, 32, 32), (20, 40, 36), [(1, 1, 1), (2, 2, 2), (4, 4, 4)])
     src = cases[0]["data"]

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 PATCH, STRIDES = (16, 32, 32), [(1, 1, 1), (2, 2, 2), (4, 4, 4), (4, 8, 8)]
 ALL_ON = dict(p_rot=1.0, p_scale=1.0, p_noise=1.0, p_blur=1.0, p_blur_per_channel=1.0, p_brightness=1.0, p_contrast=1.0,
-              p_gamma_inverted=1.0, p_gamma=1.0)
+              p_lowres=1.0, p_lowres_per_channel=1.0, p_gamma_inverted=1.0, p_gamma=1.0)
 
 
 def _compare(pipe, cases, plan, exact_seg):
@@ -61,7 +61,7 @@ def test_default_probabilities_many_batches():
     seen = set()
     for _ in range(12):
         plan = pipe.draw_plan()
-        for k in ("noise", "blur", "brightness", "contrast", "gamma_inv", "gamma"):
+        for k in ("noise", "blur", "brightness", "contrast", "lowres", "gamma_inv", "gamma"):
             if any(v is not None for row in plan[k] for v in (row if isinstance(row, list) else [row])):
                 seen.add(k)
         _compare(pipe, cases, plan, exact_seg=False)
@@ -79,6 +79,25 @@ def test_no_augmentation_generator_is_exact_and_iterable():
     assert out["data"].shape == (3, 2) + PATCH and [tuple(t.shape[2:]) for t in out["target"]] == [(16, 32, 32), (8, 16, 16), (4, 8, 8), (4, 4, 4)]
     b = next(tr)
     assert b["data"].is_cuda and torch.isfinite(b["data"]).all() and len(b["target"]) == 4 and 4 <= tr.launches_last <= 30
+
+
+def test_low_resolution_simulation_alone_matches_scipy_zoom():
+    """SimulateLowResolutionTransform in isolation (no other transform): nearest down / cubic up == scipy.ndimage.zoom pair;
+    a voxel may pick the neighbouring source sample when (q + 0.5) p / t lands within rounding of an integer"""
+    from b200unet import augment
+    cases = _cases(13)
+    only = dict(p_rot=0.0, p_scale=0.0, p_noise=0.0, p_blur=0.0, p_brightness=0.0, p_contrast=0.0, p_gamma_inverted=0.0, p_gamma=0.0,
+                p_lowres=1.0, p_lowres_per_channel=1.0, do_mirror=False)
+    pipe = augment.GPUPatchPipeline(cases, PATCH, 3, STRIDES, params=only, seed=6, prefetch=False)
+    for _ in range(3):
+        plan = pipe.draw_plan()
+        assert all(z is not None and 0.5 <= z <= 1.0 for row in plan["lowres"] for z in row)
+        _compare(pipe, cases, plan, exact_seg=False)
+    plan["lowres"] = [[0.5, 1.0]] * 3                    # zoom 1: the spline interpolates its own samples;  zoom 0.5: every second voxel
+    out = _compare(pipe, cases, plan, exact_seg=False)
+    plain = pipe.run_plan(dict(plan, lowres=[[None, None]] * 3))
+    assert torch.allclose(out["data"][:, 1], plain["data"][:, 1], atol=1e-4)
+    assert float((out["data"][:, 0] - plain["data"][:, 0]).abs().max()) > 0.1
 
 
 def test_retain_stats_gamma_keeps_mean_and_std():
