@@ -800,7 +800,14 @@ int conv_tc_gather(const TcGather& g, cudaStream_t st) {
     if (KC == 64) { if (g.mes) B2_TC_LAUNCH(64, true, 0); else B2_TC_LAUNCH(64, false, 1); }
     else { if (g.mes) B2_TC_LAUNCH(32, true, 2); else B2_TC_LAUNCH(32, false, 3); }
 #undef B2_TC_LAUNCH
-    if (p.ksplit > 1) {
+    if (g.defer) g.defer->deferred = 0;
+    if (p.ksplit > 1 && g.defer && !g.accumulate && !g.q_scatter && !g.out_f32 && g.nclass <= 1 && !g.mes && p.os_d == 1 && p.os_h == 1 &&
+        p.os_w == 1 && p.oo_d == 0 && p.oo_h == 0 && p.oo_w == 0 && p.LD == p.D && p.LH == p.H && p.LW == p.W && BN % 8 == 0) {
+        SplitKDefer& k = *g.defer;       // the consumer (small-tensor norm kernel) sums the partials: no reduce launch here
+        k.deferred = 1;
+        k.TN = p.TN; k.TD = p.TD; k.TH = p.TH; k.TW = p.TW; k.nt_d = p.nt_d; k.nt_h = p.nt_h; k.nt_w = p.nt_w;
+        k.nblk = p.nblk; k.BN = p.BN; k.ksplit = p.ksplit; k.otiles = otiles; k.partial = g.splitk_scratch;
+    } else if (p.ksplit > 1) {
         const long long total = (long long)otiles * 128 * (BN / 8);
         long long rg = (total + 255) / 256, cap = (long long)num_sms() * 8;
         if (rg > cap) rg = cap;
@@ -849,10 +856,12 @@ int gemm_tn_bf16(const __nv_bfloat16* A, int M, int K, int lda, const __nv_bfloa
 // 3x3x3, padding 1, any stride (forward) / stride 1 with the flipped shadow (dgrad)
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
-                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes, int* stat_slots, int w_pitch, int w_row0) {
+                   int accumulate, cudaStream_t st, float* scratch, size_t scratch_bytes, int* stat_slots, int w_pitch, int w_row0,
+                   SplitKDefer* defer) {
     // stat_slots != nullptr: the caller wants InstanceNorm partials in `scratch` ([N][*stat_slots][Nout][2], see EpiStats);
     // *stat_slots == 0 on return means the chosen kernel could not produce them (split-K, batch-spanning boxes, ...)
     if (stat_slots) *stat_slots = 0;
+    if (defer) defer->deferred = 0;
     if (stride[0] == 1 && stride[1] == 1 && stride[2] == 1 && conv_tc_halo_supported(K, Nout, N, Dd, Hd, Wd))
         return conv_tc_halo_launch(src, N, Dd, Hd, Wd, K, src_pitch, wmat, Nout, bias, dst, dst_pitch, accumulate, st,
                                    stat_slots ? scratch : nullptr, scratch_bytes / sizeof(float), stat_slots, w_pitch, w_row0);
@@ -862,6 +871,7 @@ int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int 
     g.ntaps = 27; g.w_rows = 27 * Nout;
     if (w_pitch > 0) { g.w_rows = 27 * w_pitch; g.rows_per_tap = w_pitch; g.w_row0 = w_row0; }   // output-channel window
     g.splitk_scratch = scratch; g.splitk_scratch_bytes = scratch_bytes;
+    g.defer = defer;
     g.stat_part = stat_slots ? scratch : nullptr; g.stat_part_floats = scratch_bytes / sizeof(float); g.stat_slots = stat_slots;
     for (int t = 0; t < 27; ++t) {
         g.tap_off[t][0] = t / 9 - 1; g.tap_off[t][1] = (t / 3) % 3 - 1; g.tap_off[t][2] = t % 3 - 1;

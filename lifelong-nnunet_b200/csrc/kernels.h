@@ -46,6 +46,14 @@ int weight_shadow_bf16(const float* w_pt, int cout, int cin, __nv_bfloat16* wk, 
 struct ShadowJob { const float* w; __nv_bfloat16* oab; __nv_bfloat16* oba; int A, B, T, flip; };
 bool shadow_job_supported(int A, int B, int T);
 int shadow_multi(const ShadowJob* jobs, int n, cudaStream_t st);
+// split-K second stage left to the consumer: in the deep stages the small-tensor norm kernel sums the fp32 partials itself
+// (one launch and one round trip of z less per layer).  Filled by conv_tc_gather when it skipped splitk_reduce_kernel.
+struct SplitKDefer {
+    int deferred;
+    int TN, TD, TH, TW, nt_d, nt_h, nt_w, nblk, BN, ksplit, otiles;
+    const float* partial;        // [ksplit][otiles][128][BN]
+};
+
 struct TcGather {
     const __nv_bfloat16* src; int N, Ds, Hs, Ws, K, src_pitch;     // gathered tensor (NDHWC) and its channel count (GEMM K)
     const __nv_bfloat16* wmat; int w_rows, rows_per_tap, Nout;      // weight matrix [w_rows][K]; GEMM N
@@ -67,6 +75,7 @@ struct TcGather {
     // optional InstanceNorm partials from the epilogue: part[N][*stat_slots][Nout][2] (see EpiStats in tc_common.cuh)
     float* stat_part; size_t stat_part_floats; int* stat_slots;
     int out_f32;                                                    // produced tensor is fp32 (GEMM use)
+    SplitKDefer* defer;                                             // optional: leave a split-K reduction to the consumer
 };
 int conv_tc_gather(const TcGather& g, cudaStream_t st);
 int gemm_tn_bf16(const __nv_bfloat16* A, int M, int K, int lda, const __nv_bfloat16* W, int N, const float* bias, void* out, int ldo,
@@ -82,7 +91,7 @@ int tconv_shadow_bf16(const float* w_pt, int cin, int cout, int k8, __nv_bfloat1
 int conv_tc_launch(const __nv_bfloat16* src, int N, int Ds, int Hs, int Ws, int K, int src_pitch, const __nv_bfloat16* wmat,
                    int Nout, const float* bias, __nv_bfloat16* dst, int Dd, int Hd, int Wd, int dst_pitch, const int stride[3],
                    int accumulate, cudaStream_t st, float* scratch = nullptr, size_t scratch_bytes = 0, int* stat_slots = nullptr,
-                   int w_pitch = 0, int w_row0 = 0);
+                   int w_pitch = 0, int w_row0 = 0, SplitKDefer* defer = nullptr);
 // mean / rstd from epilogue partials part[n][slots][c][2]
 int stats_finalize(const float* part, int slots, int n, long long vox, int c, float eps, float* stats, cudaStream_t st);
 size_t conv_tc_splitk_scratch_floats(int N, int D, int H, int W, int Nout);
@@ -118,7 +127,11 @@ bool norm_small_supported(long long vox, int c, int p0, int p1, int p2, int p3);
 template <typename T>
 int norm_lrelu_fwd_small(const T* z, const float* gamma, const float* beta, T* y, float* stats, int n, long long vox, int c,
                          int z_pitch, int y_pitch, float slope, float eps, cudaStream_t st);
-extern int g_norm_small, g_norm_cfg;
+// the same on un-reduced split-K partials of the producing convolution: z = bf16(bias + sum_ks partial) is written on the way
+int splitk_norm_small_fwd(const SplitKDefer& k, const float* bias, __nv_bfloat16* z, const float* gamma, const float* beta,
+                          __nv_bfloat16* y, float* stats, int n, int D, int H, int W, int c, int z_pitch, int y_pitch, float slope,
+                          float eps, cudaStream_t st);
+extern int g_norm_small, g_norm_cfg, g_splitk_fuse;
 size_t norm_bwd_scratch_floats(int n, long long vox, int c);
 // dz = d(loss)/dz given dy; dgamma/dbeta overwritten. scratch: norm_bwd_scratch_floats floats.
 template <typename T>

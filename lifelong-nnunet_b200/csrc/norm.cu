@@ -346,6 +346,89 @@ __global__ void __launch_bounds__(NS_THREADS) norm_small_fwd_kernel(const T* __r
     }
 }
 
+// The same kernel fed with the UN-REDUCED split-K partials of the producing convolution (conv3d_tc.cu: fp32
+// [ksplit][otile][128 rows][BN]): pass 1 forms z = bf16(bias + sum_ks partial) in the reduce kernel's order (bit-identical z),
+// writes it (the backward pass reads it) and accumulates the statistics of the ROUNDED values, as the two-launch path does;
+// pass 2 re-reads z (L2-hot) and writes y.  Saves splitk_reduce_kernel and one round trip of z per deep-stage layer.
+__global__ void __launch_bounds__(NS_THREADS) splitk_norm_small_fwd_kernel(SplitKDefer k, const float* __restrict__ bias,
+                                                                           __nv_bfloat16* __restrict__ z, const float* __restrict__ gamma,
+                                                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                                           float* __restrict__ stats, int D, int H, int W, int c,
+                                                                           int z_pitch, int y_pitch, float slope, float eps) {
+    pdl_grid_sync();
+    __shared__ float sh[NS_WARPS][16];
+    const int c0 = blockIdx.x * 8, n = blockIdx.y, vox = D * H * W;
+    const int nb = c0 / k.BN, col = c0 - nb * k.BN, tn = n / k.TN, n_ = n - tn * k.TN;
+    __nv_bfloat16* zp = z + (long long)n * vox * z_pitch + c0;
+    float bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = bias ? bias[c0 + j] : 0.f;
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = 0.f;
+    for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
+        const int w = v % W, h = (v / W) % H, d = v / (W * H);
+        const int td = d / k.TD, d_ = d - td * k.TD, th = h / k.TH, h_ = h - th * k.TH, tw = w / k.TW, w_ = w - tw * k.TW;
+        const int r = ((n_ * k.TD + d_) * k.TH + h_) * k.TW + w_;
+        const long long otile = ((((long long)tn * k.nt_d + td) * k.nt_h + th) * k.nt_w + tw) * k.nblk + nb;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = bs[j];
+        for (int ks = 0; ks < k.ksplit; ++ks) {
+            const float* pp = k.partial + (((size_t)ks * k.otiles + otile) * 128 + r) * k.BN + col;
+            const float4 a = *reinterpret_cast<const float4*>(pp), b = *reinterpret_cast<const float4*>(pp + 4);
+            f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+        }
+        store8(zp + (long long)v * z_pitch, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __bfloat162float(__float2bfloat16_rn(f[j]));
+            s[j] += a; s[8 + j] += a * a;
+        }
+    }
+    block_sum_vec<16>(s, sh);       // (ends with a block barrier: every z row of this block is visible to it below)
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double m = (double)s[j] * (1.0 / (double)vox);
+        double var = (double)s[8 + j] * (1.0 / (double)vox) - m * m;
+        if (var < 0.0) var = 0.0;
+        mean[j] = (float)m;
+        rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+        ga[j] = gamma[c0 + j];
+        be[j] = beta[c0 + j];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            stats[((long long)n * c + c0 + j) * 2] = mean[j];
+            stats[((long long)n * c + c0 + j) * 2 + 1] = rstd[j];
+        }
+    }
+    __nv_bfloat16* yp = y + (long long)n * vox * y_pitch + c0;
+    for (int v = threadIdx.x; v < vox; v += NS_THREADS) {
+        float a[8], o[8];
+        load8(zp + (long long)v * z_pitch, a);      // written by this same thread in pass 1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float u = ga[j] * ((a[j] - mean[j]) * rstd[j]) + be[j];
+            o[j] = u > 0.f ? u : u * slope;
+        }
+        store8(yp + (long long)v * y_pitch, o);
+    }
+}
+
+int g_splitk_fuse = 0;   // measured neutral at cfg2 (6.238 vs 6.209 ms/step, 230 vs 240 launches): off by default
+
+int splitk_norm_small_fwd(const SplitKDefer& k, const float* bias, __nv_bfloat16* z, const float* gamma, const float* beta,
+                          __nv_bfloat16* y, float* stats, int n, int D, int H, int W, int c, int z_pitch, int y_pitch, float slope,
+                          float eps, cudaStream_t st) {
+    B2_CHECK_ARG(k.deferred && k.partial && c % 8 == 0 && k.BN % 8 == 0 && z_pitch % 8 == 0 && y_pitch % 8 == 0);
+    dim3 grid(c / 8, n);
+    B2_LAUNCH(splitk_norm_small_fwd_kernel, grid, NS_THREADS, 0, st, k, bias, z, gamma, beta, y, stats, D, H, W, c, z_pitch, y_pitch, slope, eps);
+    return B2_OK;
+}
+
 template <typename T, bool RECOMPUTE>
 __global__ void __launch_bounds__(NS_THREADS) norm_small_bwd_kernel(const T* __restrict__ z, const T* __restrict__ y, const T* __restrict__ dy,
                                                              const float* __restrict__ stats, const float* __restrict__ gamma,

@@ -412,6 +412,8 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
         int r = weight_shadow(prm[cb.p_w], cb.shape.cout, cb.shape.cin, need_wf ? wf : nullptr, need_wb ? wb : nullptr, st);
         if (r) return r;
         bool done = false;
+        SplitKDefer defer;
+        defer.deferred = 0;
         // deep stages: statistics + normalisation + activation in one launch (norm.cu, small tensors)
         const bool small = norm_small_supported(cb.z.vox(), cb.shape.cout, cb.z.pitch, cb.y.pitch, 8, 8);
         if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -453,13 +455,19 @@ static int forward_t(b2_unet_plan* p, const float* const* prm, const float* inpu
                 r = conv_tc_launch(P<T>(ws, p, cb.in, false), g.batch, cb.in.d, cb.in.h, cb.in.w, cb.shape.cin, cb.in.pitch,
                                    (const __nv_bfloat16*)F32(ws, p, cb.wk_off), cb.shape.cout, prm[cb.p_b], P<T>(ws, p, cb.z, false),
                                    cb.z.d, cb.z.h, cb.z.w, cb.z.pitch, cb.shape.stride, 0, st, SCR(ws, p), p->scratch_floats * sizeof(float),
-                                   small ? nullptr : &stat_slots);
+                                   small ? nullptr : &stat_slots, 0, 0, (small && g_splitk_fuse) ? &defer : nullptr);
                 if (r) return r;
                 if (stat_slots > 0) r = stats_finalize(SCR(ws, p), stat_slots, g.batch, cb.z.vox(), cb.shape.cout, g.norm_eps, stats, st);
                 else if (!small) r = instnorm_stats<T>(P<T>(ws, p, cb.z, false), g.batch, cb.z.vox(), cb.shape.cout, cb.z.pitch, SCR(ws, p), stats, g.norm_eps, st);
                 if (r) return r;
                 done = true;
             }
+        }
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            if (done && small && defer.deferred)     // the convolution left its split-K partials un-reduced: sum them here
+                return splitk_norm_small_fwd(defer, prm[cb.p_b], P<T>(ws, p, cb.z, false), prm[cb.p_g], prm[cb.p_be], P<T>(ws, p, cb.y, false),
+                                             stats, g.batch, cb.z.d, cb.z.h, cb.z.w, cb.shape.cout, cb.z.pitch, cb.y.pitch, g.lrelu_slope,
+                                             g.norm_eps, st);
         }
         if (done && small)
             return norm_lrelu_fwd_small<T>(P<T>(ws, p, cb.z, false), prm[cb.p_g], prm[cb.p_be], P<T>(ws, p, cb.y, false), stats, g.batch,
@@ -761,6 +769,7 @@ extern "C" int b2_set_option(const char* name, int value) {
     if (!strcmp(name, "bwd_overlap")) { g_bwd_overlap = value; return B2_OK; }
     if (!strcmp(name, "norm_cfg")) { g_norm_cfg = value; return B2_OK; }
     if (!strcmp(name, "norm_small")) { g_norm_small = value; return B2_OK; }
+    if (!strcmp(name, "splitk_fuse")) { g_splitk_fuse = value; return B2_OK; }
     if (!strcmp(name, "norm_recompute")) { g_norm_recompute = value; return B2_OK; }
     if (!strcmp(name, "wgrad_desc_mode")) { g_wgrad_desc_mode = value; return B2_OK; }
     return fail(B2_EINVAL, "unknown option %s", name);

@@ -88,3 +88,21 @@ def test_ewc_penalty_closed_form_and_sgd_step_full_size(setup):
     opt.clip_and_step(12)
     for q, (n, p) in zip(ref_params, named):
         assert rel_err(p, q) < 1e-5, n
+
+
+def test_fused_splitk_norm_is_bit_identical_to_the_two_launch_path(setup):
+    """deep stages: the small-tensor norm kernel can sum the convolution's split-K partials itself (option splitk_fuse; measured
+    neutral, so off by default);
+    z is formed in the reduce kernel's order and the statistics use the rounded values, so logits AND gradients are bit-identical
+    to splitk_reduce_kernel + norm_small_fwd_kernel"""
+    from b200unet import ops
+    geom, net, data, targets, loss = setup
+    try:
+        ops.set_option("splitk_fuse", 0)
+        _, o0, g0 = _fwd_bwd(net, data, targets, loss, "bf16")
+        ops.set_option("splitk_fuse", 1)
+        _, o1, g1 = _fwd_bwd(net, data, targets, loss, "bf16")
+    finally:
+        ops.set_option("splitk_fuse", 0)
+    assert torch.equal(o0.view(torch.int32), o1.view(torch.int32))
+    assert torch.equal(g0.view(torch.int32), g1.view(torch.int32))
