@@ -695,6 +695,62 @@ class nnUNetTrainerFrozenNonLN(_FreezeAfterFirstTask):
         return 'norm' not in name or 'ViT' not in name          # frozen_nonln:36-43: everything but the ViT's LayerNorms
 
 
+class nnUNetTrainerFrozenBody(nnUNetTrainerMultiHead):
+    """reference frozen_body_seq/nnUNetTrainerFrozenUNet.py:169-229: from the second task on the shared body is frozen
+    (`assemble_model(task, freeze_body=True)`), only the task's head -- whose parameters are re-enabled explicitly (:203-204) --
+    is trained; the first task trains everything."""
+    EXTENSION = "frozen_body_seq"
+
+    def start_task(self, task):
+        if task not in self.mh_network.heads:
+            self.mh_network.add_new_task(task, use_init=not self.transfer_heads)
+        for _, param in self.mh_network.heads[task].named_parameters():
+            param.requires_grad = True
+        self.network = self.mh_network.assemble_model(task, freeze_body=len(self.mh_network.heads) > 1)
+        self.task = task
+        self.already_trained_on[str(self.fold)]["start_training_on"] = task
+        self._steps = {}
+        self.initialize_optimizer_and_scheduler()            # :226
+
+
+class nnUNetTrainerRehearsal(nnUNetTrainerMultiHead):
+    """reference rehearsal/nnUNetTrainerRehearsal.py:65-173: the training set of a task is fused with a seeded sample
+    (`samples_in_perc`) of the training cases of every task already in the heads; the iteration itself is the plain MultiHead one.
+    Here the fused case list feeds the GPU patch pipeline (b200unet/augment.py) instead of nnunet's DataLoader3D."""
+    EXTENSION = "rehearsal"
+
+    def __init__(self, *a, samples_in_perc=0.25, rehearsal_seed=3299, **kw):
+        super().__init__(*a, **kw)
+        assert 0 < samples_in_perc <= 1, "samples_in_perc should be between 0 and 1: (0, 1]."       # rehearsal:30-31
+        self.samples, self.rehearsal_seed = samples_in_perc, rehearsal_seed
+
+    def fuse_datasets(self, cases_current, cases_by_previous_task):
+        """cases_*: {case key: case dict}.  Returns the fused training dict (:80-124): `random.seed(seed)`, then per previous
+        task -- in head order -- `random.sample(items, round(len * samples))`; later tasks overwrite equal keys"""
+        import random
+        random.seed(self.rehearsal_seed)
+        fused = dict(cases_current)
+        done = [t for t in (self.mh_network.heads.keys() if self.mh_network is not None else []) if t in cases_by_previous_task]
+        for task in done:
+            items = list(cases_by_previous_task[task].items())
+            fused.update(random.sample(items, round(len(items) * self.samples)))
+        random.seed()
+        return fused
+
+    def get_basic_generators(self, cases_current, cases_by_previous_task, cases_val, ds_strides=None, **pipeline_kw):
+        """(training pipeline over the fused cases, validation pipeline of the current task), as :151-171 builds the DataLoader3D pair"""
+        from . import augment
+        if ds_strides is None:
+            ds_strides, cum = [(1, 1, 1)], [1, 1, 1]
+            for k in self.geometry.pool[:-1]:
+                cum = [a * b for a, b in zip(cum, k)]
+                ds_strides.append(tuple(cum))
+        fused = self.fuse_datasets(cases_current, cases_by_previous_task)
+        mk = lambda cases, train: augment.GPUPatchPipeline([dict(c, key=k) for k, c in cases.items()], self.geometry.patch,
+                                                           self.geometry.batch, ds_strides, device=self.device, train=train, **pipeline_kw)
+        return mk(fused, True), mk(cases_val, False)
+
+
 class nnUNetTrainerFrozEWC(nnUNetTrainerEWCViT):
     """reference froz_ewc/nnUNetTrainerFrozEWC.py:81-161: the ViT is frozen on every second task and EWC-regularised on the
     others; `adaptive` scales the EWC weight by e^(-1/3) while the ViT is frozen (:107,:117)."""

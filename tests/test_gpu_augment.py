@@ -129,3 +129,24 @@ def test_trainer_consumes_the_pipeline():
     tr.initialize()
     losses = [float(tr.run_iteration(pipe)) for _ in range(4)]
     assert all(np.isfinite(l) for l in losses)
+
+
+def test_rehearsal_trainer_trains_from_the_fused_pipeline():
+    """reference rehearsal:65-173 with the GPU pipeline in the place of DataLoader3D: fused case list -> batches -> iterations"""
+    from b200unet.configs import CONFIGS
+    from b200unet.trainers import nnUNetTrainerRehearsal
+    geom = CONFIGS["tiny"]
+    mk = lambda seed, tag: {"%s%d" % (tag, i): {"data": c["data"][[0, 2]]} for i, c in enumerate(_cases(seed))}
+    tr = nnUNetTrainerRehearsal(geom, precision="fp32", task="A", samples_in_perc=0.67)
+    tr.initialize()
+    tr.start_task("B")
+    gen_tr, gen_val = tr.get_basic_generators(mk(1, "b"), {"A": mk(2, "a")}, mk(3, "v"), seed=5)
+    assert sorted(gen_tr.keys) == ["a%d" % i for i in sorted(int(k[1]) for k in gen_tr.keys if k[0] == "a")] + ["b0", "b1", "b2"]
+    assert sum(k[0] == "a" for k in gen_tr.keys) == 2 and gen_val.keys == ["v0", "v1", "v2"] and not gen_val.train
+    seen = set()
+    for _ in range(6):
+        b = next(gen_tr)
+        seen.update(b["keys"])
+    assert any(k.startswith("a") for k in seen) and any(k.startswith("b") for k in seen)
+    assert all(np.isfinite(float(tr.run_iteration(gen_tr))) for _ in range(3))
+    assert np.isfinite(float(tr.run_iteration(gen_val, do_backprop=False)))

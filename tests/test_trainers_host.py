@@ -191,3 +191,34 @@ def test_plop_median_thresholds_equal_oracle_on_random_histograms():
         prev = cum[b - 1] if b else 0
         thr.append(max(b / 100 + ((total / 2 - prev) / hist[c, b]) / 100, 0.001))
     assert np.allclose(mine, thr, atol=1e-12) and mine[1] == 0.001 and mine[2] > 0.4
+
+
+def test_frozen_body_trainer_freezes_the_body_from_the_second_task():
+    """reference frozen_body_seq: first task trains everything; from the second task on only the task's head requires grad"""
+    from b200unet.trainers import nnUNetTrainerFrozenBody
+    tr = _mk(nnUNetTrainerFrozenBody, task="A")
+    tr.start_task("A")
+    assert all(p.requires_grad for p in tr.network.parameters())
+    tr.start_task("B")
+    head = {n for n, _ in tr.network.named_parameters() if n.startswith("seg_outputs")}
+    for n, p in tr.network.named_parameters():
+        assert p.requires_grad == (n in head), n
+    assert tr.mh_network.body_freezed and tr.mh_network.active_task == "B"
+
+
+def test_rehearsal_fuses_a_seeded_sample_of_previous_tasks():
+    """reference rehearsal:80-124: random.seed(seed); per previous task (head order) random.sample(items, round(len * samples))"""
+    import random
+    from b200unet.trainers import nnUNetTrainerRehearsal
+    tr = _mk(nnUNetTrainerRehearsal, task="A", samples_in_perc=0.25, rehearsal_seed=3299)
+    tr.start_task("B")
+    tr.start_task("C")
+    prev = {"A": {"a%02d" % i: {"data": i} for i in range(20)}, "B": {"b%02d" % i: {"data": i} for i in range(10)}}
+    cur = {"c%02d" % i: {"data": i} for i in range(6)}
+    fused = tr.fuse_datasets(cur, prev)
+    random.seed(3299)
+    exp = dict(cur)
+    exp.update(random.sample(list(prev["A"].items()), 5))
+    exp.update(random.sample(list(prev["B"].items()), 2))      # round(2.5) == 2 (banker's rounding, as in the reference)
+    assert fused == exp and len(fused) == 6 + 5 + 2
+    assert tr.fuse_datasets(cur, prev) == fused                 # seeded: reproducible
