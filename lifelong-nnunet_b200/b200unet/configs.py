@@ -3,7 +3,7 @@
 nnU-Net planner conventions: widths min(base * 2^d, 320), two 3x3x3 convs per stage, stride-conv pooling,
 kernel==stride transposed-conv upsampling, one 1x1x1 head per decoder level.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Tuple
 
 
