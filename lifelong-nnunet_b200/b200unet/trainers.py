@@ -245,6 +245,19 @@ class nnUNetTrainerMultiHead:
 
     # -- reference MultiHead:598-656 (fp32 branch; bf16 needs no loss scaling) ----------------------------------------
     # -- fused iteration (fused_step.py) ----------------------------------------------------------------------------------
+    def _matched_param_names(self):
+        """parameter names the loss's name filter selects, walked once per (network, filter) -- not per iteration: the walk over
+        named_parameters() costs ~0.25 ms of host time, which sits between two steps while the GPU idles.  The cache is tied to
+        the identity of the self._steps dict, so everything that invalidates the step programs by replacing that dict (start_task,
+        new LayerNorm sets, checkpoint loading, ...) invalidates it too."""
+        key = (id(self.network), self.loss.match_case, tuple(self.loss.match or ()), self.loss.match_true)
+        c = getattr(self, "_names_cache", None)
+        if c is None or c[0] is not self._steps or c[1] != key:
+            names = [n for n, _ in self.network.named_parameters()
+                     if ds._match(n, self.loss.match_case, self.loss.match, self.loss.match_true)]
+            c = self._names_cache = (self._steps, key, names)
+        return c[2]
+
     def _use_fused(self, do_backprop, no_loss):
         return (self.fused_step and do_backprop and not no_loss and not self.use_vit and
                 type(self.network) is Generic_UNet and self._fused_supported())
@@ -536,8 +549,7 @@ class nnUNetTrainerEWC(nnUNetTrainerMultiHead):
         return type(self.loss) is ds.MultipleOutputLossEWC and hasattr(self.loss.loss, 'cfg')
 
     def _penalty_names(self):
-        return [n for n, _ in self.network.named_parameters()
-                if ds._match(n, self.loss.match_case, self.loss.match, self.loss.match_true)]
+        return self._matched_param_names()
 
     def _fused_spec(self):
         tasks = list(self.loss.tasks)
@@ -818,8 +830,7 @@ class nnUNetTrainerRW(nnUNetTrainerMultiHead):
         tasks = list(self.loss.tasks)
         if self.strict_reference:
             tasks = tasks[:1] if getattr(self, "_rw_params_fresh", False) else []
-        names = [n for n, _ in self.network.named_parameters()
-                 if ds._match(n, self.loss.match_case, self.loss.match, self.loss.match_true)]
+        names = self._matched_param_names()
         pen = [(self.rw_lambda, self.fisher[t], self.params[t], self.scores[t], names) for t in tasks] if names else []
         key = ("rw", tuple(tasks), tuple(id(self.fisher[t]) for t in tasks), tuple(id(self.scores[t]) for t in tasks))
         return key, dict(base='dcce', cfg=self.loss.loss.cfg(list(self.ds_loss_weights)), penalty=pen)
