@@ -259,3 +259,39 @@ def test_plop_threshold_extraction_strict_and_documented():
     assert float(thr[0].max()) > 1e-3          # a real median, not the floor
     l = float(tr.run_iteration(mk()))          # the extracted thresholds feed the pseudo-label loss
     assert np.isfinite(l)
+
+
+def test_fisher_and_rw_single_update_strict():
+    """The quantities EWC / RW store, at IDENTICAL parameters (no preceding SGD steps, so no chaotic divergence between the two
+    fp32 implementations): Fisher = g^2 of `after_train` and the first RW Fisher / score update within 1e-2 of the oracle per
+    tensor (i.e. 5e-3 on the gradient; the multi-step tests above allow 0.1-0.15 because three SGD steps amplify LeakyReLU
+    branch flips)."""
+    from b200unet.trainers import nnUNetTrainerEWC, nnUNetTrainerRW
+    from oracle import cl_losses, step
+    geom, onet, tr, data, targets, gen = _setup(nnUNetTrainerEWC, task="A")
+    weights = cl_losses.ds_loss_weights(geom.num_pool)
+    out = onet(data)
+    cl_losses.multiple_output_loss2(out, targets, weights).backward()
+    of, _ = cl_losses.ewc_fisher_from_grads(list(onet.named_parameters()))
+    tr.after_train(gen, num_batches=1)
+    worst = 0.0
+    for k, v in of.items():
+        if v.numel() == 1 or ("conv.bias" in k and "seg" not in k):
+            continue
+        worst = max(worst, rel_err(tr.fisher["A"][k], v))
+    assert worst < 1e-2, worst
+    # RW: one iteration from the same weights -> first Fisher EMA / score update
+    geom, onet, tr, data, targets, gen = _setup(nnUNetTrainerRW, fisher_update_after=1)
+    tr.start_task("A")
+    oopt = step.make_optimizer(onet)
+    lf = step.base_loss_fn(weights)
+    named = dict(onet.named_parameters())
+    step.run_iteration(onet, oopt, data, targets, lf)
+    tr.run_iteration(gen)
+    worst = 0.0
+    for n, p in named.items():
+        if p.grad is None or ("conv.bias" in n and "seg" not in n):
+            continue
+        f, s_ = cl_losses.rw_update(p.detach(), p.grad.detach(), None, torch.zeros_like(p), torch.zeros_like(p), 0.9)
+        worst = max(worst, rel_err(tr.fisher["A"][n], f))
+    assert worst < 1e-2, worst
