@@ -47,6 +47,24 @@ class DeviceTable:
         self.keep = keep          # tensors the entries point to
 
 
+def bucket_bounds(names, numels, target_bytes):
+    """Gradient buckets for the overlapped all-reduce: [(first_param, end_param)] in the order backward completes them -- suffixes of
+    the plan's parameter order (backward finishes layers in DESCENDING parameter index), cut only at layer starts (a conv / tconv
+    / head weight), each at least `target_bytes` of fp32 gradients except the last, which takes what is left down to parameter 0."""
+    starts = [i for i, n in enumerate(names) if n.endswith("conv.weight") or
+              (n.endswith(".weight") and (n.startswith("tu.") or n.startswith("seg_outputs.")))]
+    bounds, cur_hi, acc, prev = [], len(names), 0, len(names)
+    for s in reversed(starts):               # greedy from the end of the arena
+        acc += sum(numels[s:prev]) * 4
+        prev = s
+        if acc >= target_bytes or s == 0:
+            bounds.append((s, cur_hi))
+            cur_hi, acc = s, 0
+    if not bounds or bounds[-1][0] != 0:
+        bounds.append((0, cur_hi))
+    return bounds
+
+
 class FusedStep:
     def __init__(self, trainer, data, targets, spec):
         self.tr, self.spec = trainer, spec
@@ -203,17 +221,7 @@ class FusedStep:
         if target_bytes is None:
             target_bytes = int(float(os.environ.get("B2_BUCKET_MB", "48")) * (1 << 20))
         names = self.plan.param_names
-        starts = [i for i, n in enumerate(names) if n.endswith("conv.weight") or
-                  (n.endswith(".weight") and (n.startswith("tu.") or n.startswith("seg_outputs.")))]
-        bounds, cur_hi, acc, prev = [], len(names), 0, len(names)
-        for s in reversed(starts):               # greedy from the end of the arena
-            acc += sum(self.plan.param_numel[s:prev]) * 4
-            prev = s
-            if acc >= target_bytes or s == 0:
-                bounds.append((s, cur_hi))
-                cur_hi, acc = s, 0
-        if not bounds or bounds[-1][0] != 0:
-            bounds.append((0, cur_hi))
+        bounds = bucket_bounds(names, self.plan.param_numel, target_bytes)
         self.comm = torch.cuda.Stream(self.dev)
         arr = (_lib.GradBucket * len(bounds))()
         for k, (lo, hi) in enumerate(bounds):

@@ -117,3 +117,45 @@ def test_fastdiv_exact(tmp_path):
     subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_gradient_buckets_follow_the_backward_order_of_the_cfg2_plan():
+    """data-parallel overlap: the buckets b2_unet_backward_buckets signals are suffixes of the plan's parameter
+    order cut at layer starts -- contiguous, covering every parameter exactly once, each >= the target size except the last,
+    first_param strictly descending (the C entry point checks the same), the full-resolution encoder layers (finished last) in
+    the last bucket"""
+    from b200unet.configs import CONFIGS
+    from b200unet.fused_step import bucket_bounds
+    from b200unet import _lib
+    geom = CONFIGS["cfg2"]
+    lib = _lib.load()
+    g = _lib.Geometry()
+    g.batch, g.in_channels, g.num_classes = geom.batch, geom.in_channels, geom.num_classes
+    g.base_features, g.max_features, g.num_pool = geom.base_features, geom.max_features, geom.num_pool
+    for i in range(3):
+        g.patch[i] = geom.patch[i]
+    for l, k in enumerate(geom.pool):
+        for i in range(3):
+            g.pool[l][i] = k[i]
+    g.act_dtype, g.lrelu_slope, g.norm_eps = 1, 1e-2, 1e-5
+    h = ctypes.c_void_p()
+    _lib.check(lib.b2_unet_plan_create(ctypes.byref(g), ctypes.byref(h)))
+    info, names, numels = _lib.ParamInfo(), [], []
+    for i in range(lib.b2_unet_num_params(h)):
+        _lib.check(lib.b2_unet_param_info(h, i, ctypes.byref(info)))
+        names.append(info.name.decode())
+        numels.append(int(info.numel))
+    lib.b2_unet_plan_destroy(h)
+    assert sum(numels) == 30_787_840 or sum(numels) > 30e6          # 30.8 M parameters: the 123 MB arena of DESIGN section 5
+    for target_mb in (8, 48, 10 ** 6):
+        bounds = bucket_bounds(names, numels, target_mb << 20)
+        assert bounds[0][1] == len(names) and bounds[-1][0] == 0
+        assert all(bounds[k][0] == bounds[k + 1][1] for k in range(len(bounds) - 1))
+        assert all(bounds[k][0] > bounds[k + 1][0] for k in range(len(bounds) - 1))
+        sizes = [4 * sum(numels[lo:hi]) for lo, hi in bounds]
+        assert sum(sizes) == 4 * sum(numels) and all(s >= (target_mb << 20) for s in sizes[:-1])
+        for lo, _ in bounds:
+            assert names[lo].endswith("conv.weight") or names[lo].startswith(("tu.", "seg_outputs."))
+    b48 = bucket_bounds(names, numels, 48 << 20)
+    assert len(b48) == 3 and "conv_blocks_context.0.blocks.0.conv.weight" in names[b48[-1][0]:b48[-1][1]]
+    assert len(bucket_bounds(names, numels, 10 ** 12)) == 1
