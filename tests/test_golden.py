@@ -124,3 +124,24 @@ def test_vit_unet_oracle_against_reference_fixture():
     assert set(gold.files) == set(vals)
     for k in gold.files:
         np.testing.assert_allclose(gold[k], vals[k], rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_augment_and_sliding_window_oracles_reproduce_their_fixtures():
+    """tests/golden/augment_tiny.npz / sliding_window_tiny.npz (oracle/gen_golden_f.py) == what the oracles produce today: pins the
+    scipy.ndimage-based patch-pipeline restatement and the tiled-prediction restatement; the GPU tests hold the CUDA path to the
+    same files"""
+    import util
+    from oracle import augment as oaug, gen_golden_f
+    cases, plan, patch, strides, gen_patch, params, data, targets, margin = util.load_augment_fixture()
+    assert len(plan["cases"]) == 2 and all(s["angles"] is not None for s in plan["spatial"]) and gen_patch[0] > patch[0]
+    d, t, m = oaug.apply_plan([c["data"] for c in cases], plan, patch, gen_patch, strides)
+    np.testing.assert_allclose(d, data, rtol=1e-5, atol=1e-6)
+    for a, b in zip(t, targets):
+        assert np.array_equal(a, b)
+    bad, agree = util.augment_mismatch(d, t, data, targets, margin)
+    assert bad == 0.0 and agree == 1.0
+    z = np.load(os.path.join(util.ROOT, "tests", "golden", "sliding_window_tiny.npz"))
+    v = gen_golden_f.sliding_values()
+    np.testing.assert_allclose(v["prob"], z["prob"], rtol=1e-4, atol=1e-6)
+    assert (v["seg"] == z["seg"]).mean() > 0.9999 and np.array_equal(v["x"], z["x"])
+    assert abs(float(z["prob"].sum(0).mean()) - 1) < 1e-5

@@ -150,3 +150,16 @@ def test_rehearsal_trainer_trains_from_the_fused_pipeline():
     assert any(k.startswith("a") for k in seen) and any(k.startswith("b") for k in seen)
     assert all(np.isfinite(float(tr.run_iteration(gen_tr))) for _ in range(3))
     assert np.isfinite(float(tr.run_iteration(gen_val, do_backprop=False)))
+
+
+def test_pipeline_matches_the_committed_fixture():
+    """the CUDA pipeline on the plan stored in tests/golden/augment_tiny.npz (every transform on) against the oracle output
+    committed beside it -- same tolerances as the live comparison above"""
+    from b200unet import augment
+    cases, plan, patch, strides, gen_patch, params, data, targets, margin = util.load_augment_fixture()
+    pipe = augment.GPUPatchPipeline(cases, patch, len(plan["cases"]), strides, params=params, seed=0, prefetch=False)
+    assert pipe.gen_patch == gen_patch
+    out = pipe.run_plan(plan)
+    torch.cuda.synchronize()
+    bad, agree = util.augment_mismatch(out["data"].cpu().numpy(), [t.cpu().numpy() for t in out["target"]], data, targets, margin)
+    assert bad < 2e-3 and agree > 0.999, (bad, agree)

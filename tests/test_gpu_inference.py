@@ -84,3 +84,22 @@ def test_per_subject_validation_sweep_matches_oracle_counts():
             assert abs(res[name]['mask_%d' % (c + 1)]['Dice'] - 2 * tp[c] / (2 * tp[c] + fp[c] + fn[c])) < 1e-3
             assert abs(res[name]['mask_%d' % (c + 1)]['IoU'] - tp[c] / (tp[c] + fp[c] + fn[c])) < 1e-3
     assert tr.eval_batch is True and tr.online_eval_tp == [] and tr.network.training
+
+
+def test_sliding_window_matches_the_committed_fixture():
+    """tests/golden/sliding_window_tiny.npz (oracle/gen_golden_f.py): tiled prediction of the seeded tiny network with Gaussian
+    weighting and full mirroring; probabilities within 1e-3, labels equal wherever the fixture's top two differ by > 2e-3"""
+    import os
+    import util
+    from b200unet import inference
+    from b200unet.configs import CONFIGS
+    z = np.load(os.path.join(util.ROOT, "tests", "golden", "sliding_window_tiny.npz"))
+    geom = CONFIGS["tiny"]
+    cnet = cuda_net(geom, oracle_net(geom).state_dict())
+    cnet.eval()
+    cseg, cprob = inference.predict_3D(cnet, torch.from_numpy(z["x"]), geom.patch, True, (0, 1, 2), 0.5, True)
+    prob = torch.from_numpy(z["prob"])
+    assert float((cprob.cpu() - prob).abs().max()) < 1e-3
+    top2 = prob.topk(2, 0).values
+    decided = (top2[0] - top2[1]) > 2e-3
+    assert bool((cseg.cpu()[decided] == torch.from_numpy(z["seg"]).long()[decided]).all())
