@@ -13,6 +13,8 @@
 //   aug_pointwise_kernel  Gaussian noise (counter-based generator), multiplicative brightness, contrast, gamma (with
 //                         retain_stats, optionally on the inverted image)
 //   aug_blur_kernel       Gaussian blur along one axis (scipy gaussian_filter: reflect boundaries, truncate 4)
+//   aug_lowres_*          SimulateLowResolutionTransform: nearest-neighbour resize down into an edge-padded volume (min / max by
+//                         integer atomics), the prefilter above, cubic B-spline resize back with clipping (scipy zoom pair)
 //   aug_finalize_kernel   MirrorTransform + RemoveLabelTransform(-1, 0) + DownsampleSegForDSTransform2 (order 0): writes the
 //                         network input and every deep-supervision target in one pass
 // All of it is HBM-bound elementwise / gather work on a few MB per batch.
